@@ -1,0 +1,450 @@
+// abi.cu — the extern "C" surface of libeasylp_b200.so (declared in include/easylp_abi.h).
+// Every entry point converts C++ exceptions into a nonzero return code + elp_last_error() text.
+#include "common.cuh"
+#include "comm.cuh"
+#include "../../include/easylp_abi.h"
+#include <algorithm>
+#include <cmath>
+
+namespace elp {
+
+std::atomic<int64_t> g_launches{0};
+thread_local std::string g_last_error;
+
+// implemented in the other translation units
+struct Pdlp;
+int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_col, const double* d_val, int32_t m,
+                            int32_t n, int32_t* d_row_ptr, int32_t* d_col_idx, double* d_vals, cudaStream_t st);
+Pdlp* pdlp_create(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                  const int8_t* sense, const double* rhs, const double* c, int maximize, const double* lb,
+                  const double* ub, const elp_options& opt, bool dist, elp_stats* stats);
+void pdlp_run(Pdlp* p, int max_new_iters, elp_stats* stats);
+void pdlp_reset(Pdlp* p);
+void pdlp_solution(Pdlp* p, double* x, double* y, double* obj);
+void pdlp_probe(Pdlp* p, int reps, double* a, double* b);
+void pdlp_destroy(Pdlp* p);
+void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals, const double* x,
+               double* out, const int8_t* sense, const double* rhs, double tol, uint8_t* feasible);
+size_t simplex_smem_bytes(int m, int n);
+void simplex_batch_device(int64_t B, int m, int n, const double* A, const double* b, const double* c, const double* lb,
+                          const double* ub, const int8_t* sense, int maximize, int max_pivots, int32_t* status,
+                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st);
+void densify_device(int m, int n, const int* ptr, const int* idx, const double* val, double* A, cudaStream_t st);
+
+static void require_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Error(format("no CUDA device available (%s); libeasylp_b200 has no CPU fallback",
+                           e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+}
+
+static elp_options effective_options(const elp_options* opt) {
+    elp_options o;
+    elp_default_options(&o);
+    if (opt) {
+        o = *opt;
+        elp_options d;
+        elp_default_options(&d);
+        if (!(o.eps_rel > 0)) o.eps_rel = d.eps_rel;
+        if (o.check_every <= 1) o.check_every = d.check_every;
+        if (o.ruiz_iters < 0) o.ruiz_iters = d.ruiz_iters;
+    }
+    return o;
+}
+
+struct Batch {
+    int64_t B = 0;
+    int m = 0, n = 0, maximize = 0;
+    DevBuf<double> A, b, c, lb, ub, obj, x;
+    DevBuf<int8_t> sense;
+    DevBuf<int32_t> status, pivots;
+    bool has_lb = false, has_ub = false, has_sense = false;
+    int64_t h2d = 0;
+};
+
+}  // namespace elp
+
+using namespace elp;
+
+#define ELP_TRY try {
+#define ELP_CATCH                                   \
+    }                                               \
+    catch (const std::exception& e) {               \
+        elp::g_last_error = e.what();               \
+        return 1;                                   \
+    }                                               \
+    catch (...) {                                   \
+        elp::g_last_error = "unknown C++ exception"; \
+        return 1;                                   \
+    }                                               \
+    return 0;
+
+extern "C" {
+
+const char* elp_version(void) { return "easylp_b200 0.1 (sm_100a)"; }
+
+int elp_last_error(char* buf, int32_t len) {
+    if (!buf || len <= 0) return 1;
+    snprintf(buf, (size_t)len, "%s", elp::g_last_error.c_str());
+    return 0;
+}
+
+int elp_device_count(int32_t* count) {
+    ELP_TRY
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { c = 0; cudaGetLastError(); }
+    *count = c;
+    ELP_CATCH
+}
+
+int elp_set_device(int32_t device) {
+    ELP_TRY
+    ELP_CUDA(cudaSetDevice(device));
+    ELP_CATCH
+}
+
+int elp_default_options(elp_options* o) {
+    if (!o) return 1;
+    o->eps_rel = 1e-6;
+    o->time_limit_s = 0.0;
+    o->max_iter = 0;
+    o->check_every = 64;
+    o->method = ELP_METHOD_AUTO;
+    o->verbose = 0;
+    o->use_graph = 1;
+    o->ruiz_iters = 10;
+    return 0;
+}
+
+const char* elp_status_string(int32_t status) {
+    switch (status) {   // /root/reference/R/class.R:279-295
+        case 0: return "optimal";
+        case 1: return "sub-optimal";
+        case 2: return "unfeasible";
+        case 3: return "unbounded";
+        case 4: return "degenerate model";
+        case 5: return "numerical failure encountered";
+        case 6: return "process aborted";
+        case 7: return "timeout";
+        case 9: return "the model was solved by presolve";
+        case 10: return "the branch and bound routine failed";
+        case 11: return "the branch and bound was stopped because of a break-at-first or break-at-value";
+        case 12: return "a feasible branch and bound solution was found";
+        case 13: return "no feasible branch and bound solution was found";
+        default: return "undocumented status";
+    }
+}
+
+int64_t elp_kernel_launches(void) { return elp::g_launches.load(); }
+
+int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
+                     int32_t m, int32_t n, int32_t* row_ptr, int32_t* col_idx, double* vals, int64_t* nnz_out,
+                     elp_stats* stats) {
+    ELP_TRY
+    require_device();
+    WallTimer wall;
+    const int64_t l0 = g_launches.load();
+    ELP_REQUIRE(n_terms >= 0 && m >= 0 && n >= 0, "assemble: negative size");
+    cudaStream_t st = 0;
+    const size_t T = (size_t)n_terms;
+    DevBuf<int32_t> drow(std::max<size_t>(T, 1)), dcol(std::max<size_t>(T, 1)), dptr((size_t)m + 1), dci(std::max<size_t>(T, 1));
+    DevBuf<double> dval(std::max<size_t>(T, 1)), dv(std::max<size_t>(T, 1));
+    drow.upload(term_row, T, st); dcol.upload(term_col, T, st); dval.upload(term_val, T, st);
+    cudaEvent_t e0, e1;
+    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    ELP_CUDA(cudaEventRecord(e0, st));
+    const int64_t nnz = assemble_csr_device(n_terms, drow.p, dcol.p, dval.p, m, n, dptr.p, dci.p, dv.p, st);
+    ELP_CUDA(cudaEventRecord(e1, st));
+    dptr.download(row_ptr, (size_t)m + 1, st);
+    dci.download(col_idx, (size_t)nnz, st);
+    dv.download(vals, (size_t)nnz, st);
+    ELP_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *nnz_out = nnz;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->solve_ms = ms;
+        stats->total_ms = wall.ms();
+        stats->kernel_launches = g_launches.load() - l0;
+        stats->h2d_bytes = (int64_t)T * 16;
+        stats->d2h_bytes = nnz * 12 + ((int64_t)m + 1) * 4;
+    }
+    ELP_CATCH
+}
+
+static void solve_small(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                        const int8_t* sense, const double* rhs, const double* c, int32_t maximize, const double* lb,
+                        const double* ub, const elp_options& o, int32_t* status, double* objval, double* x, double* y,
+                        elp_stats* stats) {
+    WallTimer wall;
+    const int64_t l0 = g_launches.load();
+    cudaStream_t st = 0;
+    const int64_t nnz = m > 0 ? row_ptr[m] : 0;
+    DevBuf<int> ptr((size_t)m + 1), idx(std::max<int64_t>(nnz, 1));
+    DevBuf<double> val(std::max<int64_t>(nnz, 1)), A((size_t)std::max(m, 1) * n), b(std::max(m, 1)), cd(n), lbd(n), ubd(n),
+        obj(1), xd(n), yd(std::max(m, 1));
+    DevBuf<int8_t> sd(std::max(m, 1));
+    DevBuf<int32_t> stat(1), piv(1);
+    if (m > 0) { ptr.upload(row_ptr, (size_t)m + 1, st); idx.upload(col_idx, nnz, st); val.upload(vals, nnz, st);
+                 b.upload(rhs, m, st); sd.upload(sense, m, st); }
+    cd.upload(c, n, st); lbd.upload(lb, n, st); ubd.upload(ub, n, st);
+    cudaEvent_t e0, e1;
+    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    ELP_CUDA(cudaEventRecord(e0, st));
+    densify_device(m, n, ptr.p, idx.p, val.p, A.p, st);
+    simplex_batch_device(1, m, n, A.p, b.p, cd.p, lbd.p, ubd.p, sd.p, maximize, o.max_iter, stat.p, obj.p, xd.p, yd.p,
+                         piv.p, st);
+    ELP_CUDA(cudaEventRecord(e1, st));
+    int32_t s = 0, pv = 0;
+    stat.download(&s, 1, st); piv.download(&pv, 1, st); obj.download(objval, 1, st); xd.download(x, n, st);
+    if (y && m > 0) yd.download(y, m, st);
+    ELP_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *status = s;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->status = s;
+        stats->method_used = ELP_METHOD_SIMPLEX;
+        stats->iterations = pv;
+        stats->primal_obj = *objval;
+        stats->dual_obj = *objval;
+        stats->solve_ms = ms;
+        stats->total_ms = wall.ms();
+        stats->kernel_launches = g_launches.load() - l0;
+        stats->h2d_bytes = nnz * 12 + (int64_t)m * 13 + (int64_t)n * 24;
+        stats->d2h_bytes = (int64_t)n * 8 + (int64_t)m * 8 + 16;
+    }
+}
+
+int elp_solve_lp(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                 const int8_t* sense, const double* rhs, const double* c, int32_t maximize, const double* lb,
+                 const double* ub, const elp_options* opt, int32_t* status, double* objval, double* x, double* y,
+                 elp_stats* stats) {
+    ELP_TRY
+    require_device();
+    ELP_REQUIRE(n > 0, "Problem contains no variables.");   // R/class.R:253-254
+    ELP_REQUIRE(m >= 0 && status && objval && x && c && lb && ub, "elp_solve_lp: bad arguments");
+    const elp_options o = effective_options(opt);
+    int method = o.method;
+    if (method == ELP_METHOD_AUTO)   // size rule, not a backend switch: does the dense tableau fit in one SM?
+        method = (simplex_smem_bytes(m, n) <= 200 * 1024) ? ELP_METHOD_SIMPLEX : ELP_METHOD_PDLP;
+    // any block with lower > upper forces "unfeasible" (R/class.R:297-298); both solvers also detect it
+    if (method == ELP_METHOD_SIMPLEX) {
+        solve_small(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
+    } else {
+        WallTimer wall;
+        bool bad_bounds = false;
+        for (int j = 0; j < n; ++j) if (lb[j] > ub[j]) { bad_bounds = true; break; }
+        elp_stats s1;
+        memset(&s1, 0, sizeof s1);
+        Pdlp* p = pdlp_create(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, false, &s1);
+        try {
+            elp_stats s2;
+            memset(&s2, 0, sizeof s2);
+            if (!bad_bounds) pdlp_run(p, 0, &s2);
+            pdlp_solution(p, x, y, objval);
+            *status = bad_bounds ? ELP_STATUS_INFEASIBLE : s2.status;
+            if (*status == ELP_STATUS_UNBOUNDED) *objval = maximize ? INFINITY : -INFINITY;
+            if (stats) {
+                *stats = s2;
+                stats->status = *status;
+                stats->setup_ms = s1.setup_ms;
+                stats->total_ms = wall.ms();
+                stats->kernel_launches += 0;
+            }
+        } catch (...) {
+            pdlp_destroy(p);
+            throw;
+        }
+        pdlp_destroy(p);
+    }
+    ELP_CATCH
+}
+
+int elp_batch_create(int64_t B, int32_t m, int32_t n, const double* A, const double* b, const double* c,
+                     const double* lb, const double* ub, const int8_t* sense, int32_t maximize, elp_batch** out) {
+    ELP_TRY
+    require_device();
+    ELP_REQUIRE(B > 0 && m >= 0 && n > 0 && A && b && c && out, "elp_batch_create: bad arguments");
+    auto* h = new Batch();
+    try {
+        cudaStream_t st = 0;
+        h->B = B; h->m = m; h->n = n; h->maximize = maximize;
+        h->A.alloc((size_t)B * m * n); h->b.alloc((size_t)B * m); h->c.alloc((size_t)B * n);
+        h->A.upload(A, (size_t)B * m * n, st); h->b.upload(b, (size_t)B * m, st); h->c.upload(c, (size_t)B * n, st);
+        h->h2d = (int64_t)B * (m * n + m + n) * 8;
+        if (lb) { h->lb.alloc((size_t)B * n); h->lb.upload(lb, (size_t)B * n, st); h->has_lb = true; h->h2d += (int64_t)B * n * 8; }
+        if (ub) { h->ub.alloc((size_t)B * n); h->ub.upload(ub, (size_t)B * n, st); h->has_ub = true; h->h2d += (int64_t)B * n * 8; }
+        if (sense) { h->sense.alloc((size_t)B * m); h->sense.upload(sense, (size_t)B * m, st); h->has_sense = true; h->h2d += (int64_t)B * m; }
+        h->obj.alloc(B); h->x.alloc((size_t)B * n); h->status.alloc(B); h->pivots.alloc(B);
+        ELP_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    *out = reinterpret_cast<elp_batch*>(h);
+    ELP_CATCH
+}
+
+int elp_batch_run(elp_batch* hh, const elp_options* opt, elp_stats* stats) {
+    ELP_TRY
+    auto* h = reinterpret_cast<Batch*>(hh);
+    ELP_REQUIRE(h, "elp_batch_run: null handle");
+    const elp_options o = effective_options(opt);
+    WallTimer wall;
+    const int64_t l0 = g_launches.load();
+    cudaStream_t st = 0;
+    cudaEvent_t e0, e1;
+    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    ELP_CUDA(cudaEventRecord(e0, st));
+    simplex_batch_device(h->B, h->m, h->n, h->A.p, h->b.p, h->c.p, h->has_lb ? h->lb.p : nullptr,
+                         h->has_ub ? h->ub.p : nullptr, h->has_sense ? h->sense.p : nullptr, h->maximize, o.max_iter,
+                         h->status.p, h->obj.p, h->x.p, nullptr, h->pivots.p, st);
+    ELP_CUDA(cudaEventRecord(e1, st));
+    ELP_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->method_used = ELP_METHOD_SIMPLEX;
+        stats->solve_ms = ms;
+        stats->total_ms = wall.ms();
+        stats->kernel_launches = g_launches.load() - l0;
+    }
+    ELP_CATCH
+}
+
+int elp_batch_fetch(elp_batch* hh, int32_t* status, double* obj, double* x) {
+    ELP_TRY
+    auto* h = reinterpret_cast<Batch*>(hh);
+    ELP_REQUIRE(h, "elp_batch_fetch: null handle");
+    cudaStream_t st = 0;
+    if (status) h->status.download(status, h->B, st);
+    if (obj) h->obj.download(obj, h->B, st);
+    if (x) h->x.download(x, (size_t)h->B * h->n, st);
+    ELP_CUDA(cudaStreamSynchronize(st));
+    ELP_CATCH
+}
+
+int elp_batch_destroy(elp_batch* hh) {
+    ELP_TRY
+    delete reinterpret_cast<Batch*>(hh);
+    ELP_CATCH
+}
+
+int elp_solve_batch(int64_t B, int32_t m, int32_t n, const double* A, const double* b, const double* c,
+                    const double* lb, const double* ub, const int8_t* sense, int32_t maximize, const elp_options* opt,
+                    int32_t* status, double* obj, double* x, elp_stats* stats) {
+    WallTimer wall;
+    elp_batch* h = nullptr;
+    if (elp_batch_create(B, m, n, A, b, c, lb, ub, sense, maximize, &h)) return 1;
+    elp_stats s;
+    memset(&s, 0, sizeof s);
+    int rc = elp_batch_run(h, opt, &s);
+    if (!rc) rc = elp_batch_fetch(h, status, obj, x);
+    if (!rc && stats) {
+        auto* bh = reinterpret_cast<Batch*>(h);
+        *stats = s;
+        stats->h2d_bytes = bh->h2d;
+        stats->d2h_bytes = B * ((int64_t)n * 8 + 12);
+        int64_t piv = 0;
+        std::vector<int32_t> pv((size_t)B);
+        cudaMemcpy(pv.data(), bh->pivots.p, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        for (int32_t v : pv) piv += v;
+        stats->iterations = (int32_t)std::min<int64_t>(piv, 0x7fffffff);
+        stats->total_ms = wall.ms();
+    }
+    elp_batch_destroy(h);
+    return rc;
+}
+
+int elp_spmv(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals, const double* x,
+             double* out) {
+    ELP_TRY
+    require_device();
+    spmv_host(m, n, row_ptr, col_idx, vals, x, out, nullptr, nullptr, 0.0, nullptr);
+    ELP_CATCH
+}
+
+int elp_check_feasible(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                       const double* x, const int8_t* sense, const double* rhs, double tol, uint8_t* feasible) {
+    ELP_TRY
+    require_device();
+    spmv_host(m, n, row_ptr, col_idx, vals, x, nullptr, sense, rhs, tol, feasible);
+    ELP_CATCH
+}
+
+int elp_pdlp_create(int32_t m_local, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                    const int8_t* sense, const double* rhs, const double* c, int32_t maximize, const double* lb,
+                    const double* ub, const elp_options* opt, int32_t dist, elp_pdlp** out, elp_stats* stats) {
+    ELP_TRY
+    require_device();
+    ELP_REQUIRE(out, "elp_pdlp_create: null out");
+    if (stats) memset(stats, 0, sizeof *stats);
+    const elp_options o = effective_options(opt);
+    *out = reinterpret_cast<elp_pdlp*>(
+        pdlp_create(m_local, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, dist != 0, stats));
+    ELP_CATCH
+}
+int elp_pdlp_run(elp_pdlp* h, int32_t max_new_iters, elp_stats* stats) {
+    ELP_TRY
+    ELP_REQUIRE(h, "null handle");
+    if (stats) memset(stats, 0, sizeof *stats);
+    pdlp_run(reinterpret_cast<Pdlp*>(h), max_new_iters, stats);
+    ELP_CATCH
+}
+int elp_pdlp_reset(elp_pdlp* h) {
+    ELP_TRY
+    ELP_REQUIRE(h, "null handle");
+    pdlp_reset(reinterpret_cast<Pdlp*>(h));
+    ELP_CATCH
+}
+int elp_pdlp_solution(elp_pdlp* h, double* x, double* y, double* objval) {
+    ELP_TRY
+    ELP_REQUIRE(h, "null handle");
+    pdlp_solution(reinterpret_cast<Pdlp*>(h), x, y, objval);
+    ELP_CATCH
+}
+int elp_pdlp_probe_spmv(elp_pdlp* h, int32_t reps, double* ms_csr, double* ms_csc) {
+    ELP_TRY
+    ELP_REQUIRE(h && reps > 0, "bad arguments");
+    pdlp_probe(reinterpret_cast<Pdlp*>(h), reps, ms_csr, ms_csc);
+    ELP_CATCH
+}
+int elp_pdlp_destroy(elp_pdlp* h) {
+    ELP_TRY
+    if (h) pdlp_destroy(reinterpret_cast<Pdlp*>(h));
+    ELP_CATCH
+}
+
+int elp_comm_unique_id(void* id) {
+    ELP_TRY
+    comm_unique_id(id);
+    ELP_CATCH
+}
+int elp_comm_init(int32_t nranks, int32_t rank, const void* id) {
+    ELP_TRY
+    require_device();
+    comm_init(nranks, rank, id);
+    ELP_CATCH
+}
+int elp_comm_size(int32_t* nranks, int32_t* rank) {
+    ELP_TRY
+    if (nranks) *nranks = comm().nranks;
+    if (rank) *rank = comm().rank;
+    ELP_CATCH
+}
+int elp_comm_destroy(void) {
+    ELP_TRY
+    comm_destroy();
+    ELP_CATCH
+}
+
+}  // extern "C"

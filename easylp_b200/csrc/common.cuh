@@ -1,0 +1,135 @@
+// common.cuh — error handling, device buffers, launch accounting, small device helpers.
+// Part of libeasylp_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <stdexcept>
+#include <atomic>
+#include <chrono>
+#include <vector>
+
+namespace elp {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline std::string format(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    return std::string(buf);
+}
+
+#define ELP_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            throw elp::Error(elp::format("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,  \
+                                         cudaGetErrorString(e__)));                             \
+    } while (0)
+
+#define ELP_REQUIRE(cond, ...)                                    \
+    do {                                                          \
+        if (!(cond)) throw elp::Error(elp::format(__VA_ARGS__)); \
+    } while (0)
+
+extern std::atomic<int64_t> g_launches;        // every kernel launch of the library is counted here
+extern thread_local std::string g_last_error;
+
+// Launch wrapper: counts, launches, checks the launch error (not the execution).
+#define ELP_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
+    do {                                                                           \
+        elp::g_launches.fetch_add(1, std::memory_order_relaxed);                   \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                \
+        ELP_CUDA(cudaGetLastError());                                              \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) ELP_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    void upload(const T* host, size_t count, cudaStream_t s = 0) {
+        if (count) ELP_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T* host, size_t count, cudaStream_t s = 0) const {
+        if (count) ELP_CUDA(cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+    void zero(cudaStream_t s = 0) {
+        if (n) ELP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+};
+
+struct WallTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int L>
+__device__ __forceinline__ double group_sum(double v) {   // sum over aligned groups of L lanes
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int L>
+__device__ __forceinline__ double group_max(double v) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming (read-once) loads of the matrix arrays: read-only path, do not allocate in L1
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+}  // namespace elp

@@ -1,0 +1,451 @@
+// simplex.cu — batched dense simplex: one LP per CTA, tableau resident in shared memory.
+//
+// Replaces `status <- solve(prob)` (/root/reference/R/class.R:276) for LPs whose dense tableau fits in
+// one SM's shared memory, and is the engine of the additive batch entry point (BASELINE config 3:
+// 200k LPs of 20x30).  Method: bounded-variable primal simplex on  A x + s = b  with a composite
+// phase 1 (minimise the sum of infeasibilities), Dantzig pricing, a two-pass ratio test and Bland's
+// rule after a run of degenerate pivots.  The CPU restatement is oracle/simplex_ref.c.
+//
+// Data movement: each LP's A (m*n doubles), b, c, lb, ub are read ONCE from HBM with 1-D TMA bulk
+// copies (cp.async.bulk -> mbarrier complete_tx) straight into their shared-memory homes; results
+// (status, objective, x) are written once.  Everything in between — pricing argmax, ratio-test
+// argmin (warp shuffles), the rank-1 pivot update — runs out of shared memory in fp64.
+// Algorithmic HBM bytes per LP: 8 (m n + m + 3 n) + m   in,   8 (n + 1) + 4   out.
+// The serial pivot chain, not HBM, bounds this kernel; bench.py reports LPs/s, pivots/s and the HBM
+// fraction side by side.
+#include "common.cuh"
+#include "../../include/easylp_abi.h"
+#include <algorithm>
+#include <cmath>
+
+namespace elp {
+
+#define ST_BASIC 0
+#define ST_LOWER 1
+#define ST_UPPER 2
+#define ST_FREE 3
+
+constexpr double TOL_PRIMAL = 1e-9;
+constexpr double TOL_DUAL = 1e-9;
+constexpr double TOL_PIVOT = 1e-9;
+
+__device__ __forceinline__ double ptol(double bound) { return TOL_PRIMAL * fmax(1.0, fabs(bound)); }
+
+// ---- TMA (bulk async copy) + mbarrier helpers, raw PTX -----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool tma_ok(const void* src, size_t bytes) {
+    return bytes > 0 && (bytes & 15) == 0 && (((uintptr_t)src) & 15) == 0;
+}
+
+// ---- block-wide reductions (value, index) ----------------------------------------------------
+struct ValIdx {
+    double v;
+    int i;
+};
+// "better" = larger v, ties -> smaller index.  Use negated values for argmin.
+__device__ __forceinline__ ValIdx better(ValIdx a, ValIdx b) {
+    if (b.i < 0) return a;
+    if (a.i < 0) return b;
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+template <int THREADS>
+__device__ __forceinline__ ValIdx block_argmax(ValIdx x, double* red_v, int* red_i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ValIdx y;
+        y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+        y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+        x = better(x, y);
+    }
+    if (THREADS == 32) return x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();   // protect scratch reuse
+    if (lane == 0) { red_v[warp] = x.v; red_i[warp] = x.i; }
+    __syncthreads();
+    ValIdx r{red_v[0], red_i[0]};
+#pragma unroll
+    for (int w = 1; w < THREADS / 32; ++w) r = better(r, ValIdx{red_v[w], red_i[w]});
+    return r;
+}
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double x, double* red_v) {
+    x = warp_sum(x);
+    if (THREADS == 32) return x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red_v[warp] = x;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) r += red_v[w];
+    return r;
+}
+template <int THREADS>
+__device__ __forceinline__ void block_sync() {
+    if (THREADS == 32) __syncwarp();
+    else __syncthreads();
+}
+
+struct SimplexSmemLayout {
+    int m, n, N;
+    size_t off_TA, off_TS, off_beta, off_lo, off_hi, off_cost, off_xn, off_cb, off_colq, off_rowr, off_redv;
+    size_t off_basis, off_state, off_redi, off_bar, total;
+    __host__ __device__ SimplexSmemLayout(int m_, int n_) : m(m_), n(n_), N(m_ + n_) {
+        auto up2 = [](size_t v) { return (v + 1) & ~(size_t)1; };   // keep every double array 16B aligned
+        size_t o = 0;
+        off_TA = o;   o += up2((size_t)m * n);
+        off_TS = o;   o += up2((size_t)m * m);
+        off_beta = o; o += up2(m);
+        off_lo = o;   o += up2(N);
+        off_hi = o;   o += up2(N);
+        off_cost = o; o += up2(N);
+        off_xn = o;   o += up2(N);
+        off_cb = o;   o += up2(m);
+        off_colq = o; o += up2(m);
+        off_rowr = o; o += up2(N);
+        off_redv = o; o += 8;
+        size_t bytes = o * sizeof(double);
+        off_bar = bytes;   bytes += 16;
+        off_basis = bytes; bytes += (size_t)((m + 3) & ~3) * sizeof(int);
+        off_state = bytes; bytes += (size_t)((N + 3) & ~3) * sizeof(int);
+        off_redi = bytes;  bytes += 8 * sizeof(int);
+        total = bytes;
+    }
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+simplex_batch_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, const double* __restrict__ bg,
+                     const double* __restrict__ cg, const double* __restrict__ lbg, const double* __restrict__ ubg,
+                     const int8_t* __restrict__ senseg, int maximize, int max_pivots, int32_t* __restrict__ status_out,
+                     double* __restrict__ obj_out, double* __restrict__ x_out, double* __restrict__ y_out,
+                     int32_t* __restrict__ pivots_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const SimplexSmemLayout lay(m, n);
+    const int N = lay.N;
+    double* sd = reinterpret_cast<double*>(smem_raw);
+    double* TA = sd + lay.off_TA;
+    double* TS = sd + lay.off_TS;
+    double* beta = sd + lay.off_beta;
+    double* lo = sd + lay.off_lo;
+    double* hi = sd + lay.off_hi;
+    double* cost = sd + lay.off_cost;
+    double* xn = sd + lay.off_xn;
+    double* cb = sd + lay.off_cb;
+    double* colq = sd + lay.off_colq;
+    double* rowr = sd + lay.off_rowr;
+    double* red_v = sd + lay.off_redv;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + lay.off_bar);
+    int* basis = reinterpret_cast<int*>(smem_raw + lay.off_basis);
+    int* state = reinterpret_cast<int*>(smem_raw + lay.off_state);
+    int* red_i = reinterpret_cast<int*>(smem_raw + lay.off_redi);
+    const int tid = threadIdx.x;
+
+    const int64_t lp = blockIdx.x;
+    if (lp >= B) return;
+    const double* A = Ag + lp * (int64_t)m * n;
+    const double* b = bg + lp * (int64_t)m;
+    const double* c = cg + lp * (int64_t)n;
+    const double* lb = lbg ? lbg + lp * (int64_t)n : nullptr;
+    const double* ub = ubg ? ubg + lp * (int64_t)n : nullptr;
+    const int8_t* sense = senseg ? senseg + lp * (int64_t)m : nullptr;
+
+    // ---- stage the LP: TMA bulk copies where alignment allows, cooperative loads otherwise ----------
+    const size_t bytesA = (size_t)m * n * 8, bytesb = (size_t)m * 8, bytesn = (size_t)n * 8;
+    const bool tA = tma_ok(A, bytesA), tb = tma_ok(b, bytesb), tc = tma_ok(c, bytesn);
+    const bool tl = lb && tma_ok(lb, bytesn), tu = ub && tma_ok(ub, bytesn);
+    if (tid == 0) mbar_init(bar, 1);
+    block_sync<THREADS>();
+    if (tid == 0) {
+        const uint32_t tx = (uint32_t)((tA ? bytesA : 0) + (tb ? bytesb : 0) + (tc ? bytesn : 0) + (tl ? bytesn : 0) +
+                                       (tu ? bytesn : 0));
+        mbar_expect_tx(bar, tx);
+        if (tA) tma_load_1d(TA, A, (uint32_t)bytesA, bar);
+        if (tb) tma_load_1d(beta, b, (uint32_t)bytesb, bar);
+        if (tc) tma_load_1d(cost, c, (uint32_t)bytesn, bar);
+        if (tl) tma_load_1d(lo, lb, (uint32_t)bytesn, bar);
+        if (tu) tma_load_1d(hi, ub, (uint32_t)bytesn, bar);
+    }
+    // meanwhile: everything that does not depend on the copies
+    for (int e = tid; e < m * m; e += THREADS) TS[e] = (e / m == e % m) ? 1.0 : 0.0;
+    if (!tA) for (int e = tid; e < m * n; e += THREADS) TA[e] = A[e];
+    if (!tb) for (int i = tid; i < m; i += THREADS) beta[i] = b[i];
+    if (!tc) for (int j = tid; j < n; j += THREADS) cost[j] = c[j];
+    if (!tl) for (int j = tid; j < n; j += THREADS) lo[j] = lb ? lb[j] : 0.0;
+    if (!tu) for (int j = tid; j < n; j += THREADS) hi[j] = ub ? ub[j] : INFINITY;
+    for (int i = tid; i < m; i += THREADS) {
+        const int s = sense ? sense[i] : 0;
+        lo[n + i] = (s == ELP_GE) ? -INFINITY : 0.0;
+        hi[n + i] = (s == ELP_LE) ? INFINITY : 0.0;
+        cost[n + i] = 0.0;
+        xn[n + i] = 0.0;
+        state[n + i] = ST_BASIC;
+        basis[i] = n + i;
+    }
+    mbar_wait(bar, 0);
+    block_sync<THREADS>();
+
+    int bad = 0;
+    for (int j = tid; j < n; j += THREADS) {
+        if (maximize) cost[j] = -cost[j];
+        const double l = lo[j], u = hi[j];
+        if (l > u) bad = 1;
+        if (isfinite(l)) { state[j] = ST_LOWER; xn[j] = l; }
+        else if (isfinite(u)) { state[j] = ST_UPPER; xn[j] = u; }
+        else { state[j] = ST_FREE; xn[j] = 0.0; }
+    }
+    bad = __syncthreads_or(bad);
+    // beta = b - A xN
+    for (int i = tid; i < m; i += THREADS) {
+        double r = beta[i];
+        for (int j = 0; j < n; ++j) r -= TA[i * n + j] * xn[j];
+        beta[i] = r;
+    }
+    block_sync<THREADS>();
+
+    int status = ELP_STATUS_TIMEOUT, pivots = 0, degenerate_run = 0, bland = 0;
+    int qfinal = -1;
+    if (max_pivots <= 0) max_pivots = 50 * (m + n) + 1000;
+    if (bad) status = ELP_STATUS_INFEASIBLE;
+
+    while (!bad) {
+        // ---- phase detection ------------------------------------------------------------------
+        double wpart = 0.0;
+        for (int i = tid; i < m; i += THREADS) {
+            const int k = basis[i];
+            const double bi = beta[i];
+            double g = 0.0;
+            if (bi < lo[k] - ptol(lo[k])) { g = -1.0; wpart += lo[k] - bi; }
+            else if (bi > hi[k] + ptol(hi[k])) { g = 1.0; wpart += bi - hi[k]; }
+            cb[i] = g;
+        }
+        const double w = block_sum<THREADS>(wpart, red_v);
+        const bool phase1 = w > 0.0;
+        if (!phase1) for (int i = tid; i < m; i += THREADS) cb[i] = cost[basis[i]];
+        block_sync<THREADS>();
+        // ---- pricing: d_j = cost_j - cb' T[:,j]; Dantzig (largest |d_j|) or Bland (smallest j) ----
+        ValIdx cand{0.0, -1};
+        for (int j = tid; j < N; j += THREADS) {
+            const int st = state[j];
+            if (st == ST_BASIC || !(lo[j] < hi[j])) continue;
+            double d = phase1 ? 0.0 : cost[j];
+            if (j < n) { for (int i = 0; i < m; ++i) d -= cb[i] * TA[i * n + j]; }
+            else { const int jj = j - n; for (int i = 0; i < m; ++i) d -= cb[i] * TS[i * m + jj]; }
+            int dd = 0;
+            if ((st == ST_LOWER || st == ST_FREE) && d < -TOL_DUAL) dd = 1;
+            else if ((st == ST_UPPER || st == ST_FREE) && d > TOL_DUAL) dd = -1;
+            if (!dd) continue;
+            // encode the direction in the index: idx = 2*j + (dd<0)
+            ValIdx me{bland ? -(double)j : fabs(d), 2 * j + (dd < 0 ? 1 : 0)};
+            cand = better(cand, me);
+        }
+        cand = block_argmax<THREADS>(cand, red_v, red_i);
+        if (cand.i < 0) { status = phase1 ? ELP_STATUS_INFEASIBLE : ELP_STATUS_OPTIMAL; break; }
+        if (pivots >= max_pivots) { status = ELP_STATUS_TIMEOUT; break; }
+        const int q = cand.i >> 1;
+        const double dir = (cand.i & 1) ? -1.0 : 1.0;
+        // ---- entering column ------------------------------------------------------------------
+        for (int i = tid; i < m; i += THREADS) colq[i] = (q < n) ? TA[i * n + q] : TS[i * m + (q - n)];
+        block_sync<THREADS>();
+        // ---- ratio test, pass 1: the minimum step (warp-shuffle argmin) ----------------------------
+        double tloc = INFINITY;
+        for (int i = tid; i < m; i += THREADS) {
+            const double a = dir * colq[i];
+            if (fabs(a) <= TOL_PIVOT) continue;
+            const int k = basis[i];
+            const double bi = beta[i], l = lo[k], u = hi[k];
+            double t = INFINITY;
+            if (a > 0.0) {
+                if (bi > u + ptol(u)) t = (bi - u) / a;
+                else if (bi >= l - ptol(l)) { if (isfinite(l)) t = fmax(bi - l, 0.0) / a; }
+            } else {
+                if (bi < l - ptol(l)) t = (bi - l) / a;
+                else if (bi <= u + ptol(u)) { if (isfinite(u)) t = fmin(bi - u, 0.0) / a; }
+            }
+            tloc = fmin(tloc, t);
+        }
+        ValIdx tm = block_argmax<THREADS>(ValIdx{-tloc, tid}, red_v, red_i);
+        const double tmin = -tm.v;
+        double tflip = (state[q] == ST_FREE) ? INFINITY : hi[q] - lo[q];
+        if (tflip <= tmin) {
+            if (!isfinite(tflip)) {
+                if (phase1) { status = ELP_STATUS_NUMFAILURE; break; }
+                status = ELP_STATUS_UNBOUNDED;
+                qfinal = q;
+                block_sync<THREADS>();
+                if (tid == 0) xn[q] = dir > 0 ? INFINITY : -INFINITY;
+                break;
+            }
+            for (int i = tid; i < m; i += THREADS) beta[i] -= dir * tflip * colq[i];
+            block_sync<THREADS>();
+            if (tid == 0) {
+                if (dir > 0) { state[q] = ST_UPPER; xn[q] = hi[q]; }
+                else { state[q] = ST_LOWER; xn[q] = lo[q]; }
+            }
+            ++pivots; degenerate_run = 0; bland = 0;
+            block_sync<THREADS>();
+            continue;
+        }
+        // ---- pass 2: among rows within a hair of tmin take the largest pivot (Bland: smallest basic id) ----
+        const double window = tmin + 1e-12 * fmax(1.0, fabs(tmin));
+        ValIdx rc{0.0, -1};
+        for (int i = tid; i < m; i += THREADS) {
+            const double a = dir * colq[i];
+            if (fabs(a) <= TOL_PIVOT) continue;
+            const int k = basis[i];
+            const double bi = beta[i], l = lo[k], u = hi[k];
+            double t = INFINITY; int up = 0;
+            if (a > 0.0) {
+                if (bi > u + ptol(u)) { t = (bi - u) / a; up = 1; }
+                else if (bi >= l - ptol(l)) { if (isfinite(l)) { t = fmax(bi - l, 0.0) / a; up = 0; } }
+            } else {
+                if (bi < l - ptol(l)) { t = (bi - l) / a; up = 0; }
+                else if (bi <= u + ptol(u)) { if (isfinite(u)) { t = fmin(bi - u, 0.0) / a; up = 1; } }
+            }
+            if (t > window) continue;
+            ValIdx me{bland ? -(double)k : fabs(a), 2 * i + up};
+            rc = better(rc, me);
+        }
+        rc = block_argmax<THREADS>(rc, red_v, red_i);
+        if (rc.i < 0) { status = ELP_STATUS_NUMFAILURE; break; }
+        const int r = rc.i >> 1;
+        const int to_upper = rc.i & 1;
+        // ---- step + basis change --------------------------------------------------------------
+        const double t = tmin;
+        const double piv = colq[r];
+        for (int i = tid; i < m; i += THREADS) beta[i] -= dir * t * colq[i];
+        for (int j = tid; j < N; j += THREADS) rowr[j] = ((j < n) ? TA[r * n + j] : TS[r * m + (j - n)]) / piv;
+        block_sync<THREADS>();
+        if (tid == 0) {
+            const int kl = basis[r];
+            if (to_upper) { state[kl] = ST_UPPER; xn[kl] = hi[kl]; }
+            else { state[kl] = ST_LOWER; xn[kl] = lo[kl]; }
+            beta[r] = xn[q] + dir * t;
+            basis[r] = q;
+            state[q] = ST_BASIC;
+            rowr[q] = 1.0;
+        }
+        block_sync<THREADS>();
+        // ---- rank-1 update of the tableau:  T -= colq * rowr  (row r := rowr) ----------------------
+        for (int i = 0; i < m; ++i) {
+            const double f = colq[i];
+            if (i == r) {
+                for (int j = tid; j < N; j += THREADS) { if (j < n) TA[i * n + j] = rowr[j]; else TS[i * m + (j - n)] = rowr[j]; }
+            } else if (f != 0.0) {
+                for (int j = tid; j < N; j += THREADS) {
+                    double* e = (j < n) ? &TA[i * n + j] : &TS[i * m + (j - n)];
+                    *e = (j == q) ? 0.0 : *e - f * rowr[j];      // the pivot column becomes a unit vector exactly
+                }
+            }
+        }
+        ++pivots;
+        if (t <= 1e-12) { if (++degenerate_run > 30) bland = 1; }
+        else { degenerate_run = 0; bland = 0; }
+        block_sync<THREADS>();
+    }
+    block_sync<THREADS>();
+
+    // ---- write back ---------------------------------------------------------------------------
+    double* xo = x_out + lp * (int64_t)n;
+    for (int j = tid; j < n; j += THREADS) if (state[j] != ST_BASIC) xo[j] = xn[j];
+    for (int i = tid; i < m; i += THREADS) if (basis[i] < n) xo[basis[i]] = beta[i];
+    double opart = 0.0;
+    for (int j = tid; j < n; j += THREADS) {
+        if (state[j] != ST_BASIC) opart += cost[j] * ((j == qfinal) ? 0.0 : xn[j]);
+    }
+    for (int i = tid; i < m; i += THREADS) if (basis[i] < n) opart += cost[basis[i]] * beta[i];
+    double obj = block_sum<THREADS>(opart, red_v);
+    if (status == ELP_STATUS_UNBOUNDED) obj = -INFINITY;
+    if (tid == 0) {
+        status_out[lp] = status;
+        obj_out[lp] = maximize ? -obj : obj;
+        if (pivots_out) pivots_out[lp] = pivots;
+    }
+    if (y_out) {
+        double* yo = y_out + lp * (int64_t)m;
+        for (int i = tid; i < m; i += THREADS) {
+            double s = 0.0;
+            for (int k = 0; k < m; ++k) s += cost[basis[k]] * TS[k * m + i];
+            yo[i] = maximize ? -s : s;
+        }
+    }
+}
+
+__global__ void k_densify(int m, int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+                          const double* __restrict__ val, double* __restrict__ A) {
+    const int i = blockIdx.x;
+    if (i >= m) return;
+    for (int k = ptr[i] + threadIdx.x; k < ptr[i + 1]; k += blockDim.x) atomicAdd(&A[(size_t)i * n + idx[k]], val[k]);
+}
+
+size_t simplex_smem_bytes(int m, int n) { return SimplexSmemLayout(m, n).total; }
+
+int simplex_pick_threads(int m, int n) {
+    const int N = m + n;
+    if (const char* e = getenv("ELP_SIMPLEX_THREADS")) {
+        const int t = atoi(e);
+        if (t == 32 || t == 64 || t == 128) return t;
+    }
+    if (N <= 32) return 32;
+    if (N <= 96) return 64;
+    return 128;
+}
+
+// all pointers are device pointers
+void simplex_batch_device(int64_t B, int m, int n, const double* A, const double* b, const double* c, const double* lb,
+                          const double* ub, const int8_t* sense, int maximize, int max_pivots, int32_t* status,
+                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st) {
+    if (B <= 0) return;
+    ELP_REQUIRE(n > 0 && m >= 0, "simplex: bad shape %d x %d", m, n);
+    ELP_REQUIRE(B < 0x7fffffffll, "simplex: batch too large");
+    const size_t smem = simplex_smem_bytes(m, n);
+    ELP_REQUIRE(smem <= 227 * 1024, "simplex: tableau of %d x %d needs %zu bytes of shared memory (max 227 KB)", m, n,
+                smem);
+    const int threads = simplex_pick_threads(m, n);
+#define ELP_SIMPLEX_LAUNCH(T)                                                                                     \
+    do {                                                                                                          \
+        ELP_CUDA(cudaFuncSetAttribute(simplex_batch_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)smem));                                                                \
+        ELP_LAUNCH((simplex_batch_kernel<T>), (unsigned)B, T, smem, st, B, m, n, A, b, c, lb, ub, sense, maximize, \
+                   max_pivots, status, obj, x, y, pivots);                                                        \
+    } while (0)
+    if (threads == 32) ELP_SIMPLEX_LAUNCH(32);
+    else if (threads == 64) ELP_SIMPLEX_LAUNCH(64);
+    else ELP_SIMPLEX_LAUNCH(128);
+#undef ELP_SIMPLEX_LAUNCH
+}
+
+void densify_device(int m, int n, const int* ptr, const int* idx, const double* val, double* A, cudaStream_t st) {
+    ELP_CUDA(cudaMemsetAsync(A, 0, (size_t)std::max(m, 1) * n * sizeof(double), st));
+    if (m > 0) ELP_LAUNCH(k_densify, m, 64, 0, st, m, n, ptr, idx, val, A);
+}
+
+}  // namespace elp

@@ -1,0 +1,168 @@
+/*
+ * easylp_abi.h — C ABI of libeasylp_b200.so: the B200-native solve path behind EasyLP's R6 API.
+ *
+ * This is the drop-in boundary.  In the reference the boundary is the set of
+ * lpSolveAPI R functions called from `$solve()` (/root/reference/R/class.R:260-278) plus the dense
+ * R matrix algebra that `$con()` uses to build `constraint$mat` (/root/reference/R/class.R:189-220,
+ * R/utils.R:95-106, R/methods.R:82-111,244-257).  Each entry point below names the reference
+ * interface it replaces.  The R `.Call` glue that binds these lives in rpkg/src/r_glue.c; the ctypes
+ * binding used by the tests lives in easylp_b200/_lib.py; INTEGRATION.md shows both.
+ *
+ * Conventions
+ *   - plain C, POD arguments, caller-owned buffers, no exceptions cross the boundary;
+ *   - every function returns 0 on success, nonzero on failure (then elp_last_error() has text);
+ *   - indices are 0-based int32 (the R glue subtracts 1 from `ind`); doubles cross bit-for-bit;
+ *   - +/-Inf bounds cross as IEEE infinities;
+ *   - row sense codes: 0 "<=" (also "<"), 1 ">=" (also ">"), 2 "==" — the reference hands "<"/">"
+ *     to lpSolveAPI::add.constraint, which treats them as "<="/">=" (R/class.R:271-274);
+ *   - status codes are lp_solve's, exactly the keys of the switch at R/class.R:279-295:
+ *     0 optimal, 2 unfeasible, 3 unbounded, 5 numerical failure, 7 timeout (iteration/time limit);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with rc != 0.
+ */
+#ifndef EASYLP_ABI_H
+#define EASYLP_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELP_LE 0
+#define ELP_GE 1
+#define ELP_EQ 2
+
+#define ELP_STATUS_OPTIMAL 0
+#define ELP_STATUS_SUBOPTIMAL 1
+#define ELP_STATUS_INFEASIBLE 2
+#define ELP_STATUS_UNBOUNDED 3
+#define ELP_STATUS_NUMFAILURE 5
+#define ELP_STATUS_TIMEOUT 7
+
+#define ELP_METHOD_AUTO 0    /* size rule: dense tableau fits in shared memory -> simplex, else PDLP */
+#define ELP_METHOD_SIMPLEX 1
+#define ELP_METHOD_PDLP 2
+
+/* Options of a solve; mirrors the `...` that `$solve()` forwards to lpSolveAPI::lp.control()
+ * (R/class.R:249-262): `timeout`, `epsilon`, `verbose` are mapped, the rest has no GPU meaning. */
+typedef struct elp_options {
+    double eps_rel;        /* PDLP relative KKT tolerance (default 1e-6; north_star) */
+    double time_limit_s;   /* <=0: none. lp.control(timeout=) */
+    int32_t max_iter;      /* PDLP iteration limit / simplex pivot limit (<=0: default) */
+    int32_t check_every;   /* PDLP: iterations between termination/restart checks (<=0: default 64) */
+    int32_t method;        /* ELP_METHOD_* */
+    int32_t verbose;       /* lp.control(verbose=): 0 silent, >=1 progress lines to stderr */
+    int32_t use_graph;     /* PDLP: replay the iteration chunk from a CUDA graph (default 1) */
+    int32_t ruiz_iters;    /* <0: default 10 */
+} elp_options;
+
+/* Per-solve statistics (SURVEY.md §5 "metrics"): returned to R as a list. */
+typedef struct elp_stats {
+    int32_t status;
+    int32_t method_used;
+    int32_t iterations;        /* PDHG iterations or simplex pivots (batch: total pivots) */
+    int32_t restarts;
+    double primal_obj;         /* in the problem's own sense, without objective_add */
+    double dual_obj;
+    double rel_primal_res;     /* ||Ax - proj(Ax)|| / (1 + ||b||) */
+    double rel_dual_res;       /* ||r - proj(r)|| / (1 + ||c||) */
+    double rel_gap;            /* |p - d| / (1 + |p| + |d|) */
+    double setup_ms;           /* H2D + transpose + scaling + power iteration */
+    double solve_ms;           /* device time of the iteration loop (CUDA events) */
+    double total_ms;           /* host wall clock of the call */
+    int64_t kernel_launches;   /* kernels launched by this call */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    double spmv_ms;            /* device time of the timed A.x / A'.y probe (elp_pdlp_probe_spmv) */
+} elp_stats;
+
+/* ---- housekeeping -------------------------------------------------------------------------- */
+const char* elp_version(void);
+int elp_last_error(char* buf, int32_t len);          /* copies the calling thread's last error text */
+int elp_device_count(int32_t* count);
+int elp_set_device(int32_t device);
+int elp_default_options(elp_options* opt);
+const char* elp_status_string(int32_t status);       /* the strings of R/class.R:279-295 */
+int64_t elp_kernel_launches(void);                   /* process-wide counter of launched kernels */
+
+/* ---- (1) assembly: terms -> CSR ------------------------------------------------------------
+ * Replaces the dense `constraint$mat` construction of `$con()`: rbind of evaluated atoms
+ * (R/utils.R:95-106) whose entries were produced by dense adds in left-fold order
+ * (R/methods.R:98-111, 244-257).  Input: T terms (row, col, val) in *emission order* (the order the
+ * expression tree is folded in).  Output: canonical CSR = entries of the dense matrix that are != 0,
+ * row-major, ascending column; duplicates of one (row, col) are summed strictly left-to-right in
+ * emission order so the result is bit-identical to the reference's dense arithmetic.
+ * row_ptr has m+1 entries; col_idx/vals must have room for n_terms entries; *nnz_out receives the count. */
+int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* term_col,
+                     const double* term_val, int32_t m, int32_t n,
+                     int32_t* row_ptr, int32_t* col_idx, double* vals, int64_t* nnz_out,
+                     elp_stats* stats /* may be NULL */);
+
+/* ---- (2) one LP: replaces make.lp/set.objfn/lp.control/set.bounds/add.constraint/solve/
+ *      get.objective/get.variables  (R/class.R:260-278) ------------------------------------- */
+int elp_solve_lp(int32_t m, int32_t n,
+                 const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                 const int8_t* sense, const double* rhs,
+                 const double* c, int32_t maximize,
+                 const double* lb, const double* ub,
+                 const elp_options* opt /* may be NULL */,
+                 int32_t* status, double* objval, double* x /* n */, double* y /* m, may be NULL */,
+                 elp_stats* stats /* may be NULL */);
+
+/* ---- (3) a batch of small dense LPs (BASELINE config 3; additive entry point) ---
+ * A is [B][m][n] row-major, b [B][m], c [B][n], lb/ub [B][n] (NULL => 0 / +Inf), sense [B][m]
+ * (NULL => all "<=").  One LP per CTA; outputs status[B], obj[B], x[B][n]. */
+int elp_solve_batch(int64_t B, int32_t m, int32_t n,
+                    const double* A, const double* b, const double* c,
+                    const double* lb, const double* ub, const int8_t* sense, int32_t maximize,
+                    const elp_options* opt, int32_t* status, double* obj, double* x,
+                    elp_stats* stats);
+
+/* Device-resident batch (bench `value`: inputs already in HBM when the timed region starts). */
+typedef struct elp_batch elp_batch;
+int elp_batch_create(int64_t B, int32_t m, int32_t n,
+                     const double* A, const double* b, const double* c,
+                     const double* lb, const double* ub, const int8_t* sense, int32_t maximize,
+                     elp_batch** out);
+int elp_batch_run(elp_batch* h, const elp_options* opt, elp_stats* stats);   /* solve in place, on device */
+int elp_batch_fetch(elp_batch* h, int32_t* status, double* obj, double* x);
+int elp_batch_destroy(elp_batch* h);
+
+/* ---- (S4) post-solve feasibility re-check: replaces `mat %*% sol` + compare_tol
+ *      (R/class.R:533-540, R/utils.R:167-171).  sense here keeps strictness: 0 <=, 1 >=, 2 ==,
+ *      3 "<", 4 ">".  feasible[i] = 1/0. -------------------------------------------------------- */
+int elp_spmv(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+             const double* x, double* out /* m */);
+int elp_check_feasible(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx,
+                       const double* vals, const double* x, const int8_t* sense, const double* rhs,
+                       double tol, uint8_t* feasible /* m */);
+
+/* ---- PDLP with device-resident state (bench + multi-GPU) -------------------------------------
+ * elp_pdlp_create uploads the LP, builds the CSC copy, scales (Ruiz + Pock-Chambolle), estimates
+ * ||A||_2.  elp_pdlp_run advances until convergence or `max_new_iters` more iterations.
+ * With a communicator initialised (elp_comm_init) and dist != 0 the caller passes ITS row block:
+ * rows [row_begin, row_begin + m_local) of the global matrix (column ids global, 0..n-1); x, c, lb, ub
+ * are replicated; one allreduce of the partial A'y per iteration. */
+typedef struct elp_pdlp elp_pdlp;
+int elp_pdlp_create(int32_t m_local, int32_t n,
+                    const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                    const int8_t* sense, const double* rhs,
+                    const double* c, int32_t maximize, const double* lb, const double* ub,
+                    const elp_options* opt, int32_t dist, elp_pdlp** out, elp_stats* stats);
+int elp_pdlp_run(elp_pdlp* h, int32_t max_new_iters, elp_stats* stats);
+int elp_pdlp_reset(elp_pdlp* h);                                   /* back to the initial iterate */
+int elp_pdlp_solution(elp_pdlp* h, double* x /* n */, double* y /* m_local, may be NULL */, double* objval);
+int elp_pdlp_probe_spmv(elp_pdlp* h, int32_t reps, double* ms_csr, double* ms_csc);  /* times bare A.x and A'.y */
+int elp_pdlp_destroy(elp_pdlp* h);
+
+/* ---- multi-GPU plumbing (one process per GPU; NCCL resolved with dlopen at first use) -------- */
+#define ELP_UNIQUE_ID_BYTES 128
+int elp_comm_unique_id(void* id /* ELP_UNIQUE_ID_BYTES */);
+int elp_comm_init(int32_t nranks, int32_t rank, const void* id);
+int elp_comm_size(int32_t* nranks, int32_t* rank);
+int elp_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EASYLP_ABI_H */

@@ -1,0 +1,141 @@
+"""GPU parity tests for the three kernels, through the C ABI (ctypes).  Run on the B200 box."""
+import numpy as np
+import pytest
+
+from easylp_b200 import _lib as L
+from oracle import cbind, gen
+
+pytestmark = pytest.mark.gpu
+
+
+def _assemble_ref(row, col, val, m, n):
+    """left-fold in emission order, drop zeros, row-major ascending col (what the dense reference yields)."""
+    acc = {}
+    for r, c, v in zip(row.tolist(), col.tolist(), val.tolist()):
+        acc[(r, c)] = acc.get((r, c), 0.0) + v
+    keys = sorted(k for k, v in acc.items() if v != 0.0)
+    row_ptr = np.zeros(m + 1, np.int32)
+    for r, _ in keys:
+        row_ptr[r + 1] += 1
+    row_ptr = np.cumsum(row_ptr).astype(np.int32)
+    return row_ptr, np.array([c for _, c in keys], np.int32), np.array([acc[k] for k in keys])
+
+
+@pytest.mark.parametrize("T,m,n,seed", [(0, 3, 4, 0), (1, 1, 1, 1), (50, 5, 7, 2), (5000, 40, 60, 3),
+                                        (100_000, 300, 500, 4), (300_000, 2000, 100_000, 5)])
+def test_assemble_bit_exact(T, m, n, seed):
+    rng = np.random.default_rng(seed)
+    row = rng.integers(0, m, size=T).astype(np.int32)
+    col = rng.integers(0, max(n // 3, 1), size=T).astype(np.int32) * 3 % n
+    val = rng.normal(size=T) * 10.0 ** rng.integers(-8, 8, size=T)
+    if T > 10:
+        # exact cancellations and duplicates
+        row[1], col[1], val[1] = row[0], col[0], -val[0]
+        row[5:9] = row[4]; col[5:9] = col[4]
+    rp, ci, v, st = L.assemble_csr(row, col, val, m, n)
+    rp0, ci0, v0 = _assemble_ref(row, col, val, m, n)
+    assert np.array_equal(rp, rp0)
+    assert np.array_equal(ci, ci0)
+    assert v.tobytes() == v0.tobytes()          # bit-exact
+
+
+def test_assemble_long_duplicate_run_order():
+    # one key hit 10k times with values whose sum depends on the order
+    rng = np.random.default_rng(7)
+    T = 10_000
+    val = rng.normal(size=T) * 10.0 ** rng.integers(-10, 10, size=T)
+    row = np.zeros(T, np.int32); col = np.full(T, 2, np.int32)
+    rp, ci, v, _ = L.assemble_csr(row, col, val, 1, 5)
+    s = 0.0
+    for t in val.tolist():
+        s += t
+    assert ci.tolist() == [2] and v[0] == s
+
+
+def test_assemble_rejects_out_of_range():
+    with pytest.raises(L.ElpError):
+        L.assemble_csr([0, 5], [0, 0], [1.0, 1.0], 2, 2)
+
+
+def test_spmv_and_feasible():
+    p = gen.sparse_planted(3000, seed=1)
+    x = np.random.default_rng(0).normal(size=p["n"])
+    out = L.spmv(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], x)
+    ref = gen._csr_matvec(p["row_ptr"].astype(np.int64), p["col_idx"], p["vals"], x, p["m"])
+    assert np.allclose(out, ref, rtol=1e-12, atol=1e-12)
+    feas = L.check_feasible(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], p["x_opt"], p["sense"], p["rhs"])
+    assert feas.all()
+
+
+def test_readme_lp_simplex():
+    p = gen.readme_lp()
+    r = L.solve_lp(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], p["sense"], p["rhs"], p["c"], p["lb"], p["ub"],
+                   maximize=True)
+    assert r.status == 0 and r.status_string == "optimal"
+    assert abs(r.objval - 2.0) < 1e-9 and np.allclose(r.x, [1.0, 1.0], atol=1e-9)
+    assert r.stats.method_used == L.METHOD_SIMPLEX
+
+
+def test_unbounded_no_rows():
+    # /root/reference/tests/testthat/test-unbounded.R: max x, x free, no rows
+    r = L.solve_lp(0, 1, [0], [], [], [], [], [1.0], [-np.inf], [np.inf], maximize=True)
+    assert r.status == 3 and r.objval == np.inf and r.x[0] == np.inf
+
+
+def test_batch_simplex_vs_oracle():
+    d = gen.dense_batch(B=4000, seed=11)
+    status, obj, x, st = L.solve_batch(d["A"], d["b"], d["c"], d["lb"], d["ub"], d["sense"])
+    s0, o0, x0, piv = cbind.simplex_batch(d["A"], d["b"], d["c"], d["lb"], d["ub"], d["sense"], nthreads=8)
+    assert np.array_equal(status, s0)
+    assert np.all(np.abs(obj - o0) <= 1e-6 * np.maximum(1.0, np.abs(o0)))
+    # primal feasibility of the returned points
+    ax = np.einsum("bij,bj->bi", d["A"], x)
+    assert np.all(ax <= d["b"] + 1e-7) and np.all(x >= -1e-9) and np.all(x <= 10 + 1e-9)
+
+
+def test_batch_mixed_senses_free_vars():
+    rng = np.random.default_rng(5)
+    B, m, n = 3000, 6, 7
+    A = np.round(rng.normal(size=(B, m, n)) * 2) / 2 * (rng.random((B, m, n)) < 0.7)
+    b = np.round(rng.normal(size=(B, m)) * 4) / 2
+    sense = rng.integers(0, 3, size=(B, m)).astype(np.int8)
+    c = np.round(rng.normal(size=(B, n)) * 2) / 2
+    lb = np.where(rng.random((B, n)) < 0.5, -np.inf, np.round(rng.normal(size=(B, n))))
+    ub = np.where(rng.random((B, n)) < 0.5, np.inf, np.where(np.isfinite(lb), lb, 0.0) + np.round(rng.random((B, n)) * 4))
+    status, obj, x, _ = L.solve_batch(A, b, c, lb, ub, sense)
+    s0, o0, x0, _ = cbind.simplex_batch(A, b, c, lb, ub, sense, nthreads=8)
+    assert np.array_equal(status, s0)
+    ok = status == 0
+    assert ok.sum() > 100 and (status == 2).sum() > 100 and (status == 3).sum() > 100
+    assert np.all(np.abs(obj[ok] - o0[ok]) <= 1e-6 * np.maximum(1.0, np.abs(o0[ok])))
+
+
+def _pdlp_check(p, eps=1e-6, **kw):
+    r = L.solve_lp(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], p["sense"], p["rhs"], p["c"], p["lb"], p["ub"],
+                   maximize=p["maximize"], options=L.default_options(method=L.METHOD_PDLP, **kw))
+    return r
+
+
+def test_pdlp_readme():
+    p = gen.readme_lp()
+    r = _pdlp_check(p)
+    assert r.status == 0 and abs(r.objval - 2.0) <= 1e-5
+    assert r.stats.rel_primal_res <= 1e-6 and r.stats.rel_dual_res <= 1e-6 and r.stats.rel_gap <= 1e-6
+
+
+@pytest.mark.parametrize("graph", [0, 1])
+def test_pdlp_planted(graph):
+    p = gen.sparse_planted(2000, seed=0)
+    r = _pdlp_check(p, use_graph=graph)
+    assert r.status == 0
+    assert abs(r.objval - p["obj_opt"]) <= 1e-5 * max(1.0, abs(p["obj_opt"]))
+    assert r.stats.rel_primal_res <= 1e-6 and r.stats.rel_dual_res <= 1e-6 and r.stats.rel_gap <= 1e-6
+
+
+def test_pdlp_transport_vs_simplex_oracle():
+    p = gen.transport(12, 15, seed=3)
+    r = _pdlp_check(p)
+    st, obj, x, y, piv = cbind.simplex_csr(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], p["sense"], p["rhs"],
+                                           p["c"], p["lb"], p["ub"])
+    assert st == 0 and r.status == 0
+    assert abs(r.objval - obj) <= 2e-6 * max(1.0, abs(obj))
