@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the EasyLP B200 solve path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pdlp|batch|transport]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+BASELINE.json's metric is compound: "batched LPs/sec; large-LP PDLP iter/s & time-to-1e-6 gap".  The JSON
+line's primary `metric` is the large-LP PDLP iteration rate on config 4 (synthetic sparse LP, 2M rows x 4M
+cols, ~20M nnz) — the configuration whose SpMV roofline north_star sets the target on.  One step = one
+complete solve from the initial iterate to the 1e-6 relative KKT tolerance, so `ms_per_step` IS the
+time-to-1e-6-gap.  The batched-simplex number (config 3: 200k dense 20x30 LPs) rides in the same line under
+`"batch"` with its own value / e2e / roofline / cpu_baseline; `--workload batch` makes it the primary.
+
+Timing: device time comes from CUDA events recorded by the library on the stream its kernels run on
+(elp_stats.solve_ms); under torchrun the MAX over ranks is taken.  Inputs (2 x 240 MB of matrix per
+iteration; 1.1 GB of tableaux per batch) exceed the 126 MB L2, so no flush is needed between steps.
+`e2e` goes through the C-ABI call a user of the R package triggers (`$solve()` -> elp_pdlp_create/run/
+solution, i.e. what elp_solve_lp does), with pinned HOST buffers, H2D + setup + D2H inside the timed region.
+
+The oracle (oracle/) is loaded ONLY for the `cpu_baseline` leg and `--impl reference`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import gen  # noqa: E402  (seeded input generators; not a solve path)
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned(a):
+    """Copy of `a` in page-locked host memory (torch's pinned allocator; plumbing only)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    try:
+        return t.pin_memory().numpy()
+    except Exception:
+        return t.numpy()
+
+
+def row_block(p, rank, nranks):
+    """Row block of rank `rank`: contiguous rows, balanced by nnz."""
+    m = p["m"]
+    rp = p["row_ptr"].astype(np.int64)
+    nnz = int(rp[m])
+    cuts = [int(np.searchsorted(rp, nnz * g / nranks, side="left")) for g in range(nranks)] + [m]
+    cuts[0] = 0
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    q = dict(p)
+    q["m"] = r1 - r0
+    q["row_ptr"] = (rp[r0:r1 + 1] - rp[r0]).astype(np.int32)
+    q["col_idx"] = p["col_idx"][rp[r0]:rp[r1]]
+    q["vals"] = p["vals"][rp[r0]:rp[r1]]
+    q["sense"] = p["sense"][r0:r1]
+    q["rhs"] = p["rhs"][r0:r1]
+    return q, r0, r1
+
+
+def pdlp_bytes(m, n, nnz):
+    """Algorithmic HBM bytes: per kernel launch and per iteration."""
+    csc = 12 * nnz + 4 * (n + 1) + 8 * m + 56 * n    # A'y SpMV (vals+idx+ptr+y gather) + x,c,l,u,x0 read, x,xbar written
+    csr = 12 * nnz + 4 * (m + 1) + 8 * n + 40 * m    # A xbar SpMV + y,lc,uc,y0 read, y written
+    return csc, csr, csc + csr
+
+
+class Dist:
+    def __init__(self, want):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.td = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as td
+            torch.cuda.set_device(self.local)
+            td.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.td = td
+            self.torch = torch
+        elif want > 1:
+            raise SystemExit(f"--gpus {want} needs torchrun (one process per GPU); see the module docstring")
+
+    def barrier(self):
+        if self.td:
+            self.td.barrier()
+            self.torch.cuda.synchronize()
+
+    def vmax(self, v):
+        if not self.td:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t.item())
+
+    def vsum(self, v):
+        if not self.td:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+        return float(t.item())
+
+    def bcast_obj(self, o):
+        if not self.td:
+            return o
+        box = [o]
+        self.td.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def close(self):
+        if self.td:
+            self.td.barrier()
+            self.td.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_pdlp_baseline(p, max_iter, threads):
+    from oracle import cbind
+    st, out, _, _ = cbind.pdlp(p, eps=1e-6, max_iter=max_iter, nthreads=threads)
+    iters, loop_s, setup_s = int(out[1]), float(out[6]), float(out[7])
+    return {"value": iters / loop_s, "unit": "iter/s", "cores": threads, "kind": "port",
+            "sample": f"first {iters} PDHG iterations of the same LP with oracle/pdlp_ref.c (C + OpenMP r2HPDHG "
+                      f"restatement; the reference's lp_solve is not in the image), loop {loop_s:.1f} s + setup {setup_s:.1f} s"}
+
+
+def cpu_batch_baseline(d, sample, threads):
+    from oracle import cbind
+    s = slice(0, sample)
+    t0 = time.perf_counter()
+    cbind.simplex_batch(d["A"][s], d["b"][s], d["c"][s], d["lb"][s], d["ub"][s], d["sense"][s], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "LP/s", "cores": threads, "kind": "port",
+            "sample": f"first {sample} LPs of the same batch with oracle/simplex_ref.c (C + OpenMP bounded primal "
+                      f"simplex restatement; the reference's lp_solve is not in the image), {dt:.1f} s"}
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+# ------------------------------------------------------------------------------------------------
+def bench_pdlp(args, dist, L, p, workload_name):
+    """Primary arm: PDLP on a large sparse LP, row-partitioned over dist.world GPUs."""
+    N = dist.world
+    m, n = p["m"], p["n"]
+    nnz = int(p["row_ptr"][m])
+    if N > 1:
+        uid = dist.bcast_obj(L.comm_unique_id() if dist.rank == 0 else None)
+        L.comm_init(N, dist.rank, uid)
+        q, r0, r1 = row_block(p, dist.rank, N)
+    else:
+        q = p
+    keys = ("row_ptr", "col_idx", "vals", "sense", "rhs", "c", "lb", "ub")
+    hp = {k: pinned(q[k]) for k in keys}
+    opt = L.default_options(method=L.METHOD_PDLP, eps_rel=1e-6, max_iter=args.max_iter)
+
+    def create():
+        return L.Pdlp(q["m"], n, hp["row_ptr"], hp["col_idx"], hp["vals"], hp["sense"], hp["rhs"], hp["c"], hp["lb"],
+                      hp["ub"], maximize=p["maximize"], options=opt, dist=N > 1)
+
+    # ---- value: device-resident handle, one step = one solve to 1e-6 -------------------------------
+    h = create()
+    for _ in range(args.warmup):
+        h.reset()
+        h.run()
+    sampler = ClockSampler(dist.local)
+    dist.barrier()
+    if dist.rank == 0:
+        sampler.start()
+    launches = 0
+    dev_ms = 0.0
+    iters = 0
+    last = None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.reset()
+        st = h.run()
+        dev_ms += st.solve_ms
+        launches += st.kernel_launches
+        iters += st.iterations
+        last = st
+    dist.barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if dist.rank == 0 else None
+    dev_ms = dist.vmax(dev_ms)
+    x, y, obj = h.solution()
+    ms_csr, ms_csc = h.probe_spmv(20)
+    ms_primal, ms_dual = h.probe_step(50)
+    h.close()
+
+    # ---- e2e: the user-facing call with host buffers; H2D + setup + solve + D2H timed -------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    dist.barrier()
+    t0 = time.perf_counter()
+    e2e_iters, h2d, d2h = 0, 0, 0
+    for _ in range(e2e_steps):
+        hh = create()
+        st = hh.run()
+        hh.solution()
+        e2e_iters += st.iterations
+        h2d += st.h2d_bytes
+        d2h += st.d2h_bytes + 8 * (n + q["m"])
+        launches_e2e = st.kernel_launches
+        hh.close()
+    dist.barrier()
+    e2e_s = dist.vmax(time.perf_counter() - t0)
+
+    peak, peak_src = measured_peak()
+    # local matrix of this rank for the roofline (N = 1: the whole matrix)
+    ml, nnzl = q["m"], int(q["row_ptr"][q["m"]])
+    b_csc, b_csr, b_iter = pdlp_bytes(ml, n, nnzl)
+    dom_ms, dom_b, dom_name = (ms_primal, b_csc, "spmv_kernel<L,PrimalEpi> (CSC A'y + fused primal update)") \
+        if ms_primal >= ms_dual else (ms_dual, b_csr, "spmv_kernel<L,DualEpi> (CSR A.xbar + fused dual update)")
+    ach = dom_b / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    iter_ms = dev_ms / max(iters, 1)
+    res = {
+        "metric": "pdlp_iter_per_s", "value": iters / (dev_ms * 1e-3), "unit": "iter/s", "n_gpus": N,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name, "m": m, "n": n, "nnz": nnz, "eps_rel": 1e-6,
+                   "step": "one complete PDLP solve to 1e-6 relative KKT (ms_per_step = time-to-1e-6-gap)",
+                   "parallelism": f"row-block x{N}" + (" + NCCL allreduce(A'y)" if N > 1 else ""),
+                   "l2": "matrix (2 x %.0f MB/iter) exceeds the 126 MB L2; no flush needed" % (12 * nnz / 1e6)},
+        "time_to_gap_s": dev_ms / args.steps / 1e3,
+        "iterations_per_solve": iters / args.steps,
+        "status": L.status_string(last.status), "objective": obj, "planted_objective": p.get("obj_opt"),
+        "rel_primal_res": last.rel_primal_res, "rel_dual_res": last.rel_dual_res, "rel_gap": last.rel_gap,
+        "restarts": last.restarts, "wall_ms_per_step": wall_ms / args.steps,
+        "e2e": {"value": e2e_iters / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": int(h2d / e2e_steps),
+                "d2h_bytes_per_step": int(d2h / e2e_steps), "s_per_solve": e2e_s / e2e_steps, "steps": e2e_steps,
+                "path": "elp_pdlp_create(host CSR) -> elp_pdlp_run -> elp_pdlp_solution (= elp_solve_lp)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "peak_source": peak_src, "traffic": None,
+                     "bytes_per_launch": dom_b, "ms_per_launch": dom_ms,
+                     "iteration": {"bytes": b_iter, "ms": iter_ms, "achieved": b_iter / (iter_ms * 1e-3) / 1e9,
+                                   "frac": b_iter / (iter_ms * 1e-3) / 1e9 / peak,
+                                   "note": "whole-solve average incl. check iterations, per rank's local block"},
+                     "fused_primal_ms": ms_primal, "fused_dual_ms": ms_dual,
+                     "bare_spmv": {"csr_ms": ms_csr, "csc_ms": ms_csc,
+                                   "csr_gbs": (12 * nnzl + 4 * (ml + 1) + 8 * n + 8 * ml) / (ms_csr * 1e-3) / 1e9,
+                                   "csc_gbs": (12 * nnzl + 4 * (n + 1) + 8 * ml + 8 * n) / (ms_csc * 1e-3) / 1e9}},
+        "clocks": clocks,
+    }
+    if N > 1:
+        L.comm_destroy()
+    return res
+
+
+def bench_batch(args, dist, L, d):
+    """Batched dense simplex; LPs sharded contiguously over ranks, no collective."""
+    N = dist.world
+    B, m, n = d["B"], d["m"], d["n"]
+    lo, hi = B * dist.rank // N, B * (dist.rank + 1) // N
+    keys = ("A", "b", "c", "lb", "ub", "sense")
+    hp = {k: pinned(d[k][lo:hi]) for k in keys}
+    Bl = hi - lo
+    h = L.Batch(hp["A"], hp["b"], hp["c"], hp["lb"], hp["ub"], hp["sense"])
+    for _ in range(args.warmup):
+        h.run()
+    sampler = ClockSampler(dist.local)
+    dist.barrier()
+    if dist.rank == 0:
+        sampler.start()
+    dev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        st = h.run()
+        dev_ms += st.solve_ms
+        launches += st.kernel_launches
+    dist.barrier()
+    clocks = sampler.stop() if dist.rank == 0 else None
+    dev_ms = dist.vmax(dev_ms)
+    status, obj, x = h.fetch()
+    h.close()
+    n_opt = dist.vsum(float((status == 0).sum()))
+    # e2e through elp_solve_batch with host buffers
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s2, o2, x2, st2 = L.solve_batch(hp["A"], hp["b"], hp["c"], hp["lb"], hp["ub"], hp["sense"])
+    dist.barrier()
+    e2e_s = dist.vmax(time.perf_counter() - t0)
+    pivots = dist.vsum(float(st2.iterations))
+    peak, peak_src = measured_peak()
+    bytes_lp = 8 * (m * n + m + 3 * n) + m + 8 * (n + 1) + 4 + 4
+    ms = dev_ms / args.steps
+    ach = bytes_lp * Bl / (ms * 1e-3) / 1e9
+    return {
+        "metric": "batched_lps_per_s", "value": B * args.steps / (dev_ms * 1e-3), "unit": "LP/s", "n_gpus": N,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3: batch of {B} random feasible dense LPs ({m} constraints x {n} vars), batched simplex",
+                   "parallelism": f"LP ranges x{N}, no collective",
+                   "l2": "batch data (%.2f GB) exceeds the 126 MB L2; no flush needed" % (bytes_lp * B / 1e9)},
+        "optimal": int(n_opt), "pivots_per_lp": pivots / B, "pivots_per_s": pivots / ms * 1e3,
+        "e2e": {"value": B * e2e_steps / e2e_s, "unit": "LP/s", "h2d_bytes_per_step": int(st2.h2d_bytes * N),
+                "d2h_bytes_per_step": int(st2.d2h_bytes * N), "path": "elp_solve_batch(host arrays)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "simplex_batch_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "peak_source": peak_src, "traffic": None, "bytes_per_launch": bytes_lp * Bl,
+                     "ms_per_launch": ms,
+                     "note": "HBM fraction is the mandated figure; the serial pivot chain in shared memory bounds this kernel"},
+        "clocks": clocks,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def make_problem(args):
+    w = args.workload
+    if w == "pdlp":
+        m = int(round(2_000_000 * args.scale))
+        return gen.sparse_planted(m, seed=0), f"C4: synthetic sparse LP {m} rows x {2 * m} cols, planted optimum, PDLP to 1e-6"
+    if w == "transport":
+        return gen.transport(300, 300, seed=0), "C2: transportation 300 x 300 (90k vars, 600 rows), PDLP to 1e-6"
+    if w == "mcnf":
+        K = max(1, int(round(50 * args.scale)))
+        return gen.mcnf(K=K), f"C5: multi-commodity flow, {K} commodities on 20k nodes / 100k arcs, PDLP to 1e-6"
+    raise SystemExit(f"unknown workload {w}")
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the path on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    if args.workload == "batch":
+        d = gen.dense_batch(B=int(200_000 * args.scale), seed=0)
+        sample = min(d["B"], args.cpu_sample_lps)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_batch_baseline(d, sample, threads)
+            if i >= args.warmup:
+                vals.append(r["value"])
+        v = float(np.mean(vals))
+        line = {"metric": "batched_lps_per_s", "value": v, "unit": "LP/s", "ms_per_step": sample / v * 1e3,
+                "config": {"workload": f"C3: batch of {d['B']} dense LPs (20 x 30); each step = first {sample} LPs"}}
+        base = r
+    else:
+        p, name = make_problem(args)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_pdlp_baseline(p, args.cpu_sample_iters, threads)
+            if i >= args.warmup:
+                vals.append(r["value"])
+        v = float(np.mean(vals))
+        line = {"metric": "pdlp_iter_per_s", "value": v, "unit": "iter/s", "ms_per_step": args.cpu_sample_iters / v * 1e3,
+                "config": {"workload": name + f"; each step = first {args.cpu_sample_iters} iterations"}}
+        base = r
+    base = dict(base)
+    base["value"] = v
+    line.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                 "cpu_baseline": base, "gpu_launches": 0,
+                 "e2e": {"value": v, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pdlp", choices=["pdlp", "batch", "transport", "mcnf"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (smoke runs only; 1.0 = BASELINE size)")
+    ap.add_argument("--max-iter", type=int, default=400_000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-iters", type=int, default=150)
+    ap.add_argument("--cpu-sample-lps", type=int, default=20_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (batch) arm in the pdlp line")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    dist = Dist(args.gpus)
+    from easylp_b200 import _lib as L
+    if L.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: libeasylp_b200 has no CPU fallback")
+    L.set_device(dist.local)
+    threads = host_threads()
+
+    if args.workload == "batch":
+        d = gen.dense_batch(B=int(200_000 * args.scale), seed=0)
+        res = bench_batch(args, dist, L, d)
+        if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
+            res["cpu_baseline"] = cpu_batch_baseline(d, min(d["B"], args.cpu_sample_lps), threads)
+    else:
+        p, name = make_problem(args)
+        res = bench_pdlp(args, dist, L, p, name)
+        if not args.no_secondary:
+            d = gen.dense_batch(B=int(200_000 * args.scale), seed=0)
+            sec = bench_batch(args, dist, L, d)
+            if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
+                sec["cpu_baseline"] = cpu_batch_baseline(d, min(d["B"], args.cpu_sample_lps), threads)
+            res["batch"] = {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "optimal",
+                                                "pivots_per_lp", "pivots_per_s", "e2e", "gpu_launches", "roofline")
+                            if k in sec}
+            if "cpu_baseline" in sec:
+                res["batch"]["cpu_baseline"] = sec["cpu_baseline"]
+            res["gpu_launches"] += sec["gpu_launches"]
+        if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
+            res["cpu_baseline"] = cpu_pdlp_baseline(p, args.cpu_sample_iters, threads)
+    if dist.rank == 0:
+        print(json.dumps(res), flush=True)
+    dist.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,7 +49,7 @@ ABI_SYMBOLS = [
     "elp_status_string", "elp_kernel_launches", "elp_assemble_csr", "elp_solve_lp", "elp_solve_batch",
     "elp_batch_create", "elp_batch_run", "elp_batch_fetch", "elp_batch_destroy", "elp_spmv",
     "elp_check_feasible", "elp_pdlp_create", "elp_pdlp_run", "elp_pdlp_reset", "elp_pdlp_solution",
-    "elp_pdlp_probe_spmv", "elp_pdlp_destroy", "elp_comm_unique_id", "elp_comm_init", "elp_comm_size",
+    "elp_pdlp_probe_spmv", "elp_pdlp_probe_step", "elp_pdlp_destroy", "elp_comm_unique_id", "elp_comm_init", "elp_comm_size",
     "elp_comm_destroy",
 ]
 
@@ -283,6 +283,11 @@ class Pdlp:
     def probe_spmv(self, reps=20):
         a, b = C.c_double(), C.c_double()
         _check(lib().elp_pdlp_probe_spmv(self._h, C.c_int32(reps), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def probe_step(self, reps=20):
+        a, b = C.c_double(), C.c_double()
+        _check(lib().elp_pdlp_probe_step(self._h, C.c_int32(reps), C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def close(self):

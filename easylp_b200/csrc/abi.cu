@@ -22,6 +22,7 @@ void pdlp_run(Pdlp* p, int max_new_iters, elp_stats* stats);
 void pdlp_reset(Pdlp* p);
 void pdlp_solution(Pdlp* p, double* x, double* y, double* obj);
 void pdlp_probe(Pdlp* p, int reps, double* a, double* b);
+void pdlp_probe_step(Pdlp* p, int reps, double* a, double* b);
 void pdlp_destroy(Pdlp* p);
 void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals, const double* x,
                double* out, const int8_t* sense, const double* rhs, double tol, uint8_t* feasible);
@@ -416,6 +417,12 @@ int elp_pdlp_probe_spmv(elp_pdlp* h, int32_t reps, double* ms_csr, double* ms_cs
     ELP_TRY
     ELP_REQUIRE(h && reps > 0, "bad arguments");
     pdlp_probe(reinterpret_cast<Pdlp*>(h), reps, ms_csr, ms_csc);
+    ELP_CATCH
+}
+int elp_pdlp_probe_step(elp_pdlp* h, int32_t reps, double* ms_primal, double* ms_dual) {
+    ELP_TRY
+    ELP_REQUIRE(h && reps > 0, "bad arguments");
+    pdlp_probe_step(reinterpret_cast<Pdlp*>(h), reps, ms_primal, ms_dual);
     ELP_CATCH
 }
 int elp_pdlp_destroy(elp_pdlp* h) {

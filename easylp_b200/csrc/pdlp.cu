@@ -921,6 +921,38 @@ struct Pdlp {
         if (obj) *obj = maximize ? -pobj : pobj;
     }
 
+    // Times the two fused iteration kernels in isolation (local part only when distributed: no collective).
+    // Leaves the iterate in an arbitrary state: the caller resets afterwards.
+    void probe_step(int reps, double* ms_primal, double* ms_dual) {
+        cudaEvent_t e0, e1;
+        ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+        float ms = 0;
+        PrimalEpi<false> pe{c.p, l.p, u.p, x0.p, x.p, xbar.p, xp.p, params.p, 0};
+        auto primal = [&] {
+            if (!dist) { launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, pe, st); }
+            else {
+                launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
+                ELP_LAUNCH((apply_epi_kernel<PrimalEpi<false>>), grid1(n), 256, 0, st, n, gbuf.p, pe);
+            }
+        };
+        for (int i = 0; i < 3; ++i) primal();
+        ELP_CUDA(cudaEventRecord(e0, st));
+        for (int i = 0; i < reps; ++i) primal();
+        ELP_CUDA(cudaEventRecord(e1, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_primal) *ms_primal = ms / reps;
+        for (int i = 0; i < 3; ++i) dual_step<false>(0);
+        ELP_CUDA(cudaEventRecord(e0, st));
+        for (int i = 0; i < reps; ++i) dual_step<false>(0);
+        ELP_CUDA(cudaEventRecord(e1, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_dual) *ms_dual = ms / reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        reset();
+    }
+
     void probe_spmv(int reps, double* ms_csr, double* ms_csc) {
         cudaEvent_t e0, e1;
         ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
@@ -962,6 +994,7 @@ void pdlp_run(Pdlp* p, int max_new_iters, elp_stats* stats) { p->run(max_new_ite
 void pdlp_reset(Pdlp* p) { p->reset(); }
 void pdlp_solution(Pdlp* p, double* x, double* y, double* obj) { p->solution(x, y, obj); }
 void pdlp_probe(Pdlp* p, int reps, double* a, double* b) { p->probe_spmv(reps, a, b); }
+void pdlp_probe_step(Pdlp* p, int reps, double* a, double* b) { p->probe_step(reps, a, b); }
 void pdlp_destroy(Pdlp* p) { delete p; }
 
 // plain SpMV + feasibility re-check (S4: /root/reference/R/class.R:533-540, R/utils.R:167-171)

@@ -153,6 +153,8 @@ int elp_pdlp_run(elp_pdlp* h, int32_t max_new_iters, elp_stats* stats);
 int elp_pdlp_reset(elp_pdlp* h);                                   /* back to the initial iterate */
 int elp_pdlp_solution(elp_pdlp* h, double* x /* n */, double* y /* m_local, may be NULL */, double* objval);
 int elp_pdlp_probe_spmv(elp_pdlp* h, int32_t reps, double* ms_csr, double* ms_csc);  /* times bare A.x and A'.y */
+/* times the two fused iteration kernels alone (A'y + primal update; A.xbar + dual update); resets the iterate */
+int elp_pdlp_probe_step(elp_pdlp* h, int32_t reps, double* ms_primal, double* ms_dual);
 int elp_pdlp_destroy(elp_pdlp* h);
 
 /* ---- multi-GPU plumbing (one process per GPU; NCCL resolved with dlopen at first use) -------- */

@@ -65,3 +65,29 @@ def simplex_csr(m, n, row_ptr, col_idx, vals, sense, rhs, c, lb, ub, maximize=Fa
     st = f(m, n, _p(row_ptr), _p(col_idx), _p(vals), _p(sense), _p(rhs), _p(c), int(maximize), _p(lb), _p(ub),
            C.addressof(obj), _p(x), _p(y), C.addressof(piv))
     return st, obj.value, x, y[:m], piv.value
+
+
+def pdlp(p, eps=1e-6, max_iter=0, check_every=64, nthreads=0):
+    """Runs oracle/pdlp_ref.c on a problem dict (keys of oracle/gen.py).  Returns (status, out[8], x, y);
+    out = objective, iterations, restarts, rel primal res, rel dual res, rel gap, loop seconds, setup seconds."""
+    f = lib().elpo_pdlp
+    f.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 2 + \
+                 [C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3
+    f.restype = C.c_int
+    m, n = int(p["m"]), int(p["n"])
+    row_ptr = np.ascontiguousarray(p["row_ptr"], np.int32)
+    if row_ptr.size == 0:
+        row_ptr = np.zeros(1, np.int32)
+    col_idx = np.ascontiguousarray(p["col_idx"], np.int32)
+    vals = np.ascontiguousarray(p["vals"], np.float64)
+    sense = np.ascontiguousarray(p["sense"], np.int8)
+    rhs = np.ascontiguousarray(p["rhs"], np.float64)
+    c = np.ascontiguousarray(p["c"], np.float64)
+    lb = np.ascontiguousarray(np.broadcast_to(p["lb"], (n,)), np.float64)
+    ub = np.ascontiguousarray(np.broadcast_to(p["ub"], (n,)), np.float64)
+    x = np.zeros(n)
+    y = np.zeros(max(m, 1))
+    out = np.zeros(8)
+    st = f(m, n, _p(row_ptr), _p(col_idx), _p(vals), _p(sense), _p(rhs), _p(c), int(bool(p.get("maximize", False))),
+           _p(lb), _p(ub), float(eps), int(max_iter), int(check_every), int(nthreads), _p(x), _p(y), _p(out))
+    return st, out, x, y[:m]
