@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "primitives.cuh"
 #include "comm.cuh"
+#include "tma.cuh"
 #include "../../include/easylp_abi.h"
 #include <cmath>
 #include <algorithm>
@@ -38,30 +39,147 @@ struct PdlpParams {   // device-resident; the host rewrites it between iteration
 };
 
 // ------------------------------------------------------------------------------------------------
-// SpMV skeleton: L lanes per row, epilogue functor called by the group's lane 0.
+// SpMV: persistent tile kernel.  One CTA walks tiles of TR consecutive rows (one row per thread).
+//   * the tile's slice of the matrix stream (val: 8 B, idx: 4 B per entry — 80 % of the HBM bytes of an
+//     iteration) is staged into shared memory by 1-D TMA bulk copies, double-buffered on mbarriers, so
+//     the copy of the next tile overlaps the work on the current one and no LSU slot is spent on it;
+//   * phase A: every thread turns TR-strided entries into products val * vec[idx] in place — the
+//     gathers of the (L2-resident) vector are independent, several per thread in flight;
+//   * phase B: thread t adds up the products of its own row in index order (so the result equals a
+//     sequential CPU loop bit for bit) and runs the fused epilogue with operands it pre-loaded,
+//     coalesced, before phase A.
+// Tiles whose entries exceed the stage capacity are walked in pieces with a running sum.
 // ------------------------------------------------------------------------------------------------
-constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_THREADS = 256;             // block size of the setup-only helper kernels
+constexpr int SPMV_NST = 2;                 // pipeline stages
+constexpr int SPMV_PAD = 8;                 // matrix arrays are over-allocated so 16-byte-granular copies stay in bounds
 
-template <int L, class Epi>
-__global__ void __launch_bounds__(SPMV_THREADS)
-spmv_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
-            const double* __restrict__ vec, Epi epi) {
-    const int row = (int)(((int64_t)blockIdx.x * SPMV_THREADS + threadIdx.x) / L);
-    const int lane = threadIdx.x & (L - 1);
-    int start = 0, end = 0;
-    if (row < nrows) { start = __ldg(ptr + row); end = __ldg(ptr + row + 1); }
-    double s = 0.0;
-    for (int k = start + lane; k < end; k += L) s += ld_stream(val + k) * __ldg(vec + ld_stream(idx + k));
-    s = group_sum<L>(s);
-    if (lane == 0 && row < nrows) epi(row, s);
+template <int TR, class Epi>
+__global__ void __launch_bounds__(TR)
+spmv_tile_kernel(int nrows, int ntiles, int cap, int hints, const int* __restrict__ ptr, const int* __restrict__ idx,
+                 const double* __restrict__ val, const double* __restrict__ vec, Epi epi) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sval = reinterpret_cast<double*>(smem_raw);                                   // [NST][cap]
+    int* sidx = reinterpret_cast<int*>(smem_raw + (size_t)SPMV_NST * cap * 8);            // [NST][cap]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SPMV_NST * cap * 12); // [NST]
+    int* sinfo = reinterpret_cast<int*>(full + SPMV_NST);                                 // [NST][4]
+    const int tid = threadIdx.x;
+    // L2 residency: the matrix stream is read once per launch (evict first), the gathered vector is
+    // re-read ~nnz/len times (evict last)
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SPMV_NST; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- producer cursor (thread 0): the next piece to copy ------------------------------------------
+    int p_tile = blockIdx.x, p_piece = 0;
+    int p_s = 0, p_e = 0, n_s = 0, n_e = 0;       // entry range of the producer's tile, and of the tile after it
+    auto tile_bounds = [&](int tile, int& s0, int& e1) {
+        if (tile < ntiles) {
+            const int r0 = tile * TR;
+            const int r1 = min(r0 + TR, nrows);
+            s0 = __ldg(ptr + r0);
+            e1 = __ldg(ptr + r1);
+        } else { s0 = 0; e1 = 0; }
+    };
+    auto issue = [&](int stage) {
+        if (p_tile >= ntiles) return;
+        const int a0 = p_s & ~3, a1 = (p_e + 3) & ~3;
+        const int pstart = a0 + p_piece * cap;
+        const int pcnt = min(cap, a1 - pstart);
+        const bool last = pstart + pcnt >= a1;
+        int* info = sinfo + stage * 4;
+        info[0] = pstart;
+        info[1] = max(p_s, pstart) - pstart;                 // first real entry of the piece
+        info[2] = min(p_e, pstart + pcnt) - pstart;          // one past the last real entry
+        info[3] = last ? 1 : 0;
+        mbar_expect_tx(&full[stage], (uint32_t)pcnt * 12u);
+        if (pcnt > 0) {
+            if (hints & 1) {
+                tma_load_1d_hint(sval + (size_t)stage * cap, val + pstart, (uint32_t)pcnt * 8u, &full[stage], pol_stream);
+                tma_load_1d_hint(sidx + (size_t)stage * cap, idx + pstart, (uint32_t)pcnt * 4u, &full[stage], pol_stream);
+            } else {
+                tma_load_1d(sval + (size_t)stage * cap, val + pstart, (uint32_t)pcnt * 8u, &full[stage]);
+                tma_load_1d(sidx + (size_t)stage * cap, idx + pstart, (uint32_t)pcnt * 4u, &full[stage]);
+            }
+        }
+        if (last) {
+            p_tile += gridDim.x; p_piece = 0;
+            p_s = n_s; p_e = n_e;
+            tile_bounds(p_tile + gridDim.x, n_s, n_e);       // consumed one tile later: latency hidden
+        } else {
+            ++p_piece;
+        }
+    };
+    if (tid == 0) {
+        tile_bounds(p_tile, p_s, p_e);
+        tile_bounds(p_tile + gridDim.x, n_s, n_e);
+#pragma unroll
+        for (int s = 0; s < SPMV_NST; ++s) issue(s);
+    }
+
+    // ---- consumers -------------------------------------------------------------------------------
+    int q = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row = tile * TR + tid;
+        int st = 0, en = 0;
+        typename Epi::Pre pre{};
+        if (row < nrows) {
+            st = __ldg(ptr + row);
+            en = __ldg(ptr + row + 1);
+            pre = epi.preload(row);
+        }
+        double acc = 0.0;
+        for (;;) {
+            const int stage = q % SPMV_NST;
+            mbar_wait(&full[stage], (uint32_t)(q / SPMV_NST) & 1u);
+            const int* info = sinfo + stage * 4;
+            const int pstart = info[0], lo = info[1], hi = info[2], last = info[3];
+            double* sv = sval + (size_t)stage * cap;
+            const int* si = sidx + (size_t)stage * cap;
+            // phase A: products in place.  Entries are read into registers in batches so that the
+            // gathers of a batch are independent of the shared-memory stores of the batch before.
+            constexpr int U = 8;
+            for (int e0 = lo + tid; e0 < hi; e0 += U * TR) {
+                double v[U], g[U];
+                int c[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * TR;
+                    if (e < hi) { v[u] = sv[e]; c[u] = si[e]; }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (e0 + u * TR < hi) g[u] = (hints & 2) ? ldg_hint(vec + c[u], pol_keep) : __ldg(vec + c[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (e0 + u * TR < hi) sv[e0 + u * TR] = v[u] * g[u];
+            }
+            __syncthreads();
+            // phase B: my row's share of this piece, in index order
+            const int b = max(st, pstart + lo) - pstart, f = min(en, pstart + hi) - pstart;
+            for (int k = b; k < f; ++k) acc += sv[k];
+            // generic-proxy accesses to the stage must be ordered before the next bulk copy into it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();                                   // stage fully consumed
+            if (tid == 0) issue(stage);
+            ++q;
+            if (last) break;
+        }
+        if (row < nrows) epi.apply(row, acc, pre);
+    }
 }
 
 template <class Epi>
 __global__ void __launch_bounds__(256) apply_epi_kernel(int n, const double* __restrict__ g, Epi epi) {
     const int j = blockIdx.x * 256 + threadIdx.x;
-    if (j < n) epi(j, g[j]);
+    if (j < n) epi.apply(j, g[j], epi.preload(j));
 }
 
+// lanes per row for the setup-only helper kernels (row statistics, value scaling, row expansion)
 inline int pick_lanes(int64_t nnz, int64_t nrows) {
     const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
     int L = 1;
@@ -69,25 +187,71 @@ inline int pick_lanes(int64_t nnz, int64_t nrows) {
     return L;
 }
 
-template <class Epi>
-void launch_spmv(int L, int nrows, const int* ptr, const int* idx, const double* val, const double* vec, Epi epi,
-                 cudaStream_t st) {
-    if (nrows <= 0) return;
-    const int grid = ceil_div((int64_t)nrows * L, SPMV_THREADS);
-    switch (L) {
-        case 1:  ELP_LAUNCH((spmv_kernel<1, Epi>), grid, SPMV_THREADS, 0, st, nrows, ptr, idx, val, vec, epi); break;
-        case 2:  ELP_LAUNCH((spmv_kernel<2, Epi>), grid, SPMV_THREADS, 0, st, nrows, ptr, idx, val, vec, epi); break;
-        case 4:  ELP_LAUNCH((spmv_kernel<4, Epi>), grid, SPMV_THREADS, 0, st, nrows, ptr, idx, val, vec, epi); break;
-        case 8:  ELP_LAUNCH((spmv_kernel<8, Epi>), grid, SPMV_THREADS, 0, st, nrows, ptr, idx, val, vec, epi); break;
-        case 16: ELP_LAUNCH((spmv_kernel<16, Epi>), grid, SPMV_THREADS, 0, st, nrows, ptr, idx, val, vec, epi); break;
-        default: ELP_LAUNCH((spmv_kernel<32, Epi>), grid, SPMV_THREADS, 0, st, nrows, ptr, idx, val, vec, epi); break;
-    }
+struct SpmvPlan {
+    int tr = 256, cap = 2048, ctas_cap = 8, ntiles = 0, hints = 3;
+    size_t smem = 0;
+};
+
+inline int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
-// ---- epilogues -------------------------------------------------------------------------------
+inline SpmvPlan plan_spmv(int64_t nnz, int nrows) {
+    SpmvPlan p;
+    const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+    p.tr = env_int("ELP_SPMV_TR", 256);
+    if (p.tr != 128 && p.tr != 256) p.tr = 256;
+    const double mul = env_int("ELP_SPMV_CAPMUL_PCT", 150) / 100.0;
+    int64_t cap = (int64_t)(avg * p.tr * mul) + 64;
+    cap = (cap + 255) / 256 * 256;
+    cap = std::max<int64_t>(512, std::min<int64_t>(cap, 6144));
+    if (const int c = env_int("ELP_SPMV_CAP", 0)) cap = std::max(64, c / 4 * 4);
+    p.cap = (int)cap;
+    p.smem = (size_t)SPMV_NST * p.cap * 12 + SPMV_NST * 8 + SPMV_NST * 16;
+    p.ntiles = ceil_div(nrows, p.tr);
+    p.ctas_cap = std::max(1, env_int("ELP_SPMV_CTAS", 8));
+    p.hints = env_int("ELP_SPMV_HINTS", 3);
+    return p;
+}
+
+template <int TR, class Epi>
+void configure_spmv_kernel() {
+    ELP_CUDA(cudaFuncSetAttribute(spmv_tile_kernel<TR, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
+template <int TR, class Epi>
+void launch_spmv_tr(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val, const double* vec,
+                    Epi epi, cudaStream_t st) {
+    // persistent grid: one wave of resident CTAs (occupancy of this instantiation at this stage size)
+    static size_t occ_smem = (size_t)-1;
+    static int occ = 1;
+    if (occ_smem != p.smem) {
+        int o = 0;
+        ELP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, spmv_tile_kernel<TR, Epi>, TR, p.smem));
+        occ = std::max(1, o);
+        occ_smem = p.smem;
+    }
+    const int grid = std::max(1, std::min(p.ntiles, kNumSMs * std::min(occ, p.ctas_cap)));
+    ELP_LAUNCH((spmv_tile_kernel<TR, Epi>), grid, TR, p.smem, st, nrows, p.ntiles, p.cap, p.hints, ptr, idx, val, vec,
+               epi);
+}
+
+// The matrix arrays must be over-allocated by SPMV_PAD entries (16-byte-granular TMA copies).
+template <class Epi>
+void launch_spmv(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val, const double* vec,
+                 Epi epi, cudaStream_t st) {
+    if (nrows <= 0) return;
+    if (p.tr == 128) launch_spmv_tr<128, Epi>(p, nrows, ptr, idx, val, vec, epi, st);
+    else launch_spmv_tr<256, Epi>(p, nrows, ptr, idx, val, vec, epi, st);
+}
+
+// ---- epilogues: preload() runs before the products are formed, apply() after the row sum ----------
 struct StoreEpi {
     double* out;
-    __device__ __forceinline__ void operator()(int r, double s) const { out[r] = s; }
+    struct Pre {};
+    __device__ __forceinline__ Pre preload(int) const { return Pre{}; }
+    __device__ __forceinline__ void apply(int r, double s, const Pre&) const { out[r] = s; }
 };
 
 // primal half of T(z) + reflection + Halpern combine.  g = (A'y)_j
@@ -102,18 +266,24 @@ struct PrimalEpi {
     double* __restrict__ xp;
     const PdlpParams* __restrict__ P;
     int it;
-    __device__ __forceinline__ void operator()(int j, double g) const {
+    struct Pre { double x, c, l, u, x0; };
+    __device__ __forceinline__ Pre preload(int j) const {
+        Pre p;
+        p.x = x[j]; p.c = c[j]; p.l = l[j]; p.u = u[j];
+        p.x0 = CHECK ? 0.0 : x0[j];
+        return p;
+    }
+    __device__ __forceinline__ void apply(int j, double g, const Pre& p) const {
         const double tau = P->tau;
-        const double xj = x[j];
-        const double xpj = fmin(fmax(xj - tau * (c[j] - g), l[j]), u[j]);
-        const double xb = 2.0 * xpj - xj;
+        const double xpj = fmin(fmax(p.x - tau * (p.c - g), p.l), p.u);
+        const double xb = 2.0 * xpj - p.x;
         xbar[j] = xb;
         if (CHECK) {
             xp[j] = xpj;
         } else {
             const double k = (double)(P->k_base + it);
             const double w = (k + 1.0) / (k + 2.0);
-            x[j] = w * xb + (1.0 - w) * x0[j];
+            x[j] = w * xb + (1.0 - w) * p.x0;
         }
     }
 };
@@ -129,12 +299,18 @@ struct DualEpi {
     double* __restrict__ axbar;
     const PdlpParams* __restrict__ P;
     int it;
-    __device__ __forceinline__ void operator()(int i, double ax) const {
+    struct Pre { double y, lc, uc, y0; };
+    __device__ __forceinline__ Pre preload(int i) const {
+        Pre p;
+        p.y = y[i]; p.lc = lc[i]; p.uc = uc[i];
+        p.y0 = CHECK ? 0.0 : y0[i];
+        return p;
+    }
+    __device__ __forceinline__ void apply(int i, double ax, const Pre& p) const {
         const double sigma = P->sigma;
-        const double yi = y[i];
-        const double v = yi - sigma * ax;
-        const double lo = v + sigma * lc[i];     // -inf when the row has no lower bound
-        const double hi = v + sigma * uc[i];     // +inf when the row has no upper bound
+        const double v = p.y - sigma * ax;
+        const double lo = v + sigma * p.lc;     // -inf when the row has no lower bound
+        const double hi = v + sigma * p.uc;     // +inf when the row has no upper bound
         const double ypi = lo > 0.0 ? lo : (hi < 0.0 ? hi : 0.0);
         if (CHECK) {
             yp[i] = ypi;
@@ -142,10 +318,20 @@ struct DualEpi {
         } else {
             const double k = (double)(P->k_base + it);
             const double w = (k + 1.0) / (k + 2.0);
-            y[i] = w * (2.0 * ypi - yi) + (1.0 - w) * y0[i];
+            y[i] = w * (2.0 * ypi - p.y) + (1.0 - w) * p.y0;
         }
     }
 };
+
+// Raises the dynamic shared-memory limit of every SpMV instantiation (per device; called from setup,
+// outside any stream capture).
+void configure_spmv_kernels() {
+    configure_spmv_kernel<128, StoreEpi>();         configure_spmv_kernel<256, StoreEpi>();
+    configure_spmv_kernel<128, PrimalEpi<false>>(); configure_spmv_kernel<256, PrimalEpi<false>>();
+    configure_spmv_kernel<128, PrimalEpi<true>>();  configure_spmv_kernel<256, PrimalEpi<true>>();
+    configure_spmv_kernel<128, DualEpi<false>>();   configure_spmv_kernel<256, DualEpi<false>>();
+    configure_spmv_kernel<128, DualEpi<true>>();    configure_spmv_kernel<256, DualEpi<true>>();
+}
 
 // ---- row statistics for the scaling: out[r] = s_self[r] * reduce_k |val[k]| * s_other[idx[k]] ------
 template <int L, int MODE /*0 max, 1 sum*/>
@@ -469,7 +655,8 @@ struct Pdlp {
     // matrix (scaled in place after setup)
     DevBuf<int> csr_ptr, csr_idx, csc_ptr, csc_idx;
     DevBuf<double> csr_val, csc_val;
-    int Lr = 8, Lc = 4;
+    int Lr = 8, Lc = 4;          // lanes per row of the setup helper kernels
+    SpmvPlan plan_r, plan_c;     // tile plans of the two iteration SpMVs (CSR rows / CSC columns)
     // vectors (scaled)
     DevBuf<double> c, l, u, lc, uc, dr, dc;
     DevBuf<double> x, x0, xbar, xp, y, y0, yp, axbar, axp, gbuf;   // gbuf: n + NACC (allreduce buffer)
@@ -511,11 +698,11 @@ struct Pdlp {
 
     // y_out[m] = A * v      (local rows)
     void spmv_rows(const double* v, double* out) {
-        launch_spmv(Lr, m, csr_ptr.p, csr_idx.p, csr_val.p, v, StoreEpi{out}, st);
+        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, v, StoreEpi{out}, st);
     }
     // out[n] = A' * v  (summed over ranks)
     void spmv_cols(const double* v, double* out) {
-        launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, v, StoreEpi{out}, st);
+        launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, v, StoreEpi{out}, st);
         if (dist) comm_allreduce_sum(out, n, st);
     }
 
@@ -555,8 +742,10 @@ struct Pdlp {
         ELP_REQUIRE(m >= 0 && n > 0, "pdlp: bad shape %d x %d", m, n);
         nnz = m > 0 ? row_ptr[m] : 0;
         ELP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        csr_ptr.alloc(m + 1); csr_idx.alloc(std::max<int64_t>(nnz, 1)); csr_val.alloc(std::max<int64_t>(nnz, 1));
-        csc_ptr.alloc(n + 1); csc_idx.alloc(std::max<int64_t>(nnz, 1)); csc_val.alloc(std::max<int64_t>(nnz, 1));
+        configure_spmv_kernels();
+        csr_ptr.alloc(m + 1); csr_idx.alloc(nnz + SPMV_PAD); csr_val.alloc(nnz + SPMV_PAD);
+        csc_ptr.alloc(n + 1); csc_idx.alloc(nnz + SPMV_PAD); csc_val.alloc(nnz + SPMV_PAD);
+        csr_idx.zero(st); csr_val.zero(st); csc_idx.zero(st); csc_val.zero(st);
         c.alloc(n); l.alloc(n); u.alloc(n); dc.alloc(n);
         lc.alloc(std::max(m, 1)); uc.alloc(std::max(m, 1)); dr.alloc(std::max(m, 1));
         x.alloc(n); x0.alloc(n); xbar.alloc(n); xp.alloc(n); gbuf.alloc(n + NACC);
@@ -582,6 +771,8 @@ struct Pdlp {
         if (maximize) ELP_LAUNCH(k_scale_scalar, grid1(n), 256, 0, st, n, c.p, -1.0);
         Lr = pick_lanes(nnz, m);
         Lc = pick_lanes(nnz, n);
+        plan_r = plan_spmv(nnz, m);
+        plan_c = plan_spmv(nnz, n);
 
         build_csc();
         // unscaled norms for the relative termination test
@@ -713,9 +904,9 @@ struct Pdlp {
     void primal_step(int it) {
         PrimalEpi<CHECK> epi{c.p, l.p, u.p, x0.p, x.p, xbar.p, xp.p, params.p, it};
         if (!dist) {
-            launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, epi, st);
+            launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, epi, st);
         } else {
-            launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
+            launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
             comm_allreduce_sum(gbuf.p, n, st);
             ELP_LAUNCH((apply_epi_kernel<PrimalEpi<CHECK>>), grid1(n), 256, 0, st, n, gbuf.p, epi);
         }
@@ -723,7 +914,7 @@ struct Pdlp {
     template <bool CHECK>
     void dual_step(int it) {
         DualEpi<CHECK> epi{lc.p, uc.p, y0.p, y.p, yp.p, axbar.p, params.p, it};
-        launch_spmv(Lr, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar.p, epi, st);
+        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar.p, epi, st);
     }
     int kernels_per_iter() const { return (m > 0 ? 1 : 0) + (dist ? 2 : 1); }
 
@@ -770,7 +961,7 @@ struct Pdlp {
                    partials.p);
         // row sums travel in the tail of the A'y buffer so a distributed check costs one allreduce
         reduce_to(gbuf.p + n);
-        launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, yp.p, StoreEpi{gbuf.p}, st);
+        launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, yp.p, StoreEpi{gbuf.p}, st);
         if (dist) comm_allreduce_sum(gbuf.p, (size_t)n + NACC, st);
         ELP_LAUNCH(k_check_cols, RED_BLOCKS, RED_THREADS, 0, st, n, gbuf.p, c.p, l.p, u.p, x.p, xp.p, x0.p, dc.p,
                    partials.p);
@@ -929,9 +1120,9 @@ struct Pdlp {
         float ms = 0;
         PrimalEpi<false> pe{c.p, l.p, u.p, x0.p, x.p, xbar.p, xp.p, params.p, 0};
         auto primal = [&] {
-            if (!dist) { launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, pe, st); }
+            if (!dist) { launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, pe, st); }
             else {
-                launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
+                launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
                 ELP_LAUNCH((apply_epi_kernel<PrimalEpi<false>>), grid1(n), 256, 0, st, n, gbuf.p, pe);
             }
         };
@@ -964,9 +1155,9 @@ struct Pdlp {
         ELP_CUDA(cudaStreamSynchronize(st));
         ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (ms_csr) *ms_csr = ms / reps;
-        for (int i = 0; i < 3; ++i) launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
+        for (int i = 0; i < 3; ++i) launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
         ELP_CUDA(cudaEventRecord(e0, st));
-        for (int i = 0; i < reps; ++i) launch_spmv(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
+        for (int i = 0; i < reps; ++i) launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
         ELP_CUDA(cudaEventRecord(e1, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -1019,10 +1210,12 @@ void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, con
     cudaStream_t st = 0;
     const int64_t nnz = m > 0 ? row_ptr[m] : 0;
     if (m == 0) return;
-    DevBuf<int> ptr(m + 1), idx(std::max<int64_t>(nnz, 1));
-    DevBuf<double> val(std::max<int64_t>(nnz, 1)), xd(std::max(n, 1)), od(m);
+    configure_spmv_kernels();
+    DevBuf<int> ptr(m + 1), idx(nnz + SPMV_PAD);
+    DevBuf<double> val(nnz + SPMV_PAD), xd(std::max(n, 1)), od(m);
+    idx.zero(st); val.zero(st);
     ptr.upload(row_ptr, m + 1, st); idx.upload(col_idx, nnz, st); val.upload(vals, nnz, st); xd.upload(x, n, st);
-    launch_spmv(pick_lanes(nnz, m), m, ptr.p, idx.p, val.p, xd.p, StoreEpi{od.p}, st);
+    launch_spmv(plan_spmv(nnz, m), m, ptr.p, idx.p, val.p, xd.p, StoreEpi{od.p}, st);
     if (out) od.download(out, m, st);
     if (feasible) {
         DevBuf<int8_t> sd(m);

@@ -14,6 +14,7 @@
 // The serial pivot chain, not HBM, bounds this kernel; bench.py reports LPs/s, pivots/s and the HBM
 // fraction side by side.
 #include "common.cuh"
+#include "tma.cuh"
 #include "../../include/easylp_abi.h"
 #include <algorithm>
 #include <cmath>
@@ -30,39 +31,6 @@ constexpr double TOL_DUAL = 1e-9;
 constexpr double TOL_PIVOT = 1e-9;
 
 __device__ __forceinline__ double ptol(double bound) { return TOL_PRIMAL * fmax(1.0, fabs(bound)); }
-
-// ---- TMA (bulk async copy) + mbarrier helpers, raw PTX -----------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ bool tma_ok(const void* src, size_t bytes) {
-    return bytes > 0 && (bytes & 15) == 0 && (((uintptr_t)src) & 15) == 0;
-}
 
 // ---- block-wide reductions (value, index) ----------------------------------------------------
 struct ValIdx {
@@ -182,7 +150,7 @@ simplex_batch_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, con
     const size_t bytesA = (size_t)m * n * 8, bytesb = (size_t)m * 8, bytesn = (size_t)n * 8;
     const bool tA = tma_ok(A, bytesA), tb = tma_ok(b, bytesb), tc = tma_ok(c, bytesn);
     const bool tl = lb && tma_ok(lb, bytesn), tu = ub && tma_ok(ub, bytesn);
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     block_sync<THREADS>();
     if (tid == 0) {
         const uint32_t tx = (uint32_t)((tA ? bytesA : 0) + (tb ? bytesb : 0) + (tc ? bytesn : 0) + (tl ? bytesn : 0) +
