@@ -303,7 +303,8 @@ class lp_var:
             x.dimnames, x.dimtitles, x.has_dim = None, None, False
         else:
             x.ind = self.ind[np.ix_(*pos)]
-            x.dimnames = [[self.dimnames[d][i] for i in p] for d, p in enumerate(pos)]
+            x.dimnames = ([[self.dimnames[d][i] for i in p] for d, p in enumerate(pos)]
+                          if self.dimnames is not None else None)
             lin = np.ravel_multi_index(np.ix_(*pos), self.ind.shape, order="F").ravel() if len(pos) > 1 else pos[0]
         if self.ind.size != self.nrow:
             raise EasyLpError("Variable was wrongly indexed.")
@@ -888,13 +889,13 @@ class easylp:
     def solve(self, **control):
         if self._n_var == 0:
             raise EasyLpError("Problem contains no variables.")
+        if self.any_integer():
+            raise EasyLpError("integer/binary variables need lp_solve's branch and bound; the B200 path solves LPs only "
+                              "(SURVEY.md §2 row 14)")
         if np.all(self.objective_fun == 0):
             raise EasyLpError("Must specify objective function.")
         if self._dir not in ("min", "max"):
             raise EasyLpError("Direction must be either 'min' or 'max'.")
-        if self.any_integer():
-            raise EasyLpError("integer/binary variables need lp_solve's branch and bound; the B200 path solves LPs only "
-                              "(SURVEY.md §2 row 14)")
         opt = _lib.default_options()
         for k, v in control.items():             # the `...` of lp.control() (R/class.R:262)
             if k == "timeout":

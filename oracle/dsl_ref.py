@@ -223,7 +223,8 @@ class lp_var:
             x.dimnames, x.dimtitles, x.has_dim = None, None, False
         else:
             x.ind = self.ind[np.ix_(*pos)]
-            x.dimnames = [[self.dimnames[d][i] for i in p] for d, p in enumerate(pos)]
+            x.dimnames = ([[self.dimnames[d][i] for i in p] for d, p in enumerate(pos)]
+                          if self.dimnames is not None else None)
         rows = np.isin(old, x.ind)
         x.raw = False
         x.coef = self.coef[rows, :]

@@ -41,6 +41,8 @@ def ruiz_pc_scaling(A: sp.csr_matrix, ruiz_iters=10, pc_alpha=1.0):
     m, n = A.shape
     dr = np.ones(m)
     dc = np.ones(n)
+    if m == 0 or n == 0 or A.nnz == 0:
+        return dr, dc
     As = A.copy().tocsr()
     absA = abs(As)
     for _ in range(ruiz_iters):
