@@ -11,12 +11,11 @@
 // sigma = eta*w), primal weight w re-balanced at restarts, fixed-point-error restarts and PDLP's
 // relative KKT termination test.  The CPU restatement of this loop is oracle/pdlp_ref.py.
 //
-// Kernels per iteration (single GPU) — exactly two, both HBM-bound SpMVs with fused epilogues:
+// Kernels per iteration (single GPU) — exactly two, both HBM-bound SpMVs with fused epilogues (spmv.cuh):
 //   K1  CSC (transposed) SpMV  g = A'y  + projection + reflection + Halpern combine  -> x, xbar
 //   K2  CSR SpMV  A xbar       + dual prox + reflection + Halpern combine            -> y
-// A group of L lanes (L = 1..32, picked from the mean row length) walks one row; the reduction over
-// the group uses warp shuffles.  Matrix arrays stream through the read-only path without L1
-// allocation; the gathered vector (x: 8n bytes, y: 8m bytes) lives in the 126 MB L2.
+// Matrix stream, row pointers and the epilogue operands arrive in shared memory by TMA bulk copies;
+// the gathered vector (x: 8n bytes, y: 8m bytes) lives in the 126 MB L2.
 // Algorithmic bytes per iteration: 24 nnz + 4 (m+n+2) + 56 n + 40 m.
 //
 // Multi-GPU (row partition): each rank owns a row block (its CSR, the CSC of the same
@@ -26,6 +25,7 @@
 #include "primitives.cuh"
 #include "comm.cuh"
 #include "tma.cuh"
+#include "spmv.cuh"
 #include "../../include/easylp_abi.h"
 #include <cmath>
 #include <algorithm>
@@ -38,225 +38,30 @@ struct PdlpParams {   // device-resident; the host rewrites it between iteration
     int pad;
 };
 
-// ------------------------------------------------------------------------------------------------
-// SpMV: persistent tile kernel.  One CTA walks tiles of TR consecutive rows (one row per thread).
-//   * the tile's slice of the matrix stream (val: 8 B, idx: 4 B per entry — 80 % of the HBM bytes of an
-//     iteration) is staged into shared memory by 1-D TMA bulk copies, double-buffered on mbarriers, so
-//     the copy of the next tile overlaps the work on the current one and no LSU slot is spent on it;
-//   * phase A: every thread turns TR-strided entries into products val * vec[idx] in place — the
-//     gathers of the (L2-resident) vector are independent, several per thread in flight;
-//   * phase B: thread t adds up the products of its own row in index order (so the result equals a
-//     sequential CPU loop bit for bit) and runs the fused epilogue with operands it pre-loaded,
-//     coalesced, before phase A.
-// Tiles whose entries exceed the stage capacity are walked in pieces with a running sum.
-// ------------------------------------------------------------------------------------------------
 constexpr int SPMV_THREADS = 256;             // block size of the setup-only helper kernels
-constexpr int SPMV_NST = 2;                 // pipeline stages
-constexpr int SPMV_PAD = 8;                 // matrix arrays are over-allocated so 16-byte-granular copies stay in bounds
-
-template <int TR, class Epi>
-__global__ void __launch_bounds__(TR)
-spmv_tile_kernel(int nrows, int ntiles, int cap, int hints, const int* __restrict__ ptr, const int* __restrict__ idx,
-                 const double* __restrict__ val, const double* __restrict__ vec, Epi epi) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* sval = reinterpret_cast<double*>(smem_raw);                                   // [NST][cap]
-    int* sidx = reinterpret_cast<int*>(smem_raw + (size_t)SPMV_NST * cap * 8);            // [NST][cap]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SPMV_NST * cap * 12); // [NST]
-    int* sinfo = reinterpret_cast<int*>(full + SPMV_NST);                                 // [NST][4]
-    const int tid = threadIdx.x;
-    // L2 residency: the matrix stream is read once per launch (evict first), the gathered vector is
-    // re-read ~nnz/len times (evict last)
-    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < SPMV_NST; ++s) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // ---- producer cursor (thread 0): the next piece to copy ------------------------------------------
-    int p_tile = blockIdx.x, p_piece = 0;
-    int p_s = 0, p_e = 0, n_s = 0, n_e = 0;       // entry range of the producer's tile, and of the tile after it
-    auto tile_bounds = [&](int tile, int& s0, int& e1) {
-        if (tile < ntiles) {
-            const int r0 = tile * TR;
-            const int r1 = min(r0 + TR, nrows);
-            s0 = __ldg(ptr + r0);
-            e1 = __ldg(ptr + r1);
-        } else { s0 = 0; e1 = 0; }
-    };
-    auto issue = [&](int stage) {
-        if (p_tile >= ntiles) return;
-        const int a0 = p_s & ~3, a1 = (p_e + 3) & ~3;
-        const int pstart = a0 + p_piece * cap;
-        const int pcnt = min(cap, a1 - pstart);
-        const bool last = pstart + pcnt >= a1;
-        int* info = sinfo + stage * 4;
-        info[0] = pstart;
-        info[1] = max(p_s, pstart) - pstart;                 // first real entry of the piece
-        info[2] = min(p_e, pstart + pcnt) - pstart;          // one past the last real entry
-        info[3] = last ? 1 : 0;
-        mbar_expect_tx(&full[stage], (uint32_t)pcnt * 12u);
-        if (pcnt > 0) {
-            if (hints & 1) {
-                tma_load_1d_hint(sval + (size_t)stage * cap, val + pstart, (uint32_t)pcnt * 8u, &full[stage], pol_stream);
-                tma_load_1d_hint(sidx + (size_t)stage * cap, idx + pstart, (uint32_t)pcnt * 4u, &full[stage], pol_stream);
-            } else {
-                tma_load_1d(sval + (size_t)stage * cap, val + pstart, (uint32_t)pcnt * 8u, &full[stage]);
-                tma_load_1d(sidx + (size_t)stage * cap, idx + pstart, (uint32_t)pcnt * 4u, &full[stage]);
-            }
-        }
-        if (last) {
-            p_tile += gridDim.x; p_piece = 0;
-            p_s = n_s; p_e = n_e;
-            tile_bounds(p_tile + gridDim.x, n_s, n_e);       // consumed one tile later: latency hidden
-        } else {
-            ++p_piece;
-        }
-    };
-    if (tid == 0) {
-        tile_bounds(p_tile, p_s, p_e);
-        tile_bounds(p_tile + gridDim.x, n_s, n_e);
-#pragma unroll
-        for (int s = 0; s < SPMV_NST; ++s) issue(s);
-    }
-
-    // ---- consumers -------------------------------------------------------------------------------
-    int q = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int row = tile * TR + tid;
-        int st = 0, en = 0;
-        typename Epi::Pre pre{};
-        if (row < nrows) {
-            st = __ldg(ptr + row);
-            en = __ldg(ptr + row + 1);
-            pre = epi.preload(row);
-        }
-        double acc = 0.0;
-        for (;;) {
-            const int stage = q % SPMV_NST;
-            mbar_wait(&full[stage], (uint32_t)(q / SPMV_NST) & 1u);
-            const int* info = sinfo + stage * 4;
-            const int pstart = info[0], lo = info[1], hi = info[2], last = info[3];
-            double* sv = sval + (size_t)stage * cap;
-            const int* si = sidx + (size_t)stage * cap;
-            // phase A: products in place.  Entries are read into registers in batches so that the
-            // gathers of a batch are independent of the shared-memory stores of the batch before.
-            constexpr int U = 8;
-            for (int e0 = lo + tid; e0 < hi; e0 += U * TR) {
-                double v[U], g[U];
-                int c[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int e = e0 + u * TR;
-                    if (e < hi) { v[u] = sv[e]; c[u] = si[e]; }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (e0 + u * TR < hi) g[u] = (hints & 2) ? ldg_hint(vec + c[u], pol_keep) : __ldg(vec + c[u]);
-#pragma unroll
-                for (int u = 0; u < U; ++u) if (e0 + u * TR < hi) sv[e0 + u * TR] = v[u] * g[u];
-            }
-            __syncthreads();
-            // phase B: my row's share of this piece, in index order
-            const int b = max(st, pstart + lo) - pstart, f = min(en, pstart + hi) - pstart;
-            for (int k = b; k < f; ++k) acc += sv[k];
-            // generic-proxy accesses to the stage must be ordered before the next bulk copy into it
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();                                   // stage fully consumed
-            if (tid == 0) issue(stage);
-            ++q;
-            if (last) break;
-        }
-        if (row < nrows) epi.apply(row, acc, pre);
-    }
-}
 
 template <class Epi>
 __global__ void __launch_bounds__(256) apply_epi_kernel(int n, const double* __restrict__ g, Epi epi) {
     const int j = blockIdx.x * 256 + threadIdx.x;
-    if (j < n) epi.apply(j, g[j], epi.preload(j));
+    if (j < n) epi.apply(j, g[j], epi.preload_global(j));
 }
 
-// lanes per row for the setup-only helper kernels (row statistics, value scaling, row expansion)
-inline int pick_lanes(int64_t nnz, int64_t nrows) {
-    const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
-    int L = 1;
-    while (L < 32 && (double)(2 * L) <= avg * 0.75 + 1.0) L *= 2;   // avg 10 -> 8, avg 5 -> 4, avg 2 -> 1..2
-    return L;
-}
-
-struct SpmvPlan {
-    int tr = 256, cap = 2048, ctas_cap = 8, ntiles = 0, hints = 3;
-    size_t smem = 0;
-};
-
-inline int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
-inline SpmvPlan plan_spmv(int64_t nnz, int nrows) {
-    SpmvPlan p;
-    const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
-    p.tr = env_int("ELP_SPMV_TR", 256);
-    if (p.tr != 128 && p.tr != 256) p.tr = 256;
-    const double mul = env_int("ELP_SPMV_CAPMUL_PCT", 150) / 100.0;
-    int64_t cap = (int64_t)(avg * p.tr * mul) + 64;
-    cap = (cap + 255) / 256 * 256;
-    cap = std::max<int64_t>(512, std::min<int64_t>(cap, 6144));
-    if (const int c = env_int("ELP_SPMV_CAP", 0)) cap = std::max(64, c / 4 * 4);
-    p.cap = (int)cap;
-    p.smem = (size_t)SPMV_NST * p.cap * 12 + SPMV_NST * 8 + SPMV_NST * 16;
-    p.ntiles = ceil_div(nrows, p.tr);
-    p.ctas_cap = std::max(1, env_int("ELP_SPMV_CTAS", 8));
-    p.hints = env_int("ELP_SPMV_HINTS", 3);
-    return p;
-}
-
-template <int TR, class Epi>
-void configure_spmv_kernel() {
-    ELP_CUDA(cudaFuncSetAttribute(spmv_tile_kernel<TR, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-}
-
-template <int TR, class Epi>
-void launch_spmv_tr(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val, const double* vec,
-                    Epi epi, cudaStream_t st) {
-    // persistent grid: one wave of resident CTAs (occupancy of this instantiation at this stage size)
-    static size_t occ_smem = (size_t)-1;
-    static int occ = 1;
-    if (occ_smem != p.smem) {
-        int o = 0;
-        ELP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, spmv_tile_kernel<TR, Epi>, TR, p.smem));
-        occ = std::max(1, o);
-        occ_smem = p.smem;
-    }
-    const int grid = std::max(1, std::min(p.ntiles, kNumSMs * std::min(occ, p.ctas_cap)));
-    ELP_LAUNCH((spmv_tile_kernel<TR, Epi>), grid, TR, p.smem, st, nrows, p.ntiles, p.cap, p.hints, ptr, idx, val, vec,
-               epi);
-}
-
-// The matrix arrays must be over-allocated by SPMV_PAD entries (16-byte-granular TMA copies).
-template <class Epi>
-void launch_spmv(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val, const double* vec,
-                 Epi epi, cudaStream_t st) {
-    if (nrows <= 0) return;
-    if (p.tr == 128) launch_spmv_tr<128, Epi>(p, nrows, ptr, idx, val, vec, epi, st);
-    else launch_spmv_tr<256, Epi>(p, nrows, ptr, idx, val, vec, epi, st);
-}
-
-// ---- epilogues: preload() runs before the products are formed, apply() after the row sum ----------
+// ---- epilogues of the SpMV (spmv.cuh): in(i) names the operand vectors the producer stages next to the
+// matrix stream, preload() picks this row's operands out of the stage, apply() runs after the row sum ------
 struct StoreEpi {
+    static constexpr int NIN = 0;
     double* out;
     struct Pre {};
-    __device__ __forceinline__ Pre preload(int) const { return Pre{}; }
+    __device__ __forceinline__ const double* in(int) const { return nullptr; }
+    __device__ __forceinline__ Pre preload(const double*, int, int) const { return Pre{}; }
+    __device__ __forceinline__ Pre preload_global(int) const { return Pre{}; }
     __device__ __forceinline__ void apply(int r, double s, const Pre&) const { out[r] = s; }
 };
 
 // primal half of T(z) + reflection + Halpern combine.  g = (A'y)_j
 template <bool CHECK>
 struct PrimalEpi {
+    static constexpr int NIN = CHECK ? 4 : 5;
     const double* __restrict__ c;
     const double* __restrict__ l;
     const double* __restrict__ u;
@@ -267,7 +72,16 @@ struct PrimalEpi {
     const PdlpParams* __restrict__ P;
     int it;
     struct Pre { double x, c, l, u, x0; };
-    __device__ __forceinline__ Pre preload(int j) const {
+    __device__ __forceinline__ const double* in(int i) const {
+        return i == 0 ? x : i == 1 ? c : i == 2 ? l : i == 3 ? u : x0;
+    }
+    __device__ __forceinline__ Pre preload(const double* s, int rt, int g) const {
+        Pre p;
+        p.x = s[g]; p.c = s[rt + g]; p.l = s[2 * rt + g]; p.u = s[3 * rt + g];
+        p.x0 = CHECK ? 0.0 : s[(CHECK ? 0 : 4) * rt + g];
+        return p;
+    }
+    __device__ __forceinline__ Pre preload_global(int j) const {
         Pre p;
         p.x = x[j]; p.c = c[j]; p.l = l[j]; p.u = u[j];
         p.x0 = CHECK ? 0.0 : x0[j];
@@ -291,6 +105,7 @@ struct PrimalEpi {
 // dual half.  ax = (A xbar)_i
 template <bool CHECK>
 struct DualEpi {
+    static constexpr int NIN = CHECK ? 3 : 4;
     const double* __restrict__ lc;
     const double* __restrict__ uc;
     const double* __restrict__ y0;
@@ -300,7 +115,14 @@ struct DualEpi {
     const PdlpParams* __restrict__ P;
     int it;
     struct Pre { double y, lc, uc, y0; };
-    __device__ __forceinline__ Pre preload(int i) const {
+    __device__ __forceinline__ const double* in(int i) const { return i == 0 ? y : i == 1 ? lc : i == 2 ? uc : y0; }
+    __device__ __forceinline__ Pre preload(const double* s, int rt, int g) const {
+        Pre p;
+        p.y = s[g]; p.lc = s[rt + g]; p.uc = s[2 * rt + g];
+        p.y0 = CHECK ? 0.0 : s[(CHECK ? 0 : 3) * rt + g];
+        return p;
+    }
+    __device__ __forceinline__ Pre preload_global(int i) const {
         Pre p;
         p.y = y[i]; p.lc = lc[i]; p.uc = uc[i];
         p.y0 = CHECK ? 0.0 : y0[i];
@@ -323,14 +145,12 @@ struct DualEpi {
     }
 };
 
-// Raises the dynamic shared-memory limit of every SpMV instantiation (per device; called from setup,
-// outside any stream capture).
-void configure_spmv_kernels() {
-    configure_spmv_kernel<128, StoreEpi>();         configure_spmv_kernel<256, StoreEpi>();
-    configure_spmv_kernel<128, PrimalEpi<false>>(); configure_spmv_kernel<256, PrimalEpi<false>>();
-    configure_spmv_kernel<128, PrimalEpi<true>>();  configure_spmv_kernel<256, PrimalEpi<true>>();
-    configure_spmv_kernel<128, DualEpi<false>>();   configure_spmv_kernel<256, DualEpi<false>>();
-    configure_spmv_kernel<128, DualEpi<true>>();    configure_spmv_kernel<256, DualEpi<true>>();
+// lanes per row for the setup-only helper kernels (row statistics, value scaling, row expansion)
+inline int pick_helper_lanes(int64_t nnz, int64_t nrows) {
+    const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+    int L = 1;
+    while (L < 32 && (double)(2 * L) <= avg * 0.75 + 1.0) L *= 2;   // avg 10 -> 8, avg 5 -> 4, avg 2 -> 1..2
+    return L;
 }
 
 // ---- row statistics for the scaling: out[r] = s_self[r] * reduce_k |val[k]| * s_other[idx[k]] ------
@@ -742,15 +562,17 @@ struct Pdlp {
         ELP_REQUIRE(m >= 0 && n > 0, "pdlp: bad shape %d x %d", m, n);
         nnz = m > 0 ? row_ptr[m] : 0;
         ELP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        configure_spmv_kernels();
-        csr_ptr.alloc(m + 1); csr_idx.alloc(nnz + SPMV_PAD); csr_val.alloc(nnz + SPMV_PAD);
-        csc_ptr.alloc(n + 1); csc_idx.alloc(nnz + SPMV_PAD); csc_val.alloc(nnz + SPMV_PAD);
-        csr_idx.zero(st); csr_val.zero(st); csc_idx.zero(st); csc_val.zero(st);
-        c.alloc(n); l.alloc(n); u.alloc(n); dc.alloc(n);
-        lc.alloc(std::max(m, 1)); uc.alloc(std::max(m, 1)); dr.alloc(std::max(m, 1));
-        x.alloc(n); x0.alloc(n); xbar.alloc(n); xp.alloc(n); gbuf.alloc(n + NACC);
-        y.alloc(std::max(m, 1)); y0.alloc(std::max(m, 1)); yp.alloc(std::max(m, 1));
-        axbar.alloc(std::max(m, 1)); axp.alloc(std::max(m, 1));
+        csr_ptr.alloc(m + 1 + SPMV_PTR_PAD); csr_idx.alloc(nnz + SPMV_PAD); csr_val.alloc(nnz + SPMV_PAD);
+        csc_ptr.alloc(n + 1 + SPMV_PTR_PAD); csc_idx.alloc(nnz + SPMV_PAD); csc_val.alloc(nnz + SPMV_PAD);
+        csr_idx.zero(st); csr_val.zero(st); csc_idx.zero(st); csc_val.zero(st); csr_ptr.zero(st); csc_ptr.zero(st);
+        // epilogue operands are staged by 16-byte-granular bulk copies: SPMV_VPAD doubles of slack each
+        const size_t np = (size_t)n + SPMV_VPAD, mp = (size_t)std::max(m, 1) + SPMV_VPAD;
+        c.alloc(np); l.alloc(np); u.alloc(np); dc.alloc(np);
+        lc.alloc(mp); uc.alloc(mp); dr.alloc(mp);
+        x.alloc(np); x0.alloc(np); xbar.alloc(np); xp.alloc(np); gbuf.alloc(n + NACC);
+        y.alloc(mp); y0.alloc(mp); yp.alloc(mp);
+        axbar.alloc(mp); axp.alloc(mp);
+        c.zero(st); l.zero(st); u.zero(st); lc.zero(st); uc.zero(st); x.zero(st); x0.zero(st);
         partials.alloc((size_t)RED_BLOCKS * NACC); scal.alloc(2 * NACC); params.alloc(1);
         partials.zero(st);
 
@@ -769,10 +591,10 @@ struct Pdlp {
             ELP_CUDA(cudaStreamSynchronize(st));
         }
         if (maximize) ELP_LAUNCH(k_scale_scalar, grid1(n), 256, 0, st, n, c.p, -1.0);
-        Lr = pick_lanes(nnz, m);
-        Lc = pick_lanes(nnz, n);
-        plan_r = plan_spmv(nnz, m);
-        plan_c = plan_spmv(nnz, n);
+        Lr = pick_helper_lanes(nnz, m);
+        Lc = pick_helper_lanes(nnz, n);
+        plan_r = plan_spmv(nnz, m, 4);
+        plan_c = plan_spmv(nnz, n, 5);
 
         build_csc();
         // unscaled norms for the relative termination test
@@ -1210,12 +1032,12 @@ void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, con
     cudaStream_t st = 0;
     const int64_t nnz = m > 0 ? row_ptr[m] : 0;
     if (m == 0) return;
-    configure_spmv_kernels();
-    DevBuf<int> ptr(m + 1), idx(nnz + SPMV_PAD);
+    DevBuf<int> ptr(m + 1 + SPMV_PTR_PAD), idx(nnz + SPMV_PAD);
     DevBuf<double> val(nnz + SPMV_PAD), xd(std::max(n, 1)), od(m);
-    idx.zero(st); val.zero(st);
+    idx.zero(st); val.zero(st); ptr.zero(st);
     ptr.upload(row_ptr, m + 1, st); idx.upload(col_idx, nnz, st); val.upload(vals, nnz, st); xd.upload(x, n, st);
-    launch_spmv(plan_spmv(nnz, m), m, ptr.p, idx.p, val.p, xd.p, StoreEpi{od.p}, st);
+    // one thread per row: the row sum is formed in index order, bit-identical to a scalar loop
+    launch_spmv(plan_spmv(nnz, m, 0, 1), m, ptr.p, idx.p, val.p, xd.p, StoreEpi{od.p}, st);
     if (out) od.download(out, m, st);
     if (feasible) {
         DevBuf<int8_t> sd(m);

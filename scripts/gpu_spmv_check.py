@@ -24,14 +24,18 @@ def check(m, n, lens, seed):
         for k in range(rp[i], rp[i + 1]):
             s += v[k] * x[ci[k]]
         ref[i] = s
-    ok = out.tobytes() == ref.tobytes()
-    print(f"spmv m={m} n={n} nnz={rp[-1]} bit-exact={ok} maxdiff={np.abs(out-ref).max() if m else 0}", flush=True)
+    exact = out.tobytes() == ref.tobytes()
+    lanes = int(os.environ.get("ELP_SPMV_L", "1"))
+    ok = exact if lanes == 1 else bool(np.allclose(out, ref, rtol=1e-12, atol=1e-12))
+    print(f"spmv L={lanes} cap={os.environ.get('ELP_SPMV_CAP')} m={m} n={n} nnz={rp[-1]} bit-exact={exact} ok={ok} "
+          f"maxdiff={np.abs(out-ref).max() if m else 0}", flush=True)
     return ok
 
 allok = True
 rng = np.random.default_rng(0)
-for cap in ("0", "64"):
+for cap, lanes in (("0", "1"), ("64", "1"), ("0", "4"), ("64", "8"), ("0", "32"), ("128", "32")):
     os.environ["ELP_SPMV_CAP"] = cap
+    os.environ["ELP_SPMV_L"] = lanes
     allok &= check(1, 5, [3], 1)
     allok &= check(7, 9, [0, 2, 0, 0, 5, 1, 0], 2)
     allok &= check(300, 50, rng.integers(0, 14, 300), 3)
@@ -39,6 +43,7 @@ for cap in ("0", "64"):
     allok &= check(5, 3000, [0, 2500, 1, 0, 9000], 5)      # rows longer than a stage -> pieces
     allok &= check(513, 100, np.r_[rng.integers(0, 3, 512), 700], 6)
 os.environ["ELP_SPMV_CAP"] = "0"
+os.environ.pop("ELP_SPMV_L")
 print("ALL SPMV OK" if allok else "SPMV MISMATCH", flush=True)
 if not allok:
     sys.exit(1)
@@ -48,14 +53,20 @@ if len(sys.argv) > 1 and sys.argv[1] == "sweep":
     m, n, nnz = p["m"], p["n"], int(p["row_ptr"][-1])
     b_csc = 12 * nnz + 4 * (n + 1) + 8 * m + 56 * n
     b_csr = 12 * nnz + 4 * (m + 1) + 8 * n + 40 * m
-    for tr in (256, 128):
-        for capmul in (110, 150, 250):
-            for ctas in (8, 2):
-                os.environ.update(ELP_SPMV_TR=str(tr), ELP_SPMV_CAPMUL_PCT=str(capmul), ELP_SPMV_CTAS=str(ctas))
-                h = L.Pdlp(m, n, p["row_ptr"], p["col_idx"], p["vals"], p["sense"], p["rhs"], p["c"], p["lb"], p["ub"],
-                           options=L.default_options(method=L.METHOD_PDLP))
-                a, b = h.probe_step(30)
-                c1, c2 = h.probe_spmv(30)
-                h.close()
-                print(json.dumps(dict(tr=tr, capmul=capmul, ctas=ctas, primal_ms=a, dual_ms=b, primal_gbs=b_csc / a / 1e6,
-                                      dual_gbs=b_csr / b / 1e6, csr_ms=c1, csc_ms=c2)), flush=True)
+    for cw, ctas, nst, capmul in ((8, 2, 0, 125), (8, 2, 3, 125), (8, 2, 2, 125), (8, 1, 0, 125), (8, 1, 4, 125),
+                                  (4, 4, 0, 125), (4, 4, 3, 125), (4, 3, 0, 125), (4, 2, 0, 125), (4, 6, 2, 110),
+                                  (8, 3, 2, 110), (8, 2, 0, 110), (8, 2, 0, 200), (4, 4, 0, 200)):
+        os.environ.update(ELP_SPMV_CW=str(cw), ELP_SPMV_CTAS=str(ctas), ELP_SPMV_NST=str(nst),
+                          ELP_SPMV_CAPMUL_PCT=str(capmul))
+        try:
+            h = L.Pdlp(m, n, p["row_ptr"], p["col_idx"], p["vals"], p["sense"], p["rhs"], p["c"], p["lb"], p["ub"],
+                       options=L.default_options(method=L.METHOD_PDLP, ruiz_iters=2))
+            a, b = h.probe_step(30)
+            c1, c2 = h.probe_spmv(30)
+            h.close()
+        except L.ElpError as e:
+            print(json.dumps(dict(cw=cw, ctas=ctas, nst=nst, capmul=capmul, error=str(e)[:200])), flush=True)
+            continue
+        print(json.dumps(dict(cw=cw, ctas=ctas, nst=nst, capmul=capmul, primal_ms=round(a, 4), dual_ms=round(b, 4),
+                              primal_gbs=round(b_csc / a / 1e6), dual_gbs=round(b_csr / b / 1e6), csr_ms=round(c1, 4),
+                              csc_ms=round(c2, 4))), flush=True)
