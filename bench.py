@@ -128,6 +128,16 @@ def row_block(p, rank, nranks):
     return q, r0, r1
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu
+    capture of this same workload (profiles/r1_ncu_traffic.json); None when no capture is on file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            return int(json.load(f)[key]["dram_bytes"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def pdlp_bytes(m, n, nnz):
     """Algorithmic HBM bytes: per kernel launch and per iteration."""
     csc = 12 * nnz + 4 * (n + 1) + 8 * m + 56 * n    # A'y SpMV (vals+idx+ptr+y gather) + x,c,l,u,x0 read, x,xbar written
@@ -282,8 +292,11 @@ def bench_pdlp(args, dist, L, p, workload_name):
     # local matrix of this rank for the roofline (N = 1: the whole matrix)
     ml, nnzl = q["m"], int(q["row_ptr"][q["m"]])
     b_csc, b_csr, b_iter = pdlp_bytes(ml, n, nnzl)
-    dom_ms, dom_b, dom_name = (ms_primal, b_csc, "spmv_kernel<L,PrimalEpi> (CSC A'y + fused primal update)") \
-        if ms_primal >= ms_dual else (ms_dual, b_csr, "spmv_kernel<L,DualEpi> (CSR A.xbar + fused dual update)")
+    dom_ms, dom_b, dom_name, dom_key = \
+        (ms_primal, b_csc, "spmv_warp_kernel<L,NSTW,PrimalEpi> (CSC A'y + fused primal update)", "primal") \
+        if ms_primal >= ms_dual else \
+        (ms_dual, b_csr, "spmv_warp_kernel<L,NSTW,DualEpi> (CSR A.xbar + fused dual update)", "dual")
+    traffic = ncu_traffic(dom_key) if (N == 1 and args.scale == 1.0 and args.workload == "pdlp") else None
     ach = dom_b / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     iter_ms = dev_ms / max(iters, 1)
     res = {
@@ -304,7 +317,7 @@ def bench_pdlp(args, dist, L, p, workload_name):
                 "path": "elp_pdlp_create(host CSR) -> elp_pdlp_run -> elp_pdlp_solution (= elp_solve_lp)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "peak_source": peak_src, "traffic": None,
+                     "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "peak_source": peak_src, "traffic": traffic,
                      "bytes_per_launch": dom_b, "ms_per_launch": dom_ms,
                      "iteration": {"bytes": b_iter, "ms": iter_ms, "achieved": b_iter / (iter_ms * 1e-3) / 1e9,
                                    "frac": b_iter / (iter_ms * 1e-3) / 1e9 / peak,

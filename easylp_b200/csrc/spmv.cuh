@@ -1,4 +1,5 @@
-// spmv.cuh — the PDLP hot kernel: a persistent, warp-specialised CSR-stream SpMV with a fused epilogue.
+// spmv.cuh — the PDLP hot kernel: a persistent CSR-stream SpMV with a fused epilogue, built from
+// warp-autonomous TMA pipelines.
 //
 //   out_r = epilogue( sum_k val[k] * vec[idx[k]],  k in [ptr[r], ptr[r+1]) )
 //
@@ -7,16 +8,16 @@
 // outputs; the gathered vector (8n or 8m bytes) lives in the 126 MB L2.
 //
 // Design (sm_100a):
-//   * a CTA is CW consumer warps + 1 producer warp and walks tiles of RT = 32*CW/L rows (persistent grid,
-//     static round-robin);
+//   * every WARP is its own producer/consumer pipeline: it walks tiles of RW = 32/L rows (persistent grid,
+//     warp-strided round-robin) and owns a private ring of NSTW stages in shared memory with one mbarrier
+//     each.  No CTA-wide or inter-warp synchronisation exists in the loop;
 //   * EVERYTHING that streams — the tile's slice of val/idx, its row pointers and the epilogue's operand
-//     vectors (x, c, l, u, x0 / y, lc, uc, y0) — is brought into shared memory by 1-D TMA bulk copies
-//     (cp.async.bulk -> mbarrier complete_tx) issued by one elected producer thread into a ring of NST
-//     stages; full/empty mbarriers hand stages back and forth, there is no CTA-wide barrier in the loop,
-//     so several stages of HBM traffic per CTA stay in flight while the consumers work;
-//   * the only loads the consumers issue to global memory are the gathers vec[idx[k]] (random 8-byte reads
+//     vectors (x, c, l, u, x0 / y, lc, uc, y0) — is brought into the ring by 1-D TMA bulk copies
+//     (cp.async.bulk -> mbarrier complete_tx); lane i of the warp issues copy i, NSTW tiles ahead of the
+//     tile being consumed, so the HBM latency is covered by the ring and not by the warp's own loads;
+//   * the only loads the lanes issue to global memory are the gathers vec[idx[k]] (random 8-byte reads
 //     that hit L2, marked evict-last; the matrix stream is marked evict-first), U of them in flight per
-//     thread; a group of L lanes walks one row (L = 1: one thread per row, the sum is formed strictly in
+//     lane; a group of L lanes walks one row (L = 1: one lane per row, the sum is formed strictly in
 //     index order with separate multiply and add, i.e. bit-identical to a scalar CPU loop);
 //   * rows longer than a stage are walked in pieces with a running sum.
 // Array contract: val/idx are over-allocated by SPMV_PAD entries, ptr by 4 ints and every epilogue
@@ -25,6 +26,7 @@
 #include "common.cuh"
 #include "tma.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 namespace elp {
@@ -32,157 +34,147 @@ namespace elp {
 constexpr int SPMV_PAD = 8;        // extra entries behind val / idx
 constexpr int SPMV_PTR_PAD = 4;    // extra ints behind ptr
 constexpr int SPMV_VPAD = 2;       // extra doubles behind every epilogue operand vector
-constexpr int SPMV_MAX_NST = 8;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-struct SpmvStageLayout {          // byte offsets inside one stage
+struct SpmvStageLayout {          // byte offsets inside one stage of one warp
     int cap;                      // entries per stage (multiple of 4)
     int off_idx, off_ptr, off_ops, bytes;
 };
-__host__ __device__ inline SpmvStageLayout spmv_stage_layout(int cap, int rt, int nin) {
+__host__ __device__ inline SpmvStageLayout spmv_stage_layout(int cap, int rw, int nin) {
     SpmvStageLayout s;
     s.cap = cap;
     s.off_idx = cap * 8;
     s.off_ptr = s.off_idx + cap * 4;
-    s.off_ops = s.off_ptr + (rt + 4) * 4;
-    s.bytes = s.off_ops + nin * rt * 8;
-    s.bytes = (s.bytes + 127) & ~127;
+    s.off_ops = s.off_ptr + (rw + 4) * 4;
+    s.bytes = s.off_ops + nin * ((rw + 1) & ~1) * 8;
+    s.bytes = (s.bytes + 15) & ~15;
     return s;
 }
 
-template <int CW, int L, class Epi>
-__global__ void __launch_bounds__(CW * 32 + 32)
-spmv_stream_kernel(int nrows, int ntiles, int cap, int nst, int hints, const int* __restrict__ ptr,
-                   const int* __restrict__ idx, const double* __restrict__ val, const double* __restrict__ vec, Epi epi) {
-    constexpr int RT = CW * 32 / L;          // rows per tile
-    constexpr int NIN = Epi::NIN;
-    constexpr int U = (L == 1) ? 8 : 4;      // gathers in flight per thread
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const SpmvStageLayout lay = spmv_stage_layout(cap, RT, NIN);
-    unsigned char* stages = smem_raw;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nst * lay.bytes);   // [nst]
-    uint64_t* empty = full + SPMV_MAX_NST;                                               // [nst]
-    int* sinfo = reinterpret_cast<int*>(empty + SPMV_MAX_NST);                           // [nst][4]
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+constexpr int SPMV_WARPS = 4;      // warps per CTA (a CTA is only a container: warps never talk)
 
-    if (tid == 0) {
-        for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+template <int L, int NSTW, class Epi>
+__global__ void __launch_bounds__(SPMV_WARPS * 32, 6)
+spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, const int* __restrict__ idx,
+                 const double* __restrict__ val, const double* __restrict__ vec, Epi epi) {
+    constexpr int RW = 32 / L;               // rows per warp tile
+    constexpr int NIN = Epi::NIN;
+    constexpr int U = (L <= 2) ? 8 : 4;      // gathers in flight per lane
+    constexpr int OPS = (RW + 1) & ~1;       // doubles per staged operand
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const SpmvStageLayout lay = spmv_stage_layout(cap, RW, NIN);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* ring = smem_raw + (size_t)warp * NSTW * lay.bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SPMV_WARPS * NSTW * lay.bytes) + warp * NSTW;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTW; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncwarp();
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const int gw = blockIdx.x * SPMV_WARPS + warp, nw = gridDim.x * SPMV_WARPS;
 
-    if (warp == CW) {
-        // ---------------- producer: one elected thread feeds the ring -----------------------------
-        if (tid != CW * 32) return;
-        const uint64_t pol_stream = l2_policy_evict_first();
-        int it = 0;
-        int tile = blockIdx.x;
-        int s0 = 0, e1 = 0, rows = 0;
-        auto bounds = [&](int t, int& a, int& b, int& nr) {
-            if (t < ntiles) {
-                const int r0 = t * RT;
-                nr = min(RT, nrows - r0);
-                a = __ldg(ptr + r0);
-                b = __ldg(ptr + r0 + nr);
-            } else { a = 0; b = 0; nr = 0; }
-        };
-        bounds(tile, s0, e1, rows);
-        while (tile < ntiles) {
-            int ns0, ne1, nrows_next;
-            bounds(tile + gridDim.x, ns0, ne1, nrows_next);       // in flight while this tile is issued
-            const int a0 = s0 & ~3, a1 = (e1 + 3) & ~3;
-            const int r0 = tile * RT;
-            int piece = 0;
-            for (;;) {
-                const int stage = it % nst;
-                if (it >= nst) mbar_wait(&empty[stage], (uint32_t)((it / nst) - 1) & 1u);
-                const int pstart = a0 + piece * cap;
-                const int pcnt = max(0, min(cap, a1 - pstart));
-                const bool last = pstart + pcnt >= a1;
-                unsigned char* sb = stages + (size_t)stage * lay.bytes;
-                int* info = sinfo + stage * 4;
-                info[0] = pstart;
-                info[1] = max(s0, pstart) - pstart;               // first real entry of the piece
-                info[2] = min(e1, pstart + pcnt) - pstart;        // one past its last real entry
-                info[3] = (piece == 0 ? 1 : 0) | (last ? 2 : 0);
-                const uint32_t ptr_bytes = (uint32_t)((rows + 1 + 3) & ~3) * 4u;
-                const uint32_t op_bytes = (uint32_t)((rows + 1) & ~1) * 8u;
-                uint32_t tx = (uint32_t)pcnt * 12u;
-                if (piece == 0) tx += ptr_bytes + (uint32_t)NIN * op_bytes;
-                mbar_expect_tx(&full[stage], tx);
-                if (pcnt > 0) {
-                    if (hints & 1) {
-                        tma_load_1d_hint(sb, val + pstart, (uint32_t)pcnt * 8u, &full[stage], pol_stream);
-                        tma_load_1d_hint(sb + lay.off_idx, idx + pstart, (uint32_t)pcnt * 4u, &full[stage], pol_stream);
-                    } else {
-                        tma_load_1d(sb, val + pstart, (uint32_t)pcnt * 8u, &full[stage]);
-                        tma_load_1d(sb + lay.off_idx, idx + pstart, (uint32_t)pcnt * 4u, &full[stage]);
-                    }
-                }
-                if (piece == 0) {
-                    tma_load_1d(sb + lay.off_ptr, ptr + r0, ptr_bytes, &full[stage]);
-#pragma unroll
-                    for (int i = 0; i < NIN; ++i)
-                        tma_load_1d(sb + lay.off_ops + i * RT * 8, epi.in(i) + r0, op_bytes, &full[stage]);
-                }
-                ++it;
-                ++piece;
-                if (last) break;
-            }
-            tile += gridDim.x;
-            s0 = ns0; e1 = ne1; rows = nrows_next;
+    // ---- producer cursor: the next piece to copy (uniform across the warp) --------------------------------
+    int p_tile = gw, p_piece = 0, p_s = 0, p_e = 0, n_s = 0, n_e = 0;
+    auto bounds = [&](int t, int& a, int& b) {
+        if (t < ntiles) {
+            const int r0 = t * RW;
+            a = __ldg(ptr + r0);
+            b = __ldg(ptr + min(r0 + RW, nrows));
+        } else { a = 0; b = 0; }
+    };
+    auto issue = [&](int stage) {
+        if (p_tile >= ntiles) return;
+        const int a0 = p_s & ~3, a1 = (p_e + 3) & ~3;
+        const int pstart = a0 + p_piece * cap;
+        const int pcnt = max(0, min(cap, a1 - pstart));
+        const bool last = pstart + pcnt >= a1;
+        const int r0 = p_tile * RW;
+        const int rows = min(RW, nrows - r0);
+        const uint32_t ptr_bytes = (uint32_t)((rows + 1 + 3) & ~3) * 4u;
+        const uint32_t op_bytes = (uint32_t)((rows + 1) & ~1) * 8u;
+        unsigned char* sb = ring + (size_t)stage * lay.bytes;
+        // lane i issues copy i: 0 val, 1 idx, 2 row pointers, 3.. epilogue operands
+        const void* src = nullptr;
+        unsigned char* dst = sb;
+        uint32_t bytes = 0;
+        if (lane == 0) { src = val + pstart; bytes = (uint32_t)pcnt * 8u; }
+        else if (lane == 1) { src = idx + pstart; dst = sb + lay.off_idx; bytes = (uint32_t)pcnt * 4u; }
+        else if (p_piece == 0) {
+            if (lane == 2) { src = ptr + r0; dst = sb + lay.off_ptr; bytes = ptr_bytes; }
+            else if (lane < 3 + NIN) { src = epi.in(lane - 3) + r0; dst = sb + lay.off_ops + (lane - 3) * OPS * 8; bytes = op_bytes; }
         }
-        return;
-    }
+        if (lane == 0) {
+            uint32_t tx = (uint32_t)pcnt * 12u;
+            if (p_piece == 0) tx += ptr_bytes + (uint32_t)NIN * op_bytes;
+            mbar_expect_tx(&full[stage], tx);
+        }
+        __syncwarp();
+        if (bytes > 0) {
+            if (lane < 2) tma_load_1d_hint(dst, src, bytes, &full[stage], pol_stream);
+            else tma_load_1d(dst, src, bytes, &full[stage]);
+        }
+        if (last) {
+            p_tile += nw; p_piece = 0;
+            p_s = n_s; p_e = n_e;
+            bounds(p_tile + nw, n_s, n_e);        // needed one tile later: its latency is hidden
+        } else {
+            ++p_piece;
+        }
+    };
+    bounds(p_tile, p_s, p_e);
+    bounds(p_tile + nw, n_s, n_e);
+#pragma unroll
+    for (int s = 0; s < NSTW; ++s) issue(s);
 
-    // ---------------- consumers ------------------------------------------------------------------
-    const uint64_t pol_keep = l2_policy_evict_last();
-    const int g = tid / L;                 // row of the tile this lane group owns
-    const int sub = tid % L;
+    // ---- consumer ------------------------------------------------------------------------------------------
+    const int g = lane / L;                // row of the tile this lane group owns
+    const int sub = lane % L;
     int q = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int row = tile * RT + g;
-        int st = 0, en = 0;
+    for (int tile = gw; tile < ntiles; tile += nw) {
+        const int row = tile * RW + g;
+        int st = 0, en = 0, a0 = 0, a1 = 0;
         typename Epi::Pre pre{};
         double acc = 0.0;
-        for (;;) {
-            const int stage = q % nst;
-            mbar_wait(&full[stage], (uint32_t)(q / nst) & 1u);
-            const unsigned char* sb = stages + (size_t)stage * lay.bytes;
-            const int* info = sinfo + stage * 4;
-            const int pstart = info[0], lo = info[1], hi = info[2], flags = info[3];
-            const double* sv = reinterpret_cast<const double*>(sb);
-            const int* si = reinterpret_cast<const int*>(sb + lay.off_idx);
-            if ((flags & 1) && row < nrows) {
+        for (int piece = 0;; ++piece) {
+            const int stage = q % NSTW;
+            mbar_wait(&full[stage], (uint32_t)(q / NSTW) & 1u);
+            const unsigned char* sb = ring + (size_t)stage * lay.bytes;
+            if (piece == 0) {
                 const int* sp = reinterpret_cast<const int*>(sb + lay.off_ptr);
-                st = sp[g];
-                en = sp[g + 1];
-                if (sub == 0) pre = epi.preload(reinterpret_cast<const double*>(sb + lay.off_ops), RT, g);
+                const int rows = min(RW, nrows - tile * RW);
+                a0 = sp[0] & ~3;
+                a1 = (sp[rows] + 3) & ~3;
+                if (row < nrows) {
+                    st = sp[g];
+                    en = sp[g + 1];
+                    if (sub == 0) pre = epi.preload(reinterpret_cast<const double*>(sb + lay.off_ops), OPS, g);
+                }
             }
-            const int b = max(st, pstart + lo) - pstart, f = min(en, pstart + hi) - pstart;
-            for (int k0 = b + sub; k0 < f; k0 += U * L) {
-                double v[U], x[U];
+            const int pstart = a0 + piece * cap;
+            const int pend = min(pstart + cap, a1);
+            // index the stage by global entry id
+            const double* sv = reinterpret_cast<const double*>(sb) - pstart;
+            const int* si = reinterpret_cast<const int*>(sb + lay.off_idx) - pstart;
+            const int f = min(en, pend);
+            for (int k0 = max(st, pstart) + sub; k0 < f; k0 += U * L) {
+                // indices first, gathers next, the values are read from the stage only when they are consumed
+                double x[U];
                 int c[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int k = k0 + u * L;
-                    if (k < f) { v[u] = sv[k]; c[u] = si[k]; }
-                }
+                for (int u = 0; u < U; ++u)
+                    if (k0 + u * L < f) c[u] = si[k0 + u * L];
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (k0 + u * L < f) x[u] = (hints & 2) ? ldg_hint(vec + c[u], pol_keep) : __ldg(vec + c[u]);
+                    if (k0 + u * L < f) x[u] = ldg_hint(vec + c[u], pol_keep);
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (k0 + u * L < f) acc = __dadd_rn(acc, __dmul_rn(v[u], x[u]));
+                    if (k0 + u * L < f) acc = __dadd_rn(acc, __dmul_rn(sv[k0 + u * L], x[u]));
             }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty[stage]);      // this warp is done reading the stage
+            __syncwarp();                      // every lane is done reading the stage
+            issue(stage);
             ++q;
-            if (flags & 2) break;
+            if (pend >= a1) break;
         }
         if (L > 1) acc = group_sum<L>(acc);
         if (sub == 0 && row < nrows) epi.apply(row, acc, pre);
@@ -191,8 +183,8 @@ spmv_stream_kernel(int nrows, int ntiles, int cap, int nst, int hints, const int
 
 // ---- launch plan ---------------------------------------------------------------------------------
 struct SpmvPlan {
-    int cw = 8, L = 1, cap = 2048, nst = 3, ctas_per_sm = 2, ntiles = 0, hints = 3;
-    int rt() const { return cw * 32 / L; }
+    int L = 1, cap = 256, nstw = 2, ctas_per_sm = 4, ntiles = 0;
+    int rw() const { return 32 / L; }
 };
 
 inline int env_int(const char* name, int dflt) {
@@ -200,16 +192,16 @@ inline int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-// lanes per row from the mean row length: short rows get one thread each, long rows a whole warp
+// lanes per row from the mean row length: about six entries or fewer per lane, at most eight lanes
 inline int pick_lanes(int64_t nnz, int64_t nrows) {
     const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
     int L = 1;
-    while (L < 32 && avg >= 24.0 * L) L *= 2;      // avg < 24 -> 1, < 48 -> 2, ..., >= 384 -> 32
+    while (L < 8 && avg > 6.0 * L) L *= 2;         // avg <= 6 -> 1, <= 12 -> 2, <= 24 -> 4, else 8
     return L;
 }
 
 inline size_t spmv_smem_bytes(const SpmvPlan& p, int nin) {
-    return (size_t)p.nst * spmv_stage_layout(p.cap, p.rt(), nin).bytes + 2 * SPMV_MAX_NST * 8 + SPMV_MAX_NST * 16;
+    return (size_t)SPMV_WARPS * p.nstw * (spmv_stage_layout(p.cap, p.rw(), nin).bytes + 8);
 }
 
 // nin_max: the largest operand count among the epilogues that will run with this plan
@@ -219,47 +211,63 @@ inline SpmvPlan plan_spmv(int64_t nnz, int nrows, int nin_max, int force_lanes =
     p.L = pick_lanes(nnz, nrows);
     if (force_lanes > 0) p.L = force_lanes;
     if (const int l = env_int("ELP_SPMV_L", 0)) p.L = l;       // debugging / sweeps
-    if (p.L < 1 || p.L > 32 || (p.L & (p.L - 1))) p.L = 1;
-    p.cw = (p.L == 1) ? env_int("ELP_SPMV_CW", 8) : 8;
-    if (p.cw != 4 && p.cw != 8) p.cw = 8;
-    const int rt = p.rt();
-    const double mul = env_int("ELP_SPMV_CAPMUL_PCT", 125) / 100.0;
-    int64_t cap = (int64_t)(avg * rt * mul) + 64;
-    cap = (cap + 255) / 256 * 256;
-    cap = std::max<int64_t>(256, std::min<int64_t>(cap, 8192));
-    if (const int c = env_int("ELP_SPMV_CAP", 0)) cap = std::max(64, c / 4 * 4);
+    if (p.L != 1 && p.L != 2 && p.L != 4 && p.L != 8) p.L = 1;   // RW = 32/L >= 4 keeps the tile copies 16-byte aligned
+    const int rw = p.rw();
+    // stage capacity: mean tile + ~1.5 sigma of a Poisson-like spread; the few larger tiles are walked in pieces
+    const double mean = avg * rw;
+    int64_t cap = (int64_t)(mean + 1.5 * std::sqrt(std::max(mean, 1.0)) * env_int("ELP_SPMV_CAPSIG_PCT", 100) / 100.0) + 8;
+    cap = (cap + 31) / 32 * 32;
+    cap = std::max<int64_t>(64, std::min<int64_t>(cap, 1024));   // <= 12.3 KB per stage; longer tiles go in pieces
+    if (const int c = env_int("ELP_SPMV_CAP", 0)) cap = std::max(16, c / 4 * 4);
     p.cap = (int)cap;
-    p.hints = env_int("ELP_SPMV_HINTS", 3);
-    p.ntiles = ceil_div(nrows, rt);
-    // ring depth and residency: fill ~200 KB of shared memory per SM with >= 3 stages per CTA
-    const int stage = spmv_stage_layout(p.cap, rt, nin_max).bytes;
-    const int budget = 200 * 1024;
-    p.nst = env_int("ELP_SPMV_NST", 0);
-    p.ctas_per_sm = env_int("ELP_SPMV_CTAS", 0);
-    if (p.ctas_per_sm <= 0) {
-        const int want = p.cw == 8 ? 2 : 4;
-        p.ctas_per_sm = std::max(1, std::min(want, budget / (2 * stage + 256)));   // two resident CTAs beat a deeper ring
-    }
-    if (p.nst <= 0) p.nst = std::max(2, std::min(SPMV_MAX_NST, (budget / p.ctas_per_sm - 256) / stage));
-    p.nst = std::max(2, std::min(p.nst, SPMV_MAX_NST));
+    p.ntiles = ceil_div(nrows, rw);
+    p.nstw = env_int("ELP_SPMV_NST", 2);
+    if (p.nstw < 2 || p.nstw > 3) p.nstw = 2;
+    // residency: as many CTAs as 64 K registers allow (80 per thread -> 6) inside 196 KB of shared memory.
+    // Measured on B200: once the CTAs of an SM take more than the 196 KB carve-out step, the L1 left over
+    // for the gathers is too small and the kernel slows down by ~30 %.
+    const size_t per_cta = spmv_smem_bytes(p, nin_max) + 1024;      // + the 1 KB the system reserves per CTA
+    int ctas = (int)std::min<size_t>(196 * 1024 / per_cta, 6);
+    if (const int c = env_int("ELP_SPMV_CTAS", 0)) ctas = c;
+    p.ctas_per_sm = std::max(1, ctas);
     return p;
 }
 
-template <int CW, int L, class Epi>
+template <int L, int NSTW, class Epi>
 void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val,
                       const double* vec, const Epi& epi, cudaStream_t st) {
-    auto kern = spmv_stream_kernel<CW, L, Epi>;
-    static bool configured[16] = {};
-    int dev = 0;
-    ELP_CUDA(cudaGetDevice(&dev));
-    if (dev < 16 && !configured[dev]) {
-        ELP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured[dev] = true;
-    }
+    auto kern = spmv_warp_kernel<L, NSTW, Epi>;
     const size_t smem = spmv_smem_bytes(p, Epi::NIN);
     ELP_REQUIRE(smem <= 227 * 1024, "spmv: stage ring of %zu bytes does not fit in shared memory", smem);
-    const int grid = std::max(1, std::min(p.ntiles, kNumSMs * p.ctas_per_sm));
-    ELP_LAUNCH(kern, grid, CW * 32 + 32, smem, st, nrows, p.ntiles, p.cap, p.nst, p.hints, ptr, idx, val, vec, epi);
+    // per device and ring size: raise the dynamic shared-memory limit once and ask how many CTAs really fit
+    static size_t cfg_smem[16] = {};
+    static int cfg_occ[16] = {};
+    int dev = 0;
+    ELP_CUDA(cudaGetDevice(&dev));
+    dev &= 15;
+    if (cfg_smem[dev] != smem + 1) {
+        ELP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int occ = 0;
+        ELP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SPMV_WARPS * 32, smem));
+        cfg_occ[dev] = std::max(1, occ);
+        cfg_smem[dev] = smem + 1;
+        if (env_int("ELP_SPMV_DEBUG", 0))
+            fprintf(stderr, "[spmv] L=%d nstw=%d nin=%d cap=%d smem/CTA=%zu planned CTAs/SM=%d resident=%d tiles=%d\n", L, NSTW,
+                    Epi::NIN, p.cap, smem, p.ctas_per_sm, occ, p.ntiles);
+    }
+    // persistent grid: exactly one wave
+    const int per_sm = std::min(p.ctas_per_sm, cfg_occ[dev]);
+    const int grid = std::max(1, std::min(ceil_div(p.ntiles, SPMV_WARPS), kNumSMs * per_sm));
+    ELP_LAUNCH(kern, grid, SPMV_WARPS * 32, smem, st, nrows, p.ntiles, p.cap, ptr, idx, val, vec, epi);
+}
+
+template <int L, class Epi>
+void launch_spmv_l(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val, const double* vec,
+                   const Epi& epi, cudaStream_t st) {
+    switch (p.nstw) {
+        case 3:  launch_spmv_inst<L, 3, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
+        default: launch_spmv_inst<L, 2, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
+    }
 }
 
 template <class Epi>
@@ -267,15 +275,10 @@ void launch_spmv(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, c
                  const Epi& epi, cudaStream_t st) {
     if (nrows <= 0) return;
     switch (p.L) {
-        case 1:
-            if (p.cw == 4) launch_spmv_inst<4, 1, Epi>(p, nrows, ptr, idx, val, vec, epi, st);
-            else launch_spmv_inst<8, 1, Epi>(p, nrows, ptr, idx, val, vec, epi, st);
-            break;
-        case 2:  launch_spmv_inst<8, 2, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
-        case 4:  launch_spmv_inst<8, 4, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
-        case 8:  launch_spmv_inst<8, 8, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
-        case 16: launch_spmv_inst<8, 16, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
-        default: launch_spmv_inst<8, 32, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
+        case 1:  launch_spmv_l<1, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
+        case 2:  launch_spmv_l<2, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
+        case 4:  launch_spmv_l<4, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
+        default: launch_spmv_l<8, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
     }
 }
 

@@ -33,7 +33,7 @@ def check(m, n, lens, seed):
 
 allok = True
 rng = np.random.default_rng(0)
-for cap, lanes in (("0", "1"), ("64", "1"), ("0", "4"), ("64", "8"), ("0", "32"), ("128", "32")):
+for cap, lanes in (("0", "1"), ("64", "1"), ("16", "1"), ("0", "2"), ("0", "4"), ("64", "8"), ("0", "8"), ("32", "4")):
     os.environ["ELP_SPMV_CAP"] = cap
     os.environ["ELP_SPMV_L"] = lanes
     allok &= check(1, 5, [3], 1)
@@ -53,11 +53,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "sweep":
     m, n, nnz = p["m"], p["n"], int(p["row_ptr"][-1])
     b_csc = 12 * nnz + 4 * (n + 1) + 8 * m + 56 * n
     b_csr = 12 * nnz + 4 * (m + 1) + 8 * n + 40 * m
-    for cw, ctas, nst, capmul in ((8, 2, 0, 125), (8, 2, 3, 125), (8, 2, 2, 125), (8, 1, 0, 125), (8, 1, 4, 125),
-                                  (4, 4, 0, 125), (4, 4, 3, 125), (4, 3, 0, 125), (4, 2, 0, 125), (4, 6, 2, 110),
-                                  (8, 3, 2, 110), (8, 2, 0, 110), (8, 2, 0, 200), (4, 4, 0, 200)):
-        os.environ.update(ELP_SPMV_CW=str(cw), ELP_SPMV_CTAS=str(ctas), ELP_SPMV_NST=str(nst),
-                          ELP_SPMV_CAPMUL_PCT=str(capmul))
+    os.environ["ELP_SPMV_DEBUG"] = "1"
+    for lanes, ctas, nst, capsig in ((0, 0, 2, 100), (0, 0, 2, 200), (0, 0, 2, 50), (0, 0, 2, 0)):
+        carve = 0
+        cw, capmul = lanes, capsig
+        os.environ.update(ELP_SPMV_L=str(lanes), ELP_SPMV_CTAS=str(ctas), ELP_SPMV_NST=str(nst),
+                          ELP_SPMV_CAPSIG_PCT=str(capsig))
         try:
             h = L.Pdlp(m, n, p["row_ptr"], p["col_idx"], p["vals"], p["sense"], p["rhs"], p["c"], p["lb"], p["ub"],
                        options=L.default_options(method=L.METHOD_PDLP, ruiz_iters=2))
@@ -65,8 +66,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "sweep":
             c1, c2 = h.probe_spmv(30)
             h.close()
         except L.ElpError as e:
-            print(json.dumps(dict(cw=cw, ctas=ctas, nst=nst, capmul=capmul, error=str(e)[:200])), flush=True)
+            print(json.dumps(dict(L=cw, ctas=ctas, nst=nst, capsig=capmul, carve=carve, error=str(e)[:200])), flush=True)
             continue
-        print(json.dumps(dict(cw=cw, ctas=ctas, nst=nst, capmul=capmul, primal_ms=round(a, 4), dual_ms=round(b, 4),
+        print(json.dumps(dict(L=cw, ctas=ctas, nst=nst, capsig=capmul, carve=carve, primal_ms=round(a, 4), dual_ms=round(b, 4),
                               primal_gbs=round(b_csc / a / 1e6), dual_gbs=round(b_csr / b / 1e6), csr_ms=round(c1, 4),
                               csc_ms=round(c2, 4))), flush=True)
