@@ -37,6 +37,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from oracle import gen  # noqa: E402  (seeded input generators; not a solve path)
+from easylp_b200.partition import lp_ranges, row_block  # noqa: E402
 
 
 # ------------------------------------------------------------------------------------------------
@@ -108,24 +109,6 @@ def pinned(a):
         return t.pin_memory().numpy()
     except Exception:
         return t.numpy()
-
-
-def row_block(p, rank, nranks):
-    """Row block of rank `rank`: contiguous rows, balanced by nnz."""
-    m = p["m"]
-    rp = p["row_ptr"].astype(np.int64)
-    nnz = int(rp[m])
-    cuts = [int(np.searchsorted(rp, nnz * g / nranks, side="left")) for g in range(nranks)] + [m]
-    cuts[0] = 0
-    r0, r1 = cuts[rank], cuts[rank + 1]
-    q = dict(p)
-    q["m"] = r1 - r0
-    q["row_ptr"] = (rp[r0:r1 + 1] - rp[r0]).astype(np.int32)
-    q["col_idx"] = p["col_idx"][rp[r0]:rp[r1]]
-    q["vals"] = p["vals"][rp[r0]:rp[r1]]
-    q["sense"] = p["sense"][r0:r1]
-    q["rhs"] = p["rhs"][r0:r1]
-    return q, r0, r1
 
 
 def ncu_traffic(key):
@@ -337,7 +320,7 @@ def bench_batch(args, dist, L, d):
     """Batched dense simplex; LPs sharded contiguously over ranks, no collective."""
     N = dist.world
     B, m, n = d["B"], d["m"], d["n"]
-    lo, hi = B * dist.rank // N, B * (dist.rank + 1) // N
+    lo, hi = lp_ranges(B, N)[dist.rank]
     keys = ("A", "b", "c", "lb", "ub", "sense")
     hp = {k: pinned(d[k][lo:hi]) for k in keys}
     Bl = hi - lo
