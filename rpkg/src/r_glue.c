@@ -1,0 +1,228 @@
+/*
+ * r_glue.c — `.Call` glue between the EasyLP R package and libeasylp_b200.so (include/easylp_abi.h).
+ *
+ * This is the file a maintainer of benet1one/EasyLP adds under src/ (with `useDynLib(easylp, .registration = TRUE)`
+ * in NAMESPACE and `PKG_LIBS = -leasylp_b200` in src/Makevars).  It replaces the lpSolveAPI calls of `$solve()`
+ * (/root/reference/R/class.R:260-278) with ONE `.Call`, and gives `$con()`/`$min()`/`$max()` a device assembly and
+ * `private$feasible()` (R/class.R:533-540) a device re-check.  It is deliberately dumb: argument unpacking, index base
+ * conversion (R is 1-based, the ABI 0-based), result lists.  No arithmetic happens here.
+ *
+ * R is not installed in the build image, so this file is only compiled against a minimal mock of R's C API
+ * (tests/r_mock/) to keep it honest; it has never been executed.
+ *
+ * Conventions: inputs are read-only views of R vectors valid during the call; outputs are freshly allocated,
+ * PROTECTed vectors; a nonzero return code of the library becomes an R error AFTER temporary memory is released
+ * (R_alloc memory is reclaimed by R itself).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "easylp_abi.h"
+
+static void elp_fail(const char* where) {
+    char buf[1024];
+    buf[0] = 0;
+    elp_last_error(buf, (int32_t)sizeof buf);
+    Rf_error("%s: %s", where, buf[0] ? buf : "unknown error in libeasylp_b200");
+}
+
+static SEXP named_list(int n, const char** names) {
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, n));
+    SEXP nm = PROTECT(Rf_allocVector(STRSXP, n));
+    for (int i = 0; i < n; ++i) SET_STRING_ELT(nm, i, Rf_mkChar(names[i]));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(2);
+    return out;
+}
+
+/* R `dir` strings -> sense codes.  strict != 0 keeps "<"/">" distinct (3/4) for check_feasible
+ * (R/utils.R:167-171 uses match.fun(dir)); for the solver they fold onto "<="/">=" like lpSolveAPI does. */
+static int8_t* sense_codes(SEXP dir, int strict) {
+    const R_xlen_t m = XLENGTH(dir);
+    int8_t* s = (int8_t*)R_alloc((size_t)(m > 0 ? m : 1), 1);
+    for (R_xlen_t i = 0; i < m; ++i) {
+        const char* d = CHAR(STRING_ELT(dir, i));
+        if (!strcmp(d, "<=")) s[i] = ELP_LE;
+        else if (!strcmp(d, ">=")) s[i] = ELP_GE;
+        else if (!strcmp(d, "==") || !strcmp(d, "=")) s[i] = ELP_EQ;
+        else if (!strcmp(d, "<")) s[i] = strict ? 3 : ELP_LE;
+        else if (!strcmp(d, ">")) s[i] = strict ? 4 : ELP_GE;
+        else Rf_error("unknown constraint direction '%s'", d);
+    }
+    return s;
+}
+
+static int32_t* zero_based(SEXP idx) {
+    const R_xlen_t k = XLENGTH(idx);
+    int32_t* out = (int32_t*)R_alloc((size_t)(k > 0 ? k : 1), sizeof(int32_t));
+    const int* p = INTEGER(idx);
+    for (R_xlen_t i = 0; i < k; ++i) out[i] = (int32_t)p[i] - 1;
+    return out;
+}
+
+/* .Call("easylp_assemble_csr", term_row, term_col, term_val, m, n)
+ * term_row / term_col: 1-based integer vectors in emission (fold) order.  Returns list(row_ptr, col_idx, vals)
+ * with 0-based row_ptr and 1-based col_idx (ready for R indexing). */
+SEXP easylp_assemble_csr(SEXP term_row, SEXP term_col, SEXP term_val, SEXP m_, SEXP n_) {
+    const int64_t T = (int64_t)XLENGTH(term_val);
+    const int32_t m = Rf_asInteger(m_), n = Rf_asInteger(n_);
+    if (XLENGTH(term_row) != T || XLENGTH(term_col) != T) Rf_error("term vectors differ in length");
+    int32_t* row = zero_based(term_row);
+    int32_t* col = zero_based(term_col);
+    int32_t* col_out = (int32_t*)R_alloc((size_t)(T > 0 ? T : 1), sizeof(int32_t));
+    double* val_out = (double*)R_alloc((size_t)(T > 0 ? T : 1), sizeof(double));
+    SEXP row_ptr = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)m + 1));
+    int64_t nnz = 0;
+    const int rc = elp_assemble_csr(T, row, col, REAL(term_val), m, n, (int32_t*)INTEGER(row_ptr), col_out, val_out, &nnz, NULL);
+    if (rc) { UNPROTECT(1); elp_fail("easylp_assemble_csr"); }
+    SEXP col_idx = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz));
+    SEXP vals = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
+    for (int64_t i = 0; i < nnz; ++i) INTEGER(col_idx)[i] = col_out[i] + 1;
+    if (nnz) memcpy(REAL(vals), val_out, (size_t)nnz * sizeof(double));
+    const char* names[] = {"row_ptr", "col_idx", "vals"};
+    SEXP out = PROTECT(named_list(3, names));
+    SET_VECTOR_ELT(out, 0, row_ptr);
+    SET_VECTOR_ELT(out, 1, col_idx);
+    SET_VECTOR_ELT(out, 2, vals);
+    UNPROTECT(4);
+    return out;
+}
+
+static void fill_options(elp_options* opt, SEXP control) {
+    /* `control`: named list built by `$solve(...)` from the arguments it used to forward to lp.control()
+     * (R/class.R:262): timeout, epsilon, verbose are mapped; gpu.* are additive. */
+    elp_default_options(opt);
+    if (control == R_NilValue) return;
+    SEXP nm = Rf_getAttrib(control, R_NamesSymbol);
+    for (R_xlen_t i = 0; i < XLENGTH(control); ++i) {
+        const char* k = CHAR(STRING_ELT(nm, i));
+        SEXP v = VECTOR_ELT(control, i);
+        if (!strcmp(k, "timeout")) opt->time_limit_s = Rf_asReal(v);
+        else if (!strcmp(k, "epsilon") || !strcmp(k, "gpu.tol")) opt->eps_rel = Rf_asReal(v);
+        else if (!strcmp(k, "verbose")) opt->verbose = Rf_asInteger(v);
+        else if (!strcmp(k, "gpu.max_iter")) opt->max_iter = Rf_asInteger(v);
+        else if (!strcmp(k, "gpu.method")) opt->method = Rf_asInteger(v);
+        /* everything else has no meaning on the GPU path; `$solve()` warns about it on the R side */
+    }
+}
+
+/* .Call("easylp_solve_lp", row_ptr, col_idx, vals, dir, rhs, objective_fun, maximize, lower, upper, control)
+ * Replaces make.lp/set.objfn/lp.control/set.bounds/add.constraint/solve/get.objective/get.variables
+ * (R/class.R:260-278).  Returns list(status = <lp_solve code>, objval, x, y, stats). */
+SEXP easylp_solve_lp(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize,
+                     SEXP lower, SEXP upper, SEXP control) {
+    const int32_t m = (int32_t)XLENGTH(row_ptr) - 1, n = (int32_t)XLENGTH(cost);
+    if (XLENGTH(lower) != n || XLENGTH(upper) != n) Rf_error("bounds must have one entry per variable");
+    if (XLENGTH(dir) != m || XLENGTH(rhs) != m) Rf_error("dir/rhs must have one entry per constraint");
+    elp_options opt;
+    fill_options(&opt, control);
+    int8_t* sense = sense_codes(dir, 0);
+    int32_t* cols = zero_based(col_idx);
+    SEXP x = PROTECT(Rf_allocVector(REALSXP, n));
+    SEXP y = PROTECT(Rf_allocVector(REALSXP, m));
+    int32_t status = 0;
+    double objval = 0.0;
+    elp_stats st;
+    memset(&st, 0, sizeof st);
+    const int rc = elp_solve_lp(m, n, (const int32_t*)INTEGER(row_ptr), cols, REAL(vals), sense, REAL(rhs), REAL(cost),
+                                Rf_asLogical(maximize) ? 1 : 0, REAL(lower), REAL(upper), &opt, &status, &objval,
+                                REAL(x), m > 0 ? REAL(y) : NULL, &st);
+    if (rc) { UNPROTECT(2); elp_fail("easylp_solve_lp"); }
+    const char* snames[] = {"method", "iterations", "restarts", "rel_primal_res", "rel_dual_res", "rel_gap",
+                            "setup_ms", "solve_ms", "kernel_launches", "h2d_bytes", "d2h_bytes"};
+    SEXP stats = PROTECT(named_list(11, snames));
+    SET_VECTOR_ELT(stats, 0, Rf_ScalarInteger(st.method_used));
+    SET_VECTOR_ELT(stats, 1, Rf_ScalarInteger(st.iterations));
+    SET_VECTOR_ELT(stats, 2, Rf_ScalarInteger(st.restarts));
+    SET_VECTOR_ELT(stats, 3, Rf_ScalarReal(st.rel_primal_res));
+    SET_VECTOR_ELT(stats, 4, Rf_ScalarReal(st.rel_dual_res));
+    SET_VECTOR_ELT(stats, 5, Rf_ScalarReal(st.rel_gap));
+    SET_VECTOR_ELT(stats, 6, Rf_ScalarReal(st.setup_ms));
+    SET_VECTOR_ELT(stats, 7, Rf_ScalarReal(st.solve_ms));
+    SET_VECTOR_ELT(stats, 8, Rf_ScalarReal((double)st.kernel_launches));
+    SET_VECTOR_ELT(stats, 9, Rf_ScalarReal((double)st.h2d_bytes));
+    SET_VECTOR_ELT(stats, 10, Rf_ScalarReal((double)st.d2h_bytes));
+    const char* names[] = {"status", "objval", "x", "y", "stats"};
+    SEXP out = PROTECT(named_list(5, names));
+    SET_VECTOR_ELT(out, 0, Rf_ScalarInteger(status));
+    SET_VECTOR_ELT(out, 1, Rf_ScalarReal(objval));
+    SET_VECTOR_ELT(out, 2, x);
+    SET_VECTOR_ELT(out, 3, y);
+    SET_VECTOR_ELT(out, 4, stats);
+    UNPROTECT(4);
+    return out;
+}
+
+/* .Call("easylp_check_feasible", row_ptr, col_idx, vals, sol, dir, rhs, tol) -> logical(m)
+ * Replaces `lhs <- mat %*% sol` + compare_tol (R/class.R:533-540, R/utils.R:167-171). */
+SEXP easylp_check_feasible(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP sol, SEXP dir, SEXP rhs, SEXP tol) {
+    const int32_t m = (int32_t)XLENGTH(row_ptr) - 1, n = (int32_t)XLENGTH(sol);
+    int8_t* sense = sense_codes(dir, 1);
+    int32_t* cols = zero_based(col_idx);
+    uint8_t* ok = (uint8_t*)R_alloc((size_t)(m > 0 ? m : 1), 1);
+    const int rc = elp_check_feasible(m, n, (const int32_t*)INTEGER(row_ptr), cols, REAL(vals), REAL(sol), sense, REAL(rhs),
+                                      Rf_asReal(tol), ok);
+    if (rc) elp_fail("easylp_check_feasible");
+    SEXP out = PROTECT(Rf_allocVector(LGLSXP, m));
+    for (int32_t i = 0; i < m; ++i) LOGICAL(out)[i] = ok[i] ? 1 : 0;
+    UNPROTECT(1);
+    return out;
+}
+
+/* .Call("easylp_solve_batch", A, b, c, lower, upper, dir, maximize, control)
+ * Additive entry point for BASELINE config 3: A is an array with dim c(n, m, B) (so that each LP's rows are
+ * contiguous: R is column-major, the ABI wants [B][m][n] row-major), b is m x B, c/lower/upper are n x B,
+ * dir a character vector of length m (recycled over the batch) or NULL for all "<=".
+ * Returns list(status = integer(B), objval = numeric(B), x = matrix(n, B)). */
+SEXP easylp_solve_batch(SEXP A, SEXP b, SEXP c, SEXP lower, SEXP upper, SEXP dir, SEXP maximize, SEXP control) {
+    SEXP dim = Rf_getAttrib(A, R_DimSymbol);
+    if (dim == R_NilValue || XLENGTH(dim) != 3) Rf_error("A must be an n x m x B array");
+    const int32_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
+    const int64_t B = INTEGER(dim)[2];
+    elp_options opt;
+    fill_options(&opt, control);
+    int8_t* sense = NULL;
+    if (dir != R_NilValue) {
+        if (XLENGTH(dir) != m) Rf_error("dir must have one entry per constraint");
+        int8_t* one = sense_codes(dir, 0);
+        sense = (int8_t*)R_alloc((size_t)(B * m > 0 ? B * m : 1), 1);
+        for (int64_t k = 0; k < B; ++k) memcpy(sense + k * m, one, (size_t)m);
+    }
+    SEXP status = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)B));
+    SEXP obj = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)B));
+    SEXP x = PROTECT(Rf_allocMatrix(REALSXP, n, (int)B));
+    const int rc = elp_solve_batch(B, m, n, REAL(A), REAL(b), REAL(c), lower == R_NilValue ? NULL : REAL(lower),
+                                   upper == R_NilValue ? NULL : REAL(upper), sense, Rf_asLogical(maximize) ? 1 : 0, &opt,
+                                   (int32_t*)INTEGER(status), REAL(obj), REAL(x), NULL);
+    if (rc) { UNPROTECT(3); elp_fail("easylp_solve_batch"); }
+    const char* names[] = {"status", "objval", "x"};
+    SEXP out = PROTECT(named_list(3, names));
+    SET_VECTOR_ELT(out, 0, status);
+    SET_VECTOR_ELT(out, 1, obj);
+    SET_VECTOR_ELT(out, 2, x);
+    UNPROTECT(4);
+    return out;
+}
+
+/* .Call("easylp_device_count") */
+SEXP easylp_device_count(void) {
+    int32_t k = 0;
+    if (elp_device_count(&k)) k = 0;
+    return Rf_ScalarInteger(k);
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"easylp_assemble_csr", (DL_FUNC)&easylp_assemble_csr, 5},
+    {"easylp_solve_lp", (DL_FUNC)&easylp_solve_lp, 10},
+    {"easylp_check_feasible", (DL_FUNC)&easylp_check_feasible, 7},
+    {"easylp_solve_batch", (DL_FUNC)&easylp_solve_batch, 8},
+    {"easylp_device_count", (DL_FUNC)&easylp_device_count, 0},
+    {NULL, NULL, 0}};
+
+void R_init_easylp(DllInfo* dll) {
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}

@@ -1,0 +1,40 @@
+/* Minimal mock of R's C API: just the declarations rpkg/src/r_glue.c uses, so that the glue can be
+ * syntax- and type-checked in an image without R.  TEST INFRASTRUCTURE ONLY — never linked, never run. */
+#ifndef R_MOCK_RINTERNALS_H
+#define R_MOCK_RINTERNALS_H
+#include <stddef.h>
+typedef struct SEXPREC* SEXP;
+typedef ptrdiff_t R_xlen_t;
+typedef enum { FALSE = 0, TRUE } Rboolean;
+#define INTSXP 13
+#define LGLSXP 10
+#define REALSXP 14
+#define STRSXP 16
+#define VECSXP 19
+extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
+SEXP Rf_allocVector(unsigned int, R_xlen_t);
+SEXP Rf_allocMatrix(unsigned int, int, int);
+SEXP Rf_protect(SEXP);
+void Rf_unprotect(int);
+#define PROTECT(s) Rf_protect(s)
+#define UNPROTECT(n) Rf_unprotect(n)
+R_xlen_t XLENGTH(SEXP);
+int* INTEGER(SEXP);
+int* LOGICAL(SEXP);
+double* REAL(SEXP);
+SEXP STRING_ELT(SEXP, R_xlen_t);
+SEXP VECTOR_ELT(SEXP, R_xlen_t);
+void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
+SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
+const char* CHAR(SEXP);
+SEXP Rf_mkChar(const char*);
+SEXP Rf_getAttrib(SEXP, SEXP);
+SEXP Rf_setAttrib(SEXP, SEXP, SEXP);
+int Rf_asInteger(SEXP);
+int Rf_asLogical(SEXP);
+double Rf_asReal(SEXP);
+SEXP Rf_ScalarInteger(int);
+SEXP Rf_ScalarReal(double);
+void Rf_error(const char*, ...) __attribute__((noreturn));
+char* R_alloc(size_t, int);
+#endif
