@@ -139,3 +139,38 @@ def test_pdlp_transport_vs_simplex_oracle():
                                            p["c"], p["lb"], p["ub"])
     assert st == 0 and r.status == 0
     assert abs(r.objval - obj) <= 2e-6 * max(1.0, abs(obj))
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (2, 2), (3, 5), (4, 4), (7, 9), (8, 20), (12, 50), (16, 16), (20, 30), (24, 40),
+                                 (28, 30), (32, 60), (5, 70), (10, 86), (33, 10), (20, 80), (40, 100)])
+def test_batch_shapes_vs_oracle(m, n):
+    """every register-tableau instantiation (rows padded to 4, 1-3 columns per lane), odd sizes (no TMA path) and
+    the shapes that fall back to the CTA-per-LP kernel"""
+    rng = np.random.default_rng(100 * m + n)
+    B = 300
+    A = rng.uniform(-0.3, 1.0, size=(B, m, n)) * (rng.random((B, m, n)) < 0.8)
+    x0 = rng.uniform(0, 1, size=(B, n))
+    b = np.einsum("bij,bj->bi", A, x0) + rng.uniform(0.1, 1.0, size=(B, m))
+    sense = (rng.random((B, m)) < 0.15).astype(np.int8)            # mostly <=, some >=
+    b = np.where(sense == 1, b - 2.0, b)
+    c = rng.normal(size=(B, n))
+    lb = np.zeros((B, n)); ub = np.full((B, n), 5.0)
+    ub[:, ::3] = np.inf
+    status, obj, x, _ = L.solve_batch(A, b, c, lb, ub, sense)
+    s0, o0, x0_, _ = cbind.simplex_batch(A, b, c, lb, ub, sense, nthreads=8)
+    assert np.array_equal(status, s0)
+    ok = status == 0
+    assert ok.sum() > 0
+    assert np.all(np.abs(obj[ok] - o0[ok]) <= 1e-6 * np.maximum(1.0, np.abs(o0[ok])))
+    ax = np.einsum("bij,bj->bi", A[ok], x[ok])
+    viol = np.where(sense[ok] == 0, ax - b[ok], b[ok] - ax)
+    assert viol.max() <= 1e-6
+
+
+def test_batch_duals_small():
+    """duals of the batched path on the README LP (y from the slack block of the final tableau)"""
+    p = gen.readme_lp()
+    r = L.solve_lp(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], p["sense"], p["rhs"], p["c"], p["lb"], p["ub"],
+                   maximize=True)
+    # strong duality: b'y == objective
+    assert abs(float(np.dot(p["rhs"], r.y)) - 2.0) <= 1e-9
