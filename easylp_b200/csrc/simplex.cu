@@ -403,14 +403,47 @@ struct WVI {
     double v;
     int i;
 };
-__device__ __forceinline__ WVI warp_best(WVI x) {     // "better" of simplex_batch_kernel over the warp
+// Warp argmax of (v, i) with v >= 0 (or i < 0 = no candidate): larger v wins, ties go to the smaller i — the
+// "better" of simplex_batch_kernel.  Non-negative doubles order like their bit patterns, so the maximum is two
+// 32-bit hardware reductions (REDUX) on the high and low words and the tie-break a third on the index.
+__device__ __forceinline__ WVI warp_best_nonneg(WVI x) {
+    const unsigned long long bits = x.i < 0 ? 0ull : (unsigned long long)__double_as_longlong(x.v + 0.0);
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const bool top = x.i >= 0 && hi == mhi && lo == mlo;
+    const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)x.i : 0xffffffffu);
+    WVI r;
+    r.i = (mi == 0xffffffffu) ? -1 : (int)mi;
+    r.v = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    return r;
+}
+// Bland's rule: the candidate with the smallest key (a variable id), index i travels with it.
+__device__ __forceinline__ int warp_best_bland(int key, int i) {
+    const unsigned k = i < 0 ? 0xffffffffu : (unsigned)key;
+    const unsigned mk = __reduce_min_sync(0xffffffffu, k);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, (i >= 0 && k == mk) ? (unsigned)i : 0xffffffffu);
+    return mi == 0xffffffffu ? -1 : (int)mi;
+}
+// Warp minimum of non-negative doubles (+inf allowed)
+__device__ __forceinline__ double warp_min_nonneg(double v) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v + 0.0);
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+}
+
+// The column c_sel (warp-uniform) of a register tableau -> shared memory.
+template <int MR, int CPL>
+__device__ __forceinline__ void tab_store_col(const double (&T)[CPL][MR], int c_sel, double* dst) {   // c_sel warp-uniform
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double v = __shfl_xor_sync(0xffffffffu, x.v, o);
-        const int i = __shfl_xor_sync(0xffffffffu, x.i, o);
-        if (i >= 0 && (x.i < 0 || v > x.v || (v == x.v && i < x.i))) { x.v = v; x.i = i; }
+    for (int c = 0; c < CPL; ++c) {
+        if (c == c_sel) {
+#pragma unroll
+            for (int i = 0; i < MR; ++i) dst[i] = T[c][i];
+        }
     }
-    return x;
 }
 
 template <int MR, int CPL>
@@ -542,14 +575,14 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
 
         while (!bad) {
             // ---- phase detection: row i on lane i --------------------------------------------------
-            double g = 0.0, wpart = 0.0;
+            double g = 0.0;
             if (lane < m) {
                 const double bi = beta[lane], l = blo[lane], u = bhi[lane];
-                if (bi < l - ptol(l)) { g = -1.0; wpart = l - bi; }
-                else if (bi > u + ptol(u)) { g = 1.0; wpart = bi - u; }
+                if (bi < l - ptol(l)) g = -1.0;
+                else if (bi > u + ptol(u)) g = 1.0;
             }
-            const double w = warp_sum(wpart);
-            const bool phase1 = w > 0.0;
+            // the sum of infeasibilities is positive iff some row is infeasible (every term is positive)
+            const bool phase1 = __any_sync(0xffffffffu, g != 0.0);
             if (lane < m) cb[lane] = phase1 ? g : bcost[lane];
             __syncwarp();
             // ---- pricing on my columns -------------------------------------------------------------
@@ -573,12 +606,14 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
                     if ((st == ST_LOWER || st == ST_FREE) && d[c] < -TOL_DUAL) dd = 1;
                     else if ((st == ST_UPPER || st == ST_FREE) && d[c] > TOL_DUAL) dd = -1;
                     if (!dd) continue;
-                    const double key = bland ? -(double)col : fabs(d[c]);
+                    const double key = bland ? (double)col : fabs(d[c]);
                     const int id = 2 * col + (dd < 0 ? 1 : 0);
-                    if (cand.i < 0 || key > cand.v || (key == cand.v && id < cand.i)) { cand.v = key; cand.i = id; }
+                    const bool take = cand.i < 0 || (bland ? key < cand.v : (key > cand.v || (key == cand.v && id < cand.i)));
+                    if (take) { cand.v = key; cand.i = id; }
                 }
             }
-            cand = warp_best(cand);
+            if (bland) cand.i = warp_best_bland((int)cand.v, cand.i);
+            else cand = warp_best_nonneg(cand);
             if (cand.i < 0) { status = phase1 ? ELP_STATUS_INFEASIBLE : ELP_STATUS_OPTIMAL; break; }
             if (pivots >= max_pivots) { status = ELP_STATUS_TIMEOUT; break; }
             const int q = cand.i >> 1;
@@ -587,16 +622,10 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             // ---- entering column to shared memory; its scalars by shuffle ----------------------------
             double q_lo = 0.0, q_hi = 0.0, q_xn = 0.0, q_cost = 0.0;
             int q_state = 0;
+            if (lane == qlane) tab_store_col<MR, CPL>(T, qc, colq);
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                if (c == qc) {
-                    if (lane == qlane) {
-#pragma unroll
-                        for (int i = 0; i < MR; ++i) colq[i] = T[c][i];
-                    }
-                    q_lo = clo[c]; q_hi = chi[c]; q_xn = cxn[c]; q_cost = ccost[c]; q_state = cstate[c];
-                }
-            }
+            for (int c = 0; c < CPL; ++c)
+                if (c == qc) { q_lo = clo[c]; q_hi = chi[c]; q_xn = cxn[c]; q_cost = ccost[c]; q_state = cstate[c]; }
             q_lo = __shfl_sync(0xffffffffu, q_lo, qlane);
             q_hi = __shfl_sync(0xffffffffu, q_hi, qlane);
             q_xn = __shfl_sync(0xffffffffu, q_xn, qlane);
@@ -604,25 +633,25 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             q_state = __shfl_sync(0xffffffffu, q_state, qlane);
             __syncwarp();
             // ---- ratio test: row i on lane i ---------------------------------------------------------
-            double tloc = INFINITY, a = 0.0, bi = 0.0, l = 0.0, u = 0.0;
+            double tloc = INFINITY, a = 0.0;
             int up = 0, kbas = -1;
             if (lane < m) {
                 a = dir * colq[lane];
                 if (fabs(a) > TOL_PIVOT) {
                     kbas = basis[lane];
-                    bi = beta[lane]; l = blo[lane]; u = bhi[lane];
+                    const double bi = beta[lane], l = blo[lane], u = bhi[lane];
+                    double num = INFINITY;                 // one division per row: t = num / a
                     if (a > 0.0) {
-                        if (bi > u + ptol(u)) { tloc = (bi - u) / a; up = 1; }
-                        else if (bi >= l - ptol(l)) { if (isfinite(l)) { tloc = fmax(bi - l, 0.0) / a; up = 0; } }
+                        if (bi > u + ptol(u)) { num = bi - u; up = 1; }
+                        else if (bi >= l - ptol(l) && isfinite(l)) { num = fmax(bi - l, 0.0); up = 0; }
                     } else {
-                        if (bi < l - ptol(l)) { tloc = (bi - l) / a; up = 0; }
-                        else if (bi <= u + ptol(u)) { if (isfinite(u)) { tloc = fmin(bi - u, 0.0) / a; up = 1; } }
+                        if (bi < l - ptol(l)) { num = bi - l; up = 0; }
+                        else if (bi <= u + ptol(u) && isfinite(u)) { num = fmin(bi - u, 0.0); up = 1; }
                     }
+                    if (num != INFINITY) tloc = num / a;
                 }
             }
-            double tmin = tloc;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+            const double tmin = warp_min_nonneg(tloc);
             const double tflip = (q_state == ST_FREE) ? INFINITY : q_hi - q_lo;
             if (tflip <= tmin) {
                 if (!isfinite(tflip)) {
@@ -649,8 +678,9 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             // ---- pass 2: among rows within a hair of tmin take the largest pivot (Bland: smallest basic id) ---
             const double window = tmin + 1e-12 * fmax(1.0, fabs(tmin));
             WVI rc{0.0, -1};
-            if (kbas >= 0 && tloc <= window) { rc.v = bland ? -(double)kbas : fabs(a); rc.i = 2 * lane + up; }
-            rc = warp_best(rc);
+            if (kbas >= 0 && tloc <= window) { rc.v = fabs(a); rc.i = 2 * lane + up; }
+            if (bland) rc.i = warp_best_bland(kbas, rc.i);
+            else rc = warp_best_nonneg(rc);
             if (rc.i < 0) { status = ELP_STATUS_NUMFAILURE; break; }
             const int r = rc.i >> 1;
             const int to_upper = rc.i & 1;
@@ -660,7 +690,7 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             const double kl_bound = to_upper ? bhi[r] : blo[r];
             __syncwarp();                                  // everyone has read row r before it is rewritten
             if (lane < m) beta[lane] -= dir * t * colq[lane];
-            // pivot row of my columns
+            // pivot row of my columns (registers cannot be indexed by the dynamic row: a select chain)
             double rr[CPL];
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
@@ -682,16 +712,13 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
                     basis[r] = q; blo[r] = q_lo; bhi[r] = q_hi; bcost[r] = q_cost;
                 }
             }
-            // ---- rank-1 update of my columns:  T -= colq * rr  (row r := rr; column q := e_r) ---------------
+            // ---- rank-1 update of my columns:  T -= colq * rr, row r := rr.  Column q needs no special case:
+            // its rr is exactly 1 and its entries ARE colq, so f - f*1 = 0 exactly and row r becomes 1. -----------
 #pragma unroll
             for (int i = 0; i < MR; ++i) {
                 const double f = colq[i];
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const int col = lane + 32 * c;
-                    const double upd = (col == q) ? 0.0 : T[c][i] - f * rr[c];
-                    T[c][i] = (i == r) ? rr[c] : ((f != 0.0) ? upd : T[c][i]);
-                }
+                for (int c = 0; c < CPL; ++c) T[c][i] = (i == r) ? rr[c] : T[c][i] - f * rr[c];
             }
             ++pivots;
             if (t <= 1e-12) { if (++degenerate_run > 30) bland = 1; }
