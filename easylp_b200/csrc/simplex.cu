@@ -368,34 +368,32 @@ simplex_batch_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, con
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-per-LP variant for small LPs (m <= 32, m + n <= 96): the tableau lives in REGISTERS.
-// Lane l owns the tableau columns l, l+32, (l+64): CPL columns x MR rows of doubles, plus the bounds, cost,
-// non-basic value and state of those columns.  Row-indexed data (basic values, basis heads, the entering
-// column) sits in a few hundred bytes of shared memory per warp.  Every step of a pivot is warp-synchronous:
-// pricing is a register dot product per column, the rank-1 update is MR fused multiply-adds per column, the
-// argmax / argmin are warp shuffles, and there is no block-wide barrier anywhere.  Compared with the
-// CTA-per-LP kernel below this executes ~6x fewer instructions per pivot (one warp instead of two, no
-// address arithmetic, no shared-memory read-modify-write of the tableau).
-// The LP's data (A, b, c, lb, ub) is read from HBM once by 1-D TMA bulk copies into a per-warp staging
-// buffer; the copy of the warp's NEXT LP is issued before the current one is solved (double buffer).
-// Arithmetic order per entry is the same as in simplex_batch_kernel / oracle/simplex_ref.c.
+// Warp-per-LP kernel for small LPs (m <= 32, m + n <= 96) — the batched path of BASELINE config 3.
+// One WARP solves one LP; a CTA is four independent warps.  The tableau T[MR][NS] (NS = 32*CPL + 2 doubles
+// per row, MR = m rounded up to 4: both compile-time, so every tableau access is `base + immediate`) lives
+// in the warp's slice of shared memory and is filled ONCE per LP by 1-D TMA bulk copies, one per row, issued
+// by the lanes in parallel (cp.async.bulk -> mbarrier complete_tx); b, c, lb, ub arrive by coalesced loads.
+// Lane l owns the tableau columns l, l+32, (l+64) and keeps their bounds / cost / non-basic value / state
+// in registers; row-indexed data (basic values, basis heads, bounds of the basic variables, the entering
+// column) sits beside the tableau.  A pivot is warp-synchronous end to end:
+//   pricing     d_j = c_j - sum_i cb_i T[i][j]      one column per lane per pass, conflict-free row reads
+//   argmax      three 32-bit hardware reductions (REDUX) on the bit pattern of |d_j| and on the index
+//   ratio test  row i on lane i, REDUX min, second pass picks the largest pivot among the ties
+//   update      T[i][j] -= colq[i] * rr[j]: MR fused multiply-adds per column straight on shared memory;
+//               the dynamic pivot row is a plain address here (registers could not be indexed by it)
+// There is no block-wide barrier, no address arithmetic in the loops and ~60 registers per thread, so many
+// LPs are resident per SM.  Arithmetic order per entry equals simplex_batch_kernel / oracle/simplex_ref.c.
 // ------------------------------------------------------------------------------------------------
 constexpr int SW_WARPS = 4;
 
 struct WarpSimplexLayout {      // per-warp shared memory, in bytes
-    int stage_bytes, off_b, off_c, off_lb, off_ub;      // one staging buffer: A | b | c | lb | ub
-    int off_rows, rows_bytes, total;
-    __host__ __device__ WarpSimplexLayout(int m, int n, int MR) {
-        auto up16 = [](int v) { return (v + 15) & ~15; };
-        off_b = up16(m * n * 8);
-        off_c = off_b + up16(m * 8);
-        off_lb = off_c + up16(n * 8);
-        off_ub = off_lb + up16(n * 8);
-        stage_bytes = off_ub + up16(n * 8);
-        off_rows = 2 * stage_bytes;
-        rows_bytes = 6 * MR * 8 + MR * 4 + 96 * 8 + 32;      // beta blo bhi bcost cb colq | basis | xs[96] | 2 mbarriers
-        rows_bytes = up16(rows_bytes);
-        total = off_rows + rows_bytes;
+    int ns, off_rows, total;
+    __host__ __device__ WarpSimplexLayout(int MR, int CPL) {
+        ns = 32 * CPL + 2;                                   // even (16-byte rows for TMA), not a multiple of 32
+        off_rows = MR * ns * 8;
+        // beta blo bhi bcost cb colq [MR each] | xs[96] | mbarrier | basis[MR]
+        total = off_rows + 6 * MR * 8 + 96 * 8 + 16 + MR * 4;
+        total = (total + 15) & ~15;
     }
 };
 
@@ -434,29 +432,20 @@ __device__ __forceinline__ double warp_min_nonneg(double v) {
     return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
 }
 
-// The column c_sel (warp-uniform) of a register tableau -> shared memory.
 template <int MR, int CPL>
-__device__ __forceinline__ void tab_store_col(const double (&T)[CPL][MR], int c_sel, double* dst) {   // c_sel warp-uniform
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-        if (c == c_sel) {
-#pragma unroll
-            for (int i = 0; i < MR; ++i) dst[i] = T[c][i];
-        }
-    }
-}
-
-template <int MR, int CPL>
-__global__ void __launch_bounds__(SW_WARPS * 32, (MR * CPL <= 40) ? 3 : 2)
+__global__ void __launch_bounds__(SW_WARPS * 32)
 simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, const double* __restrict__ bg,
                     const double* __restrict__ cg, const double* __restrict__ lbg, const double* __restrict__ ubg,
                     const int8_t* __restrict__ senseg, int maximize, int max_pivots, int use_tma,
                     int32_t* __restrict__ status_out, double* __restrict__ obj_out, double* __restrict__ x_out,
                     double* __restrict__ y_out, int32_t* __restrict__ pivots_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const WarpSimplexLayout lay(m, n, MR);
+    constexpr int NS = 32 * CPL + 2;
+    const WarpSimplexLayout lay(MR, CPL);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + (size_t)warp * lay.total;
+    double* Ts = reinterpret_cast<double*>(wbase);               // [MR][NS]
+    double* Tl = Ts + lane;                                      // my columns: Tl[i * NS + 32 * c]
     double* rows = reinterpret_cast<double*>(wbase + lay.off_rows);
     double* beta = rows;
     double* blo = rows + MR;
@@ -465,81 +454,46 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
     double* cb = rows + 4 * MR;
     double* colq = rows + 5 * MR;
     double* xs = rows + 6 * MR;                                  // [96] non-basic values by column (setup only)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 96);        // [2]
-    int* basis = reinterpret_cast<int*>(bars + 2);               // [MR]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(xs + 96);
+    int* basis = reinterpret_cast<int*>(bar + 2);                // [MR]
     const int N = n + m;
     const int64_t gw = (int64_t)blockIdx.x * SW_WARPS + warp, nw = (int64_t)gridDim.x * SW_WARPS;
     if (max_pivots <= 0) max_pivots = 50 * (m + n) + 1000;
 
-    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    // padding rows / columns stay zero for the whole kernel (updates of zero entries by zero factors)
+    for (int e = lane; e < MR * NS; e += 32) Ts[e] = 0.0;
     __syncwarp();
+    uint32_t phase = 0;
 
-    const uint32_t bytesA = (uint32_t)m * n * 8u, bytesb = (uint32_t)m * 8u, bytesn = (uint32_t)n * 8u;
-    auto stage_in = [&](int64_t lp, int buf) {
-        unsigned char* sb = wbase + (size_t)buf * lay.stage_bytes;
-        if (use_tma) {
-            if (lane == 0) {
-                const uint32_t tx = bytesA + bytesb + bytesn + (lbg ? bytesn : 0u) + (ubg ? bytesn : 0u);
-                mbar_expect_tx(&bars[buf], tx);
-                if (bytesA) tma_load_1d(sb, Ag + lp * (int64_t)m * n, bytesA, &bars[buf]);
-                if (bytesb) tma_load_1d(sb + lay.off_b, bg + lp * (int64_t)m, bytesb, &bars[buf]);
-                tma_load_1d(sb + lay.off_c, cg + lp * (int64_t)n, bytesn, &bars[buf]);
-                if (lbg) tma_load_1d(sb + lay.off_lb, lbg + lp * (int64_t)n, bytesn, &bars[buf]);
-                if (ubg) tma_load_1d(sb + lay.off_ub, ubg + lp * (int64_t)n, bytesn, &bars[buf]);
-            }
-        } else {
-            double* dA = reinterpret_cast<double*>(sb);
-            double* db = reinterpret_cast<double*>(sb + lay.off_b);
-            double* dc = reinterpret_cast<double*>(sb + lay.off_c);
-            double* dl = reinterpret_cast<double*>(sb + lay.off_lb);
-            double* du = reinterpret_cast<double*>(sb + lay.off_ub);
-            const double* A = Ag + lp * (int64_t)m * n;
-            for (int e = lane; e < m * n; e += 32) dA[e] = A[e];
-            for (int i = lane; i < m; i += 32) db[i] = bg[lp * (int64_t)m + i];
-            for (int j = lane; j < n; j += 32) {
-                dc[j] = cg[lp * (int64_t)n + j];
-                if (lbg) dl[j] = lbg[lp * (int64_t)n + j];
-                if (ubg) du[j] = ubg[lp * (int64_t)n + j];
-            }
-            __syncwarp();
-        }
-    };
-
-    int buf = 0;
-    uint32_t phase[2] = {0u, 0u};
-    if (gw < B && use_tma) stage_in(gw, 0);
-    for (int64_t lp = gw; lp < B; lp += nw, buf ^= 1) {
-        if (use_tma) {
-            if (lp + nw < B) stage_in(lp + nw, buf ^ 1);          // prefetch the next LP of this warp
-            mbar_wait(&bars[buf], phase[buf]);
-            phase[buf] ^= 1u;
-        } else {
-            stage_in(lp, buf);
-        }
-        const unsigned char* sb = wbase + (size_t)buf * lay.stage_bytes;
-        const double* sA = reinterpret_cast<const double*>(sb);
-        const double* sbv = reinterpret_cast<const double*>(sb + lay.off_b);
-        const double* scv = reinterpret_cast<const double*>(sb + lay.off_c);
-        const double* slb = reinterpret_cast<const double*>(sb + lay.off_lb);
-        const double* sub = reinterpret_cast<const double*>(sb + lay.off_ub);
+    for (int64_t lp = gw; lp < B; lp += nw) {
+        const double* A = Ag + lp * (int64_t)m * n;
         const int8_t* sense = senseg ? senseg + lp * (int64_t)m : nullptr;
-
-        // ---- registers: my columns ------------------------------------------------------------------
-        double T[CPL][MR], clo[CPL], chi[CPL], ccost[CPL], cxn[CPL];
+        // ---- tableau rows of A: one bulk copy per row, issued by the lanes in parallel ----------------
+        if (use_tma && m > 0) {
+            // generic-proxy writes to the tableau (previous LP) must be ordered before the async-proxy copies
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)m * (uint32_t)n * 8u);
+            __syncwarp();
+            for (int i = lane; i < m; i += 32) tma_load_1d(Ts + i * NS, A + (size_t)i * n, (uint32_t)n * 8u, bar);
+        } else {
+            for (int i = 0; i < m; ++i)
+                for (int j = lane; j < n; j += 32) Ts[i * NS + j] = A[(size_t)i * n + j];
+        }
+        // ---- registers: scalars of my columns; slack block of the tableau -----------------------------
+        double clo[CPL], chi[CPL], ccost[CPL], cxn[CPL];
         int cstate[CPL];
         int bad = 0;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const int col = lane + 32 * c;
             clo[c] = 0.0; chi[c] = 0.0; ccost[c] = 0.0; cxn[c] = 0.0; cstate[c] = ST_BASIC;
-#pragma unroll
-            for (int i = 0; i < MR; ++i) T[c][i] = 0.0;
             if (col < n) {
-#pragma unroll
-                for (int i = 0; i < MR; ++i) if (i < m) T[c][i] = sA[i * n + col];
-                const double l = lbg ? slb[col] : 0.0, u = ubg ? sub[col] : INFINITY;
+                const double l = lbg ? lbg[lp * (int64_t)n + col] : 0.0, u = ubg ? ubg[lp * (int64_t)n + col] : INFINITY;
+                const double cj = cg[lp * (int64_t)n + col];
                 clo[c] = l; chi[c] = u;
-                ccost[c] = maximize ? -scv[col] : scv[col];
+                ccost[c] = maximize ? -cj : cj;
                 if (l > u) bad = 1;
                 if (isfinite(l)) { cstate[c] = ST_LOWER; cxn[c] = l; }
                 else if (isfinite(u)) { cstate[c] = ST_UPPER; cxn[c] = u; }
@@ -549,7 +503,7 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
                 const int i0 = col - n;
                 const int s = sense ? sense[i0] : 0;
 #pragma unroll
-                for (int i = 0; i < MR; ++i) T[c][i] = (i == i0) ? 1.0 : 0.0;
+                for (int i = 0; i < MR; ++i) Tl[i * NS + 32 * c] = (i == i0) ? 1.0 : 0.0;
                 clo[c] = (s == ELP_GE) ? -INFINITY : 0.0;
                 chi[c] = (s == ELP_LE) ? INFINITY : 0.0;
                 basis[i0] = col;
@@ -557,21 +511,28 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             }
         }
         bad = __any_sync(0xffffffffu, bad);
+        if (use_tma && m > 0) { mbar_wait(bar, phase); phase ^= 1u; }
         __syncwarp();
         // beta = b - A xN   (row i on lane i; sequential in j like the reference loop)
-        for (int i = lane; i < MR; i += 32) {
+        if (lane < MR) {
             double r = 0.0;
-            if (i < m) {
-                r = sbv[i];
-                for (int j = 0; j < n; ++j) r -= sA[i * n + j] * xs[j];
-            } else { blo[i] = -INFINITY; bhi[i] = INFINITY; bcost[i] = 0.0; basis[i] = -1; }
-            beta[i] = r;
-            cb[i] = 0.0; colq[i] = 0.0;
+            if (lane < m) {
+                r = bg[lp * (int64_t)m + lane];
+                const double* Ti = Ts + lane * NS;
+                for (int j = 0; j < n; ++j) r -= Ti[j] * xs[j];
+            } else { blo[lane] = -INFINITY; bhi[lane] = INFINITY; bcost[lane] = 0.0; basis[lane] = -1; }
+            beta[lane] = r;
+            cb[lane] = 0.0; colq[lane] = 0.0;
         }
         __syncwarp();
 
         int status = ELP_STATUS_TIMEOUT, pivots = 0, degenerate_run = 0, bland = 0, qfinal = -1;
         if (bad) status = ELP_STATUS_INFEASIBLE;
+        double d[CPL];                       // reduced costs of my columns (phase 2: carried across pivots)
+        bool d_fresh_enough = false;
+        int d_age = 0;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) d[c] = 0.0;
 
         while (!bad) {
             // ---- phase detection: row i on lane i --------------------------------------------------
@@ -585,18 +546,24 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             const bool phase1 = __any_sync(0xffffffffu, g != 0.0);
             if (lane < m) cb[lane] = phase1 ? g : bcost[lane];
             __syncwarp();
-            // ---- pricing on my columns -------------------------------------------------------------
+            // ---- pricing on my columns.  In phase 2 the reduced costs d_j = c_j - cb' T_j are carried in registers
+            // from pivot to pivot (d -= d_q * pivot row, the objective row of the textbook tableau) and recomputed
+            // from the tableau every 32 pivots, on a phase change, and before optimality is declared. -----------
             WVI cand{0.0, -1};
-            {
-                double d[CPL];
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if (phase1 || !d_fresh_enough) {
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) d[c] = phase1 ? 0.0 : ccost[c];
+                    for (int c = 0; c < CPL; ++c) d[c] = phase1 ? 0.0 : ccost[c];
 #pragma unroll
-                for (int i = 0; i < MR; ++i) {
-                    const double cbi = cb[i];
+                    for (int i = 0; i < MR; ++i) {
+                        const double cbi = cb[i];
 #pragma unroll
-                    for (int c = 0; c < CPL; ++c) d[c] -= cbi * T[c][i];
+                        for (int c = 0; c < CPL; ++c) d[c] -= cbi * Tl[i * NS + 32 * c];
+                    }
+                    d_age = 0;
                 }
+                d_fresh_enough = !phase1;
+                cand.v = 0.0; cand.i = -1;
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
                     const int col = lane + 32 * c;
@@ -611,18 +578,19 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
                     const bool take = cand.i < 0 || (bland ? key < cand.v : (key > cand.v || (key == cand.v && id < cand.i)));
                     if (take) { cand.v = key; cand.i = id; }
                 }
+                if (bland) cand.i = warp_best_bland((int)cand.v, cand.i);
+                else cand = warp_best_nonneg(cand);
+                if (cand.i >= 0 || d_age == 0) break;      // a candidate, or no candidate on freshly computed costs
+                d_fresh_enough = false;                    // optimality is only declared on recomputed costs
             }
-            if (bland) cand.i = warp_best_bland((int)cand.v, cand.i);
-            else cand = warp_best_nonneg(cand);
             if (cand.i < 0) { status = phase1 ? ELP_STATUS_INFEASIBLE : ELP_STATUS_OPTIMAL; break; }
             if (pivots >= max_pivots) { status = ELP_STATUS_TIMEOUT; break; }
             const int q = cand.i >> 1;
             const double dir = (cand.i & 1) ? -1.0 : 1.0;
             const int qlane = q & 31, qc = q >> 5;
-            // ---- entering column to shared memory; its scalars by shuffle ----------------------------
+            // ---- entering column: row i on lane i reads T[i][q]; its scalars come from the owner by shuffle ----
             double q_lo = 0.0, q_hi = 0.0, q_xn = 0.0, q_cost = 0.0;
             int q_state = 0;
-            if (lane == qlane) tab_store_col<MR, CPL>(T, qc, colq);
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
                 if (c == qc) { q_lo = clo[c]; q_hi = chi[c]; q_xn = cxn[c]; q_cost = ccost[c]; q_state = cstate[c]; }
@@ -631,12 +599,17 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             q_xn = __shfl_sync(0xffffffffu, q_xn, qlane);
             q_cost = __shfl_sync(0xffffffffu, q_cost, qlane);
             q_state = __shfl_sync(0xffffffffu, q_state, qlane);
-            __syncwarp();
+            double d_q = 0.0;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) if (c == qc) d_q = d[c];
+            d_q = __shfl_sync(0xffffffffu, d_q, qlane);
+            const double cq = (lane < MR) ? Ts[lane * NS + q] : 0.0;
+            if (lane < MR) colq[lane] = cq;
             // ---- ratio test: row i on lane i ---------------------------------------------------------
             double tloc = INFINITY, a = 0.0;
             int up = 0, kbas = -1;
             if (lane < m) {
-                a = dir * colq[lane];
+                a = dir * cq;
                 if (fabs(a) > TOL_PIVOT) {
                     kbas = basis[lane];
                     const double bi = beta[lane], l = blo[lane], u = bhi[lane];
@@ -663,7 +636,7 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
                         if (c == qc && lane == qlane) cxn[c] = dir > 0 ? INFINITY : -INFINITY;
                     break;
                 }
-                if (lane < m) beta[lane] -= dir * tflip * colq[lane];
+                if (lane < m) beta[lane] -= dir * tflip * cq;
 #pragma unroll
                 for (int c = 0; c < CPL; ++c) {
                     if (c == qc && lane == qlane) {
@@ -685,21 +658,17 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             const int r = rc.i >> 1;
             const int to_upper = rc.i & 1;
             const double t = tmin;
+            __syncwarp();                                  // colq is complete
             const double piv = colq[r];
             const int kl = basis[r];                       // leaving variable (a column id)
             const double kl_bound = to_upper ? bhi[r] : blo[r];
-            __syncwarp();                                  // everyone has read row r before it is rewritten
-            if (lane < m) beta[lane] -= dir * t * colq[lane];
-            // pivot row of my columns (registers cannot be indexed by the dynamic row: a select chain)
+            if (lane < m) beta[lane] -= dir * t * cq;
+            // pivot row of my columns: the dynamic row is just an address in shared memory
             double rr[CPL];
+            const double* Tr = Tl + r * NS;
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                double v = 0.0;
-#pragma unroll
-                for (int i = 0; i < MR; ++i) v = (i == r) ? T[c][i] : v;
-                rr[c] = v / piv;
-            }
-            __syncwarp();
+            for (int c = 0; c < CPL; ++c) rr[c] = Tr[32 * c] / piv;
+            __syncwarp();                                  // everyone has read row r before it is rewritten
             // bookkeeping by the owners
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
@@ -712,14 +681,23 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
                     basis[r] = q; blo[r] = q_lo; bhi[r] = q_hi; bcost[r] = q_cost;
                 }
             }
-            // ---- rank-1 update of my columns:  T -= colq * rr, row r := rr.  Column q needs no special case:
-            // its rr is exactly 1 and its entries ARE colq, so f - f*1 = 0 exactly and row r becomes 1. -----------
+            // ---- rank-1 update of my columns:  T[i] -= colq[i] * rr for i != r, row r := rr.  Column q needs no
+            // special case: its rr is exactly 1 and its entries ARE colq, so f - f*1 = 0 exactly. ----------------
 #pragma unroll
             for (int i = 0; i < MR; ++i) {
                 const double f = colq[i];
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) T[c][i] = (i == r) ? rr[c] : T[c][i] - f * rr[c];
+                for (int c = 0; c < CPL; ++c) Tl[i * NS + 32 * c] -= f * rr[c];
             }
+            {
+                double* Trw = Tl + r * NS;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) Trw[32 * c] = rr[c];
+            }
+            // objective row: the entering column's reduced cost becomes exactly 0 (its rr is 1)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) d[c] -= d_q * rr[c];
+            if (++d_age >= 32) d_fresh_enough = false;
             ++pivots;
             if (t <= 1e-12) { if (++degenerate_run > 30) bland = 1; }
             else { degenerate_run = 0; bland = 0; }
@@ -750,19 +728,21 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             if (pivots_out) pivots_out[lp] = pivots;
         }
         if (y_out) {
-            // y_i = sum_k cost[basis[k]] * Tslack[k][i]: the owner of slack column n+i has that column in registers
+            // y_i = sum_k cost[basis[k]] * Tslack[k][i]: slack column n+i belongs to one lane
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const int col = lane + 32 * c;
                 if (col >= n && col < N) {
                     double s = 0.0;
 #pragma unroll
-                    for (int k = 0; k < MR; ++k) s += bcost[k] * T[c][k];
+                    for (int k = 0; k < MR; ++k) s += bcost[k] * Tl[k * NS + 32 * c];
                     y_out[lp * (int64_t)m + (col - n)] = maximize ? -s : s;
                 }
             }
         }
         __syncwarp();
+        // leave the tableau clean for the next LP: structural columns are overwritten by the copies / loads,
+        // padding never changes, the slack block is rewritten at setup — nothing to do.
     }
 }
 
@@ -797,15 +777,14 @@ static void simplex_warp_launch_inst(int64_t B, int m, int n, const double* A, c
                                      const double* lb, const double* ub, const int8_t* sense, int maximize, int max_pivots,
                                      int32_t* status, double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st) {
     auto kern = simplex_warp_kernel<MR, CPL>;
-    const WarpSimplexLayout lay(m, n, MR);
+    const WarpSimplexLayout lay(MR, CPL);
     const size_t smem = (size_t)SW_WARPS * lay.total;
     ELP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     ELP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SW_WARPS * 32, smem));
     occ = std::max(1, occ);
     auto al16 = [](const void* p) { return p == nullptr || (((uintptr_t)p) & 15) == 0; };
-    const int use_tma = (m % 2 == 0) && (n % 2 == 0) && al16(A) && al16(b) && al16(c) && al16(lb) && al16(ub) &&
-                        env_flag("ELP_SIMPLEX_TMA", 1);
+    const int use_tma = (n % 2 == 0) && al16(A) && env_flag("ELP_SIMPLEX_TMA", 1);   // 16-byte rows
     const int64_t want = (B + SW_WARPS - 1) / SW_WARPS;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * occ));
     ELP_LAUNCH(kern, grid, SW_WARPS * 32, smem, st, B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, use_tma, status,
@@ -819,8 +798,7 @@ static bool simplex_warp_launch(int64_t B, int m, int n, const double* A, const 
     const int N = m + n;
     if (m > 32 || N > 96) return false;
     const int mr = std::max(4, (m + 3) / 4 * 4), cpl = (N + 31) / 32;
-    if (mr * cpl > 72) return false;                       // register budget of the tableau (doubles per lane)
-    const size_t smem = (size_t)SW_WARPS * WarpSimplexLayout(m, n, mr).total;
+    const size_t smem = (size_t)SW_WARPS * WarpSimplexLayout(mr, cpl).total;
     if (smem > 200 * 1024) return false;
 #define ELP_SW(MR_, CPL_)                                                                                              \
     if (mr == MR_ && cpl == CPL_) {                                                                                    \
@@ -830,7 +808,7 @@ static bool simplex_warp_launch(int64_t B, int m, int n, const double* A, const 
     }
     ELP_SW(4, 1) ELP_SW(8, 1) ELP_SW(12, 1) ELP_SW(16, 1) ELP_SW(20, 1) ELP_SW(24, 1) ELP_SW(28, 1) ELP_SW(32, 1)
     ELP_SW(4, 2) ELP_SW(8, 2) ELP_SW(12, 2) ELP_SW(16, 2) ELP_SW(20, 2) ELP_SW(24, 2) ELP_SW(28, 2) ELP_SW(32, 2)
-    ELP_SW(4, 3) ELP_SW(8, 3) ELP_SW(12, 3) ELP_SW(16, 3) ELP_SW(20, 3) ELP_SW(24, 3)
+    ELP_SW(4, 3) ELP_SW(8, 3) ELP_SW(12, 3) ELP_SW(16, 3) ELP_SW(20, 3) ELP_SW(24, 3) ELP_SW(28, 3) ELP_SW(32, 3)
 #undef ELP_SW
     return false;
 }
