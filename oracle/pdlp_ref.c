@@ -235,7 +235,7 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
         pobj = po; dobj = dobj_r + dobj_c;
         rp = sqrt(pres2) / (1 + norm_b); rd = sqrt(dres2) / (1 + norm_c);
         rg = fabs(pobj - dobj) / (1 + fabs(pobj) + fabs(dobj));
-        if (rp <= eps && rd <= eps && rg <= eps) { status = 0; break; }
+        if (rp <= eps && rd <= eps && rg <= 0.25 * eps) { status = 0; break; }   /* gap at eps/4: see pdlp.cu */
         if (need_fpe0) { fpe0 = fpe; need_fpe0 = 0; }
         int restart = 0;
         if (k > 0) {

@@ -185,7 +185,7 @@ def solve(m, n, row_ptr, col_idx, vals, sense, rhs, c, lb, ub, maximize=False,
                 print(f"it {total+1:7d} pres {q['pres']:.3e} dres {q['dres']:.3e} gap {q['gap']:.3e} "
                       f"pobj {q['pobj']:.9e} fpe {fpe:.3e} w {w:.3e} restarts {n_restart}")
             ok = (q["pres"] <= eps * (1 + norm_b) and q["dres"] <= eps * (1 + norm_c)
-                  and q["gap"] <= eps * (1 + abs(q["pobj"]) + abs(q["dobj"])))
+                  and q["gap"] <= 0.25 * eps * (1 + abs(q["pobj"]) + abs(q["dobj"])))   # eps/4: see pdlp.cu
             if ok:
                 status = STATUS_OPTIMAL
                 best = (xu, yu, q)
