@@ -52,11 +52,13 @@ __host__ __device__ inline SpmvStageLayout spmv_stage_layout(int cap, int rw, in
 
 constexpr int SPMV_WARPS = 4;      // warps per CTA (a CTA is only a container: warps never talk)
 
-template <int L, int NSTW, class Epi>
-__global__ void __launch_bounds__(SPMV_WARPS * 32, 6)
+template <int L, int RPL, class Epi>
+__global__ void __launch_bounds__(SPMV_WARPS * 32, 6 / RPL)
 spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, const int* __restrict__ idx,
                  const double* __restrict__ val, const double* __restrict__ vec, Epi epi) {
-    constexpr int RW = 32 / L;               // rows per warp tile
+    constexpr int NSTW = 2;                  // stages per warp: one being consumed, one in flight
+    constexpr int G = 32 / L;                // lane groups per warp
+    constexpr int RW = G * RPL;              // rows per warp tile: group g owns rows g, g + G, ...
     constexpr int NIN = Epi::NIN;
     constexpr int U = (L <= 2) ? 8 : 4;      // gathers in flight per lane
     constexpr int OPS = (RW + 1) & ~1;       // doubles per staged operand
@@ -128,14 +130,16 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     for (int s = 0; s < NSTW; ++s) issue(s);
 
     // ---- consumer ------------------------------------------------------------------------------------------
-    const int g = lane / L;                // row of the tile this lane group owns
+    const int g = lane / L;                // first row of the tile this lane group owns
     const int sub = lane % L;
     int q = 0;
     for (int tile = gw; tile < ntiles; tile += nw) {
-        const int row = tile * RW + g;
-        int st = 0, en = 0, a0 = 0, a1 = 0;
-        typename Epi::Pre pre{};
-        double acc = 0.0;
+        const int row0 = tile * RW + g;
+        int st[RPL], en[RPL], a0 = 0, a1 = 0;
+        typename Epi::Pre pre[RPL];
+        double acc[RPL];
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) { st[j] = 0; en[j] = 0; acc[j] = 0.0; pre[j] = typename Epi::Pre{}; }
         for (int piece = 0;; ++piece) {
             const int stage = q % NSTW;
             mbar_wait(&full[stage], (uint32_t)(q / NSTW) & 1u);
@@ -145,10 +149,13 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
                 const int rows = min(RW, nrows - tile * RW);
                 a0 = sp[0] & ~3;
                 a1 = (sp[rows] + 3) & ~3;
-                if (row < nrows) {
-                    st = sp[g];
-                    en = sp[g + 1];
-                    if (sub == 0) pre = epi.preload(reinterpret_cast<const double*>(sb + lay.off_ops), OPS, g);
+#pragma unroll
+                for (int j = 0; j < RPL; ++j) {
+                    if (row0 + j * G < nrows) {
+                        st[j] = sp[g + j * G];
+                        en[j] = sp[g + j * G + 1];
+                        if (sub == 0) pre[j] = epi.preload(reinterpret_cast<const double*>(sb + lay.off_ops), OPS, g + j * G);
+                    }
                 }
             }
             const int pstart = a0 + piece * cap;
@@ -156,35 +163,56 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             // index the stage by global entry id
             const double* sv = reinterpret_cast<const double*>(sb) - pstart;
             const int* si = reinterpret_cast<const int*>(sb + lay.off_idx) - pstart;
-            const int f = min(en, pend);
-            for (int k0 = max(st, pstart) + sub; k0 < f; k0 += U * L) {
+            int k[RPL], f[RPL];
+            bool more = false;
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                k[j] = max(st[j], pstart) + sub;
+                f[j] = min(en[j], pend);
+                more |= k[j] < f[j];
+            }
+            while (more) {
+                // the RPL rows of a lane advance together: their gathers are independent and overlap.
                 // indices first, gathers next, the values are read from the stage only when they are consumed
-                double x[U];
-                int c[U];
+                double x[RPL][U];
+                int c[RPL][U];
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (k0 + u * L < f) c[u] = si[k0 + u * L];
+                for (int j = 0; j < RPL; ++j)
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (k0 + u * L < f) x[u] = ldg_hint(vec + c[u], pol_keep);
+                    for (int u = 0; u < U; ++u)
+                        if (k[j] + u * L < f[j]) c[j][u] = si[k[j] + u * L];
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (k0 + u * L < f) acc = __dadd_rn(acc, __dmul_rn(sv[k0 + u * L], x[u]));
+                for (int j = 0; j < RPL; ++j)
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (k[j] + u * L < f[j]) x[j][u] = ldg_hint(vec + c[j][u], pol_keep);
+#pragma unroll
+                for (int j = 0; j < RPL; ++j)
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (k[j] + u * L < f[j]) acc[j] = __dadd_rn(acc[j], __dmul_rn(sv[k[j] + u * L], x[j][u]));
+                more = false;
+#pragma unroll
+                for (int j = 0; j < RPL; ++j) { k[j] += U * L; more |= k[j] < f[j]; }
             }
             __syncwarp();                      // every lane is done reading the stage
             issue(stage);
             ++q;
             if (pend >= a1) break;
         }
-        if (L > 1) acc = group_sum<L>(acc);
-        if (sub == 0 && row < nrows) epi.apply(row, acc, pre);
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            double a = acc[j];
+            if (L > 1) a = group_sum<L>(a);
+            if (sub == 0 && row0 + j * G < nrows) epi.apply(row0 + j * G, a, pre[j]);
+        }
     }
 }
 
 // ---- launch plan ---------------------------------------------------------------------------------
 struct SpmvPlan {
-    int L = 1, cap = 256, nstw = 2, ctas_per_sm = 4, ntiles = 0;
-    int rw() const { return 32 / L; }
+    int L = 1, rpl = 1, cap = 256, ctas_per_sm = 6, ntiles = 0;
+    int rw() const { return 32 / L * rpl; }
 };
 
 inline int env_int(const char* name, int dflt) {
@@ -201,7 +229,7 @@ inline int pick_lanes(int64_t nnz, int64_t nrows) {
 }
 
 inline size_t spmv_smem_bytes(const SpmvPlan& p, int nin) {
-    return (size_t)SPMV_WARPS * p.nstw * (spmv_stage_layout(p.cap, p.rw(), nin).bytes + 8);
+    return (size_t)SPMV_WARPS * 2 * (spmv_stage_layout(p.cap, p.rw(), nin).bytes + 8);
 }
 
 // nin_max: the largest operand count among the epilogues that will run with this plan
@@ -212,6 +240,7 @@ inline SpmvPlan plan_spmv(int64_t nnz, int nrows, int nin_max, int force_lanes =
     if (force_lanes > 0) p.L = force_lanes;
     if (const int l = env_int("ELP_SPMV_L", 0)) p.L = l;       // debugging / sweeps
     if (p.L != 1 && p.L != 2 && p.L != 4 && p.L != 8) p.L = 1;   // RW = 32/L >= 4 keeps the tile copies 16-byte aligned
+    p.rpl = env_int("ELP_SPMV_RPL", 1) == 2 ? 2 : 1;   // measured on C4: two rows per lane (half the warps) is ~12 % slower
     const int rw = p.rw();
     // stage capacity: mean tile + ~1.5 sigma of a Poisson-like spread; the few larger tiles are walked in pieces
     const double mean = avg * rw;
@@ -221,22 +250,20 @@ inline SpmvPlan plan_spmv(int64_t nnz, int nrows, int nin_max, int force_lanes =
     if (const int c = env_int("ELP_SPMV_CAP", 0)) cap = std::max(16, c / 4 * 4);
     p.cap = (int)cap;
     p.ntiles = ceil_div(nrows, rw);
-    p.nstw = env_int("ELP_SPMV_NST", 2);
-    if (p.nstw < 2 || p.nstw > 3) p.nstw = 2;
-    // residency: as many CTAs as 64 K registers allow (80 per thread -> 6) inside 196 KB of shared memory.
+    // residency: as many CTAs as 64 K registers allow (6 CTAs of 4 warps at 80 per thread, 3 at 160 for two rows per lane) inside 196 KB of shared memory.
     // Measured on B200: once the CTAs of an SM take more than the 196 KB carve-out step, the L1 left over
     // for the gathers is too small and the kernel slows down by ~30 %.
     const size_t per_cta = spmv_smem_bytes(p, nin_max) + 1024;      // + the 1 KB the system reserves per CTA
-    int ctas = (int)std::min<size_t>(196 * 1024 / per_cta, 6);
+    int ctas = (int)std::min<size_t>(196 * 1024 / per_cta, 6 / p.rpl);
     if (const int c = env_int("ELP_SPMV_CTAS", 0)) ctas = c;
     p.ctas_per_sm = std::max(1, ctas);
     return p;
 }
 
-template <int L, int NSTW, class Epi>
+template <int L, int RPL, class Epi>
 void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val,
                       const double* vec, const Epi& epi, cudaStream_t st) {
-    auto kern = spmv_warp_kernel<L, NSTW, Epi>;
+    auto kern = spmv_warp_kernel<L, RPL, Epi>;
     const size_t smem = spmv_smem_bytes(p, Epi::NIN);
     ELP_REQUIRE(smem <= 227 * 1024, "spmv: stage ring of %zu bytes does not fit in shared memory", smem);
     // per device and ring size: raise the dynamic shared-memory limit once and ask how many CTAs really fit
@@ -252,7 +279,7 @@ void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* i
         cfg_occ[dev] = std::max(1, occ);
         cfg_smem[dev] = smem + 1;
         if (env_int("ELP_SPMV_DEBUG", 0))
-            fprintf(stderr, "[spmv] L=%d nstw=%d nin=%d cap=%d smem/CTA=%zu planned CTAs/SM=%d resident=%d tiles=%d\n", L, NSTW,
+            fprintf(stderr, "[spmv] L=%d rpl=%d nin=%d cap=%d smem/CTA=%zu planned CTAs/SM=%d resident=%d tiles=%d\n", L, RPL,
                     Epi::NIN, p.cap, smem, p.ctas_per_sm, occ, p.ntiles);
     }
     // persistent grid: exactly one wave
@@ -264,10 +291,8 @@ void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* i
 template <int L, class Epi>
 void launch_spmv_l(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val, const double* vec,
                    const Epi& epi, cudaStream_t st) {
-    switch (p.nstw) {
-        case 3:  launch_spmv_inst<L, 3, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
-        default: launch_spmv_inst<L, 2, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
-    }
+    if (p.rpl == 1) launch_spmv_inst<L, 1, Epi>(p, nrows, ptr, idx, val, vec, epi, st);
+    else launch_spmv_inst<L, 2, Epi>(p, nrows, ptr, idx, val, vec, epi, st);
 }
 
 template <class Epi>

@@ -33,9 +33,10 @@ def check(m, n, lens, seed):
 
 allok = True
 rng = np.random.default_rng(0)
-for cap, lanes in (("0", "1"), ("64", "1"), ("16", "1"), ("0", "2"), ("0", "4"), ("64", "8"), ("0", "8"), ("32", "4")):
+for cap, lanes in (("0", "1"), ("64", "1"), ("16", "1"), ("0", "2"), ("0", "4"), ("64", "8"), ("0", "8"), ("32", "4"), ("16", "2")):
     os.environ["ELP_SPMV_CAP"] = cap
     os.environ["ELP_SPMV_L"] = lanes
+    os.environ["ELP_SPMV_RPL"] = "1" if cap == "64" else "2"
     allok &= check(1, 5, [3], 1)
     allok &= check(7, 9, [0, 2, 0, 0, 5, 1, 0], 2)
     allok &= check(300, 50, rng.integers(0, 14, 300), 3)
@@ -43,7 +44,7 @@ for cap, lanes in (("0", "1"), ("64", "1"), ("16", "1"), ("0", "2"), ("0", "4"),
     allok &= check(5, 3000, [0, 2500, 1, 0, 9000], 5)      # rows longer than a stage -> pieces
     allok &= check(513, 100, np.r_[rng.integers(0, 3, 512), 700], 6)
 os.environ["ELP_SPMV_CAP"] = "0"
-os.environ.pop("ELP_SPMV_L")
+os.environ.pop("ELP_SPMV_L"); os.environ.pop("ELP_SPMV_RPL")
 print("ALL SPMV OK" if allok else "SPMV MISMATCH", flush=True)
 if not allok:
     sys.exit(1)
@@ -54,8 +55,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "sweep":
     b_csc = 12 * nnz + 4 * (n + 1) + 8 * m + 56 * n
     b_csr = 12 * nnz + 4 * (m + 1) + 8 * n + 40 * m
     os.environ["ELP_SPMV_DEBUG"] = "1"
-    for lanes, ctas, nst, capsig in ((0, 0, 2, 100), (0, 0, 2, 200), (0, 0, 2, 50), (0, 0, 2, 0)):
+    for lanes, ctas, nst, capsig in ((0, 0, 2, 100), (0, 0, 1, 100), (0, 2, 2, 100), (0, 0, 2, 200), (0, 0, 2, 0), (1, 0, 2, 100), (2, 0, 2, 100)):
         carve = 0
+        os.environ["ELP_SPMV_RPL"] = str(nst)       # third field: rows per lane
         cw, capmul = lanes, capsig
         os.environ.update(ELP_SPMV_L=str(lanes), ELP_SPMV_CTAS=str(ctas), ELP_SPMV_NST=str(nst),
                           ELP_SPMV_CAPSIG_PCT=str(capsig))
