@@ -46,7 +46,7 @@ class Stats(C.Structure):
 # every symbol include/easylp_abi.h declares (tests/test_abi_symbols.py checks the header against this)
 ABI_SYMBOLS = [
     "elp_version", "elp_last_error", "elp_device_count", "elp_set_device", "elp_default_options",
-    "elp_status_string", "elp_kernel_launches", "elp_assemble_csr", "elp_solve_lp", "elp_solve_batch",
+    "elp_status_string", "elp_kernel_launches", "elp_release_workspace", "elp_assemble_csr", "elp_solve_lp", "elp_solve_batch",
     "elp_batch_create", "elp_batch_run", "elp_batch_fetch", "elp_batch_destroy", "elp_spmv",
     "elp_check_feasible", "elp_pdlp_create", "elp_pdlp_run", "elp_pdlp_reset", "elp_pdlp_solution",
     "elp_pdlp_probe_spmv", "elp_pdlp_probe_step", "elp_pdlp_destroy", "elp_comm_unique_id", "elp_comm_init", "elp_comm_size",
@@ -120,6 +120,11 @@ def status_string(status: int) -> str:
 
 def kernel_launches() -> int:
     return int(lib().elp_kernel_launches())
+
+
+def release_workspace() -> None:
+    """Frees the calling thread's cached device scratch (the assembly keeps a grow-only workspace)."""
+    _check(lib().elp_release_workspace())
 
 
 def default_options(**kw) -> Options:

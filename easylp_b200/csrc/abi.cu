@@ -13,6 +13,12 @@ thread_local std::string g_last_error;
 
 // implemented in the other translation units
 struct Pdlp;
+struct AsmIo {
+    int32_t *row, *col, *out_ptr, *out_col;
+    double *val, *out_val;
+};
+AsmIo asm_io_buffers(size_t T, size_t m);
+void asm_workspace_release();
 int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_col, const double* d_val, int32_t m,
                             int32_t n, int32_t* d_row_ptr, int32_t* d_col_idx, double* d_vals, cudaStream_t st);
 Pdlp* pdlp_create(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
@@ -140,6 +146,12 @@ const char* elp_status_string(int32_t status) {
 
 int64_t elp_kernel_launches(void) { return elp::g_launches.load(); }
 
+int elp_release_workspace(void) {
+    ELP_TRY
+    asm_workspace_release();
+    ELP_CATCH
+}
+
 int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
                      int32_t m, int32_t n, int32_t* row_ptr, int32_t* col_idx, double* vals, int64_t* nnz_out,
                      elp_stats* stats) {
@@ -150,17 +162,22 @@ int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* te
     ELP_REQUIRE(n_terms >= 0 && m >= 0 && n >= 0, "assemble: negative size");
     cudaStream_t st = 0;
     const size_t T = (size_t)n_terms;
-    DevBuf<int32_t> drow(std::max<size_t>(T, 1)), dcol(std::max<size_t>(T, 1)), dptr((size_t)m + 1), dci(std::max<size_t>(T, 1));
-    DevBuf<double> dval(std::max<size_t>(T, 1)), dv(std::max<size_t>(T, 1));
-    drow.upload(term_row, T, st); dcol.upload(term_col, T, st); dval.upload(term_val, T, st);
+    const AsmIo io = asm_io_buffers(std::max<size_t>(T, 1), (size_t)m);      // cached staging (grow-only workspace)
+    if (T) {
+        ELP_CUDA(cudaMemcpyAsync(io.row, term_row, T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        ELP_CUDA(cudaMemcpyAsync(io.col, term_col, T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        ELP_CUDA(cudaMemcpyAsync(io.val, term_val, T * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     cudaEvent_t e0, e1;
     ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
     ELP_CUDA(cudaEventRecord(e0, st));
-    const int64_t nnz = assemble_csr_device(n_terms, drow.p, dcol.p, dval.p, m, n, dptr.p, dci.p, dv.p, st);
+    const int64_t nnz = assemble_csr_device(n_terms, io.row, io.col, io.val, m, n, io.out_ptr, io.out_col, io.out_val, st);
     ELP_CUDA(cudaEventRecord(e1, st));
-    dptr.download(row_ptr, (size_t)m + 1, st);
-    dci.download(col_idx, (size_t)nnz, st);
-    dv.download(vals, (size_t)nnz, st);
+    ELP_CUDA(cudaMemcpyAsync(row_ptr, io.out_ptr, ((size_t)m + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (nnz) {
+        ELP_CUDA(cudaMemcpyAsync(col_idx, io.out_col, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaMemcpyAsync(vals, io.out_val, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     ELP_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);

@@ -13,6 +13,7 @@
 //
 // Roofline: HBM-bound streaming passes.  Algorithmic bytes: 16*T + 12*nnz + 4*(m+1).
 #include "common.cuh"
+#include <cstdlib>
 #include "primitives.cuh"
 #include "../../include/easylp_abi.h"
 
@@ -77,6 +78,48 @@ __global__ void asm_empty_row_ptr(int32_t* row_ptr, uint32_t m) {
     if (i <= m) row_ptr[i] = 0;
 }
 
+// Grow-only device workspace of the assembly (per host thread; re-created when the thread switches device).
+struct AsmWorkspace {
+    int device = -1;
+    DevBuf<uint64_t> keys;
+    DevBuf<uint32_t> perm, keep, pos, nnz_d;
+    DevBuf<double> sums;
+    DevBuf<int32_t> rows_c;
+    DevBuf<int> bad;
+    RadixSortWorkspace sort;
+    // staging of the host entry point (elp_assemble_csr)
+    DevBuf<int32_t> in_row, in_col, out_ptr, out_col;
+    DevBuf<double> in_val, out_val;
+    void release() { *this = AsmWorkspace{}; }
+    void ensure(size_t T) {
+        int dev = 0;
+        ELP_CUDA(cudaGetDevice(&dev));
+        if (dev != device) { release(); device = dev; }
+        auto grow = [](auto& b, size_t n) { if (b.n < n) b.alloc(n + n / 8); };
+        grow(keys, T); grow(perm, T); grow(keep, T); grow(pos, T); grow(sums, T); grow(rows_c, T);
+        grow(nnz_d, 1); grow(bad, 1);
+    }
+    void ensure_io(size_t T, size_t m) {
+        ensure(T);
+        auto grow = [](auto& b, size_t n) { if (b.n < n) b.alloc(n + n / 8); };
+        grow(in_row, T); grow(in_col, T); grow(in_val, T); grow(out_col, T); grow(out_val, T); grow(out_ptr, m + 1);
+    }
+};
+AsmWorkspace& asm_workspace() {
+    static thread_local AsmWorkspace w;
+    return w;
+}
+void asm_workspace_release() { asm_workspace().release(); }
+struct AsmIo {
+    int32_t *row, *col, *out_ptr, *out_col;
+    double *val, *out_val;
+};
+AsmIo asm_io_buffers(size_t T, size_t m) {
+    AsmWorkspace& w = asm_workspace();
+    w.ensure_io(T, m);
+    return AsmIo{w.in_row.p, w.in_col.p, w.out_ptr.p, w.out_col.p, w.in_val.p, w.out_val.p};
+}
+
 // Device-resident assembly: inputs/outputs are device pointers.  d_col_idx/d_vals need room for T.
 // Returns nnz (synchronises the stream once to read it back).
 int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_col, const double* d_val, int32_t m,
@@ -91,20 +134,36 @@ int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_co
     ELP_REQUIRE(T < 0xffffffffll, "assemble: too many terms");
     ELP_REQUIRE(n > 0, "assemble: terms but no columns");
     const uint32_t Tu = (uint32_t)T;
-    DevBuf<uint64_t> keys(T);
-    DevBuf<uint32_t> perm(T), keep(T), pos(T), nnz_d(1);
-    DevBuf<double> sums(T);
-    DevBuf<int32_t> rows_c(T);
-    DevBuf<int> bad(1);
-    bad.zero(st);
-    RadixSortWorkspace ws;
+    WallTimer dbg_t;
+    const bool dbg = getenv("ELP_ASM_DEBUG") != nullptr;
+    auto mark = [&](const char* what) {
+        if (!dbg) return;
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[assemble] %-14s %9.3f ms\n", what, dbg_t.ms());
+    };
+    // Temporaries come from a grow-only per-thread workspace: cudaMalloc/cudaFree of ~50 B per term cost tens of
+    // milliseconds per call, far more than the kernels (3.2 ms for 21 M terms).
+    AsmWorkspace& w = asm_workspace();
+    w.ensure(T);
+    DevBuf<uint64_t>& keys = w.keys;
+    DevBuf<uint32_t>&perm = w.perm, &keep = w.keep, &pos = w.pos, &nnz_d = w.nnz_d;
+    DevBuf<double>& sums = w.sums;
+    DevBuf<int32_t>& rows_c = w.rows_c;
+    DevBuf<int>& bad = w.bad;
+    ELP_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    RadixSortWorkspace& ws = w.sort;
     const int grid = ceil_div(T, 256);
+    mark("alloc");
     ELP_LAUNCH(asm_make_keys, grid, 256, 0, st, d_row, d_col, Tu, (uint32_t)m, (uint32_t)n, keys.p, perm.p, bad.p);
     const int nbits = bit_length_u64((uint64_t)m * (uint64_t)n - 1);
+    mark("keys");
     radix_sort_pairs(keys.p, perm.p, T, nbits, ws, st);
+    mark("sort");
     ELP_LAUNCH(asm_segment_fold, grid, 256, 0, st, keys.p, perm.p, d_val, Tu, sums.p, keep.p);
     ELP_CUDA(cudaMemcpyAsync(pos.p, keep.p, T * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    mark("fold");
     exclusive_scan_u32(pos.p, T, ws.scan, st);
+    mark("scan");
     ELP_LAUNCH(asm_compact, grid, 256, 0, st, keys.p, sums.p, keep.p, pos.p, Tu, (uint32_t)n, d_col_idx, d_vals,
                rows_c.p, nnz_d.p);
     ELP_LAUNCH(asm_row_ptr, ceil_div(T + 1, 256), 256, 0, st, rows_c.p, nnz_d.p, (uint32_t)m, d_row_ptr, Tu);
@@ -113,6 +172,7 @@ int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_co
     ELP_CUDA(cudaMemcpyAsync(&nnz, nnz_d.p, sizeof nnz, cudaMemcpyDeviceToHost, st));
     ELP_CUDA(cudaMemcpyAsync(&bad_h, bad.p, sizeof bad_h, cudaMemcpyDeviceToHost, st));
     ELP_CUDA(cudaStreamSynchronize(st));
+    mark("compact+ptr");
     ELP_REQUIRE(!bad_h, "assemble: a term has row/col outside [0,%d) x [0,%d)", m, n);
     return (int64_t)nnz;
 }

@@ -84,6 +84,7 @@ int elp_set_device(int32_t device);
 int elp_default_options(elp_options* opt);
 const char* elp_status_string(int32_t status);       /* the strings of R/class.R:279-295 */
 int64_t elp_kernel_launches(void);                   /* process-wide counter of launched kernels */
+int elp_release_workspace(void);                     /* frees the calling thread's cached device scratch (assembly) */
 
 /* ---- (1) assembly: terms -> CSR ------------------------------------------------------------
  * Replaces the dense `constraint$mat` construction of `$con()`: rbind of evaluated atoms

@@ -206,3 +206,19 @@ def mcnf(K=50, gw=100, gh=200, extra_arcs=20_600, seed=0):
     c = np.tile(cost, K)
     return dict(m=m, n=n, row_ptr=row_ptr.astype(np.int32), col_idx=cols.astype(np.int32), vals=vals,
                 sense=sense, rhs=rhs, c=c, lb=np.zeros(n), ub=np.full(n, np.inf), maximize=False)
+
+
+def term_stream(p, dup_frac=0.05, seed=0):
+    """An emission-order term list whose canonical CSR is exactly p's matrix: every entry once, in a seeded random order,
+    with a fraction of the entries split into two halves (v/2 + v/2 folds back to v exactly) so that the ordered
+    duplicate fold of elp_assemble_csr has work to do.  Returns (row, col, val) int32/int32/float64."""
+    m = p["m"]
+    nnz = int(p["row_ptr"][m])
+    rows = np.repeat(np.arange(m, dtype=np.int32), np.diff(p["row_ptr"]))
+    rng = np.random.default_rng(seed)
+    dup = rng.random(nnz) < dup_frac
+    r = np.concatenate([rows, rows[dup]])
+    c = np.concatenate([p["col_idx"], p["col_idx"][dup]])
+    v = np.concatenate([np.where(dup, p["vals"] * 0.5, p["vals"]), p["vals"][dup] * 0.5])
+    perm = rng.permutation(r.size)
+    return r[perm], c[perm].astype(np.int32), v[perm]
