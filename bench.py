@@ -274,7 +274,15 @@ def bench_pdlp(args, dist, L, p, workload_name):
     peak, peak_src = measured_peak()
     # local matrix of this rank for the roofline (N = 1: the whole matrix)
     ml, nnzl = q["m"], int(q["row_ptr"][q["m"]])
-    b_csc, b_csr, b_iter = pdlp_bytes(ml, n, nnzl)
+    if N == 1:
+        b_csc, b_csr, b_iter = pdlp_bytes(ml, n, nnzl)
+    else:
+        # rank-local work: K1 on a column block (n/N columns, ~nnz/N entries, gathers the whole y),
+        # K2 on the row block (gathers the whole x-bar)
+        ncl, nnzc = -(-n // N), nnz // N
+        b_csc = 12 * nnzc + 4 * (ncl + 1) + 8 * m + 56 * ncl
+        b_csr = 12 * nnzl + 4 * (ml + 1) + 8 * n + 40 * ml
+        b_iter = b_csc + b_csr
     dom_ms, dom_b, dom_name, dom_key = \
         (ms_primal, b_csc, "spmv_warp_kernel<L,NSTW,PrimalEpi> (CSC A'y + fused primal update)", "primal") \
         if ms_primal >= ms_dual else \
@@ -288,7 +296,7 @@ def bench_pdlp(args, dist, L, p, workload_name):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name, "m": m, "n": n, "nnz": nnz, "eps_rel": 1e-6,
                    "step": "one complete PDLP solve to 1e-6 relative KKT (ms_per_step = time-to-1e-6-gap)",
-                   "parallelism": f"row-block x{N}" + (" + NCCL allreduce(A'y)" if N > 1 else ""),
+                   "parallelism": f"row-block x{N}" + (" (K2) + column-block (K1); x-bar / y blocks exchanged by peer stores over NVLink (NCCL all-gather fallback), scalars by NCCL allreduce" if N > 1 else ""),
                    "l2": "matrix (2 x %.0f MB/iter) exceeds the 126 MB L2; no flush needed" % (12 * nnz / 1e6)},
         "time_to_gap_s": dev_ms / args.steps / 1e3,
         "iterations_per_solve": iters / args.steps,

@@ -11,6 +11,11 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_api;
@@ -31,6 +36,11 @@ void load_api() {
     ELP_SYM(CommInitRank, "ncclCommInitRank");
     ELP_SYM(CommDestroy, "ncclCommDestroy");
     ELP_SYM(AllReduce, "ncclAllReduce");
+    ELP_SYM(AllGather, "ncclAllGather");
+    ELP_SYM(Send, "ncclSend");
+    ELP_SYM(Recv, "ncclRecv");
+    ELP_SYM(GroupStart, "ncclGroupStart");
+    ELP_SYM(GroupEnd, "ncclGroupEnd");
     ELP_SYM(GetErrorString, "ncclGetErrorString");
 #undef ELP_SYM
 }
@@ -74,6 +84,29 @@ void comm_destroy() {
 void comm_allreduce_sum(double* buf, size_t count, cudaStream_t stream) {
     if (!g_comm.active || count == 0) return;
     ELP_NCCL(g_api.AllReduce(buf, buf, count, ncclFloat64, ncclSum, g_comm.comm, stream));
+}
+
+void comm_allgather(double* buf, size_t count, cudaStream_t stream) {
+    if (!g_comm.active || count == 0) return;
+    ELP_NCCL(g_api.AllGather(buf + (size_t)g_comm.rank * count, buf, count, ncclFloat64, g_comm.comm, stream));
+}
+
+void comm_allgather_bytes(void* buf, size_t bytes, cudaStream_t stream) {
+    if (!g_comm.active || bytes == 0) return;
+    ELP_NCCL(g_api.AllGather((char*)buf + (size_t)g_comm.rank * bytes, buf, bytes, ncclInt8, g_comm.comm, stream));
+}
+
+void comm_group_start() { if (g_comm.active) ELP_NCCL(g_api.GroupStart()); }
+void comm_group_end() { if (g_comm.active) ELP_NCCL(g_api.GroupEnd()); }
+
+void comm_send(const void* buf, size_t bytes, int peer, cudaStream_t stream) {
+    if (!g_comm.active || bytes == 0) return;
+    ELP_NCCL(g_api.Send(buf, bytes, ncclInt8, peer, g_comm.comm, stream));
+}
+
+void comm_recv(void* buf, size_t bytes, int peer, cudaStream_t stream) {
+    if (!g_comm.active || bytes == 0) return;
+    ELP_NCCL(g_api.Recv(buf, bytes, ncclInt8, peer, g_comm.comm, stream));
 }
 
 void comm_allreduce_max(double* buf, size_t count, cudaStream_t stream) {

@@ -1,7 +1,8 @@
-// comm.cuh — NCCL plumbing for the row-partitioned PDLP (one process per GPU).
+// comm.cuh — NCCL plumbing for the partitioned PDLP (one process per GPU).
 // NCCL is resolved with dlopen at first use so that the single-GPU path (and the R package) has no
-// link-time NCCL dependency.  Only allreduce is needed: the partial A'y (sum), the scalar residual
-// partials (sum, packed in the tail of the same buffer) and the Ruiz column maxima (max).
+// link-time NCCL dependency.  Used: all-gather (the x-bar and y blocks every iteration, scaling vectors at
+// setup), allreduce (scalar residual partials), grouped send/recv (one-off exchange that builds each rank's
+// column block of A from the ranks' row blocks).
 #pragma once
 #include "common.cuh"
 #include <nccl.h>
@@ -21,5 +22,12 @@ void comm_destroy();
 // in-place allreduce on `stream`; no-op when the communicator is inactive
 void comm_allreduce_sum(double* buf, size_t count, cudaStream_t stream);
 void comm_allreduce_max(double* buf, size_t count, cudaStream_t stream);
+// in-place all-gather: rank r's `count` doubles live at buf + r*count before the call, everyone's after it
+void comm_allgather(double* buf, size_t count, cudaStream_t stream);
+void comm_allgather_bytes(void* buf, size_t bytes_per_rank, cudaStream_t stream);
+void comm_group_start();
+void comm_group_end();
+void comm_send(const void* buf, size_t bytes, int peer, cudaStream_t stream);
+void comm_recv(void* buf, size_t bytes, int peer, cudaStream_t stream);
 
 }  // namespace elp

@@ -18,9 +18,10 @@
 // the gathered vector (x: 8n bytes, y: 8m bytes) lives in the 126 MB L2.
 // Algorithmic bytes per iteration: 24 nnz + 4 (m+n+2) + 56 n + 40 m.
 //
-// Multi-GPU (row partition): each rank owns a row block (its CSR, the CSC of the same
-// block, its slice of y) and a replica of x.  K1 splits into [partial A_g'y_g] -> ncclAllReduce ->
-// [primal update]; scalar partial sums ride in the tail of the allreduce buffer at check points.
+// Multi-GPU: rank g owns a row block of A (for K2, its slice of y) AND a column block of A over all
+// rows (for K1, its slice of x).  Nothing is replicated; per iteration the x-bar blocks and the y blocks are
+// all-gathered over NVLink (8 (n + m) bytes received per rank) and the scalar residuals of a check travel in one
+// 16-double allreduce.  See `struct Pdlp`.
 #include "common.cuh"
 #include "primitives.cuh"
 #include "comm.cuh"
@@ -58,6 +59,14 @@ struct StoreEpi {
     __device__ __forceinline__ void apply(int r, double s, const Pre&) const { out[r] = s; }
 };
 
+// Where an epilogue publishes the block it produces: its own copy of the gathered vector, or — when the ranks have
+// mapped each other's buffers (CUDA IPC over NVLink) — the copy of EVERY rank, so that the all-gather is done by the
+// stores of the kernel itself, overlapped with the rest of the tile walk.
+struct PeerOut {
+    double* p[8];
+    int n;          // 0: single destination (the local pointer of the epilogue)
+};
+
 // primal half of T(z) + reflection + Halpern combine.  g = (A'y)_j
 template <bool CHECK>
 struct PrimalEpi {
@@ -71,6 +80,7 @@ struct PrimalEpi {
     double* __restrict__ xp;
     const PdlpParams* __restrict__ P;
     int it;
+    PeerOut peers;
     struct Pre { double x, c, l, u, x0; };
     __device__ __forceinline__ const double* in(int i) const {
         return i == 0 ? x : i == 1 ? c : i == 2 ? l : i == 3 ? u : x0;
@@ -91,7 +101,12 @@ struct PrimalEpi {
         const double tau = P->tau;
         const double xpj = fmin(fmax(p.x - tau * (p.c - g), p.l), p.u);
         const double xb = 2.0 * xpj - p.x;
-        xbar[j] = xb;
+        if (!CHECK && peers.n > 0) {
+#pragma unroll 8
+            for (int r = 0; r < peers.n; ++r) peers.p[r][j] = xb;
+        } else {
+            xbar[j] = xb;
+        }
         if (CHECK) {
             xp[j] = xpj;
         } else {
@@ -114,6 +129,7 @@ struct DualEpi {
     double* __restrict__ axbar;
     const PdlpParams* __restrict__ P;
     int it;
+    PeerOut peers;
     struct Pre { double y, lc, uc, y0; };
     __device__ __forceinline__ const double* in(int i) const { return i == 0 ? y : i == 1 ? lc : i == 2 ? uc : y0; }
     __device__ __forceinline__ Pre preload(const double* s, int rt, int g) const {
@@ -140,7 +156,13 @@ struct DualEpi {
         } else {
             const double k = (double)(P->k_base + it);
             const double w = (k + 1.0) / (k + 2.0);
-            y[i] = w * (2.0 * ypi - p.y) + (1.0 - w) * p.y0;
+            const double yn = w * (2.0 * ypi - p.y) + (1.0 - w) * p.y0;
+            if (peers.n > 0) {
+#pragma unroll 8
+                for (int r = 0; r < peers.n; ++r) peers.p[r][i] = yn;
+            } else {
+                y[i] = yn;
+            }
         }
     }
 };
@@ -462,13 +484,95 @@ void launch_diff(int n, const double* a, const double* b, double* out, cudaStrea
     if (n > 0) ELP_LAUNCH(k_diff, ceil_div(n, 256), 256, 0, st, n, a, b, out);
 }
 
+// ---- cross-GPU hand-off of the blocks written by peer stores ------------------------------------------------
+// Every rank runs the same sequence of (signal, wait) pairs; the epoch lives in device memory so the pair can be
+// replayed from a CUDA graph.  signal: runs after the producing kernel in stream order (its peer stores are complete),
+// bumps this rank's epoch and publishes it in slot `rank` of every peer's flag row.  wait: spins (bounded) until all
+// N slots of the local flag row have reached the local expectation.
+struct PeerFlags {
+    unsigned long long* row[8];   // row[r]: rank r's flag row (N slots), mapped into this process
+};
+__global__ void k_peer_signal(PeerFlags f, int nranks, int rank, unsigned long long* __restrict__ epoch) {
+    if (threadIdx.x == 0) { *epoch += 1ull; __threadfence_system(); }
+    __syncthreads();
+    const unsigned long long e = *epoch;
+    if ((int)threadIdx.x < nranks) {
+        volatile unsigned long long* dst = f.row[threadIdx.x] + rank;
+        *dst = e;
+    }
+    __threadfence_system();
+}
+__global__ void k_peer_wait(const unsigned long long* __restrict__ my_row, int nranks, unsigned long long* __restrict__ expect) {
+    __shared__ unsigned long long want;
+    if (threadIdx.x == 0) { *expect += 1ull; want = *expect; }
+    __syncthreads();
+    if ((int)threadIdx.x < nranks) {
+        const volatile unsigned long long* src = my_row + threadIdx.x;
+        unsigned long long spins = 0;
+        while (*src < want) {
+            if (++spins > (1ull << 31)) __trap();           // a peer died: fail instead of hanging the GPU
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+}
+
+// ---- kernels of the one-off exchange that builds each rank's column block of A ---------------------
+__global__ void k_shift_idx(uint32_t nnz, int* __restrict__ idx, int offset) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) idx[i] += offset;
+}
+// lens[j] = length of local CSC column j0 + j (0 beyond the matrix)
+__global__ void k_col_lens(const int* __restrict__ ptr, int j0, int count, int ncols, uint32_t* __restrict__ lens) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const int col = j0 + j;
+    lens[j] = col < ncols ? (uint32_t)(ptr[col + 1] - ptr[col]) : 0u;
+}
+__global__ void k_sum_lens(int nranks, int nb, const uint32_t* __restrict__ lens, uint32_t* __restrict__ tot) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nb) return;
+    uint32_t s = 0;
+    if (j < nb) for (int r = 0; r < nranks; ++r) s += lens[(size_t)r * nb + j];
+    tot[j] = s;                                      // tot[nb] = 0: the scan leaves the total there
+}
+// column j of my block = concatenation over the source ranks (ascending = ascending global row) of their pieces
+__global__ void k_merge_cols(int nranks, int nb, const uint32_t* __restrict__ lens, const uint32_t* __restrict__ srcptr,
+                             const uint32_t* __restrict__ newptr, const uint32_t* __restrict__ roff,
+                             const int* __restrict__ in_idx, const double* __restrict__ in_val,
+                             int* __restrict__ out_ptr, int* __restrict__ out_idx, double* __restrict__ out_val) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nb) return;
+    out_ptr[j] = (int)newptr[j];
+    if (j == nb) return;
+    uint32_t dst = newptr[j];
+    for (int r = 0; r < nranks; ++r) {
+        const uint32_t len = lens[(size_t)r * nb + j];
+        const uint32_t src = roff[r] + srcptr[(size_t)r * nb + j];
+        for (uint32_t k = 0; k < len; ++k) { out_idx[dst + k] = in_idx[src + k]; out_val[dst + k] = in_val[src + k]; }
+        dst += len;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side solver object
+//
+// Partition (N ranks; N = 1 is the same code with the collectives compiled out of the picture):
+//   rows     rank g owns the row block the caller hands it (balanced by non-zeros): CSR with GLOBAL column ids,
+//            the slices of y / lc / uc.  y lives in a padded global layout y_full[N][mb] (mb = largest block).
+//   columns  rank g owns the columns [g*nb, (g+1)*nb): the CSC of that column block over ALL rows (built once by
+//            a grouped send/recv of the ranks' local CSC slices), the slices of x / c / l / u.
+//   K1 (A'y + primal update) runs on the column block and gathers from y_full; it writes its x-bar block into
+//   xbar_full, which is then all-gathered.  K2 (A x-bar + dual update) runs on the row block and gathers from
+//   xbar_full; it updates its y block inside y_full, which is then all-gathered.  All work is sharded (nothing is
+//   replicated), the exchange per iteration is 8 (n + m) bytes received per rank, and the scalar residuals of a
+//   check travel in one 16-double allreduce.
 // ------------------------------------------------------------------------------------------------
 struct Pdlp {
-    int m = 0, n = 0;           // local rows, global columns
-    int64_t nnz = 0;
-    bool dist = false;
+    int N = 1, rank = 0;
+    int m = 0, mb = 0;          // local rows, padded rows per rank
+    int n = 0, nb = 0, n0 = 0, nl = 0;   // global columns, columns per rank, my first column, my column count
+    int64_t nnz = 0, nnzc = 0;  // entries of the row block / of the column block
     bool maximize = false;
     elp_options opt{};
     cudaStream_t st = nullptr;
@@ -477,11 +581,17 @@ struct Pdlp {
     DevBuf<double> csr_val, csc_val;
     int Lr = 8, Lc = 4;          // lanes per row of the setup helper kernels
     SpmvPlan plan_r, plan_c;     // tile plans of the two iteration SpMVs (CSR rows / CSC columns)
-    // vectors (scaled)
-    DevBuf<double> c, l, u, lc, uc, dr, dc;
-    DevBuf<double> x, x0, xbar, xp, y, y0, yp, axbar, axp, gbuf;   // gbuf: n + NACC (allreduce buffer)
-    DevBuf<double> ray_dx, ray_dy, ray_ax, ray_g;                    // certificate scratch (lazy)
-    DevBuf<double> partials, scal;                                   // scal: 2*NACC
+    // vectors (scaled); column-side ones have nl entries, row-side ones m
+    DevBuf<double> c, l, u, dc, x, x0, xp, gcol;
+    DevBuf<double> lc, uc, dr, y0, yp, axbar, axp;
+    DevBuf<double> xbar_full, y_full, xaux_full, yaux_full;   // [N*nb], [N*mb]: gathered vectors + scratch
+    // peer-store exchange (N > 1, CUDA IPC): every rank's xbar_full / y_full / flag rows mapped here
+    bool p2p = false;
+    PeerOut x_out{}, y_out{};            // peers' xbar_full + n0, y_full + rank*mb
+    PeerFlags xflags{}, yflags{};
+    DevBuf<unsigned long long> flags;    // [2][8] flag rows (x, y) + [4] epochs/expectations
+    std::vector<void*> ipc_opened;
+    DevBuf<double> partials, scal;                              // scal: 2*NACC
     DevBuf<PdlpParams> params;
     // scalars
     double eta = 1.0, w = 1.0, w_init = 1.0, norm_b = 0.0, norm_c = 0.0, sigma_max = 0.0;
@@ -499,31 +609,94 @@ struct Pdlp {
 
     ~Pdlp() {
         if (graph) cudaGraphExecDestroy(graph);
+        if (st) cudaStreamSynchronize(st);
+        for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
         if (st) cudaStreamDestroy(st);
     }
 
+    // Maps every rank's gathered buffers into this process (CUDA IPC) so that the iteration kernels can store their
+    // block straight into all copies over NVLink.  Falls back to the NCCL all-gather when IPC is not available.
+    void setup_peer_stores() {
+        p2p = false;
+        if (N <= 1 || N > 8 || env_int("ELP_PDLP_P2P", 1) == 0) return;
+        flags.alloc(2 * 8 + 4);
+        flags.zero(st);
+        ELP_CUDA(cudaStreamSynchronize(st));
+        struct Handles { cudaIpcMemHandle_t x, y, f; };
+        static_assert(sizeof(Handles) % 8 == 0, "handle block must be a multiple of 8 bytes");
+        std::vector<Handles> all(N);
+        int ok = 1;
+        if (cudaIpcGetMemHandle(&all[rank].x, xbar_full.p) != cudaSuccess) ok = 0;
+        if (cudaIpcGetMemHandle(&all[rank].y, y_full.p) != cudaSuccess) ok = 0;
+        if (cudaIpcGetMemHandle(&all[rank].f, flags.p) != cudaSuccess) ok = 0;
+        cudaGetLastError();
+        DevBuf<unsigned char> hbuf((size_t)N * sizeof(Handles));
+        ELP_CUDA(cudaMemcpyAsync(hbuf.p + (size_t)rank * sizeof(Handles), &all[rank], sizeof(Handles), cudaMemcpyHostToDevice, st));
+        comm_allgather_bytes(hbuf.p, sizeof(Handles), st);
+        ELP_CUDA(cudaMemcpyAsync(all.data(), hbuf.p, (size_t)N * sizeof(Handles), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        std::vector<double*> xs(N), ys(N);
+        std::vector<unsigned long long*> fs(N);
+        for (int r = 0; r < N && ok; ++r) {
+            if (r == rank) { xs[r] = xbar_full.p; ys[r] = y_full.p; fs[r] = flags.p; continue; }
+            void *px = nullptr, *py = nullptr, *pf = nullptr;
+            if (cudaIpcOpenMemHandle(&px, all[r].x, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+            ipc_opened.push_back(px);
+            if (cudaIpcOpenMemHandle(&py, all[r].y, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+            ipc_opened.push_back(py);
+            if (cudaIpcOpenMemHandle(&pf, all[r].f, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+            ipc_opened.push_back(pf);
+            xs[r] = (double*)px; ys[r] = (double*)py; fs[r] = (unsigned long long*)pf;
+        }
+        cudaGetLastError();
+        // everyone or no one
+        double okd = (double)ok;
+        ELP_CUDA(cudaMemcpyAsync(scal.p, &okd, sizeof okd, cudaMemcpyHostToDevice, st));
+        comm_allreduce_sum(scal.p, 1, st);
+        ELP_CUDA(cudaMemcpyAsync(&okd, scal.p, sizeof okd, cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        if ((int)okd != N) {
+            if (opt.verbose > 0 && rank == 0) fprintf(stderr, "[pdlp] CUDA IPC unavailable: NCCL all-gather exchange\n");
+            return;
+        }
+        x_out.n = y_out.n = N;
+        for (int r = 0; r < N; ++r) {
+            x_out.p[r] = xs[r] + n0;
+            y_out.p[r] = ys[r] + (size_t)rank * mb;
+            xflags.row[r] = fs[r];
+            yflags.row[r] = fs[r] + 8;
+        }
+        p2p = true;
+    }
+    void barrier_stream() {              // all ranks have finished everything they queued before this point
+        if (N > 1) comm_allreduce_sum(scal.p + NACC, 1, st);
+    }
+
     int grid1(int count) const { return std::max(1, ceil_div(count, 256)); }
+    double* xbar() { return xbar_full.p + n0; }              // my block of the gathered x-bar
+    double* y() { return y_full.p + (size_t)rank * mb; }     // my block of the gathered y
+    void gather_x(double* full) { if (N > 1) comm_allgather(full, (size_t)nb, st); }
+    void gather_y(double* full) { if (N > 1) comm_allgather(full, (size_t)mb, st); }
 
     void reduce_to(double* out_dev) {
         ELP_LAUNCH(k_final_reduce, 1, RED_THREADS, 0, st, partials.p, RED_BLOCKS, out_dev);
     }
-    // sum over (all ranks of) a k_* reduction that was just launched into `partials`; returns NACC values
-    void fetch_scalars(double* host, bool row_partitioned) {
+    // sum over all ranks of a k_* reduction that was just launched into `partials`; returns NACC values
+    void fetch_scalars(double* host) {
         reduce_to(scal.p);
-        if (dist && row_partitioned) comm_allreduce_sum(scal.p, NACC, st);
+        if (N > 1) comm_allreduce_sum(scal.p, NACC, st);
         ELP_CUDA(cudaMemcpyAsync(host, scal.p, NACC * sizeof(double), cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         d2h += NACC * sizeof(double);
     }
 
-    // y_out[m] = A * v      (local rows)
-    void spmv_rows(const double* v, double* out) {
-        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, v, StoreEpi{out}, st);
+    // out[m] = A_rows * v_full      (my rows; v_full in the flat column layout)
+    void spmv_rows(const double* v_full, double* out) {
+        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, v_full, StoreEpi{out}, st);
     }
-    // out[n] = A' * v  (summed over ranks)
-    void spmv_cols(const double* v, double* out) {
-        launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, v, StoreEpi{out}, st);
-        if (dist) comm_allreduce_sum(out, n, st);
+    // out[nl] = (A' * v_full)_mycols  (v_full in the padded row layout)
+    void spmv_cols(const double* v_full, double* out) {
+        launch_spmv(plan_c, nl, csc_ptr.p, csc_idx.p, csc_val.p, v_full, StoreEpi{out}, st);
     }
 
     template <int MODE>
@@ -553,35 +726,66 @@ struct Pdlp {
             default: ELP_LAUNCH((scale_vals_kernel<32>), grid, SPMV_THREADS, 0, st, nrows, ptr, idx, val, s_self, s_other); break;
         }
     }
+    void expand_rows(int L, int nrows, const int* ptr, int* row_of) {
+        if (nrows <= 0) return;
+        const int grid = ceil_div((int64_t)nrows * L, SPMV_THREADS);
+        switch (L) {
+            case 1:  ELP_LAUNCH((expand_rows_kernel<1>), grid, SPMV_THREADS, 0, st, nrows, ptr, row_of); break;
+            case 2:  ELP_LAUNCH((expand_rows_kernel<2>), grid, SPMV_THREADS, 0, st, nrows, ptr, row_of); break;
+            case 4:  ELP_LAUNCH((expand_rows_kernel<4>), grid, SPMV_THREADS, 0, st, nrows, ptr, row_of); break;
+            case 8:  ELP_LAUNCH((expand_rows_kernel<8>), grid, SPMV_THREADS, 0, st, nrows, ptr, row_of); break;
+            case 16: ELP_LAUNCH((expand_rows_kernel<16>), grid, SPMV_THREADS, 0, st, nrows, ptr, row_of); break;
+            default: ELP_LAUNCH((expand_rows_kernel<32>), grid, SPMV_THREADS, 0, st, nrows, ptr, row_of); break;
+        }
+    }
 
     // ---- setup ---------------------------------------------------------------------------------
     void setup(int m_, int n_, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
                const int8_t* sense, const double* rhs, const double* c_h, int maximize_, const double* lb,
                const double* ub, const elp_options& o, bool dist_) {
-        m = m_; n = n_; dist = dist_ && comm().active; maximize = maximize_ != 0; opt = o;
+        m = m_; n = n_; maximize = maximize_ != 0; opt = o;
+        const bool dist = dist_ && comm().active;
+        N = dist ? comm().nranks : 1;
+        rank = dist ? comm().rank : 0;
         ELP_REQUIRE(m >= 0 && n > 0, "pdlp: bad shape %d x %d", m, n);
         nnz = m > 0 ? row_ptr[m] : 0;
         ELP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        csr_ptr.alloc(m + 1 + SPMV_PTR_PAD); csr_idx.alloc(nnz + SPMV_PAD); csr_val.alloc(nnz + SPMV_PAD);
-        csc_ptr.alloc(n + 1 + SPMV_PTR_PAD); csc_idx.alloc(nnz + SPMV_PAD); csc_val.alloc(nnz + SPMV_PAD);
-        csr_idx.zero(st); csr_val.zero(st); csc_idx.zero(st); csc_val.zero(st); csr_ptr.zero(st); csc_ptr.zero(st);
-        // epilogue operands are staged by 16-byte-granular bulk copies: SPMV_VPAD doubles of slack each
-        const size_t np = (size_t)n + SPMV_VPAD, mp = (size_t)std::max(m, 1) + SPMV_VPAD;
-        c.alloc(np); l.alloc(np); u.alloc(np); dc.alloc(np);
-        lc.alloc(mp); uc.alloc(mp); dr.alloc(mp);
-        x.alloc(np); x0.alloc(np); xbar.alloc(np); xp.alloc(np); gbuf.alloc(n + NACC);
-        y.alloc(mp); y0.alloc(mp); yp.alloc(mp);
-        axbar.alloc(mp); axp.alloc(mp);
-        c.zero(st); l.zero(st); u.zero(st); lc.zero(st); uc.zero(st); x.zero(st); x0.zero(st);
         partials.alloc((size_t)RED_BLOCKS * NACC); scal.alloc(2 * NACC); params.alloc(1);
         partials.zero(st);
+        // block sizes: multiples of 4 keep every block 32-byte aligned (16-byte-granular bulk copies)
+        nb = (ceil_div(n, N) + 3) & ~3;
+        n0 = std::min(n, rank * nb);
+        nl = std::max(0, std::min(n, (rank + 1) * nb) - n0);
+        {
+            double mx = (double)m;
+            if (N > 1) {
+                ELP_CUDA(cudaMemcpyAsync(scal.p, &mx, sizeof mx, cudaMemcpyHostToDevice, st));
+                comm_allreduce_max(scal.p, 1, st);
+                ELP_CUDA(cudaMemcpyAsync(&mx, scal.p, sizeof mx, cudaMemcpyDeviceToHost, st));
+                ELP_CUDA(cudaStreamSynchronize(st));
+            }
+            mb = (std::max(1, (int)mx) + 3) & ~3;
+        }
+        ELP_REQUIRE((int64_t)N * mb < 0x7fffffffll && (int64_t)N * nb < 0x7fffffffll, "pdlp: problem too large for int32 ids");
+
+        csr_ptr.alloc(m + 1 + SPMV_PTR_PAD); csr_idx.alloc(nnz + SPMV_PAD); csr_val.alloc(nnz + SPMV_PAD);
+        csr_idx.zero(st); csr_val.zero(st); csr_ptr.zero(st);
+        // epilogue operands are staged by 16-byte-granular bulk copies: SPMV_VPAD doubles of slack each
+        const size_t np = (size_t)std::max(nl, 1) + SPMV_VPAD, mp = (size_t)std::max(m, 1) + SPMV_VPAD;
+        c.alloc(np); l.alloc(np); u.alloc(np); dc.alloc(np); x.alloc(np); x0.alloc(np); xp.alloc(np); gcol.alloc(np);
+        lc.alloc(mp); uc.alloc(mp); dr.alloc(mp); y0.alloc(mp); yp.alloc(mp); axbar.alloc(mp); axp.alloc(mp);
+        xbar_full.alloc((size_t)N * nb + SPMV_VPAD); xaux_full.alloc((size_t)N * nb + SPMV_VPAD);
+        y_full.alloc((size_t)N * mb + SPMV_VPAD); yaux_full.alloc((size_t)N * mb + SPMV_VPAD);
+        for (DevBuf<double>* b : {&c, &l, &u, &dc, &x, &x0, &xp, &gcol, &lc, &uc, &dr, &y0, &yp, &axbar, &axp, &xbar_full,
+                                  &xaux_full, &y_full, &yaux_full})
+            b->zero(st);
 
         if (m == 0) { int z = 0; csr_ptr.upload(&z, 1, st); }
         else csr_ptr.upload(row_ptr, m + 1, st);
         csr_idx.upload(col_idx, nnz, st);
         csr_val.upload(vals, nnz, st);
-        c.upload(c_h, n, st); l.upload(lb, n, st); u.upload(ub, n, st);
-        h2d += (int64_t)(m + 1) * 4 + nnz * 12 + (int64_t)n * 24;
+        c.upload(c_h + n0, nl, st); l.upload(lb + n0, nl, st); u.upload(ub + n0, nl, st);
+        h2d += (int64_t)(m + 1) * 4 + nnz * 12 + (int64_t)nl * 24;
         {
             DevBuf<int8_t> sense_d(std::max(m, 1));
             DevBuf<double> rhs_d(std::max(m, 1));
@@ -590,20 +794,21 @@ struct Pdlp {
             if (m > 0) ELP_LAUNCH(k_row_bounds, grid1(m), 256, 0, st, m, sense_d.p, rhs_d.p, lc.p, uc.p);
             ELP_CUDA(cudaStreamSynchronize(st));
         }
-        if (maximize) ELP_LAUNCH(k_scale_scalar, grid1(n), 256, 0, st, n, c.p, -1.0);
-        Lr = pick_helper_lanes(nnz, m);
-        Lc = pick_helper_lanes(nnz, n);
-        plan_r = plan_spmv(nnz, m, 4);
-        plan_c = plan_spmv(nnz, n, 5);
+        if (maximize && nl > 0) ELP_LAUNCH(k_scale_scalar, grid1(nl), 256, 0, st, nl, c.p, -1.0);
 
-        build_csc();
+        build_column_block();
+        Lr = pick_helper_lanes(nnz, m);
+        Lc = pick_helper_lanes(nnzc, nl);
+        plan_r = plan_spmv(nnz, m, 4);
+        plan_c = plan_spmv(nnzc, nl, 5);
+
         // unscaled norms for the relative termination test
         double h[NACC];
         ELP_LAUNCH(k_bound_norm, RED_BLOCKS, RED_THREADS, 0, st, m, lc.p, uc.p, partials.p);
-        fetch_scalars(h, true);
+        fetch_scalars(h);
         norm_b = std::sqrt(h[0]);
-        ELP_LAUNCH(k_dot2, RED_BLOCKS, RED_THREADS, 0, st, n, c.p, c.p, partials.p);
-        fetch_scalars(h, false);
+        ELP_LAUNCH(k_dot2, RED_BLOCKS, RED_THREADS, 0, st, nl, c.p, c.p, partials.p);
+        fetch_scalars(h);
         norm_c = std::sqrt(h[0]);
 
         scale_problem();
@@ -611,66 +816,136 @@ struct Pdlp {
         eta = sigma_max > 0 ? 0.998 / sigma_max : 1.0;
         // initial primal weight from the scaled data: ||c|| / ||b||
         ELP_LAUNCH(k_bound_norm, RED_BLOCKS, RED_THREADS, 0, st, m, lc.p, uc.p, partials.p);
-        fetch_scalars(h, true);
-        const double nb = std::sqrt(h[0]);
-        ELP_LAUNCH(k_dot2, RED_BLOCKS, RED_THREADS, 0, st, n, c.p, c.p, partials.p);
-        fetch_scalars(h, false);
-        const double nc = std::sqrt(h[0]);
-        w_init = (nb > 1e-10 && nc > 1e-10) ? nc / nb : 1.0;
+        fetch_scalars(h);
+        const double nbn = std::sqrt(h[0]);
+        ELP_LAUNCH(k_dot2, RED_BLOCKS, RED_THREADS, 0, st, nl, c.p, c.p, partials.p);
+        fetch_scalars(h);
+        const double ncn = std::sqrt(h[0]);
+        w_init = (nbn > 1e-10 && ncn > 1e-10) ? ncn / nbn : 1.0;
+        setup_peer_stores();
         reset();
     }
 
-    void build_csc() {
-        // transpose of the local block with the same stable sort that backs the assembly
-        if (nnz == 0) { csc_ptr.zero(st); return; }
-        DevBuf<uint64_t> keys(nnz);
-        DevBuf<uint32_t> perm(nnz), nnz_d(1);
-        DevBuf<int> row_of(nnz), cols_sorted(nnz);
-        RadixSortWorkspace ws;
-        {
-            const int grid = ceil_div((int64_t)m * Lr, SPMV_THREADS);
-            switch (Lr) {
-                case 1:  ELP_LAUNCH((expand_rows_kernel<1>), grid, SPMV_THREADS, 0, st, m, csr_ptr.p, row_of.p); break;
-                case 2:  ELP_LAUNCH((expand_rows_kernel<2>), grid, SPMV_THREADS, 0, st, m, csr_ptr.p, row_of.p); break;
-                case 4:  ELP_LAUNCH((expand_rows_kernel<4>), grid, SPMV_THREADS, 0, st, m, csr_ptr.p, row_of.p); break;
-                case 8:  ELP_LAUNCH((expand_rows_kernel<8>), grid, SPMV_THREADS, 0, st, m, csr_ptr.p, row_of.p); break;
-                case 16: ELP_LAUNCH((expand_rows_kernel<16>), grid, SPMV_THREADS, 0, st, m, csr_ptr.p, row_of.p); break;
-                default: ELP_LAUNCH((expand_rows_kernel<32>), grid, SPMV_THREADS, 0, st, m, csr_ptr.p, row_of.p); break;
-            }
+    // CSC of my column block over all rows, row ids in the padded y_full layout.  Every rank transposes its own row
+    // block with the stable radix sort that backs the assembly, then the column slices travel to their owners in
+    // one grouped send/recv and are merged source by source (= ascending global row).
+    void build_column_block() {
+        // ---- local transpose: CSC of my row block over all n columns ----------------------------------
+        DevBuf<int> lptr((size_t)n + 1), lidx(std::max<int64_t>(nnz, 1));
+        DevBuf<double> lval(std::max<int64_t>(nnz, 1));
+        if (nnz == 0) {
+            lptr.zero(st);
+        } else {
+            DevBuf<uint64_t> keys(nnz);
+            DevBuf<uint32_t> perm(nnz), nnz_d(1);
+            DevBuf<int> row_of(nnz), cols_sorted(nnz);
+            RadixSortWorkspace ws;
+            expand_rows(pick_helper_lanes(nnz, m), m, csr_ptr.p, row_of.p);
+            launch_transpose_keys(csr_idx.p, (uint32_t)nnz, keys.p, perm.p, st);
+            radix_sort_pairs(keys.p, perm.p, nnz, bit_length_u64((uint64_t)n - 1), ws, st);
+            launch_transpose_gather(keys.p, perm.p, row_of.p, csr_val.p, (uint32_t)nnz, lidx.p, lval.p, cols_sorted.p,
+                                    nnz_d.p, st);
+            launch_fill_ptr(cols_sorted.p, nnz_d.p, (uint32_t)n, lptr.p, (uint32_t)nnz, st);
+            if (rank > 0) ELP_LAUNCH(k_shift_idx, ceil_div(nnz, 256), 256, 0, st, (uint32_t)nnz, lidx.p, rank * mb);
+            ELP_CUDA(cudaStreamSynchronize(st));
         }
-        launch_transpose_keys(csr_idx.p, (uint32_t)nnz, keys.p, perm.p, st);
-        radix_sort_pairs(keys.p, perm.p, nnz, bit_length_u64((uint64_t)n - 1), ws, st);
-        launch_transpose_gather(keys.p, perm.p, row_of.p, csr_val.p, (uint32_t)nnz, csc_idx.p, csc_val.p, cols_sorted.p,
-                                nnz_d.p, st);
-        launch_fill_ptr(cols_sorted.p, nnz_d.p, (uint32_t)n, csc_ptr.p, (uint32_t)nnz, st);
+        if (N == 1) {
+            nnzc = nnz;
+            csc_ptr.alloc((size_t)nl + 1 + SPMV_PTR_PAD); csc_idx.alloc(nnzc + SPMV_PAD); csc_val.alloc(nnzc + SPMV_PAD);
+            csc_ptr.zero(st); csc_idx.zero(st); csc_val.zero(st);
+            ELP_CUDA(cudaMemcpyAsync(csc_ptr.p, lptr.p, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            if (nnz) {
+                ELP_CUDA(cudaMemcpyAsync(csc_idx.p, lidx.p, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, st));
+                ELP_CUDA(cudaMemcpyAsync(csc_val.p, lval.p, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            }
+            ELP_CUDA(cudaStreamSynchronize(st));
+            return;
+        }
+        // ---- how much goes where ----------------------------------------------------------------------
+        std::vector<int> cut(N + 1);
+        for (int g = 0; g <= N; ++g) {
+            const int col = std::min(n, g * nb);
+            ELP_CUDA(cudaMemcpyAsync(&cut[g], lptr.p + col, sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
+        ELP_CUDA(cudaStreamSynchronize(st));
+        DevBuf<double> cnt_d((size_t)N * N);
+        std::vector<double> cnt((size_t)N * N, 0.0);
+        for (int g = 0; g < N; ++g) cnt[(size_t)rank * N + g] = (double)(cut[g + 1] - cut[g]);
+        ELP_CUDA(cudaMemcpyAsync(cnt_d.p + (size_t)rank * N, cnt.data() + (size_t)rank * N, N * sizeof(double),
+                                 cudaMemcpyHostToDevice, st));
+        comm_allgather(cnt_d.p, (size_t)N, st);
+        ELP_CUDA(cudaMemcpyAsync(cnt.data(), cnt_d.p, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        std::vector<uint32_t> roff(N + 1, 0);
+        for (int r = 0; r < N; ++r) roff[r + 1] = roff[r] + (uint32_t)cnt[(size_t)r * N + rank];   // what r sends me
+        const int64_t total_in = roff[N];
+        // ---- lens of every column slice I send, then the grouped exchange -------------------------------
+        DevBuf<uint32_t> lens_out((size_t)N * nb), lens_in((size_t)N * nb + 1), srcptr((size_t)N * nb), newptr((size_t)nb + 1);
+        DevBuf<uint32_t> roff_d(N + 1);
+        DevBuf<int> in_idx(std::max<int64_t>(total_in, 1));
+        DevBuf<double> in_val(std::max<int64_t>(total_in, 1));
+        for (int g = 0; g < N; ++g)
+            ELP_LAUNCH(k_col_lens, ceil_div(nb, 256), 256, 0, st, lptr.p, g * nb, nb, n, lens_out.p + (size_t)g * nb);
+        comm_group_start();
+        for (int g = 0; g < N; ++g) {
+            const size_t cntg = (size_t)(cut[g + 1] - cut[g]);
+            comm_send(lens_out.p + (size_t)g * nb, (size_t)nb * sizeof(uint32_t), g, st);
+            comm_send(lidx.p + cut[g], cntg * sizeof(int), g, st);
+            comm_send(lval.p + cut[g], cntg * sizeof(double), g, st);
+            const size_t cin = (size_t)(roff[g + 1] - roff[g]);
+            comm_recv(lens_in.p + (size_t)g * nb, (size_t)nb * sizeof(uint32_t), g, st);
+            comm_recv(in_idx.p + roff[g], cin * sizeof(int), g, st);
+            comm_recv(in_val.p + roff[g], cin * sizeof(double), g, st);
+        }
+        comm_group_end();
+        // ---- merge ---------------------------------------------------------------------------------------
+        ScanWorkspace sw;
+        ELP_LAUNCH(k_sum_lens, ceil_div(nb + 1, 256), 256, 0, st, N, nb, lens_in.p, newptr.p);
+        exclusive_scan_u32(newptr.p, (size_t)nb + 1, sw, st);
+        ELP_CUDA(cudaMemcpyAsync(srcptr.p, lens_in.p, (size_t)N * nb * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        for (int r = 0; r < N; ++r) exclusive_scan_u32(srcptr.p + (size_t)r * nb, (size_t)nb, sw, st);
+        roff_d.upload(roff.data(), N + 1, st);
+        nnzc = total_in;
+        csc_ptr.alloc((size_t)nb + 1 + SPMV_PTR_PAD); csc_idx.alloc(nnzc + SPMV_PAD); csc_val.alloc(nnzc + SPMV_PAD);
+        csc_ptr.zero(st); csc_idx.zero(st); csc_val.zero(st);
+        ELP_LAUNCH(k_merge_cols, ceil_div(nb + 1, 256), 256, 0, st, N, nb, lens_in.p, srcptr.p, newptr.p, roff_d.p,
+                   in_idx.p, in_val.p, csc_ptr.p, csc_idx.p, csc_val.p);
         ELP_CUDA(cudaStreamSynchronize(st));
     }
 
     void scale_problem() {
         const int ruiz = opt.ruiz_iters >= 0 ? opt.ruiz_iters : 10;
-        if (m > 0) ELP_LAUNCH(k_fill, grid1(m), 256, 0, st, m, dr.p, 1.0);
-        ELP_LAUNCH(k_fill, grid1(n), 256, 0, st, n, dc.p, 1.0);
-        if (nnz == 0) return;
-        DevBuf<double> rstat(std::max(m, 1)), cstat(n);
+        // dr_full = yaux_full (padded row layout), dc_full = xaux_full (flat column layout) during scaling
+        double* dr_full = yaux_full.p;
+        double* dc_full = xaux_full.p;
+        double* drl = dr_full + (size_t)rank * mb;
+        double* dcl = dc_full + n0;
+        ELP_LAUNCH(k_fill, grid1(N * mb), 256, 0, st, N * mb, dr_full, 1.0);
+        ELP_LAUNCH(k_fill, grid1(N * nb), 256, 0, st, N * nb, dc_full, 1.0);
+        DevBuf<double> rstat(std::max(m, 1)), cstat(std::max(nl, 1));
         for (int it = 0; it < ruiz + 1; ++it) {
             const bool pc = it == ruiz;   // last pass: Pock-Chambolle (alpha = 1) with L1 norms
             if (!pc) {
-                rowstat<0>(Lr, m, csr_ptr.p, csr_idx.p, csr_val.p, dr.p, dc.p, rstat.p);
-                rowstat<0>(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, dc.p, dr.p, cstat.p);
-                if (dist) comm_allreduce_max(cstat.p, n, st);
+                rowstat<0>(Lr, m, csr_ptr.p, csr_idx.p, csr_val.p, drl, dc_full, rstat.p);
+                rowstat<0>(Lc, nl, csc_ptr.p, csc_idx.p, csc_val.p, dcl, dr_full, cstat.p);
             } else {
-                rowstat<1>(Lr, m, csr_ptr.p, csr_idx.p, csr_val.p, dr.p, dc.p, rstat.p);
-                rowstat<1>(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, dc.p, dr.p, cstat.p);
-                if (dist) comm_allreduce_sum(cstat.p, n, st);
+                rowstat<1>(Lr, m, csr_ptr.p, csr_idx.p, csr_val.p, drl, dc_full, rstat.p);
+                rowstat<1>(Lc, nl, csc_ptr.p, csc_idx.p, csc_val.p, dcl, dr_full, cstat.p);
             }
-            ELP_LAUNCH(k_ruiz_update, grid1(m), 256, 0, st, m, dr.p, rstat.p);
-            ELP_LAUNCH(k_ruiz_update, grid1(n), 256, 0, st, n, dc.p, cstat.p);
+            if (m > 0) ELP_LAUNCH(k_ruiz_update, grid1(m), 256, 0, st, m, drl, rstat.p);
+            if (nl > 0) ELP_LAUNCH(k_ruiz_update, grid1(nl), 256, 0, st, nl, dcl, cstat.p);
+            gather_y(dr_full);
+            gather_x(dc_full);
         }
-        scale_vals(Lr, m, csr_ptr.p, csr_idx.p, csr_val.p, dr.p, dc.p);
-        scale_vals(Lc, n, csc_ptr.p, csc_idx.p, csc_val.p, dc.p, dr.p);
-        ELP_LAUNCH(k_mul, grid1(n), 256, 0, st, n, c.p, dc.p);
-        ELP_LAUNCH(k_div, grid1(n), 256, 0, st, n, l.p, dc.p);
-        ELP_LAUNCH(k_div, grid1(n), 256, 0, st, n, u.p, dc.p);
+        scale_vals(Lr, m, csr_ptr.p, csr_idx.p, csr_val.p, drl, dc_full);
+        scale_vals(Lc, nl, csc_ptr.p, csc_idx.p, csc_val.p, dcl, dr_full);
+        if (m > 0) ELP_CUDA(cudaMemcpyAsync(dr.p, drl, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (nl > 0) ELP_CUDA(cudaMemcpyAsync(dc.p, dcl, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (nl > 0) {
+            ELP_LAUNCH(k_mul, grid1(nl), 256, 0, st, nl, c.p, dc.p);
+            ELP_LAUNCH(k_div, grid1(nl), 256, 0, st, nl, l.p, dc.p);
+            ELP_LAUNCH(k_div, grid1(nl), 256, 0, st, nl, u.p, dc.p);
+        }
         if (m > 0) {
             ELP_LAUNCH(k_mul, grid1(m), 256, 0, st, m, lc.p, dr.p);
             ELP_LAUNCH(k_mul, grid1(m), 256, 0, st, m, uc.p, dr.p);
@@ -679,24 +954,40 @@ struct Pdlp {
 
     void estimate_sigma_max() {
         sigma_max = 0.0;
-        if (nnz == 0 || m == 0) return;
         double h[NACC];
-        // power iteration on A'A, vector in xbar, A v in axbar, A'(A v) in gbuf
-        ELP_LAUNCH(k_pseudo_random, grid1(n), 256, 0, st, n, xbar.p, 12345u);
-        ELP_LAUNCH(k_dot2, RED_BLOCKS, RED_THREADS, 0, st, n, xbar.p, xbar.p, partials.p);
-        fetch_scalars(h, false);
-        ELP_LAUNCH(k_scale_scalar, grid1(n), 256, 0, st, n, xbar.p, 1.0 / std::sqrt(h[0]));
+        // has the matrix any entry at all?
+        double tot = (double)nnz;
+        if (N > 1) {
+            ELP_CUDA(cudaMemcpyAsync(scal.p, &tot, sizeof tot, cudaMemcpyHostToDevice, st));
+            comm_allreduce_sum(scal.p, 1, st);
+            ELP_CUDA(cudaMemcpyAsync(&tot, scal.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaStreamSynchronize(st));
+        }
+        if (tot == 0.0) return;
+        // power iteration on A'A: v in xaux_full (my block at n0), A v in yaux_full (my block), A'(A v) in gcol
+        double* v = xaux_full.p + n0;
+        double* av = yaux_full.p + (size_t)rank * mb;
+        ELP_CUDA(cudaMemsetAsync(xaux_full.p, 0, (size_t)N * nb * sizeof(double), st));
+        ELP_CUDA(cudaMemsetAsync(yaux_full.p, 0, (size_t)N * mb * sizeof(double), st));
+        if (nl > 0) ELP_LAUNCH(k_pseudo_random, grid1(nl), 256, 0, st, nl, v, 12345u + 7919u * (uint32_t)n0);
+        ELP_LAUNCH(k_dot2, RED_BLOCKS, RED_THREADS, 0, st, nl, v, v, partials.p);
+        fetch_scalars(h);
+        if (nl > 0) ELP_LAUNCH(k_scale_scalar, grid1(nl), 256, 0, st, nl, v, 1.0 / std::sqrt(h[0]));
         double s = 1.0;
         for (int it = 0; it < 60; ++it) {
-            spmv_rows(xbar.p, axbar.p);
-            spmv_cols(axbar.p, gbuf.p);
-            ELP_LAUNCH(k_dot2, RED_BLOCKS, RED_THREADS, 0, st, n, gbuf.p, gbuf.p, partials.p);
-            fetch_scalars(h, false);
+            gather_x(xaux_full.p);
+            spmv_rows(xaux_full.p, av);
+            gather_y(yaux_full.p);
+            spmv_cols(yaux_full.p, gcol.p);
+            ELP_LAUNCH(k_dot2, RED_BLOCKS, RED_THREADS, 0, st, nl, gcol.p, gcol.p, partials.p);
+            fetch_scalars(h);
             const double nrm = std::sqrt(h[0]);
             if (!(nrm > 0.0)) { s = 0.0; break; }
             const double s_new = std::sqrt(nrm);
-            ELP_CUDA(cudaMemcpyAsync(xbar.p, gbuf.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            ELP_LAUNCH(k_scale_scalar, grid1(n), 256, 0, st, n, xbar.p, 1.0 / nrm);
+            if (nl > 0) {
+                ELP_CUDA(cudaMemcpyAsync(v, gcol.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                ELP_LAUNCH(k_scale_scalar, grid1(nl), 256, 0, st, nl, v, 1.0 / nrm);
+            }
             const bool conv = std::fabs(s_new - s) <= 1e-4 * s_new;
             s = s_new;
             if (conv && it >= 10) break;
@@ -705,13 +996,14 @@ struct Pdlp {
     }
 
     void reset() {
-        ELP_LAUNCH(k_init_x, grid1(n), 256, 0, st, n, x.p, l.p, u.p);
-        ELP_CUDA(cudaMemcpyAsync(x0.p, x.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        y.zero(st); y0.zero(st); yp.zero(st); axbar.zero(st); axp.zero(st);
-        ELP_CUDA(cudaMemcpyAsync(xp.p, x.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (nl > 0) ELP_LAUNCH(k_init_x, grid1(nl), 256, 0, st, nl, x.p, l.p, u.p);
+        ELP_CUDA(cudaMemcpyAsync(x0.p, x.p, (size_t)std::max(nl, 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        ELP_CUDA(cudaMemcpyAsync(xp.p, x.p, (size_t)std::max(nl, 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        y_full.zero(st); y0.zero(st); yp.zero(st); axbar.zero(st); axp.zero(st); xbar_full.zero(st);
         w = w_init; k = 0; total = 0; restarts = 0; fpe0 = -1; fpe_prev = -1; need_fpe0 = true;
         status = ELP_STATUS_TIMEOUT; finished = false; checks = 0;
         push_params();
+        barrier_stream();          // nobody stores into a peer's copy before that peer has cleared it
         ELP_CUDA(cudaStreamSynchronize(st));
     }
 
@@ -723,22 +1015,32 @@ struct Pdlp {
 
     // ---- iteration pieces ------------------------------------------------------------------------
     template <bool CHECK>
-    void primal_step(int it) {
-        PrimalEpi<CHECK> epi{c.p, l.p, u.p, x0.p, x.p, xbar.p, xp.p, params.p, it};
-        if (!dist) {
-            launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, epi, st);
+    void primal_step(int it, bool exchange = true) {
+        const bool direct = !CHECK && exchange && p2p;
+        PrimalEpi<CHECK> epi{c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, direct ? x_out : PeerOut{}};
+        launch_spmv(plan_c, nl, csc_ptr.p, csc_idx.p, csc_val.p, y_full.p, epi, st);
+        if (!exchange) return;
+        if (direct) {
+            ELP_LAUNCH(k_peer_signal, 1, 32, 0, st, xflags, N, rank, flags.p + 16);
+            ELP_LAUNCH(k_peer_wait, 1, 32, 0, st, flags.p, N, flags.p + 17);
         } else {
-            launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
-            comm_allreduce_sum(gbuf.p, n, st);
-            ELP_LAUNCH((apply_epi_kernel<PrimalEpi<CHECK>>), grid1(n), 256, 0, st, n, gbuf.p, epi);
+            gather_x(xbar_full.p);
         }
     }
     template <bool CHECK>
-    void dual_step(int it) {
-        DualEpi<CHECK> epi{lc.p, uc.p, y0.p, y.p, yp.p, axbar.p, params.p, it};
-        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar.p, epi, st);
+    void dual_step(int it, bool exchange = true) {
+        const bool direct = !CHECK && exchange && p2p;
+        DualEpi<CHECK> epi{lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, direct ? y_out : PeerOut{}};
+        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
+        if (!exchange || CHECK) return;                      // a check iteration does not change y here
+        if (direct) {
+            ELP_LAUNCH(k_peer_signal, 1, 32, 0, st, yflags, N, rank, flags.p + 18);
+            ELP_LAUNCH(k_peer_wait, 1, 32, 0, st, flags.p + 8, N, flags.p + 19);
+        } else {
+            gather_y(y_full.p);
+        }
     }
-    int kernels_per_iter() const { return (m > 0 ? 1 : 0) + (dist ? 2 : 1); }
+    int kernels_per_iter() const { return (m > 0 ? 1 : 0) + (nl > 0 ? 1 : 0) + (p2p ? 4 : 0); }
 
     void plain_iterations(int count) {
         if (count <= 0) return;
@@ -775,24 +1077,29 @@ struct Pdlp {
     // One check iteration: computes T(z) with side products, evaluates KKT + fixed-point error, then
     // either restarts from T(z) or completes the Halpern step.  Returns true when the solve is over.
     bool check_iteration() {
-        double hr[NACC], hc[NACC];
-        primal_step<true>(0);
-        dual_step<true>(0);
-        spmv_rows(xp.p, axp.p);
-        ELP_LAUNCH(k_check_rows, RED_BLOCKS, RED_THREADS, 0, st, m, axp.p, axbar.p, y.p, yp.p, y0.p, lc.p, uc.p, dr.p,
-                   partials.p);
-        // row sums travel in the tail of the A'y buffer so a distributed check costs one allreduce
-        reduce_to(gbuf.p + n);
-        launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, yp.p, StoreEpi{gbuf.p}, st);
-        if (dist) comm_allreduce_sum(gbuf.p, (size_t)n + NACC, st);
-        ELP_LAUNCH(k_check_cols, RED_BLOCKS, RED_THREADS, 0, st, n, gbuf.p, c.p, l.p, u.p, x.p, xp.p, x0.p, dc.p,
+        double h[2 * NACC];
+        primal_step<true>(0);                      // xbar (gathered), xp
+        dual_step<true>(0);                        // yp, axbar; y unchanged
+        // A xp on my rows (needs everyone's xp) and A' yp on my columns (needs everyone's yp)
+        if (nl > 0) ELP_CUDA(cudaMemcpyAsync(xaux_full.p + n0, xp.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        gather_x(xaux_full.p);
+        spmv_rows(xaux_full.p, axp.p);
+        if (m > 0) ELP_CUDA(cudaMemcpyAsync(yaux_full.p + (size_t)rank * mb, yp.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        gather_y(yaux_full.p);
+        spmv_cols(yaux_full.p, gcol.p);
+        ELP_LAUNCH(k_check_rows, RED_BLOCKS, RED_THREADS, 0, st, m, axp.p, axbar.p, y(), yp.p, y0.p, lc.p, uc.p, dr.p,
                    partials.p);
         reduce_to(scal.p);
-        ELP_CUDA(cudaMemcpyAsync(hr, gbuf.p + n, NACC * sizeof(double), cudaMemcpyDeviceToHost, st));
-        ELP_CUDA(cudaMemcpyAsync(hc, scal.p, NACC * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ELP_LAUNCH(k_check_cols, RED_BLOCKS, RED_THREADS, 0, st, nl, gcol.p, c.p, l.p, u.p, x.p, xp.p, x0.p, dc.p,
+                   partials.p);
+        reduce_to(scal.p + NACC);
+        if (N > 1) comm_allreduce_sum(scal.p, 2 * NACC, st);       // the scalar residuals: ONE collective
+        ELP_CUDA(cudaMemcpyAsync(h, scal.p, 2 * NACC * sizeof(double), cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         d2h += 2 * NACC * sizeof(double);
         ++checks;
+        const double* hr = h;
+        const double* hc = h + NACC;
 
         const double tau = eta / w, sigma = eta * w;
         const double fpe2 = hc[1] / tau + 2.0 * hr[1] + hr[2] / sigma;
@@ -803,7 +1110,7 @@ struct Pdlp {
         rel_dres = std::sqrt(hc[0]) / (1.0 + norm_c);
         rel_gap = std::fabs(pobj - dobj) / (1.0 + std::fabs(pobj) + std::fabs(dobj));
         const double eps = opt.eps_rel;
-        if (opt.verbose > 0)
+        if (opt.verbose > 0 && rank == 0)
             fprintf(stderr, "[pdlp] it %7d k %6d pres %.3e dres %.3e gap %.3e pobj %.10e fpe %.3e w %.3e restarts %d\n",
                     total + 1, k, rel_pres, rel_dres, rel_gap, maximize ? -pobj : pobj, fpe, w, restarts);
         ++total;   // this check iteration is a full PDHG iteration
@@ -825,35 +1132,45 @@ struct Pdlp {
             else if ((double)k >= 0.36 * (double)total) restart = true;
         }
         fpe_prev = fpe;
+        const int span = std::max(std::max(nl, m), 1);
         if (restart) {
             const double ddx = std::sqrt(hc[2]), ddy = std::sqrt(hr[3]);
             if (ddx > 1e-10 && ddy > 1e-10) w = std::exp(0.5 * std::log(ddy / ddx) + 0.5 * std::log(w));
-            ELP_LAUNCH(k_restart, grid1(std::max(n, m)), 256, 0, st, n, x.p, x0.p, xp.p, m, y.p, y0.p, yp.p);
+            ELP_LAUNCH(k_restart, grid1(span), 256, 0, st, nl, x.p, x0.p, xp.p, m, y(), y0.p, yp.p);
             k = 0; ++restarts; need_fpe0 = true; fpe_prev = -1;
         } else {
             const double wk = (k + 1.0) / (k + 2.0);
-            ELP_LAUNCH(k_halpern_finish, grid1(std::max(n, m)), 256, 0, st, n, x.p, xbar.p, x0.p, m, y.p, yp.p, y0.p, wk);
+            ELP_LAUNCH(k_halpern_finish, grid1(span), 256, 0, st, nl, x.p, xbar(), x0.p, m, y(), yp.p, y0.p, wk);
             ++k;
         }
+        gather_y(y_full.p);                        // y changed: everyone needs the new blocks
         push_params();
         return false;
     }
 
     // Farkas-type certificates from the displacement (xp - x0, yp - y0); see oracle/pdlp_ref.py::_certificate
     bool detect_infeasible() {
-        double hr[NACC], hc[NACC];
+        double h[2 * NACC];
         const double tol = 1e-6;
-        // ray vectors: reuse xbar/axbar as scratch is not possible (needed for the Halpern finish) -> gbuf + axp
-        if (ray_dx.n == 0) { ray_dx.alloc(n); ray_dy.alloc(std::max(m, 1)); ray_ax.alloc(std::max(m, 1)); ray_g.alloc(n); }
-        DevBuf<double>&dxv = ray_dx, &dyv = ray_dy, &axray = ray_ax, &gray = ray_g;
-        launch_diff(n, xp.p, x0.p, dxv.p, st);
-        launch_diff(m, yp.p, y0.p, dyv.p, st);
-        spmv_rows(dxv.p, axray.p);
-        ELP_LAUNCH(k_ray_rows, RED_BLOCKS, RED_THREADS, 0, st, m, axray.p, yp.p, y0.p, lc.p, uc.p, dr.p, partials.p);
-        fetch_scalars(hr, true);
-        spmv_cols(dyv.p, gray.p);
-        ELP_LAUNCH(k_ray_cols, RED_BLOCKS, RED_THREADS, 0, st, n, xp.p, x0.p, c.p, l.p, u.p, gray.p, dc.p, partials.p);
-        fetch_scalars(hc, false);
+        // ray vectors in the scratch gathered buffers; their images in axp / gcol (both free at this point)
+        double* dxl = xaux_full.p + n0;
+        double* dyl = yaux_full.p + (size_t)rank * mb;
+        launch_diff(nl, xp.p, x0.p, dxl, st);
+        launch_diff(m, yp.p, y0.p, dyl, st);
+        gather_x(xaux_full.p);
+        gather_y(yaux_full.p);
+        spmv_rows(xaux_full.p, axp.p);
+        spmv_cols(yaux_full.p, gcol.p);
+        ELP_LAUNCH(k_ray_rows, RED_BLOCKS, RED_THREADS, 0, st, m, axp.p, yp.p, y0.p, lc.p, uc.p, dr.p, partials.p);
+        reduce_to(scal.p);
+        ELP_LAUNCH(k_ray_cols, RED_BLOCKS, RED_THREADS, 0, st, nl, xp.p, x0.p, c.p, l.p, u.p, gcol.p, dc.p, partials.p);
+        reduce_to(scal.p + NACC);
+        if (N > 1) comm_allreduce_sum(scal.p, 2 * NACC, st);
+        ELP_CUDA(cudaMemcpyAsync(h, scal.p, 2 * NACC * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        d2h += 2 * NACC * sizeof(double);
+        const double* hr = h;
+        const double* hc = h + NACC;
         // primal infeasibility: dual ray with positive objective and vanishing residual
         const double ray_obj = hr[2] + hc[5];
         const double ny = std::sqrt(hr[1]);
@@ -888,7 +1205,7 @@ struct Pdlp {
             if (k % ce == 0) {
                 if (check_iteration()) break;
                 --budget;
-                if (!dist && opt.time_limit_s > 0 && wall.ms() > opt.time_limit_s * 1e3) break;   // ranks must agree: no wall-clock exit when distributed
+                if (N == 1 && opt.time_limit_s > 0 && wall.ms() > opt.time_limit_s * 1e3) break;   // ranks must agree: no wall-clock exit when distributed
                 continue;
             }
             int cnt = ce - (k % ce);
@@ -919,47 +1236,40 @@ struct Pdlp {
         }
     }
 
+    // x: all n columns (gathered from the ranks' blocks); y: my rows
     void solution(double* x_h, double* y_h, double* obj) {
-        DevBuf<double> tmp(std::max(n, std::max(m, 1)));
         if (x_h) {
-            ELP_LAUNCH(k_unscale, grid1(n), 256, 0, st, n, xp.p, dc.p, 1.0, tmp.p);
-            tmp.download(x_h, n, st);
+            if (nl > 0) ELP_LAUNCH(k_unscale, grid1(nl), 256, 0, st, nl, xp.p, dc.p, 1.0, xaux_full.p + n0);
+            gather_x(xaux_full.p);
+            xaux_full.download(x_h, n, st);
             ELP_CUDA(cudaStreamSynchronize(st));
             d2h += (int64_t)n * 8;
         }
         if (y_h && m > 0) {
-            ELP_LAUNCH(k_unscale, grid1(m), 256, 0, st, m, yp.p, dr.p, maximize ? -1.0 : 1.0, tmp.p);
-            tmp.download(y_h, m, st);
+            ELP_LAUNCH(k_unscale, grid1(m), 256, 0, st, m, yp.p, dr.p, maximize ? -1.0 : 1.0, axp.p);
+            axp.download(y_h, m, st);
             ELP_CUDA(cudaStreamSynchronize(st));
             d2h += (int64_t)m * 8;
         }
         if (obj) *obj = maximize ? -pobj : pobj;
     }
 
-    // Times the two fused iteration kernels in isolation (local part only when distributed: no collective).
+    // Times the two fused iteration kernels in isolation (no collective).
     // Leaves the iterate in an arbitrary state: the caller resets afterwards.
     void probe_step(int reps, double* ms_primal, double* ms_dual) {
         cudaEvent_t e0, e1;
         ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
         float ms = 0;
-        PrimalEpi<false> pe{c.p, l.p, u.p, x0.p, x.p, xbar.p, xp.p, params.p, 0};
-        auto primal = [&] {
-            if (!dist) { launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, pe, st); }
-            else {
-                launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
-                ELP_LAUNCH((apply_epi_kernel<PrimalEpi<false>>), grid1(n), 256, 0, st, n, gbuf.p, pe);
-            }
-        };
-        for (int i = 0; i < 3; ++i) primal();
+        for (int i = 0; i < 3; ++i) primal_step<false>(0, false);
         ELP_CUDA(cudaEventRecord(e0, st));
-        for (int i = 0; i < reps; ++i) primal();
+        for (int i = 0; i < reps; ++i) primal_step<false>(0, false);
         ELP_CUDA(cudaEventRecord(e1, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (ms_primal) *ms_primal = ms / reps;
-        for (int i = 0; i < 3; ++i) dual_step<false>(0);
+        for (int i = 0; i < 3; ++i) dual_step<false>(0, false);
         ELP_CUDA(cudaEventRecord(e0, st));
-        for (int i = 0; i < reps; ++i) dual_step<false>(0);
+        for (int i = 0; i < reps; ++i) dual_step<false>(0, false);
         ELP_CUDA(cudaEventRecord(e1, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -972,16 +1282,16 @@ struct Pdlp {
         cudaEvent_t e0, e1;
         ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
         float ms = 0;
-        for (int i = 0; i < 3; ++i) { spmv_rows(xbar.p, axp.p); }
+        for (int i = 0; i < 3; ++i) { spmv_rows(xbar_full.p, axp.p); }
         ELP_CUDA(cudaEventRecord(e0, st));
-        for (int i = 0; i < reps; ++i) spmv_rows(xbar.p, axp.p);
+        for (int i = 0; i < reps; ++i) spmv_rows(xbar_full.p, axp.p);
         ELP_CUDA(cudaEventRecord(e1, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (ms_csr) *ms_csr = ms / reps;
-        for (int i = 0; i < 3; ++i) launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
+        for (int i = 0; i < 3; ++i) spmv_cols(y_full.p, gcol.p);
         ELP_CUDA(cudaEventRecord(e0, st));
-        for (int i = 0; i < reps; ++i) launch_spmv(plan_c, n, csc_ptr.p, csc_idx.p, csc_val.p, y.p, StoreEpi{gbuf.p}, st);
+        for (int i = 0; i < reps; ++i) spmv_cols(y_full.p, gcol.p);
         ELP_CUDA(cudaEventRecord(e1, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
