@@ -1,9 +1,11 @@
 """CPU, world_size 2 over gloo: the host-side logic of the multi-GPU paths.
 
-PDLP: every rank holds a row block of A (easylp_b200.partition.row_block) and a replica of x.  The identities the
-CUDA path relies on are checked with real collectives: local A_g x is the rank's slice of A x; the allreduce(sum) of
-the partial A_g' y_g is A' y; scalar partial sums ride in the tail of the same buffer (one collective per check).
-One full distributed PDHG iteration built from those pieces equals the single-process iteration of the oracle.
+PDLP: every rank holds a ROW block of A (easylp_b200.partition.row_block; K2 = A x-bar + dual update on its rows,
+gathering the whole x-bar) and a COLUMN block of A over all rows (K1 = A'y + primal update on its columns, gathering
+the whole y in the padded layout y_full[N][mb]).  Nothing is replicated; the blocks of x-bar and y are all-gathered.
+The identities the CUDA path relies on are checked with real collectives: the column block assembled from the ranks'
+row-block transposes equals the column slice of A; K1/K2 on the blocks + all-gathers reproduce the single-process
+PDHG step; the scalar partials of a check travel in one allreduce.
 Batched simplex: contiguous LP ranges, no collective — concatenating the ranks' results equals the whole batch."""
 import os
 import socket
@@ -39,37 +41,64 @@ def _worker(rank, world, port, out):
         nnz_local = int(q["row_ptr"][-1])
         assert abs(nnz_local - int(p["row_ptr"][m]) / world) <= 20          # balanced by non-zeros
 
-        rng = np.random.default_rng(1)                                        # same stream on every rank = replicas
+        import scipy.sparse as sp
+        A = sp.csr_matrix((p["vals"], p["col_idx"], p["row_ptr"]), shape=(m, n))
+        rp = q["row_ptr"].astype(np.int64)
+        Ar = sp.csr_matrix((q["vals"], q["col_idx"], q["row_ptr"]), shape=(q["m"], n))      # my row block
+        # block sizes exactly as pdlp.cu: equal column blocks (multiple of 4), rows padded to the largest block
+        nb = (-(-n // world) + 3) & ~3
+        n0 = min(n, rank * nb)
+        nl = max(0, min(n, (rank + 1) * nb) - n0)
+        sizes = [None] * world
+        td.all_gather_object(sizes, q["m"])
+        mb = (max(max(sizes), 1) + 3) & ~3
+        # the column block is assembled from every rank's transposed row block (pdlp.cu::build_column_block):
+        # each rank sends the slice of its local CSC that falls into my columns, row ids shifted into y_full
+        pieces = [None] * world
+        loc = Ar.tocsc()
+        mine = [(g, loc[:, min(n, g * nb):min(n, (g + 1) * nb)].tocoo()) for g in range(world)]
+        td.all_gather_object(pieces, [(g, c.row + rank * mb, c.col, c.data) for g, c in mine])
+        rows_, cols_, vals_ = [], [], []
+        for src in range(world):                                  # source order = ascending global row
+            g, r_, c_, v_ = pieces[src][rank]
+            assert g == rank
+            rows_.append(r_); cols_.append(c_); vals_.append(v_)
+        Ac = sp.coo_matrix((np.concatenate(vals_), (np.concatenate(rows_), np.concatenate(cols_))),
+                           shape=(world * mb, nl)).tocsc()          # [padded rows] x [my columns]
+        ref = A[:, n0:n0 + nl].tocsc()
+        pad_of = np.concatenate([np.arange(cuts[g], cuts[g + 1]) - cuts[g] + g * mb for g in range(world)])
+        assert (Ac[pad_of, :] != ref).nnz == 0                    # it IS the column slice of A
+
+        rng = np.random.default_rng(1)                             # same stream on every rank: a common (x, y)
         x = rng.normal(size=n)
         y = rng.normal(size=m)
-        rp_full = p["row_ptr"].astype(np.int64)
-        ax_full = gen._csr_matvec(rp_full, p["col_idx"], p["vals"], x, m)
-        aty_full = gen._csr_rmatvec(rp_full, p["col_idx"], p["vals"], y, n)
-
-        rp = q["row_ptr"].astype(np.int64)
-        ax_loc = gen._csr_matvec(rp, q["col_idx"], q["vals"], x, q["m"])
-        assert np.array_equal(ax_loc, ax_full[r0:r1])                          # local rows need no exchange
-
-        # partial A_g' y_g with the scalar partials packed behind it: ONE allreduce (pdlp.cu check_iteration)
-        part = gen._csr_rmatvec(rp, q["col_idx"], q["vals"], y[r0:r1], n)
-        tail = np.array([np.sum(ax_loc ** 2), np.dot(y[r0:r1], ax_loc)])
-        buf = torch.from_numpy(np.concatenate([part, tail]))
-        td.all_reduce(buf, op=td.ReduceOp.SUM)
-        buf = buf.numpy()
-        assert np.allclose(buf[:n], aty_full, rtol=1e-13, atol=1e-13)
-        assert np.isclose(buf[n], np.sum(ax_full ** 2), rtol=1e-12) and np.isclose(buf[n + 1], np.dot(y, ax_full), rtol=1e-12)
-
-        # one PDHG step T(z) assembled the distributed way == the single-process step
         tau, sigma = 0.3, 0.2
         lc, uc = row_bounds(p["sense"], p["rhs"])
-        xp = np.clip(x - tau * (p["c"] - buf[:n]), p["lb"], p["ub"])          # replicated primal update
-        xbar = 2 * xp - x
-        axb_loc = gen._csr_matvec(rp, q["col_idx"], q["vals"], xbar, q["m"])
-        yp_loc = dual_prox(y[r0:r1] - sigma * axb_loc, sigma, lc[r0:r1], uc[r0:r1])
-        xp1 = np.clip(x - tau * (p["c"] - aty_full), p["lb"], p["ub"])
-        yp1 = dual_prox(y - sigma * gen._csr_matvec(rp_full, p["col_idx"], p["vals"], 2 * xp1 - x, m), sigma, lc, uc)
-        assert np.allclose(xp, xp1, rtol=1e-12, atol=1e-12)
-        assert np.allclose(yp_loc, yp1[r0:r1], rtol=1e-12, atol=1e-12)
+        # single-process reference step T(z)
+        xp1 = np.clip(x - tau * (p["c"] - A.T @ y), p["lb"], p["ub"])
+        yp1 = dual_prox(y - sigma * (A @ (2 * xp1 - x)), sigma, lc, uc)
+
+        def gather(block, width):                                 # in-place all-gather of equal-sized blocks
+            buf = torch.zeros(world * width, dtype=torch.float64)
+            buf[rank * width:rank * width + block.size] = torch.from_numpy(block)
+            outs = [torch.zeros(width, dtype=torch.float64) for _ in range(world)]
+            td.all_gather(outs, buf[rank * width:(rank + 1) * width].clone())
+            return torch.cat(outs).numpy()
+
+        y_full = gather(y[r0:r1], mb)                              # padded row layout
+        # K1 on my column block: g = A' y over ALL rows, primal update of my x block, x-bar block published
+        gcol = Ac.T @ y_full
+        xp_blk = np.clip(x[n0:n0 + nl] - tau * (p["c"][n0:n0 + nl] - gcol), p["lb"][n0:n0 + nl], p["ub"][n0:n0 + nl])
+        assert np.allclose(xp_blk, xp1[n0:n0 + nl], rtol=1e-12, atol=1e-12)
+        xbar_full = gather(2 * xp_blk - x[n0:n0 + nl], nb)[:n]      # flat column layout
+        # K2 on my row block
+        yp_blk = dual_prox(y[r0:r1] - sigma * (Ar @ xbar_full), sigma, lc[r0:r1], uc[r0:r1])
+        assert np.allclose(yp_blk, yp1[r0:r1], rtol=1e-12, atol=1e-12)
+        # scalar partials of a check: row-side from the row block, column-side from the column block, ONE allreduce
+        part = torch.tensor([float(np.sum((Ar @ xbar_full) ** 2)), float(np.sum(gcol ** 2))], dtype=torch.float64)
+        td.all_reduce(part, op=td.ReduceOp.SUM)
+        assert np.isclose(part[0].item(), np.sum((A @ (2 * xp1 - x)) ** 2), rtol=1e-12)
+        assert np.isclose(part[1].item(), np.sum((A.T @ y) ** 2), rtol=1e-12)
 
         # batched path: contiguous ranges, no collective
         d = gen.dense_batch(B=101, seed=3)
