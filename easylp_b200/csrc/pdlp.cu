@@ -510,7 +510,7 @@ __global__ void k_peer_wait(const unsigned long long* __restrict__ my_row, int n
         const volatile unsigned long long* src = my_row + threadIdx.x;
         unsigned long long spins = 0;
         while (*src < want) {
-            if (++spins > (1ull << 31)) __trap();           // a peer died: fail instead of hanging the GPU
+            if (++spins > (1ull << 28)) __trap();           // ~30 s: a peer died — fail instead of hanging the GPU
             __nanosleep(64);
         }
     }

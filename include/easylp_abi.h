@@ -142,8 +142,11 @@ int elp_check_feasible(int32_t m, int32_t n, const int32_t* row_ptr, const int32
  * elp_pdlp_create uploads the LP, builds the CSC copy, scales (Ruiz + Pock-Chambolle), estimates
  * ||A||_2.  elp_pdlp_run advances until convergence or `max_new_iters` more iterations.
  * With a communicator initialised (elp_comm_init) and dist != 0 the caller passes ITS row block:
- * rows [row_begin, row_begin + m_local) of the global matrix (column ids global, 0..n-1); x, c, lb, ub
- * are replicated; one allreduce of the partial A'y per iteration. */
+ * rows [row_begin, row_begin + m_local) of the global matrix (column ids global, 0..n-1) and the FULL c, lb, ub.
+ * The library keeps the row block for A.x-bar and builds, by one exchange among the ranks, the column block it
+ * needs for A'.y; per iteration the ranks exchange their x-bar / y blocks over NVLink (peer stores from the kernel
+ * epilogues, NCCL all-gather as fallback) and the scalar residuals travel in one allreduce.
+ * elp_pdlp_solution returns all n entries of x on every rank and the rank's own m_local entries of y. */
 typedef struct elp_pdlp elp_pdlp;
 int elp_pdlp_create(int32_t m_local, int32_t n,
                     const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
