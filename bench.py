@@ -259,15 +259,24 @@ def bench_pdlp(args, dist, L, p, workload_name):
     dist.barrier()
     t0 = time.perf_counter()
     e2e_iters, h2d, d2h = 0, 0, 0
+    parts = {"create_s": 0.0, "run_s": 0.0, "solution_s": 0.0, "close_s": 0.0, "run_device_s": 0.0}
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         hh = create()
+        tb = time.perf_counter()
         st = hh.run()
+        tc = time.perf_counter()
         hh.solution()
+        td_ = time.perf_counter()
         e2e_iters += st.iterations
         h2d += st.h2d_bytes
         d2h += st.d2h_bytes + 8 * (n + q["m"])
         launches_e2e = st.kernel_launches
         hh.close()
+        te = time.perf_counter()
+        for key, v in (("create_s", tb - ta), ("run_s", tc - tb), ("solution_s", td_ - tc), ("close_s", te - td_),
+                       ("run_device_s", st.solve_ms * 1e-3)):
+            parts[key] += v / e2e_steps
     dist.barrier()
     e2e_s = dist.vmax(time.perf_counter() - t0)
 
@@ -305,6 +314,7 @@ def bench_pdlp(args, dist, L, p, workload_name):
         "restarts": last.restarts, "wall_ms_per_step": wall_ms / args.steps,
         "e2e": {"value": e2e_iters / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": int(h2d / e2e_steps),
                 "d2h_bytes_per_step": int(d2h / e2e_steps), "s_per_solve": e2e_s / e2e_steps, "steps": e2e_steps,
+                "breakdown": {k: round(v, 4) for k, v in parts.items()},
                 "path": "elp_pdlp_create(host CSR) -> elp_pdlp_run -> elp_pdlp_solution (= elp_solve_lp)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",

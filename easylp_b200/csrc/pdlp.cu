@@ -744,6 +744,13 @@ struct Pdlp {
                const int8_t* sense, const double* rhs, const double* c_h, int maximize_, const double* lb,
                const double* ub, const elp_options& o, bool dist_) {
         m = m_; n = n_; maximize = maximize_ != 0; opt = o;
+        WallTimer dbg_t;
+        const bool dbg = getenv("ELP_PDLP_DEBUG") != nullptr;
+        auto mark = [&](const char* what) {
+            if (!dbg) return;
+            cudaStreamSynchronize(st);
+            fprintf(stderr, "[pdlp setup] %-16s %9.3f ms\n", what, dbg_t.ms());
+        };
         const bool dist = dist_ && comm().active;
         N = dist ? comm().nranks : 1;
         rank = dist ? comm().rank : 0;
@@ -796,7 +803,9 @@ struct Pdlp {
         }
         if (maximize && nl > 0) ELP_LAUNCH(k_scale_scalar, grid1(nl), 256, 0, st, nl, c.p, -1.0);
 
+        mark("upload");
         build_column_block();
+        mark("column block");
         Lr = pick_helper_lanes(nnz, m);
         Lc = pick_helper_lanes(nnzc, nl);
         plan_r = plan_spmv(nnz, m, 4);
@@ -811,8 +820,11 @@ struct Pdlp {
         fetch_scalars(h);
         norm_c = std::sqrt(h[0]);
 
+        mark("norms");
         scale_problem();
+        mark("scaling");
         estimate_sigma_max();
+        mark("power iteration");
         eta = sigma_max > 0 ? 0.998 / sigma_max : 1.0;
         // initial primal weight from the scaled data: ||c|| / ||b||
         ELP_LAUNCH(k_bound_norm, RED_BLOCKS, RED_THREADS, 0, st, m, lc.p, uc.p, partials.p);
@@ -824,6 +836,7 @@ struct Pdlp {
         w_init = (nbn > 1e-10 && ncn > 1e-10) ? ncn / nbn : 1.0;
         setup_peer_stores();
         reset();
+        mark("reset");
     }
 
     // CSC of my column block over all rows, row ids in the padded y_full layout.  Every rank transposes its own row
