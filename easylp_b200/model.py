@@ -1070,6 +1070,55 @@ class easylp:
             out += [f"{name}[{','.join(reversed(g))}]" for g in grids]
         return out
 
+    # ---- lp_solve LP-format export ------------------------------------------------
+    def write_lp(self, path=None):
+        """The assembled model in lp_solve's LP format (17-digit coefficients, the canonical CSR row by row), so that a
+        machine with R + lpSolveAPI can solve byte-identical input with `read.lp()` and time / check the reference
+        backend at sizes the dense DSL cannot build.  Returns the text; writes it to `path` when given."""
+        rp, ci, v = self._csr()
+        names = [_lp_name(s) for s in self.variable_names()]
+        c = self.objective_fun
+        fmt = lambda a: repr(float(a))
+
+        def lin(cols, vals):
+            if len(cols) == 0:
+                return "0"
+            return " ".join(f"{'+' if a >= 0 else '-'}{fmt(abs(a))} {names[j]}" for j, a in zip(cols, vals))
+
+        nz = np.flatnonzero(c)
+        out = [f"/* easylp_b200 export: {self._n_var} variables, {rp.size - 1} constraints */",
+               f"{'max' if self._dir == 'max' else 'min'}: {lin(nz, c[nz])};", ""]
+        ops = {"<=": "<=", "<": "<=", ">=": ">=", ">": ">=", "==": "="}
+        rown = self.constraint.rownames
+        for i in range(rp.size - 1):
+            a, b = rp[i], rp[i + 1]
+            label = f"{_lp_name(rown[i])}: " if rown[i] else ""
+            out.append(f"{label}{lin(ci[a:b], v[a:b])} {ops[self.constraint.dir[i]]} {fmt(self.constraint.rhs[i])};")
+        out.append("")
+        lb, ub = self._bounds()
+        free = [names[j] for j in range(self._n_var) if lb[j] == -np.inf and ub[j] == np.inf]
+        for j in range(self._n_var):
+            if lb[j] == -np.inf and ub[j] == np.inf:
+                continue
+            if lb[j] == -np.inf:
+                out.append(f"{names[j]} >= -1e30;")
+                out.append(f"{names[j]} <= {fmt(ub[j])};")
+            elif ub[j] == np.inf:
+                if lb[j] != 0.0:
+                    out.append(f"{names[j]} >= {fmt(lb[j])};")
+            else:
+                out.append(f"{fmt(lb[j])} <= {names[j]} <= {fmt(ub[j])};")
+        if free:
+            out.append("free " + ", ".join(free) + ";")
+        ints = [n_ for n_, x in zip(names, (t for x in self.variables.values() for t in [x] * x.ind.size)) if x.integer or x.binary]
+        if ints:
+            out.append("int " + ", ".join(ints) + ";")
+        text = "\n".join(out) + "\n"
+        if path is not None:
+            with open(path, "w") as fh:
+                fh.write(text)
+        return text
+
     def __repr__(self):                 # $print  R/class.R:470-494
         s = f"Easy Linear Problem \nStatus: {self._stat}"
         if self._stat != "optimal":
@@ -1078,6 +1127,11 @@ class easylp:
         if self.objective_add != 0:
             s += f" {'+' if self.objective_add > 0 else '-'} {abs(self.objective_add)} = {self.objective_value}"
         return s + f"\n\nSolution:\n\n{self.solution}"
+
+
+def _lp_name(s):
+    """an identifier lp_solve's LP parser accepts: letters, digits and _ [ ] . only"""
+    return "".join(ch if (ch.isascii() and (ch.isalnum() or ch in "_[].")) else "_" for ch in s)
 
 
 def _warn_decreasing_transformation(f, lower, upper):    # R/utils.R:199-217

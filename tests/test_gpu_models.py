@@ -97,3 +97,29 @@ def test_new_constraint_invalidates_solution_message():
     x = lp["x"]
     lp.con(cut=M.Sum(x) <= 1)
     assert lp.status == "unsolved" and any("are unfeasible" in m for m in lp.messages)
+
+
+def test_write_lp_readme():
+    # lp_solve LP-format export of the assembled model
+    lp = _build("readme")
+    text = lp.write_lp()
+    assert "max: +1.0 x +1.0 y;" in text
+    assert "+1.0 x +2.0 y <= 3.0;" in text
+    assert "-3.0 x +1.0 y >= -2.0;" in text
+    assert "free x, y;" in text
+
+
+def test_write_lp_round_trip_dop(tmp_path):
+    """every coefficient survives the text round trip bit for bit (repr of a double is exact)"""
+    import re
+    lp = _build("dop")
+    text = lp.write_lp(tmp_path / "dop.lp")
+    g = GOLD["dop"]
+    rows = [ln for ln in text.splitlines() if re.match(r"^[A-Za-z_].*: ", ln) and not ln.startswith(("min", "max"))]
+    assert len(rows) == g["m"]
+    vals = []
+    for ln in rows:
+        body = ln.split(": ", 1)[1]
+        lhs = re.split(r" (<=|>=|=) ", body)[0]
+        vals += [float(sign + num) for sign, num in re.findall(r"([+-])([0-9.e+-]+) ", lhs + " ")]
+    assert np.array(vals).tobytes() == g["vals"].tobytes()
