@@ -53,12 +53,12 @@ __device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 __device__ __forceinline__ double ldg_hint(const double* ptr, uint64_t policy) {

@@ -55,7 +55,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "sweep":
     b_csc = 12 * nnz + 4 * (n + 1) + 8 * m + 56 * n
     b_csr = 12 * nnz + 4 * (m + 1) + 8 * n + 40 * m
     os.environ["ELP_SPMV_DEBUG"] = "1"
-    for lanes, ctas, nst, capsig in ((0, 0, 2, 100), (0, 0, 1, 100), (0, 2, 2, 100), (0, 0, 2, 200), (0, 0, 2, 0), (1, 0, 2, 100), (2, 0, 2, 100)):
+    for lanes, ctas, nst, capsig in ((0, 0, 1, 100), (0, 0, 1, 100), (1, 0, 1, 100), (2, 0, 1, 100), (0, 5, 1, 100), (0, 4, 1, 100)):
         carve = 0
         os.environ["ELP_SPMV_RPL"] = str(nst)       # third field: rows per lane
         cw, capmul = lanes, capsig
