@@ -73,7 +73,7 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
         mbar_fence_init();
     }
     __syncwarp();
-    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    const uint64_t pol_stream = l2_policy_evict_first();
     const int gw = blockIdx.x * SPMV_WARPS + warp, nw = gridDim.x * SPMV_WARPS;
 
     // ---- producer cursor: the next piece to copy (uniform across the warp) --------------------------------
@@ -173,24 +173,30 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             }
             while (more) {
                 // the RPL rows of a lane advance together: their gathers are independent and overlap.
-                // indices first, gathers next, the values are read from the stage only when they are consumed
+                // indices first, gathers next, the values are read from the stage only when they are consumed.
+                // Instruction economy matters here (the kernel is issue-bound): one compare against an immediate per
+                // entry, plain read-only loads for the gathers.
                 double x[RPL][U];
-                int c[RPL][U];
+                int c[RPL][U], cnt[RPL];
+                const int* sij[RPL];
+                const double* svj[RPL];
+#pragma unroll
+                for (int j = 0; j < RPL; ++j) { cnt[j] = f[j] - k[j]; sij[j] = si + k[j]; svj[j] = sv + k[j]; }
 #pragma unroll
                 for (int j = 0; j < RPL; ++j)
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (k[j] + u * L < f[j]) c[j][u] = si[k[j] + u * L];
+                        if (u * L < cnt[j]) c[j][u] = sij[j][u * L];
 #pragma unroll
                 for (int j = 0; j < RPL; ++j)
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (k[j] + u * L < f[j]) x[j][u] = ldg_hint(vec + c[j][u], pol_keep);
+                        if (u * L < cnt[j]) x[j][u] = __ldg(vec + c[j][u]);
 #pragma unroll
                 for (int j = 0; j < RPL; ++j)
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (k[j] + u * L < f[j]) acc[j] = __dadd_rn(acc[j], __dmul_rn(sv[k[j] + u * L], x[j][u]));
+                        if (u * L < cnt[j]) acc[j] = __dadd_rn(acc[j], __dmul_rn(svj[j][u * L], x[j][u]));
                 more = false;
 #pragma unroll
                 for (int j = 0; j < RPL; ++j) { k[j] += U * L; more |= k[j] < f[j]; }
