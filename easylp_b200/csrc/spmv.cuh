@@ -15,9 +15,9 @@
 //     vectors (x, c, l, u, x0 / y, lc, uc, y0) — is brought into the ring by 1-D TMA bulk copies
 //     (cp.async.bulk -> mbarrier complete_tx); lane i of the warp issues copy i, NSTW tiles ahead of the
 //     tile being consumed, so the HBM latency is covered by the ring and not by the warp's own loads;
-//   * the only loads the lanes issue to global memory are the gathers vec[idx[k]] (random 8-byte reads
-//     that hit L2, marked evict-last; the matrix stream is marked evict-first), U of them in flight per
-//     lane; a group of L lanes walks one row (L = 1: one lane per row, the sum is formed strictly in
+//   * the only loads the lanes issue to global memory are the gathers vec[idx[k]] (random 8-byte read-only
+//     loads that hit L2; the matrix stream is marked evict-first so it does not push the vector out), U of
+//     them in flight per lane; a group of L lanes walks one row (L = 1: one lane per row, the sum is formed strictly in
 //     index order with separate multiply and add, i.e. bit-identical to a scalar CPU loop);
 //   * rows longer than a stage are walked in pieces with a running sum.
 // Array contract: val/idx are over-allocated by SPMV_PAD entries, ptr by 4 ints and every epilogue
