@@ -23,6 +23,18 @@ __global__ void __launch_bounds__(256) gather_kernel(const int* __restrict__ idx
     }
 }
 
+// the dual question: 20 M random fire-and-forget fp64 reductions (RED.ADD) into the same vector
+template <int PER>
+__global__ void __launch_bounds__(256) scatter_kernel(const int* __restrict__ idx, double* __restrict__ vec, int nrows) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+        int c[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) c[u] = __ldg(idx + (size_t)u * nrows + r);
+#pragma unroll
+        for (int u = 0; u < PER; ++u) atomicAdd(vec + c[u], 1.0);
+    }
+}
+
 template <int PER>
 static void run(int nvec, int nrows) {
     std::vector<int> h((size_t)PER * nrows);
@@ -41,6 +53,16 @@ static void run(int nvec, int nrows) {
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
         const double g = (double)PER * nrows;
         printf("{\"gathers\": %.0f, \"per_row\": %d, \"vec_MB\": %.0f, \"grid\": %d, \"ms\": %.4f, \"Ggather_per_s\": %.1f}\n", g, PER,
+               nvec * 8 / 1e6, grid, ms, g / ms / 1e6);
+    }
+    for (int grid : {148 * 8, 148 * 32}) {
+        for (int i = 0; i < 3; ++i) scatter_kernel<PER><<<grid, 256>>>(idx, vec, nrows);
+        cudaEventRecord(e0);
+        for (int i = 0; i < 20; ++i) scatter_kernel<PER><<<grid, 256>>>(idx, vec, nrows);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
+        const double g = (double)PER * nrows;
+        printf("{\"red_adds\": %.0f, \"per_row\": %d, \"vec_MB\": %.0f, \"grid\": %d, \"ms\": %.4f, \"Gred_per_s\": %.1f}\n", g, PER,
                nvec * 8 / 1e6, grid, ms, g / ms / 1e6);
     }
     cudaFree(idx); cudaFree(vec); cudaFree(out);
