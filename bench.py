@@ -250,6 +250,7 @@ def bench_pdlp(args, dist, L, p, workload_name):
     clocks = sampler.stop() if dist.rank == 0 else None
     dev_ms = dist.vmax(dev_ms)
     x, y, obj = h.solution()
+    scatter = h.transpose() == L.TRANSPOSE_SCATTER
     ms_csr, ms_csc = h.probe_spmv(20)
     ms_primal, ms_dual = h.probe_step(50)
     h.close()
@@ -292,10 +293,23 @@ def bench_pdlp(args, dist, L, p, workload_name):
         b_csc = 12 * nnzc + 4 * (ncl + 1) + 8 * m + 56 * ncl
         b_csr = 12 * nnzl + 4 * (ml + 1) + 8 * n + 40 * ml
         b_iter = b_csc + b_csr
+    b_two_spmv = b_iter                  # what an iteration built from two SpMVs must move
+    name_primal = "spmv_warp_kernel<L,NSTW,PrimalEpi> (CSC A'y + fused primal update)"
+    name_dual = "spmv_warp_kernel<L,NSTW,DualEpi> (CSR A.xbar + fused dual update)"
+    key_primal, key_dual = "primal", "dual"
+    if scatter:
+        # scatter formulation (single GPU): ONE matrix stream per iteration.  The dual kernel reads the CSR stream, gathers
+        # x-bar, updates y and sends val*y_new into g (fp64 reductions resolved in L2: g costs its 8n-byte write-back
+        # at most, counted with the primal pass that reads and clears it); the primal pass is elementwise:
+        # g, x, c, l, u, x0 read, x-bar, x, g written.
+        b_csr = 12 * nnzl + 4 * (ml + 1) + 8 * n + 40 * ml
+        b_csc = 72 * n
+        b_iter = b_csr + b_csc
+        name_primal = "k_primal_from_g (gather-free primal update; reads and clears g = A'y)"
+        name_dual = "spmv_warp_kernel<L,NSTW,DualEpi<scatter>> (CSR A.xbar + dual update + RED.ADD.F64 scatter of A'y)"
+        key_primal, key_dual = "primal_from_g", "dual_scatter"
     dom_ms, dom_b, dom_name, dom_key = \
-        (ms_primal, b_csc, "spmv_warp_kernel<L,NSTW,PrimalEpi> (CSC A'y + fused primal update)", "primal") \
-        if ms_primal >= ms_dual else \
-        (ms_dual, b_csr, "spmv_warp_kernel<L,NSTW,DualEpi> (CSR A.xbar + fused dual update)", "dual")
+        (ms_primal, b_csc, name_primal, key_primal) if ms_primal >= ms_dual else (ms_dual, b_csr, name_dual, key_dual)
     traffic = ncu_traffic(dom_key) if (N == 1 and args.scale == 1.0 and args.workload == "pdlp") else None
     ach = dom_b / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     iter_ms = dev_ms / max(iters, 1)
@@ -320,10 +334,17 @@ def bench_pdlp(args, dist, L, p, workload_name):
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "peak_source": peak_src, "traffic": traffic,
                      "bytes_per_launch": dom_b, "ms_per_launch": dom_ms,
+                     "formulation": "scatter" if scatter else "gather",
                      "iteration": {"bytes": b_iter, "ms": iter_ms, "achieved": b_iter / (iter_ms * 1e-3) / 1e9,
                                    "frac": b_iter / (iter_ms * 1e-3) / 1e9 / peak,
-                                   "note": "whole-solve average incl. check iterations, per rank's local block"},
+                                   "two_spmv_bytes": b_two_spmv,
+                                   "two_spmv_equivalent_gbs": b_two_spmv / (iter_ms * 1e-3) / 1e9,
+                                   "two_spmv_equivalent_frac": b_two_spmv / (iter_ms * 1e-3) / 1e9 / peak,
+                                   "note": "whole-solve average incl. check iterations, per rank's local block; "
+                                           "`bytes` = what THIS formulation must move, `two_spmv_*` = SURVEY 8d's "
+                                           "A.x + A'.y iteration bytes over the same time (equal for 'gather')"},
                      "fused_primal_ms": ms_primal, "fused_dual_ms": ms_dual,
+                     "kernel_timing": "CUDA events between the launches of 50 consecutive iterations from a mid-solve iterate",
                      "bare_spmv": {"csr_ms": ms_csr, "csc_ms": ms_csc,
                                    "csr_gbs": (12 * nnzl + 4 * (ml + 1) + 8 * n + 8 * ml) / (ms_csr * 1e-3) / 1e9,
                                    "csc_gbs": (12 * nnzl + 4 * (n + 1) + 8 * ml + 8 * n) / (ms_csc * 1e-3) / 1e9}},
@@ -362,12 +383,15 @@ def bench_batch(args, dist, L, d):
     n_opt = dist.vsum(float((status == 0).sum()))
     # e2e through elp_solve_batch with host buffers
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    out = (pinned(np.zeros(Bl, np.int32)), pinned(np.zeros(Bl)), pinned(np.zeros((Bl, n))))
+    L.solve_batch(hp["A"], hp["b"], hp["c"], hp["lb"], hp["ub"], hp["sense"], out=out)      # warm-up: workspace + streams
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        s2, o2, x2, st2 = L.solve_batch(hp["A"], hp["b"], hp["c"], hp["lb"], hp["ub"], hp["sense"])
+        s2, o2, x2, st2 = L.solve_batch(hp["A"], hp["b"], hp["c"], hp["lb"], hp["ub"], hp["sense"], out=out)
     dist.barrier()
     e2e_s = dist.vmax(time.perf_counter() - t0)
+    assert np.array_equal(s2, status) and np.array_equal(o2, obj), "streamed elp_solve_batch differs from the resident batch"
     pivots = dist.vsum(float(st2.iterations))
     peak, peak_src = measured_peak()
     bytes_lp = 8 * (m * n + m + 3 * n) + m + 8 * (n + 1) + 4 + 4

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libeasylp_b200.so")
 LE, GE, EQ = 0, 1, 2
 STATUS_OPTIMAL, STATUS_INFEASIBLE, STATUS_UNBOUNDED, STATUS_NUMFAILURE, STATUS_TIMEOUT = 0, 2, 3, 5, 7
 METHOD_AUTO, METHOD_SIMPLEX, METHOD_PDLP = 0, 1, 2
+TRANSPOSE_AUTO, TRANSPOSE_GATHER, TRANSPOSE_SCATTER = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 
 
@@ -28,7 +29,8 @@ class ElpError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("eps_rel", C.c_double), ("time_limit_s", C.c_double), ("max_iter", C.c_int32),
                 ("check_every", C.c_int32), ("method", C.c_int32), ("verbose", C.c_int32),
-                ("use_graph", C.c_int32), ("ruiz_iters", C.c_int32)]
+                ("use_graph", C.c_int32), ("ruiz_iters", C.c_int32), ("transpose", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -49,7 +51,7 @@ ABI_SYMBOLS = [
     "elp_status_string", "elp_kernel_launches", "elp_release_workspace", "elp_assemble_csr", "elp_solve_lp", "elp_solve_batch",
     "elp_batch_create", "elp_batch_run", "elp_batch_fetch", "elp_batch_destroy", "elp_spmv",
     "elp_check_feasible", "elp_pdlp_create", "elp_pdlp_run", "elp_pdlp_reset", "elp_pdlp_solution",
-    "elp_pdlp_probe_spmv", "elp_pdlp_probe_step", "elp_pdlp_destroy", "elp_comm_unique_id", "elp_comm_init", "elp_comm_size",
+    "elp_pdlp_probe_spmv", "elp_pdlp_probe_step", "elp_pdlp_transpose", "elp_pdlp_destroy", "elp_comm_unique_id", "elp_comm_init", "elp_comm_size",
     "elp_comm_destroy",
 ]
 
@@ -186,16 +188,24 @@ def solve_lp(m, n, row_ptr, col_idx, vals, sense, rhs, c, lb, ub, maximize=False
     return LpResult(status.value, obj.value, x, y[:m], st)
 
 
-def solve_batch(A, b, c, lb=None, ub=None, sense=None, maximize=False, options: Options | None = None):
+def solve_batch(A, b, c, lb=None, ub=None, sense=None, maximize=False, options: Options | None = None, out=None):
+    """elp_solve_batch on host arrays.  `out` = (status int32[B], obj f64[B], x f64[B, n]) lets the caller supply the result
+    buffers (e.g. page-locked ones, so the device->host copies of the streamed call stay asynchronous)."""
     A = _f64(A)
     B, m, n = A.shape
     b, c = _f64(b, (B, m)), _f64(c, (B, n))
     lb = _f64(lb, (B, n)) if lb is not None else None
     ub = _f64(ub, (B, n)) if ub is not None else None
     sense = _i8(np.broadcast_to(sense, (B, m))) if sense is not None else None
-    status = np.zeros(B, np.int32)
-    obj = np.zeros(B)
-    x = np.zeros((B, n))
+    if out is not None:
+        status, obj, x = out
+        assert status.dtype == np.int32 and status.shape == (B,) and status.flags.c_contiguous
+        assert obj.dtype == np.float64 and obj.shape == (B,) and obj.flags.c_contiguous
+        assert x.dtype == np.float64 and x.shape == (B, n) and x.flags.c_contiguous
+    else:
+        status = np.zeros(B, np.int32)
+        obj = np.zeros(B)
+        x = np.zeros((B, n))
     st = Stats()
     _check(lib().elp_solve_batch(C.c_int64(B), C.c_int32(m), C.c_int32(n), _p(A), _p(b), _p(c), _p(lb), _p(ub), _p(sense),
                                  C.c_int32(1 if maximize else 0), C.byref(options) if options is not None else None,
@@ -294,6 +304,12 @@ class Pdlp:
         a, b = C.c_double(), C.c_double()
         _check(lib().elp_pdlp_probe_step(self._h, C.c_int32(reps), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def transpose(self) -> int:
+        """TRANSPOSE_GATHER or TRANSPOSE_SCATTER: how the plain iterations of this handle form A'y."""
+        mode = C.c_int32(0)
+        _check(lib().elp_pdlp_transpose(self._h, C.byref(mode)))
+        return mode.value
 
     def close(self):
         if self._h:

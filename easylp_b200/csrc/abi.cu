@@ -29,6 +29,7 @@ void pdlp_reset(Pdlp* p);
 void pdlp_solution(Pdlp* p, double* x, double* y, double* obj);
 void pdlp_probe(Pdlp* p, int reps, double* a, double* b);
 void pdlp_probe_step(Pdlp* p, int reps, double* a, double* b);
+int pdlp_transpose(Pdlp* p);
 void pdlp_destroy(Pdlp* p);
 void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals, const double* x,
                double* out, const int8_t* sense, const double* rhs, double tol, uint8_t* feasible);
@@ -69,6 +70,55 @@ struct Batch {
     bool has_lb = false, has_ub = false, has_sense = false;
     int64_t h2d = 0;
 };
+
+// Grow-only workspace of the streamed elp_solve_batch (per host thread; re-created when the thread switches device).
+struct BatchStreamWorkspace {
+    static constexpr int NS = 3;
+    int device = -1;
+    cudaStream_t st[NS] = {};
+    cudaEvent_t done[NS] = {};
+    DevBuf<double> A[NS], b[NS], c[NS], lb[NS], ub[NS], obj[NS], x[NS];
+    DevBuf<int8_t> sense[NS];
+    DevBuf<int32_t> status[NS], piv[NS];
+    int32_t* piv_host = nullptr;       // page-locked, one counter per LP of the whole batch
+    size_t piv_cap = 0;
+    void release() {
+        for (int s = 0; s < NS; ++s) {
+            if (st[s]) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); st[s] = nullptr; }
+            if (done[s]) { cudaEventDestroy(done[s]); done[s] = nullptr; }
+            A[s].release(); b[s].release(); c[s].release(); lb[s].release(); ub[s].release(); obj[s].release();
+            x[s].release(); sense[s].release(); status[s].release(); piv[s].release();
+        }
+        if (piv_host) cudaFreeHost(piv_host);
+        piv_host = nullptr; piv_cap = 0; device = -1;
+    }
+    ~BatchStreamWorkspace() { release(); }
+    void ensure(size_t chunk, size_t B, int m, int n, bool has_lb, bool has_ub, bool has_sense) {
+        int dev = 0;
+        ELP_CUDA(cudaGetDevice(&dev));
+        if (dev != device) { release(); device = dev; }
+        auto grow = [](auto& buf, size_t cnt) { if (buf.n < cnt) buf.alloc(cnt + cnt / 8); };
+        for (int s = 0; s < NS; ++s) {
+            if (!st[s]) ELP_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+            if (!done[s]) ELP_CUDA(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
+            grow(A[s], chunk * (size_t)std::max(m, 1) * n); grow(b[s], chunk * (size_t)std::max(m, 1)); grow(c[s], chunk * n);
+            if (has_lb) grow(lb[s], chunk * n);
+            if (has_ub) grow(ub[s], chunk * n);
+            if (has_sense) grow(sense[s], chunk * (size_t)std::max(m, 1));
+            grow(obj[s], chunk); grow(x[s], chunk * n); grow(status[s], chunk); grow(piv[s], chunk);
+        }
+        if (piv_cap < B) {
+            if (piv_host) cudaFreeHost(piv_host);
+            piv_host = nullptr; piv_cap = 0;
+            ELP_CUDA(cudaMallocHost(&piv_host, (B + B / 8) * sizeof(int32_t)));
+            piv_cap = B + B / 8;
+        }
+    }
+};
+BatchStreamWorkspace& batch_stream_workspace() {
+    static thread_local BatchStreamWorkspace w;
+    return w;
+}
 
 }  // namespace elp
 
@@ -122,6 +172,8 @@ int elp_default_options(elp_options* o) {
     o->verbose = 0;
     o->use_graph = 1;
     o->ruiz_iters = 10;
+    o->transpose = ELP_TRANSPOSE_AUTO;
+    o->reserved = 0;
     return 0;
 }
 
@@ -149,6 +201,7 @@ int64_t elp_kernel_launches(void) { return elp::g_launches.load(); }
 int elp_release_workspace(void) {
     ELP_TRY
     asm_workspace_release();
+    batch_stream_workspace().release();
     ELP_CATCH
 }
 
@@ -357,30 +410,73 @@ int elp_batch_destroy(elp_batch* hh) {
     ELP_CATCH
 }
 
+// Host-buffer entry point: the batch is streamed through the GPU in chunks.  Chunk i's host->device copies, its kernel
+// and its device->host copies are queued on stream i % 3, each slot with its own device buffers, so the copy engines
+// (both directions) and the SMs work on different chunks at the same time; with page-locked caller buffers the call runs
+// at PCIe speed (5.7 KB per 20x30 LP in, 0.25 KB out).  Device buffers, streams and the pinned pivot counters come from
+// a grow-only per-thread workspace (elp_release_workspace frees it).
 int elp_solve_batch(int64_t B, int32_t m, int32_t n, const double* A, const double* b, const double* c,
                     const double* lb, const double* ub, const int8_t* sense, int32_t maximize, const elp_options* opt,
                     int32_t* status, double* obj, double* x, elp_stats* stats) {
+    ELP_TRY
     WallTimer wall;
-    elp_batch* h = nullptr;
-    if (elp_batch_create(B, m, n, A, b, c, lb, ub, sense, maximize, &h)) return 1;
-    elp_stats s;
-    memset(&s, 0, sizeof s);
-    int rc = elp_batch_run(h, opt, &s);
-    if (!rc) rc = elp_batch_fetch(h, status, obj, x);
-    if (!rc && stats) {
-        auto* bh = reinterpret_cast<Batch*>(h);
-        *stats = s;
-        stats->h2d_bytes = bh->h2d;
-        stats->d2h_bytes = B * ((int64_t)n * 8 + 12);
+    require_device();
+    ELP_REQUIRE(B > 0 && m >= 0 && n > 0 && A && b && c, "elp_solve_batch: bad arguments");
+    ELP_REQUIRE(status && obj && x, "elp_solve_batch: status, obj and x must be provided");
+    const elp_options o = effective_options(opt);
+    const int64_t l0 = g_launches.load();
+    BatchStreamWorkspace& w = batch_stream_workspace();
+    // chunk size: ~64 MB of input per chunk, at least 3 chunks when the batch is worth splitting, at most B
+    const int64_t in_per_lp = (int64_t)8 * ((int64_t)m * n + m + n) + (lb ? 8 * n : 0) + (ub ? 8 * n : 0) + (sense ? m : 0);
+    int64_t chunk = std::max<int64_t>(1, (64ll << 20) / std::max<int64_t>(in_per_lp, 1));
+    if (B >= 3 * 4096) chunk = std::min(chunk, (B + 2) / 3);
+    chunk = std::min(chunk, B);
+    const int64_t nchunks = (B + chunk - 1) / chunk;
+    w.ensure((size_t)chunk, (size_t)B, m, n, lb != nullptr, ub != nullptr, sense != nullptr);
+    cudaEvent_t e0, e1;
+    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    ELP_CUDA(cudaEventRecord(e0, w.st[0]));
+    for (int64_t i = 0; i < nchunks; ++i) {
+        const int s = (int)(i % BatchStreamWorkspace::NS);
+        cudaStream_t st = w.st[s];
+        const int64_t lo = i * chunk, cnt = std::min(chunk, B - lo);
+        const size_t mn = (size_t)m * n;
+        w.A[s].upload(A + lo * mn, (size_t)cnt * mn, st);
+        w.b[s].upload(b + lo * m, (size_t)cnt * m, st);
+        w.c[s].upload(c + lo * n, (size_t)cnt * n, st);
+        if (lb) w.lb[s].upload(lb + lo * n, (size_t)cnt * n, st);
+        if (ub) w.ub[s].upload(ub + lo * n, (size_t)cnt * n, st);
+        if (sense) w.sense[s].upload(sense + lo * m, (size_t)cnt * m, st);
+        simplex_batch_device(cnt, m, n, w.A[s].p, w.b[s].p, w.c[s].p, lb ? w.lb[s].p : nullptr, ub ? w.ub[s].p : nullptr,
+                             sense ? w.sense[s].p : nullptr, maximize, o.max_iter, w.status[s].p, w.obj[s].p, w.x[s].p,
+                             nullptr, w.piv[s].p, st);
+        w.status[s].download(status + lo, (size_t)cnt, st);
+        w.obj[s].download(obj + lo, (size_t)cnt, st);
+        w.x[s].download(x + lo * n, (size_t)cnt * n, st);
+        ELP_CUDA(cudaMemcpyAsync(w.piv_host + lo, w.piv[s].p, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 1; s < BatchStreamWorkspace::NS; ++s) {     // join the other slots into stream 0 for the closing event
+        ELP_CUDA(cudaEventRecord(w.done[s], w.st[s]));
+        ELP_CUDA(cudaStreamWaitEvent(w.st[0], w.done[s], 0));
+    }
+    ELP_CUDA(cudaEventRecord(e1, w.st[0]));
+    ELP_CUDA(cudaStreamSynchronize(w.st[0]));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->method_used = ELP_METHOD_SIMPLEX;
+        stats->solve_ms = ms;                       // device time of the whole streamed call (copies included)
+        stats->kernel_launches = g_launches.load() - l0;
+        stats->h2d_bytes = B * in_per_lp;
+        stats->d2h_bytes = B * ((int64_t)n * 8 + 16);
         int64_t piv = 0;
-        std::vector<int32_t> pv((size_t)B);
-        cudaMemcpy(pv.data(), bh->pivots.p, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost);
-        for (int32_t v : pv) piv += v;
+        for (int64_t i = 0; i < B; ++i) piv += w.piv_host[i];
         stats->iterations = (int32_t)std::min<int64_t>(piv, 0x7fffffff);
         stats->total_ms = wall.ms();
     }
-    elp_batch_destroy(h);
-    return rc;
+    ELP_CATCH
 }
 
 int elp_spmv(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals, const double* x,
@@ -440,6 +536,12 @@ int elp_pdlp_probe_step(elp_pdlp* h, int32_t reps, double* ms_primal, double* ms
     ELP_TRY
     ELP_REQUIRE(h && reps > 0, "bad arguments");
     pdlp_probe_step(reinterpret_cast<Pdlp*>(h), reps, ms_primal, ms_dual);
+    ELP_CATCH
+}
+int elp_pdlp_transpose(elp_pdlp* h, int32_t* mode) {
+    ELP_TRY
+    ELP_REQUIRE(h && mode, "bad arguments");
+    *mode = pdlp_transpose(reinterpret_cast<Pdlp*>(h));
     ELP_CATCH
 }
 int elp_pdlp_destroy(elp_pdlp* h) {

@@ -44,20 +44,24 @@ constexpr int SPMV_THREADS = 256;             // block size of the setup-only he
 template <class Epi>
 __global__ void __launch_bounds__(256) apply_epi_kernel(int n, const double* __restrict__ g, Epi epi) {
     const int j = blockIdx.x * 256 + threadIdx.x;
-    if (j < n) epi.apply(j, g[j], epi.preload_global(j));
+    if (j < n) epi.apply(j, g[j], epi.preload_global(j), L2Hints{0, 0, 0});
 }
 
 // ---- epilogues of the SpMV (spmv.cuh): in(i) names the operand vectors the producer stages next to the
 // matrix stream, preload() picks this row's operands out of the stage, apply() runs after the row sum ------
 struct StoreEpi {
     static constexpr int NIN = 0;
+    static constexpr bool SCATTER = false;
+    double* scat = nullptr;
     double* out;
     struct Pre {};
     __device__ __forceinline__ const double* in(int) const { return nullptr; }
     __device__ __forceinline__ Pre preload(const double*, int, int) const { return Pre{}; }
     __device__ __forceinline__ Pre preload_global(int) const { return Pre{}; }
-    __device__ __forceinline__ void apply(int r, double s, const Pre&) const { out[r] = s; }
+    __device__ __forceinline__ double apply(int r, double s, const Pre&, const L2Hints&) const { out[r] = s; return 0.0; }
 };
+
+inline StoreEpi store_epi(double* out) { StoreEpi e; e.out = out; return e; }
 
 // Where an epilogue publishes the block it produces: its own copy of the gathered vector, or — when the ranks have
 // mapped each other's buffers (CUDA IPC over NVLink) — the copy of EVERY rank, so that the all-gather is done by the
@@ -71,6 +75,8 @@ struct PeerOut {
 template <bool CHECK>
 struct PrimalEpi {
     static constexpr int NIN = CHECK ? 4 : 5;
+    static constexpr bool SCATTER = false;
+    double* scat;
     const double* __restrict__ c;
     const double* __restrict__ l;
     const double* __restrict__ u;
@@ -97,7 +103,7 @@ struct PrimalEpi {
         p.x0 = CHECK ? 0.0 : x0[j];
         return p;
     }
-    __device__ __forceinline__ void apply(int j, double g, const Pre& p) const {
+    __device__ __forceinline__ double apply(int j, double g, const Pre& p, const L2Hints& h) const {
         const double tau = P->tau;
         const double xpj = fmin(fmax(p.x - tau * (p.c - g), p.l), p.u);
         const double xb = 2.0 * xpj - p.x;
@@ -105,22 +111,26 @@ struct PrimalEpi {
 #pragma unroll 8
             for (int r = 0; r < peers.n; ++r) peers.p[r][j] = xb;
         } else {
-            xbar[j] = xb;
+            st_out(xbar + j, xb, h, true);
         }
         if (CHECK) {
             xp[j] = xpj;
         } else {
             const double k = (double)(P->k_base + it);
             const double w = (k + 1.0) / (k + 2.0);
-            x[j] = w * xb + (1.0 - w) * p.x0;
+            st_out(x + j, w * xb + (1.0 - w) * p.x0, h, false);
         }
+        return 0.0;
     }
 };
 
-// dual half.  ax = (A xbar)_i
-template <bool CHECK>
+// dual half.  ax = (A xbar)_i.  SCAT: the kernel then adds val[k] * y_new_i into scat[idx[k]] over the entries of row i,
+// i.e. it leaves g = A'y_new behind for the next (gather-free) primal update.
+template <bool CHECK, bool SCAT = false>
 struct DualEpi {
     static constexpr int NIN = CHECK ? 3 : 4;
+    static constexpr bool SCATTER = SCAT;
+    double* scat;
     const double* __restrict__ lc;
     const double* __restrict__ uc;
     const double* __restrict__ y0;
@@ -144,7 +154,7 @@ struct DualEpi {
         p.y0 = CHECK ? 0.0 : y0[i];
         return p;
     }
-    __device__ __forceinline__ void apply(int i, double ax, const Pre& p) const {
+    __device__ __forceinline__ double apply(int i, double ax, const Pre& p, const L2Hints& h) const {
         const double sigma = P->sigma;
         const double v = p.y - sigma * ax;
         const double lo = v + sigma * p.lc;     // -inf when the row has no lower bound
@@ -161,11 +171,48 @@ struct DualEpi {
 #pragma unroll 8
                 for (int r = 0; r < peers.n; ++r) peers.p[r][i] = yn;
             } else {
-                y[i] = yn;
+                st_out(y + i, yn, h, true);
             }
+            return yn;
         }
+        return 0.0;
     }
 };
+
+// Gather-free primal update of the scatter formulation: g = A'y was accumulated by the previous dual kernel.
+// Reads g, x, c, l, u, x0; writes x-bar, x and clears g for the next accumulation.  Two columns per thread (16-byte accesses).
+__global__ void __launch_bounds__(256)
+k_primal_from_g(int n, double* __restrict__ g, const double* __restrict__ c, const double* __restrict__ l,
+                const double* __restrict__ u, const double* __restrict__ x0, double* __restrict__ x,
+                double* __restrict__ xbar, const PdlpParams* __restrict__ P, int it) {
+    const double tau = P->tau;
+    const double k = (double)(P->k_base + it);
+    const double w = (k + 1.0) / (k + 2.0);
+    const int npair = n >> 1;
+    for (int q = blockIdx.x * 256 + threadIdx.x; q < npair; q += gridDim.x * 256) {
+        const double2 gv = reinterpret_cast<const double2*>(g)[q];
+        const double2 xv = reinterpret_cast<const double2*>(x)[q];
+        const double2 cv = reinterpret_cast<const double2*>(c)[q];
+        const double2 lv = reinterpret_cast<const double2*>(l)[q];
+        const double2 uv = reinterpret_cast<const double2*>(u)[q];
+        const double2 av = reinterpret_cast<const double2*>(x0)[q];
+        const double p0 = fmin(fmax(xv.x - tau * (cv.x - gv.x), lv.x), uv.x);
+        const double p1 = fmin(fmax(xv.y - tau * (cv.y - gv.y), lv.y), uv.y);
+        const double b0 = 2.0 * p0 - xv.x, b1 = 2.0 * p1 - xv.y;
+        reinterpret_cast<double2*>(xbar)[q] = make_double2(b0, b1);
+        reinterpret_cast<double2*>(x)[q] = make_double2(w * b0 + (1.0 - w) * av.x, w * b1 + (1.0 - w) * av.y);
+        reinterpret_cast<double2*>(g)[q] = make_double2(0.0, 0.0);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int j = n - 1;
+        const double xj = x[j];
+        const double pj = fmin(fmax(xj - tau * (c[j] - g[j]), l[j]), u[j]);
+        const double bj = 2.0 * pj - xj;
+        xbar[j] = bj;
+        x[j] = w * bj + (1.0 - w) * x0[j];
+        g[j] = 0.0;
+    }
+}
 
 // lanes per row for the setup-only helper kernels (row statistics, value scaling, row expansion)
 inline int pick_helper_lanes(int64_t nnz, int64_t nrows) {
@@ -586,6 +633,8 @@ struct Pdlp {
     DevBuf<double> lc, uc, dr, y0, yp, axbar, axp;
     DevBuf<double> xbar_full, y_full, xaux_full, yaux_full;   // [N*nb], [N*mb]: gathered vectors + scratch
     // peer-store exchange (N > 1, CUDA IPC): every rank's xbar_full / y_full / flag rows mapped here
+    bool scatter = false;        // plain iterations: g = A'y accumulated by the dual kernel's scatter (single GPU only)
+    SpmvPlan plan_s;             // tile plan of the scatter kernel (CSR rows)
     bool p2p = false;
     PeerOut x_out{}, y_out{};            // peers' xbar_full + n0, y_full + rank*mb
     PeerFlags xflags{}, yflags{};
@@ -597,6 +646,7 @@ struct Pdlp {
     double eta = 1.0, w = 1.0, w_init = 1.0, norm_b = 0.0, norm_c = 0.0, sigma_max = 0.0;
     int k = 0, total = 0, restarts = 0;
     double fpe0 = -1.0, fpe_prev = -1.0;
+    double beta_artificial = 0.36;   // artificial restart once the epoch is this fraction of all iterations so far
     bool need_fpe0 = true;
     int status = ELP_STATUS_TIMEOUT;
     bool finished = false;
@@ -692,11 +742,11 @@ struct Pdlp {
 
     // out[m] = A_rows * v_full      (my rows; v_full in the flat column layout)
     void spmv_rows(const double* v_full, double* out) {
-        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, v_full, StoreEpi{out}, st);
+        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, v_full, store_epi(out), st);
     }
     // out[nl] = (A' * v_full)_mycols  (v_full in the padded row layout)
     void spmv_cols(const double* v_full, double* out) {
-        launch_spmv(plan_c, nl, csc_ptr.p, csc_idx.p, csc_val.p, v_full, StoreEpi{out}, st);
+        launch_spmv(plan_c, nl, csc_ptr.p, csc_idx.p, csc_val.p, v_full, store_epi(out), st);
     }
 
     template <int MODE>
@@ -810,6 +860,15 @@ struct Pdlp {
         Lc = pick_helper_lanes(nnzc, nl);
         plan_r = plan_spmv(nnz, m, 4);
         plan_c = plan_spmv(nnzc, nl, 5);
+        {
+            int mode = opt.transpose;
+            if (const int e = env_int("ELP_PDLP_TRANSPOSE", 0)) mode = e;      // sweeps / A-B runs
+            ELP_REQUIRE(mode >= ELP_TRANSPOSE_AUTO && mode <= ELP_TRANSPOSE_SCATTER, "pdlp: bad transpose mode %d", mode);
+            ELP_REQUIRE(!(mode == ELP_TRANSPOSE_SCATTER && N > 1), "pdlp: the scatter formulation is single-GPU only");
+            scatter = N == 1 && mode == ELP_TRANSPOSE_SCATTER && m > 0;
+            if (const char* e = getenv("ELP_PDLP_BETA_ART")) beta_artificial = atof(e);       // experiments
+            plan_s = plan_spmv(nnz, m, 4, 0, env_int("ELP_SPMV_SCAT_STAGES", 2));
+        }
 
         // unscaled norms for the relative termination test
         double h[NACC];
@@ -1013,6 +1072,7 @@ struct Pdlp {
         ELP_CUDA(cudaMemcpyAsync(x0.p, x.p, (size_t)std::max(nl, 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
         ELP_CUDA(cudaMemcpyAsync(xp.p, x.p, (size_t)std::max(nl, 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
         y_full.zero(st); y0.zero(st); yp.zero(st); axbar.zero(st); axp.zero(st); xbar_full.zero(st);
+        gcol.zero(st);                             // = A'y for y = 0 (scatter formulation)
         w = w_init; k = 0; total = 0; restarts = 0; fpe0 = -1; fpe_prev = -1; need_fpe0 = true;
         status = ELP_STATUS_TIMEOUT; finished = false; checks = 0;
         push_params();
@@ -1029,8 +1089,13 @@ struct Pdlp {
     // ---- iteration pieces ------------------------------------------------------------------------
     template <bool CHECK>
     void primal_step(int it, bool exchange = true) {
+        if (!CHECK && scatter) {            // g = A'y is already in gcol (left there by the dual kernel's scatter)
+            const int grid = std::max(1, std::min(ceil_div(nl / 2, 256), kNumSMs * 8));
+            ELP_LAUNCH(k_primal_from_g, grid, 256, 0, st, nl, gcol.p, c.p, l.p, u.p, x0.p, x.p, xbar(), params.p, it);
+            return;
+        }
         const bool direct = !CHECK && exchange && p2p;
-        PrimalEpi<CHECK> epi{c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, direct ? x_out : PeerOut{}};
+        PrimalEpi<CHECK> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, direct ? x_out : PeerOut{}};
         launch_spmv(plan_c, nl, csc_ptr.p, csc_idx.p, csc_val.p, y_full.p, epi, st);
         if (!exchange) return;
         if (direct) {
@@ -1042,8 +1107,13 @@ struct Pdlp {
     }
     template <bool CHECK>
     void dual_step(int it, bool exchange = true) {
+        if (!CHECK && scatter) {            // A x-bar + dual update, then g += val * y_new over the row's entries
+            DualEpi<false, true> epi{gcol.p, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, PeerOut{}};
+            launch_spmv(plan_s, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
+            return;
+        }
         const bool direct = !CHECK && exchange && p2p;
-        DualEpi<CHECK> epi{lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, direct ? y_out : PeerOut{}};
+        DualEpi<CHECK> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, direct ? y_out : PeerOut{}};
         launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
         if (!exchange || CHECK) return;                      // a check iteration does not change y here
         if (direct) {
@@ -1142,7 +1212,7 @@ struct Pdlp {
         if (k > 0) {
             if (fpe <= 0.2 * fpe0) restart = true;
             else if (fpe <= 0.8 * fpe0 && fpe_prev >= 0 && fpe > fpe_prev) restart = true;
-            else if ((double)k >= 0.36 * (double)total) restart = true;
+            else if ((double)k >= beta_artificial * (double)total) restart = true;
         }
         fpe_prev = fpe;
         const int span = std::max(std::max(nl, m), 1);
@@ -1157,6 +1227,7 @@ struct Pdlp {
             ++k;
         }
         gather_y(y_full.p);                        // y changed: everyone needs the new blocks
+        if (scatter) spmv_cols(y_full.p, gcol.p);  // ... and the scatter formulation needs g = A'y of the new y
         push_params();
         return false;
     }
@@ -1267,27 +1338,36 @@ struct Pdlp {
         if (obj) *obj = maximize ? -pobj : pobj;
     }
 
-    // Times the two fused iteration kernels in isolation (no collective).
-    // Leaves the iterate in an arbitrary state: the caller resets afterwards.
+    // Times the two iteration kernels as they run in a solve: `reps` iterations (primal kernel, dual kernel, no
+    // collective) from a mid-solve iterate, one CUDA event between any two launches, so that the two figures add up to
+    // the iteration time.  Leaves the solver reset.
     void probe_step(int reps, double* ms_primal, double* ms_dual) {
-        cudaEvent_t e0, e1;
-        ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
-        float ms = 0;
-        for (int i = 0; i < 3; ++i) primal_step<false>(0, false);
-        ELP_CUDA(cudaEventRecord(e0, st));
-        for (int i = 0; i < reps; ++i) primal_step<false>(0, false);
-        ELP_CUDA(cudaEventRecord(e1, st));
+        reps = std::max(1, std::min(reps, 512));
+        reset();
+        run(3 * std::max(2, opt.check_every), nullptr);
+        std::vector<cudaEvent_t> ev(2 * (size_t)reps + 1);
+        for (auto& e : ev) ELP_CUDA(cudaEventCreate(&e));
+        for (int i = 0; i < 3; ++i) { primal_step<false>(i, false); dual_step<false>(i, false); }
+        const bool b2b = env_int("ELP_PROBE_B2B", 0) != 0;      // experiment: the same kernel back to back
+        for (int i = 0; i < reps; ++i) {
+            ELP_CUDA(cudaEventRecord(ev[2 * i], st));
+            if (b2b && i >= reps / 2) dual_step<false>(i, false); else primal_step<false>(i, false);
+            ELP_CUDA(cudaEventRecord(ev[2 * i + 1], st));
+            if (b2b && i < reps / 2) primal_step<false>(i, false); else dual_step<false>(i, false);
+        }
+        ELP_CUDA(cudaEventRecord(ev[2 * reps], st));
         ELP_CUDA(cudaStreamSynchronize(st));
-        ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        if (ms_primal) *ms_primal = ms / reps;
-        for (int i = 0; i < 3; ++i) dual_step<false>(0, false);
-        ELP_CUDA(cudaEventRecord(e0, st));
-        for (int i = 0; i < reps; ++i) dual_step<false>(0, false);
-        ELP_CUDA(cudaEventRecord(e1, st));
-        ELP_CUDA(cudaStreamSynchronize(st));
-        ELP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        if (ms_dual) *ms_dual = ms / reps;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        double tp = 0.0, td = 0.0;
+        for (int i = 0; i < reps; ++i) {
+            float ms = 0;
+            ELP_CUDA(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+            tp += ms;
+            ELP_CUDA(cudaEventElapsedTime(&ms, ev[2 * i + 1], ev[2 * i + 2]));
+            td += ms;
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        if (ms_primal) *ms_primal = tp / reps;
+        if (ms_dual) *ms_dual = td / reps;
         reset();
     }
 
@@ -1333,6 +1413,7 @@ void pdlp_reset(Pdlp* p) { p->reset(); }
 void pdlp_solution(Pdlp* p, double* x, double* y, double* obj) { p->solution(x, y, obj); }
 void pdlp_probe(Pdlp* p, int reps, double* a, double* b) { p->probe_spmv(reps, a, b); }
 void pdlp_probe_step(Pdlp* p, int reps, double* a, double* b) { p->probe_step(reps, a, b); }
+int pdlp_transpose(Pdlp* p) { return p->scatter ? ELP_TRANSPOSE_SCATTER : ELP_TRANSPOSE_GATHER; }
 void pdlp_destroy(Pdlp* p) { delete p; }
 
 // plain SpMV + feasibility re-check (S4: /root/reference/R/class.R:533-540, R/utils.R:167-171)
@@ -1362,7 +1443,7 @@ void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, con
     idx.zero(st); val.zero(st); ptr.zero(st);
     ptr.upload(row_ptr, m + 1, st); idx.upload(col_idx, nnz, st); val.upload(vals, nnz, st); xd.upload(x, n, st);
     // one thread per row: the row sum is formed in index order, bit-identical to a scalar loop
-    launch_spmv(plan_spmv(nnz, m, 0, 1), m, ptr.p, idx.p, val.p, xd.p, StoreEpi{od.p}, st);
+    launch_spmv(plan_spmv(nnz, m, 0, 1), m, ptr.p, idx.p, val.p, xd.p, store_epi(od.p), st);
     if (out) od.download(out, m, st);
     if (feasible) {
         DevBuf<int8_t> sd(m);

@@ -66,6 +66,20 @@ __device__ __forceinline__ double ldg_hint(const double* ptr, uint64_t policy) {
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(policy));
     return v;
 }
+__device__ __forceinline__ void stg_hint(double* ptr, double v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(policy) : "memory");
+}
+// L2 residency hints of one SpMV launch (bit flags; spmv.cuh): what the streams that are read once and the vectors
+// that the NEXT kernel gathers from ask of the L2.
+struct L2Hints {
+    uint64_t first, last;
+    int flags;      // 1: operand streams evict-first, 2: non-gathered outputs evict-first, 4: gathered outputs evict-last,
+                    // 8: gathers evict-last
+};
+__device__ __forceinline__ void st_out(double* ptr, double v, const L2Hints& h, bool gathered_next) {
+    if (gathered_next) { if (h.flags & 4) stg_hint(ptr, v, h.last); else *ptr = v; }
+    else { if (h.flags & 2) stg_hint(ptr, v, h.first); else *ptr = v; }
+}
 __device__ __forceinline__ bool tma_ok(const void* src, size_t bytes) {
     return bytes > 0 && (bytes & 15) == 0 && (((uintptr_t)src) & 15) == 0;
 }

@@ -908,6 +908,8 @@ class easylp:
                 opt.max_iter = int(v)
             elif k == "gpu_method":
                 opt.method = {"auto": 0, "simplex": 1, "pdlp": 2}[v] if isinstance(v, str) else int(v)
+            elif k == "gpu_transpose":           # PDLP: "gather" = bit-reproducible CSC SpMV, "scatter" = fp64 reductions
+                opt.transpose = {"auto": 0, "gather": 1, "scatter": 2}[v] if isinstance(v, str) else int(v)
             else:
                 warnings.warn(f"lp.control option '{k}' has no meaning on the GPU path and is ignored")
         rp, ci, v = self._csr()

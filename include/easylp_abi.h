@@ -43,6 +43,18 @@ extern "C" {
 #define ELP_METHOD_SIMPLEX 1
 #define ELP_METHOD_PDLP 2
 
+/* How the plain PDHG iterations obtain g = A'y (pdlp.cu).
+ *   GATHER  : a CSC (transposed) SpMV — deterministic, bit-reproducible run to run; the only mode when distributed.
+ *   SCATTER : the CSR kernel that forms A.x-bar and the dual update also scatters val * y_new into g with fp64
+ *             reductions (RED.ADD) while the row is still in shared memory, and the primal update becomes a gather-free
+ *             elementwise pass.  One matrix stream per iteration instead of two; the summation order inside g is not
+ *             fixed, so results agree with GATHER to rounding, not bit for bit.  Single GPU only.  Measured on C4
+ *             (B200): 4037 vs 3745 iter/s — the reductions and the gathers share the L2 request rate, so the gain is small.
+ *   AUTO    : GATHER (reproducible, and what north_star prescribes). */
+#define ELP_TRANSPOSE_AUTO 0
+#define ELP_TRANSPOSE_GATHER 1
+#define ELP_TRANSPOSE_SCATTER 2
+
 /* Options of a solve; mirrors the `...` that `$solve()` forwards to lpSolveAPI::lp.control()
  * (R/class.R:249-262): `timeout`, `epsilon`, `verbose` are mapped, the rest has no GPU meaning. */
 typedef struct elp_options {
@@ -54,6 +66,8 @@ typedef struct elp_options {
     int32_t verbose;       /* lp.control(verbose=): 0 silent, >=1 progress lines to stderr */
     int32_t use_graph;     /* PDLP: replay the iteration chunk from a CUDA graph (default 1) */
     int32_t ruiz_iters;    /* <0: default 10 */
+    int32_t transpose;     /* PDLP, how A'y is formed in the plain iterations: ELP_TRANSPOSE_* (default AUTO) */
+    int32_t reserved;      /* keeps the struct a multiple of 8 bytes; must be 0 */
 } elp_options;
 
 /* Per-solve statistics (SURVEY.md §5 "metrics"): returned to R as a list. */
@@ -159,6 +173,7 @@ int elp_pdlp_solution(elp_pdlp* h, double* x /* n */, double* y /* m_local, may 
 int elp_pdlp_probe_spmv(elp_pdlp* h, int32_t reps, double* ms_csr, double* ms_csc);  /* times bare A.x and A'.y */
 /* times the two fused iteration kernels alone (A'y + primal update; A.xbar + dual update); resets the iterate */
 int elp_pdlp_probe_step(elp_pdlp* h, int32_t reps, double* ms_primal, double* ms_dual);
+int elp_pdlp_transpose(elp_pdlp* h, int32_t* mode);   /* the ELP_TRANSPOSE_* the plain iterations of this handle use */
 int elp_pdlp_destroy(elp_pdlp* h);
 
 /* ---- multi-GPU plumbing (one process per GPU; NCCL resolved with dlopen at first use) -------- */

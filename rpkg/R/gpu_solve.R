@@ -52,7 +52,7 @@ easylp_solve_impl <- function(self, private, ...) {
         stop("integer/binary variables need lp_solve's branch and bound; the B200 path solves LPs only")
 
     control <- list(...)
-    known <- c("timeout", "epsilon", "verbose", "gpu.tol", "gpu.max_iter", "gpu.method")
+    known <- c("timeout", "epsilon", "verbose", "gpu.tol", "gpu.max_iter", "gpu.method", "gpu.transpose")
     for (k in setdiff(names(control), known))
         warning("lp.control option '", k, "' has no meaning on the GPU path and is ignored")
     control <- control[intersect(names(control), known)]

@@ -105,6 +105,7 @@ static void fill_options(elp_options* opt, SEXP control) {
         else if (!strcmp(k, "verbose")) opt->verbose = Rf_asInteger(v);
         else if (!strcmp(k, "gpu.max_iter")) opt->max_iter = Rf_asInteger(v);
         else if (!strcmp(k, "gpu.method")) opt->method = Rf_asInteger(v);
+        else if (!strcmp(k, "gpu.transpose")) opt->transpose = Rf_asInteger(v);   /* 1: bit-reproducible CSC gather */
         /* everything else has no meaning on the GPU path; `$solve()` warns about it on the R side */
     }
 }

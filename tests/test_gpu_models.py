@@ -35,12 +35,15 @@ def test_device_assembly_bit_exact(name):
 CONTINUOUS = sorted(k for k, v in GOLD.items() if "highs" in v)
 
 
-@pytest.mark.parametrize("method", ["auto", "pdlp"])
+@pytest.mark.parametrize("method", ["auto", "pdlp", "pdlp-scatter"])
 @pytest.mark.parametrize("name", CONTINUOUS)
 def test_solve_matches_goldens(name, method):
     lp = _build(name)
     g = GOLD[name]
-    lp.solve(gpu_method=method)
+    if method == "pdlp-scatter":     # A'y by fp64 reductions from the dual kernel; plain "pdlp" is the CSC gather
+        lp.solve(gpu_method="pdlp", gpu_transpose="scatter")
+    else:
+        lp.solve(gpu_method=method)
     want = g["highs"]["status"]
     assert lp.status == L.status_string(want)
     if want == 0:
