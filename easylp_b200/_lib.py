@@ -48,7 +48,8 @@ class Stats(C.Structure):
 # every symbol include/easylp_abi.h declares (tests/test_abi_symbols.py checks the header against this)
 ABI_SYMBOLS = [
     "elp_version", "elp_last_error", "elp_device_count", "elp_set_device", "elp_default_options",
-    "elp_status_string", "elp_kernel_launches", "elp_release_workspace", "elp_assemble_csr", "elp_solve_lp", "elp_solve_batch",
+    "elp_status_string", "elp_kernel_launches", "elp_release_workspace", "elp_assemble_csr", "elp_assemble_lowered",
+    "elp_expand_terms", "elp_solve_lp", "elp_solve_batch",
     "elp_batch_create", "elp_batch_run", "elp_batch_fetch", "elp_batch_destroy", "elp_spmv",
     "elp_check_feasible", "elp_pdlp_create", "elp_pdlp_run", "elp_pdlp_reset", "elp_pdlp_solution",
     "elp_pdlp_probe_spmv", "elp_pdlp_probe_step", "elp_pdlp_transpose", "elp_pdlp_destroy", "elp_comm_unique_id", "elp_comm_init", "elp_comm_size",
@@ -154,6 +155,36 @@ def assemble_csr(term_row, term_col, term_val, m: int, n: int):
                                   _p(row_ptr), _p(col_idx), _p(vals), C.byref(nnz), C.byref(st)))
     k = nnz.value
     return row_ptr, col_idx[:k].copy(), vals[:k].copy(), st
+
+
+def assemble_lowered(term_row, term_col, term_val, packed, m: int, n: int):
+    """explicit terms + index-set families (lower.pack) -> canonical CSR; the families are expanded on the device."""
+    fam, n_fam, itab, dtab, grp, n_grp, n_low = packed
+    term_row, term_col = _i32(term_row), _i32(term_col)
+    term_val = _f64(term_val)
+    T = term_row.size
+    cap = max(T + n_low, 1)
+    row_ptr = np.zeros(m + 1, np.int32)
+    col_idx = np.zeros(cap, np.int32)
+    vals = np.zeros(cap, np.float64)
+    nnz = C.c_int64(0)
+    st = Stats()
+    _check(lib().elp_assemble_lowered(C.c_int64(T), _p(term_row), _p(term_col), _p(term_val), C.c_int32(n_fam), fam,
+                                      C.c_int64(itab.size), _p(itab), C.c_int64(dtab.size), _p(dtab), C.c_int32(n_grp), grp,
+                                      C.c_int32(m), C.c_int32(n), _p(row_ptr), _p(col_idx), _p(vals), C.c_int64(cap),
+                                      C.byref(nnz), C.byref(st)))
+    k = nnz.value
+    return row_ptr, col_idx[:k].copy(), vals[:k].copy(), st
+
+
+def expand_terms(packed):
+    """the term stream the device expands the families into: (row, col, val, group) — tests"""
+    fam, n_fam, itab, dtab, _grp, _n_grp, n_low = packed
+    row, col = np.zeros(max(n_low, 1), np.int32), np.zeros(max(n_low, 1), np.int32)
+    val, grp = np.zeros(max(n_low, 1)), np.zeros(max(n_low, 1), np.int32)
+    _check(lib().elp_expand_terms(C.c_int32(n_fam), fam, C.c_int64(itab.size), _p(itab), C.c_int64(dtab.size), _p(dtab),
+                                  _p(row), _p(col), _p(val), _p(grp)))
+    return row[:n_low], col[:n_low], val[:n_low], grp[:n_low]
 
 
 @dataclass

@@ -19,8 +19,20 @@ struct AsmIo {
 };
 AsmIo asm_io_buffers(size_t T, size_t m);
 void asm_workspace_release();
+struct AsmLowered {
+    uint16_t* grp;
+    int32_t* itab;
+    double* dtab;
+    elp_fold_group* groups;
+};
+AsmLowered asm_lowered_buffers(size_t T, size_t n_itab, size_t n_dtab, size_t n_groups);
+void asm_expand_families(int n_families, const elp_term_family* fam, const int32_t* d_itab, const double* d_dtab,
+                         int64_t stream_offset, int32_t* d_row, int32_t* d_col, double* d_val, uint16_t* d_grp,
+                         cudaStream_t st);
 int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_col, const double* d_val, int32_t m,
-                            int32_t n, int32_t* d_row_ptr, int32_t* d_col_idx, double* d_vals, cudaStream_t st);
+                            int32_t n, int32_t* d_row_ptr, int32_t* d_col_idx, double* d_vals, cudaStream_t st,
+                            const uint16_t* d_grp = nullptr, const elp_fold_group* d_groups = nullptr,
+                            const double* d_dtab = nullptr);
 Pdlp* pdlp_create(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
                   const int8_t* sense, const double* rhs, const double* c, int maximize, const double* lb,
                   const double* ub, const elp_options& opt, bool dist, elp_stats* stats);
@@ -243,6 +255,131 @@ int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* te
         stats->kernel_launches = g_launches.load() - l0;
         stats->h2d_bytes = (int64_t)T * 16;
         stats->d2h_bytes = nnz * 12 + ((int64_t)m + 1) * 4;
+    }
+    ELP_CATCH
+}
+
+// checks a family against the table sizes and returns the number of terms it emits
+static int64_t check_family(const elp_term_family& f, int64_t n_itab, int64_t n_dtab, int32_t n_groups, int32_t m) {
+    ELP_REQUIRE(f.n_loops >= 0 && f.n_loops <= ELP_MAX_LOOPS, "lowered: family with %d loops (max %d)", f.n_loops, ELP_MAX_LOOPS);
+    ELP_REQUIRE(f.group >= 0 && f.group < std::max(n_groups, 1) && f.group < 65536, "lowered: family names group %d of %d", f.group, n_groups);
+    ELP_REQUIRE(f.out_stride >= 1 && f.out_offset >= 0, "lowered: bad stream placement");
+    int64_t count = 1, coef_max = f.coef_tab, row_max = f.row0;
+    for (int l = 0; l < f.n_loops; ++l) {
+        ELP_REQUIRE(f.extent[l] >= 0, "lowered: negative loop extent");
+        count *= f.extent[l];
+        ELP_REQUIRE(count < (1ll << 40), "lowered: family too large");
+        if (f.extent[l] > 0) {
+            ELP_REQUIRE(f.col_tab[l] < 0 || f.col_tab[l] + f.extent[l] <= n_itab, "lowered: column table outside itab");
+            ELP_REQUIRE(f.coef_stride[l] >= 0 && f.row_stride[l] >= 0, "lowered: negative stride");
+            coef_max += f.coef_stride[l] * (int64_t)(f.extent[l] - 1);
+            row_max += (int64_t)f.row_stride[l] * (f.extent[l] - 1);
+        }
+    }
+    ELP_REQUIRE(count == f.count, "lowered: family count %lld is not the product of its extents (%lld)", (long long)f.count, (long long)count);
+    if (count > 0) {
+        ELP_REQUIRE(f.coef_tab >= 0 && coef_max < n_dtab, "lowered: coefficient table outside dtab");
+        ELP_REQUIRE(f.row0 >= 0 && row_max < m, "lowered: family rows outside the matrix");
+    }
+    return count;
+}
+
+// explicit terms + families -> device term stream (row, col, val, grp); returns the stream length
+static int64_t stage_lowered(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
+                             int32_t n_families, const elp_term_family* families, int64_t n_itab, const int32_t* itab,
+                             int64_t n_dtab, const double* dtab, int32_t n_groups, const elp_fold_group* groups, int32_t m,
+                             AsmIo* io_out, AsmLowered* lo_out, cudaStream_t st) {
+    ELP_REQUIRE(n_terms >= 0 && n_families >= 0 && n_itab >= 0 && n_dtab >= 0 && n_groups >= 0, "lowered: negative size");
+    int64_t total = 0, span = 0;
+    for (int i = 0; i < n_families; ++i) {
+        const int64_t cnt = check_family(families[i], n_itab, n_dtab, n_groups, m);
+        total += cnt;
+        if (cnt > 0) span = std::max(span, families[i].out_offset + (cnt - 1) * families[i].out_stride + 1);
+    }
+    ELP_REQUIRE(span == total, "lowered: the families do not tile the stream (span %lld, terms %lld)", (long long)span, (long long)total);
+    ELP_REQUIRE(groups != nullptr || n_groups == 0 || n_groups == 65536, "lowered: groups missing");
+    for (int g = 0; groups && g < n_groups; ++g) {
+        ELP_REQUIRE(groups[g].n_mul >= 0 && groups[g].n_mul <= ELP_MAX_GROUP_MUL, "lowered: group with %d multipliers", groups[g].n_mul);
+        for (int k = 0; k < groups[g].n_mul; ++k)
+            ELP_REQUIRE(groups[g].mul_tab[k] >= 0 && groups[g].mul_tab[k] < std::max<int64_t>(n_dtab, 1), "lowered: multiplier outside dtab");
+    }
+    const size_t T = (size_t)(n_terms + total);
+    ELP_REQUIRE(T < 0xffffffffull, "lowered: too many terms");
+    const AsmIo io = asm_io_buffers(std::max<size_t>(T, 1), (size_t)m);
+    const AsmLowered lo = asm_lowered_buffers(T, (size_t)n_itab, (size_t)n_dtab, groups ? (size_t)n_groups : 0);
+    if (n_terms) {
+        ELP_CUDA(cudaMemcpyAsync(io.row, term_row, (size_t)n_terms * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        ELP_CUDA(cudaMemcpyAsync(io.col, term_col, (size_t)n_terms * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        ELP_CUDA(cudaMemcpyAsync(io.val, term_val, (size_t)n_terms * sizeof(double), cudaMemcpyHostToDevice, st));
+        ELP_CUDA(cudaMemsetAsync(lo.grp, 0, (size_t)n_terms * sizeof(uint16_t), st));
+    }
+    if (n_itab) ELP_CUDA(cudaMemcpyAsync(lo.itab, itab, (size_t)n_itab * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (n_dtab) ELP_CUDA(cudaMemcpyAsync(lo.dtab, dtab, (size_t)n_dtab * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (n_groups && groups) ELP_CUDA(cudaMemcpyAsync(lo.groups, groups, (size_t)n_groups * sizeof(elp_fold_group), cudaMemcpyHostToDevice, st));
+    asm_expand_families(n_families, families, lo.itab, lo.dtab, n_terms, io.row, io.col, io.val, lo.grp, st);
+    *io_out = io; *lo_out = lo;
+    return (int64_t)T;
+}
+
+int elp_assemble_lowered(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
+                         int32_t n_families, const elp_term_family* families, int64_t n_itab, const int32_t* itab,
+                         int64_t n_dtab, const double* dtab, int32_t n_groups, const elp_fold_group* groups, int32_t m,
+                         int32_t n, int32_t* row_ptr, int32_t* col_idx, double* vals, int64_t capacity, int64_t* nnz_out,
+                         elp_stats* stats) {
+    ELP_TRY
+    require_device();
+    WallTimer wall;
+    const int64_t l0 = g_launches.load();
+    ELP_REQUIRE(m >= 0 && n >= 0 && row_ptr && nnz_out, "lowered: bad arguments");
+    cudaStream_t st = 0;
+    cudaEvent_t e0, e1;
+    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    AsmIo io; AsmLowered lo;
+    ELP_CUDA(cudaEventRecord(e0, st));
+    const int64_t T = stage_lowered(n_terms, term_row, term_col, term_val, n_families, families, n_itab, itab, n_dtab, dtab,
+                                    n_groups, groups, m, &io, &lo, st);
+    const int64_t nnz = assemble_csr_device(T, io.row, io.col, io.val, m, n, io.out_ptr, io.out_col, io.out_val, st,
+                                            lo.grp, lo.groups, lo.dtab);
+    ELP_CUDA(cudaEventRecord(e1, st));
+    ELP_REQUIRE(nnz <= capacity, "lowered: %lld non-zeros but room for %lld", (long long)nnz, (long long)capacity);
+    ELP_CUDA(cudaMemcpyAsync(row_ptr, io.out_ptr, ((size_t)m + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (nnz) {
+        ELP_CUDA(cudaMemcpyAsync(col_idx, io.out_col, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaMemcpyAsync(vals, io.out_val, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    ELP_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *nnz_out = nnz;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->solve_ms = ms;                      // expansion + assembly (uploads of the descriptor tables included)
+        stats->total_ms = wall.ms();
+        stats->kernel_launches = g_launches.load() - l0;
+        stats->iterations = (int32_t)std::min<int64_t>(T, 0x7fffffff);     // terms that went through the fold
+        stats->h2d_bytes = n_terms * 16 + n_itab * 4 + n_dtab * 8 + (int64_t)n_groups * (int64_t)sizeof(elp_fold_group);
+        stats->d2h_bytes = nnz * 12 + ((int64_t)m + 1) * 4;
+    }
+    ELP_CATCH
+}
+
+int elp_expand_terms(int32_t n_families, const elp_term_family* families, int64_t n_itab, const int32_t* itab,
+                     int64_t n_dtab, const double* dtab, int32_t* row, int32_t* col, double* val, int32_t* group) {
+    ELP_TRY
+    require_device();
+    cudaStream_t st = 0;
+    AsmIo io; AsmLowered lo;
+    const int64_t T = stage_lowered(0, nullptr, nullptr, nullptr, n_families, families, n_itab, itab, n_dtab, dtab,
+                                    65536, nullptr, 0x7fffffff, &io, &lo, st);
+    if (T) {
+        std::vector<uint16_t> g16((size_t)T);
+        ELP_CUDA(cudaMemcpyAsync(row, io.row, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaMemcpyAsync(col, io.col, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaMemcpyAsync(val, io.val, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaMemcpyAsync(g16.data(), lo.grp, (size_t)T * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        if (group) for (int64_t i = 0; i < T; ++i) group[i] = g16[(size_t)i];
     }
     ELP_CATCH
 }

@@ -45,6 +45,65 @@ __global__ void asm_segment_fold(const uint64_t* __restrict__ keys, const uint32
     keep[i] = (s != 0.0) ? 1u : 0u;
 }
 
+// Two-level ordered fold (lowered assembly): inside a (row, col) run the terms arrive group-major (stable sort of a
+// group-major stream).  Each group is summed left to right, multiplied by its post-fold multipliers, dropped if it is an
+// exact zero (the host's canonical partial sums carry no zeros), and the group results are added left to right.
+__device__ __forceinline__ double asm_finish_group(double gs, uint32_t g, uint32_t row, const elp_fold_group* __restrict__ groups,
+                                                   const double* __restrict__ dtab) {
+    if (g == 0) return gs;
+    const elp_fold_group G = groups[g];
+    for (int k = 0; k < G.n_mul; ++k)
+        gs = __dmul_rn(gs, dtab[G.mul_tab[k] + (G.mul_per_row[k] ? (int64_t)(row - (uint32_t)G.row0) : 0)]);
+    return gs;
+}
+__global__ void asm_segment_fold_grouped(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+                                         const double* __restrict__ val, const uint16_t* __restrict__ grp,
+                                         const elp_fold_group* __restrict__ groups, const double* __restrict__ dtab,
+                                         uint32_t T, uint32_t n, double* __restrict__ sums, uint32_t* __restrict__ keep) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const uint64_t k = keys[i];
+    if (i > 0 && keys[i - 1] == k) { keep[i] = 0; return; }
+    const uint32_t row = (uint32_t)(k / n);
+    uint32_t p = perm[i];
+    uint32_t g = grp[p];
+    double gs = val[p], acc = 0.0;
+    bool have = false;
+    for (uint32_t j = i + 1; j < T && keys[j] == k; ++j) {
+        p = perm[j];
+        const uint32_t gj = grp[p];
+        if (gj == g) { gs = __dadd_rn(gs, val[p]); continue; }
+        gs = asm_finish_group(gs, g, row, groups, dtab);
+        if (gs != 0.0) { acc = have ? __dadd_rn(acc, gs) : gs; have = true; }
+        g = gj; gs = val[p];
+    }
+    gs = asm_finish_group(gs, g, row, groups, dtab);
+    if (gs != 0.0) { acc = have ? __dadd_rn(acc, gs) : gs; have = true; }
+    sums[i] = acc;
+    keep[i] = (have && acc != 0.0) ? 1u : 0u;
+}
+
+// One thread per term of a family: decode the position in the loop nest (loops slowest first), accumulate the row,
+// the column offset and the coefficient index, write the term at its place in the stream.
+__global__ void asm_expand_family(const elp_term_family f, const int32_t* __restrict__ itab, const double* __restrict__ dtab,
+                                  int32_t* __restrict__ row, int32_t* __restrict__ col, double* __restrict__ val,
+                                  uint16_t* __restrict__ grp) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= f.count) return;
+    int64_t rem = idx, ci = f.coef_tab;
+    int32_t r = f.row0, c = f.col0;
+    for (int l = f.n_loops - 1; l >= 0; --l) {
+        const int32_t e = f.extent[l];
+        const int32_t p = (int32_t)(rem % e);
+        rem /= e;
+        r += f.row_stride[l] * p;
+        if (f.col_tab[l] >= 0) c += itab[f.col_tab[l] + p];
+        ci += f.coef_stride[l] * p;
+    }
+    const int64_t pos = f.out_offset + idx * f.out_stride;
+    row[pos] = r; col[pos] = c; val[pos] = dtab[ci]; grp[pos] = (uint16_t)f.group;
+}
+
 __global__ void asm_compact(const uint64_t* __restrict__ keys, const double* __restrict__ sums,
                             const uint32_t* __restrict__ keep_flag, const uint32_t* __restrict__ pos, uint32_t T,
                             uint32_t n, int32_t* __restrict__ col_idx, double* __restrict__ vals,
@@ -90,6 +149,11 @@ struct AsmWorkspace {
     // staging of the host entry point (elp_assemble_csr)
     DevBuf<int32_t> in_row, in_col, out_ptr, out_col;
     DevBuf<double> in_val, out_val;
+    // lowered assembly: fold groups of the stream, descriptor tables
+    DevBuf<uint16_t> in_grp;
+    DevBuf<int32_t> itab;
+    DevBuf<double> dtab;
+    DevBuf<elp_fold_group> groups;
     void release() { *this = AsmWorkspace{}; }
     void ensure(size_t T) {
         int dev = 0;
@@ -114,16 +178,40 @@ struct AsmIo {
     int32_t *row, *col, *out_ptr, *out_col;
     double *val, *out_val;
 };
+struct AsmLowered {
+    uint16_t* grp;
+    int32_t* itab;
+    double* dtab;
+    elp_fold_group* groups;
+};
 AsmIo asm_io_buffers(size_t T, size_t m) {
     AsmWorkspace& w = asm_workspace();
     w.ensure_io(T, m);
     return AsmIo{w.in_row.p, w.in_col.p, w.out_ptr.p, w.out_col.p, w.in_val.p, w.out_val.p};
 }
+AsmLowered asm_lowered_buffers(size_t T, size_t n_itab, size_t n_dtab, size_t n_groups) {
+    AsmWorkspace& w = asm_workspace();
+    auto grow = [](auto& b, size_t n) { if (b.n < n) b.alloc(n + n / 8); };
+    grow(w.in_grp, std::max<size_t>(T, 1)); grow(w.itab, std::max<size_t>(n_itab, 1));
+    grow(w.dtab, std::max<size_t>(n_dtab, 1)); grow(w.groups, std::max<size_t>(n_groups, 1));
+    return AsmLowered{w.in_grp.p, w.itab.p, w.dtab.p, w.groups.p};
+}
+void asm_expand_families(int n_families, const elp_term_family* fam, const int32_t* d_itab, const double* d_dtab,
+                         int64_t stream_offset, int32_t* d_row, int32_t* d_col, double* d_val, uint16_t* d_grp,
+                         cudaStream_t st) {
+    for (int i = 0; i < n_families; ++i) {
+        elp_term_family f = fam[i];
+        if (f.count <= 0) continue;
+        f.out_offset += stream_offset;
+        ELP_LAUNCH(asm_expand_family, ceil_div(f.count, 256), 256, 0, st, f, d_itab, d_dtab, d_row, d_col, d_val, d_grp);
+    }
+}
 
 // Device-resident assembly: inputs/outputs are device pointers.  d_col_idx/d_vals need room for T.
 // Returns nnz (synchronises the stream once to read it back).
 int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_col, const double* d_val, int32_t m,
-                            int32_t n, int32_t* d_row_ptr, int32_t* d_col_idx, double* d_vals, cudaStream_t st) {
+                            int32_t n, int32_t* d_row_ptr, int32_t* d_col_idx, double* d_vals, cudaStream_t st,
+                            const uint16_t* d_grp, const elp_fold_group* d_groups, const double* d_dtab) {
     ELP_REQUIRE(m >= 0 && n >= 0, "assemble: negative shape");
     if (T == 0 || m == 0) {
         ELP_LAUNCH(asm_empty_row_ptr, ceil_div((int64_t)m + 1, 256), 256, 0, st, d_row_ptr, (uint32_t)m);
@@ -159,7 +247,11 @@ int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_co
     mark("keys");
     radix_sort_pairs(keys.p, perm.p, T, nbits, ws, st);
     mark("sort");
-    ELP_LAUNCH(asm_segment_fold, grid, 256, 0, st, keys.p, perm.p, d_val, Tu, sums.p, keep.p);
+    if (d_grp)
+        ELP_LAUNCH(asm_segment_fold_grouped, grid, 256, 0, st, keys.p, perm.p, d_val, d_grp, d_groups, d_dtab, Tu, (uint32_t)n,
+                   sums.p, keep.p);
+    else
+        ELP_LAUNCH(asm_segment_fold, grid, 256, 0, st, keys.p, perm.p, d_val, Tu, sums.p, keep.p);
     ELP_CUDA(cudaMemcpyAsync(pos.p, keep.p, T * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     mark("fold");
     exclusive_scan_u32(pos.p, T, ws.scan, st);

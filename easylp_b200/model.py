@@ -36,8 +36,12 @@ import warnings
 import numpy as np
 
 from . import _lib
+from . import lower as _lower
 
 LD = np.longdouble
+# `for_` / `sum_for` first try ONE symbolic evaluation of their body (lower.py) and keep the rows as
+# index-set descriptors that the device expands; bodies that cannot be traced run the reference's per-atom loop.
+LOWERING = True
 _I = np.int64
 
 
@@ -131,6 +135,8 @@ class Param:
     def __getitem__(self, key):
         if not isinstance(key, tuple):
             key = (key,)
+        if _lower.has_symbolic(key):          # inside a for/sum_for trace (lower.py)
+            return _lower.param_getitem(self, key)
         pos = _positions(self.a.shape, self.dimnames, None, key)
         if len(key) == 1 and self.a.ndim > 1:
             out = self.a.flatten(order="F")[pos[0]]
@@ -224,6 +230,10 @@ class ForSplit(list):
 def for_(body, **index):
     """`for (v in seq) body` inside `$con()` (R/utils.R:33-64).  Several indices nest, first outermost;
     write nested for_ calls when an inner range depends on an outer index (test-investments.R:35-37)."""
+    if LOWERING and index:
+        low = _lower.try_for(body, index)     # one symbolic evaluation instead of one per atom; None = not lowerable
+        if low is not None:
+            return low
     (var, seq), rest = next(iter(index.items())), dict(list(index.items())[1:])
     seq = list(seq)
     if rest:
@@ -295,6 +305,8 @@ class lp_var:
             raise EasyLpError("Cannot index this result.")
         if not isinstance(key, tuple):
             key = (key,)
+        if _lower.has_symbolic(key):          # inside a for/sum_for trace (lower.py)
+            return _lower.var_getitem(self, key)
         pos = _positions(self.ind.shape, self.dimnames, self.dimtitles, key)
         x = self.copy()
         if len(key) == 1 and self.ind.ndim > 1:
@@ -545,6 +557,10 @@ def sum_for(body, **index):
     """sum_for (R/utils.R:391-411): expand.grid with the first index fastest, evaluate, `do.call(sum, ...)`."""
     if not index:
         raise EasyLpError("No named indexing variables.")
+    if LOWERING:
+        low = _lower.try_sum_for(body, index)  # one symbolic evaluation instead of one per grid row
+        if low is not None:
+            return low
     names = list(index)
     seqs = [list(index[k]) for k in names]
     result = []
@@ -648,6 +664,10 @@ def flatten_for_split(split, init_name=""):     # R/utils.R:66-94
             name = name.replace("]", ",", 1)
             for k, item in enumerate(x):
                 add(item, f"{name}{x.variable}={_chr(x.sequence[k])}]")
+        elif isinstance(x, _lower.LoweredFor):         # an inner `for` that traced while the outer one ran per atom
+            blk = copy.copy(x.block)
+            blk.init_name, blk.head = init_name, name.replace("]", ",", 1)
+            atoms.append((name, blk))
         else:
             if isinstance(x, lp_con):
                 x = name_constraint(x, name)
@@ -785,12 +805,17 @@ class easylp:
                     c = c()
                 except Exception as e:
                     raise EasyLpError(f"Constraint '{ref}' evaluated to an error:\n{e}") from e
+            if isinstance(c, _lower.LoweredFor):      # rows kept as index-set descriptors, expanded on the device
+                blk = copy.copy(c.block)
+                blk.init_name, blk.head = name or "", (name or "") + "["
+                self._blocks.append(blk)
+                continue
             if isinstance(c, ForSplit):
                 split = flatten_for_split(c, name or "")
-                if not split or not isinstance(split[0][1], lp_con):
+                if not split or not isinstance(split[0][1], (lp_con, _lower.LoweredCon)):
                     raise EasyLpError("Constraint did not evaluate to an (in)equality.")
                 for _, atom in split:
-                    if not isinstance(atom, lp_con):
+                    if not isinstance(atom, (lp_con, _lower.LoweredCon)):
                         raise EasyLpError("is_lp_con(con) is not TRUE")
                     self._blocks.append(atom)
                 continue
@@ -821,10 +846,16 @@ class easylp:
                 self._cache = (np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
             else:
                 offs = np.cumsum([0] + [b.nrow for b in self._blocks])
-                rows = np.concatenate([b.t_row + o for b, o in zip(self._blocks, offs)])
-                cols = np.concatenate([b.t_col for b in self._blocks])
-                vals = np.concatenate([b.t_val for b in self._blocks])
-                rp, ci, v, self.assembly_stats = _lib.assemble_csr(rows, cols, vals, m, self._n_var)
+                eager = [(b, o) for b, o in zip(self._blocks, offs) if not isinstance(b, _lower.LoweredCon)]
+                lowered = [(b, int(o)) for b, o in zip(self._blocks, offs) if isinstance(b, _lower.LoweredCon)]
+                rows = np.concatenate([b.t_row + o for b, o in eager]) if eager else np.zeros(0, _I)
+                cols = np.concatenate([b.t_col for b, _ in eager]) if eager else np.zeros(0, _I)
+                vals = np.concatenate([b.t_val for b, _ in eager]) if eager else np.zeros(0)
+                if lowered:
+                    rp, ci, v, self.assembly_stats = _lib.assemble_lowered(rows, cols, vals, _lower.pack(lowered), m,
+                                                                           self._n_var)
+                else:
+                    rp, ci, v, self.assembly_stats = _lib.assemble_csr(rows, cols, vals, m, self._n_var)
                 self._cache = (rp, ci, v)
         return self._cache
 

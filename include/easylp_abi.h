@@ -113,6 +113,56 @@ int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* te
                      int32_t* row_ptr, int32_t* col_idx, double* vals, int64_t* nnz_out,
                      elp_stats* stats /* may be NULL */);
 
+/* ---- (1b) lowered assembly: index-set descriptors expanded ON THE DEVICE ----------------------------
+ * Replaces the interpreter loops of `for (v in seq) body` (R/utils.R:33-64: one `eval` per atom) and `sum_for`
+ * (R/utils.R:391-411: one `eval` per grid row) for bodies that are affine in indexed variables: instead of T expanded
+ * terms the host ships, per body term, a FAMILY descriptor — a loop nest (the `for` indices outermost first, then the
+ * `sum_for` grid with its first name fastest, R/utils.R:402), a column-offset table per loop (the variable's
+ * column-major ids, R/class.R:112-113) and a coefficient table over the loops the coefficient depends on.  One thread
+ * per term decodes its position in the nest and writes (row, col, val, group); the stream then goes through the same
+ * sort + ordered fold as elp_assemble_csr.
+ * Fold order.  The reference folds each `sum_for` result on its own (`do.call(sum, ...)` = Reduce('+'),
+ * R/methods.R:248-250) before the results of one atom are added (`e1 - e2`, R/methods.R:98-111) or scaled
+ * (R/methods.R:82-97).  A GROUP is one such partial sum: inside a (row, col) the terms of a group are added left to
+ * right in emission order, the group's sum is multiplied by its post-fold multipliers (one after the other), and the
+ * group results are added left to right in group order.  Group 0 (explicit terms, no multipliers) reproduces
+ * elp_assemble_csr.  Families of one (row, col) must be emitted in ascending group order. */
+#define ELP_MAX_LOOPS 6
+#define ELP_MAX_GROUP_MUL 4
+typedef struct elp_term_family {
+    int64_t count;                          /* terms emitted = product of the extents */
+    int64_t out_offset;                     /* position of the family's first term in the lowered stream */
+    int64_t coef_tab;                       /* offset of the coefficient table in dtab */
+    int64_t col_tab[ELP_MAX_LOOPS];         /* per loop: offset in itab of its column-offset table, -1 = none */
+    int64_t coef_stride[ELP_MAX_LOOPS];     /* per loop: stride in the coefficient table (0 = independent) */
+    int32_t extent[ELP_MAX_LOOPS];          /* loops slowest first */
+    int32_t row_stride[ELP_MAX_LOOPS];      /* per loop: contribution of one step to the row index */
+    int32_t out_stride;                     /* distance in the stream between this family's terms of consecutive cells */
+    int32_t group;                          /* fold group (index into `groups`; 0 = plain) */
+    int32_t n_loops;
+    int32_t row0;                           /* first row of the block */
+    int32_t col0;                           /* column id of the variable's first entry plus the constant subscripts */
+    int32_t reserved;
+} elp_term_family;
+typedef struct elp_fold_group {
+    int64_t mul_tab[ELP_MAX_GROUP_MUL];     /* offset in dtab of multiplier k */
+    int32_t mul_per_row[ELP_MAX_GROUP_MUL]; /* 1: one multiplier per row of the block (index row - row0), 0: a scalar */
+    int32_t n_mul;                          /* post-fold multipliers, applied in this order */
+    int32_t row0;
+} elp_fold_group;
+/* Explicit terms (may be none) + families -> canonical CSR.  col_idx/vals must have room for `capacity` entries
+ * (n_terms + sum of family counts always suffices); fails if nnz exceeds it. */
+int elp_assemble_lowered(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
+                         int32_t n_families, const elp_term_family* families,
+                         int64_t n_itab, const int32_t* itab, int64_t n_dtab, const double* dtab,
+                         int32_t n_groups, const elp_fold_group* groups,
+                         int32_t m, int32_t n, int32_t* row_ptr, int32_t* col_idx, double* vals, int64_t capacity,
+                         int64_t* nnz_out, elp_stats* stats /* may be NULL */);
+/* The expanded term stream itself (tests: parity of the device expansion with the host's eager emission).
+ * Arrays have room for the sum of the family counts. */
+int elp_expand_terms(int32_t n_families, const elp_term_family* families, int64_t n_itab, const int32_t* itab,
+                     int64_t n_dtab, const double* dtab, int32_t* row, int32_t* col, double* val, int32_t* group);
+
 /* ---- (2) one LP: replaces make.lp/set.objfn/lp.control/set.bounds/add.constraint/solve/
  *      get.objective/get.variables  (R/class.R:260-278) ------------------------------------- */
 int elp_solve_lp(int32_t m, int32_t n,

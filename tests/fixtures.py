@@ -50,6 +50,28 @@ def ordered_fold(rows, cols, vals, m, n):
             np.array([acc[k] for k in keys], dtype=float))
 
 
+def model_fold(lp):
+    """Canonical CSR of a product-side model on the CPU: the eager blocks' term lists plus the lowered blocks' families
+    expanded by the plain-Python oracle (oracle/lower_ref.py), folded by its two-level ordered fold (group 0 = the
+    plain left fold of ordered_fold).  Returns (row_ptr, col_idx, vals, m)."""
+    from easylp_b200 import lower
+    from oracle import lower_ref
+    blocks = lp._blocks
+    m = sum(b.nrow for b in blocks)
+    offs = np.cumsum([0] + [b.nrow for b in blocks])
+    eager = [(b, o) for b, o in zip(blocks, offs) if not isinstance(b, lower.LoweredCon)]
+    low = [(b, int(o)) for b, o in zip(blocks, offs) if isinstance(b, lower.LoweredCon)]
+    rows = np.concatenate([b.t_row + o for b, o in eager]) if eager else np.zeros(0, np.int64)
+    cols = np.concatenate([b.t_col for b, _ in eager]) if eager else np.zeros(0, np.int64)
+    vals = np.concatenate([b.t_val for b, _ in eager]) if eager else np.zeros(0)
+    if not low:
+        return ordered_fold(rows, cols, vals, m, lp.nvar) + (m,)
+    packed = lower.pack(low)
+    r2, c2, v2, g2 = lower_ref.expand(packed)
+    return lower_ref.fold(np.r_[rows, r2], np.r_[cols, c2], np.r_[vals, v2], np.r_[np.zeros(rows.size, np.int32), g2],
+                          packed, m) + (m,)
+
+
 def model_terms(lp):
     """(rows, cols, vals, m) of a product-side model (easylp_b200.model.easylp) before device assembly."""
     blocks = lp._blocks

@@ -12,24 +12,32 @@ import pytest
 
 import models
 from easylp_b200 import model as M
-from fixtures import load_golden, model_terms, ordered_fold
+from easylp_b200 import lower
+from fixtures import load_golden, model_fold, ordered_fold
 
 GOLD = load_golden()
 
 
-def _build(name):
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        return models.ALL[name](M)
+def _build(name, lowering=True):
+    old = M.LOWERING
+    M.LOWERING = lowering
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return models.ALL[name](M)
+    finally:
+        M.LOWERING = old
 
 
+@pytest.mark.parametrize("lowering", [False, True])
 @pytest.mark.parametrize("name", sorted(models.ALL))
-def test_term_lists_fold_to_the_reference_matrix(name):
-    lp = _build(name)
+def test_term_lists_fold_to_the_reference_matrix(name, lowering):
+    lp = _build(name, lowering)
     g = GOLD[name]
-    rows, cols, vals, m = model_terms(lp)
+    if not lowering:       # with lowering on, traceable for / sum_for rows are index-set families (lower.py)
+        assert not any(isinstance(b, lower.LoweredCon) for b in lp._blocks)
+    rp, ci, v, m = model_fold(lp)
     assert (m, lp.nvar) == (g["m"], g["n"])
-    rp, ci, v = ordered_fold(rows, cols, vals, m, lp.nvar)
     assert np.array_equal(rp, g["row_ptr"]) and np.array_equal(ci, g["col_idx"])
     assert v.tobytes() == g["vals"].tobytes()
     assert list(lp.constraint.dir) == g["dir"]
@@ -46,6 +54,13 @@ def test_term_lists_fold_to_the_reference_matrix(name):
     lb, ub = lp._bounds()
     assert lb.tobytes() == g["lb"].tobytes() and ub.tobytes() == g["ub"].tobytes()
     assert (lp.direction == "max") == g["maximize"]
+
+
+def test_some_reference_models_are_lowered():
+    """test-forsplit.R / test-constraints.R / test-investments.R write rows the trace accepts; aliases (`ext[m]`),
+    slices (`x[f, ]`) and data-dependent ranges keep the per-atom evaluation"""
+    lowered = {n for n in models.ALL if any(isinstance(b, lower.LoweredCon) for b in _build(n, True)._blocks)}
+    assert {"forsplit", "constraints", "investments_assembly"} <= lowered, lowered
 
 
 def _constraints_lp():

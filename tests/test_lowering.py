@@ -1,0 +1,218 @@
+"""Symbolic lowering of for / sum_for (easylp_b200/lower.py): the lowered rows must be the eager rows.
+
+CPU tests: the same model is built twice — with the reference's per-atom / per-grid-row evaluation (LOWERING off) and
+with one symbolic evaluation — and the lowered families, expanded and folded by the plain-Python oracle
+(oracle/lower_ref.py), must give bit for bit the canonical rows, rhs, dir and row names of the eager blocks.
+GPU tests (marked) repeat the comparison through elp_expand_terms / elp_assemble_lowered.
+"""
+import numpy as np
+import pytest
+
+from easylp_b200 import _lib as L
+from easylp_b200 import lower
+from easylp_b200 import model as M
+from oracle import lower_ref
+
+
+def _sets():
+    S, T = [1, 2, 3, 4, 5], [1, 2, 3, 4]
+    rng = np.random.default_rng(3)
+    return S, T, rng
+
+
+def m_transport(lp):
+    S, T, rng = _sets()
+    x = lp.var("x", S, T, lower=0)
+    sup, dem = M.parameter(rng.uniform(5, 9, len(S)), S), M.parameter(rng.uniform(1, 3, len(T)), T)
+    return dict(make=M.for_(lambda s: M.sum_for(lambda t: x[s, t], t=T) <= sup[s], s=S),
+                sell=M.for_(lambda t: M.sum_for(lambda s: x[s, t], s=S) >= dem[t], t=T))
+
+
+def m_coefficients(lp):
+    """parameter coefficients, loop values as numbers, division, constants on both sides"""
+    S, T, rng = _sets()
+    x = lp.var("x", S, T)
+    y = lp.var("y", S)
+    a = M.parameter(rng.normal(size=(len(S) * len(T))), S, T)
+    w = M.parameter(rng.uniform(1, 2, len(T)), T)
+    return dict(c1=M.for_(lambda s: M.sum_for(lambda t: a[s, t] * x[s, t] / w[t] + 0.25, t=T) - 3 * y[s] == 1.5 * s, s=S),
+                c2=M.for_(lambda s, t: x[s, t] - w[t] * y[s] <= a[s, t] + 1, s=S, t=T),
+                c3=M.for_(lambda t: 2 - M.sum_for(lambda s: (s + 0.5) * x[s, t], s=S) >= -w[t], t=T))
+
+
+def m_repeated_columns(lp):
+    """the same entry several times in one sum (left fold over the grid), post-fold scaling, sums on both sides"""
+    S, T, rng = _sets()
+    x = lp.var("x", S, T)
+    y = lp.var("y", S)
+    c = M.parameter(rng.normal(size=len(T)), T)
+    k = M.parameter(rng.uniform(0.3, 3, len(S)), S)
+    return dict(r1=M.for_(lambda s: M.sum_for(lambda t: c[t] * x[s, 1], t=T) <= 1, s=S),                 # one column, |T| terms
+                r2=M.for_(lambda s: k[s] * M.sum_for(lambda t: c[t] * x[s, 1] + y[s] / 3, t=T) >= 0, s=S),  # scale the folded sum
+                r3=M.for_(lambda s: M.sum_for(lambda t: c[t] * x[s, t], t=T) - M.sum_for(lambda t: x[s, t] / 7, t=T) == 0, s=S),
+                r4=M.for_(lambda s: M.sum_for(lambda t: 0.1 * x[s, t], t=T) / 3 + y[s] <= M.sum_for(lambda t: c[t] * x[s, t], t=T), s=S))
+
+
+def m_shifted_and_named(lp):
+    """index arithmetic (t + 1, t - 1) on interior ranges, named sets, a nested for, an unnamed constraint"""
+    P = ["a", "b", "c"]
+    H = [1, 2, 3, 4, 5, 6]
+    st = lp.var("stock", P, H, lower=0)
+    mk = lp.var("make", P, H, lower=0)
+    d = M.parameter(np.arange(1.0, 19.0), P, H)
+    return {"bal": M.for_(lambda p: M.for_(lambda h: st[p, h] == st[p, h - 1] + mk[p, h] - d[p, h], h=H[1:]), p=P),
+            "": M.for_(lambda h: M.sum_for(lambda p: mk[p, h + 1], p=P) <= 10 * h, h=H[:-1])}
+
+
+def m_mixed(lp):
+    """lowered blocks between eager ones: vector rows, a body the trace refuses (python `if` on the index)"""
+    S, T, rng = _sets()
+    x = lp.var("x", S, T)
+    cap = M.parameter(rng.uniform(1, 2, len(S)), S)
+    return dict(e1=lambda: x[1, ] <= 4,
+                l1=M.for_(lambda s: M.sum_for(lambda t: x[s, t], t=T) <= cap[s], s=S),
+                e2=M.for_(lambda s: (x[s, 1] if s % 2 else x[s, 2]) >= 0, s=S),
+                l2=M.for_(lambda t: x[2, t] + x[3, t] <= 1, t=T))
+
+
+MODELS = dict(transport=m_transport, coefficients=m_coefficients, repeated=m_repeated_columns,
+              shifted=m_shifted_and_named, mixed=m_mixed)
+
+
+def _build(name, lowering):
+    old = M.LOWERING
+    M.LOWERING = lowering
+    try:
+        lp = M.easylp()
+        cons = MODELS[name](lp)
+        lp._blocks = []
+        for k, c in cons.items():
+            if callable(c):
+                c = c()
+            # $con without the device round trip of check_feasible (status is "unsolved": it returns at once)
+            lp.con(**{k: c}) if k else lp.con(c)
+        return lp
+    finally:
+        M.LOWERING = old
+
+
+def _eager_rows(lp):
+    """canonical rows of eager blocks by the host's ordered fold"""
+    offs = np.cumsum([0] + [b.nrow for b in lp._blocks])
+    m = int(offs[-1])
+    rows = np.concatenate([b.t_row + o for b, o in zip(lp._blocks, offs)])
+    cols = np.concatenate([b.t_col for b in lp._blocks])
+    vals = np.concatenate([b.t_val for b in lp._blocks])
+    r, c, v = M._fold(rows, cols, vals)
+    rp = np.searchsorted(r, np.arange(m + 1)).astype(np.int32)
+    return rp, c.astype(np.int32), v
+
+
+def _lowered_parts(lp):
+    offs = np.cumsum([0] + [b.nrow for b in lp._blocks])
+    eager = [(b, o) for b, o in zip(lp._blocks, offs) if not isinstance(b, lower.LoweredCon)]
+    low = [(b, int(o)) for b, o in zip(lp._blocks, offs) if isinstance(b, lower.LoweredCon)]
+    rows = np.concatenate([b.t_row + o for b, o in eager]) if eager else np.zeros(0, np.int64)
+    cols = np.concatenate([b.t_col for b, _ in eager]) if eager else np.zeros(0, np.int64)
+    vals = np.concatenate([b.t_val for b, _ in eager]) if eager else np.zeros(0)
+    return rows, cols, vals, lower.pack(low), int(offs[-1]), len(low)
+
+
+EXPECT_LOWERED = dict(transport=2, coefficients=3, repeated=4, shifted=2, mixed=2)
+
+
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_lowered_blocks_equal_eager_blocks(name):
+    e, l = _build(name, False), _build(name, True)
+    assert all(not isinstance(b, lower.LoweredCon) for b in e._blocks)
+    rows, cols, vals, packed, m, n_low = _lowered_parts(l)
+    assert n_low == EXPECT_LOWERED[name]
+    assert e.constraint.dir == l.constraint.dir
+    assert e.constraint.rhs.tobytes() == l.constraint.rhs.tobytes()
+    assert e.constraint.names == l.constraint.names
+    assert e.constraint.rownames == l.constraint.rownames
+    r2, c2, v2, g2 = lower_ref.expand(packed)
+    rp, ci, vv = lower_ref.fold(np.r_[rows, r2], np.r_[cols, c2], np.r_[vals, v2], np.r_[np.zeros(rows.size, np.int32), g2],
+                                packed, m)
+    rp0, ci0, vv0 = _eager_rows(e)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+    assert vv.tobytes() == vv0.tobytes()
+
+
+def test_top_level_sum_for_is_the_eager_pending_list():
+    """outside a `for`, sum_for returns an ordinary lp_var: the same pending terms, emitted in one vectorised pass"""
+    S, T, rng = _sets()
+    out = {}
+    for lowering in (False, True):
+        M.LOWERING = lowering
+        try:
+            lp = M.easylp()
+            x = lp.var("x", S, T)
+            cost = M.parameter(rng.normal(size=20) if lowering is None else np.linspace(-1, 2, 20), S, T)
+            v = M.sum_for(lambda s, t: cost[s, t] * x[s, t] + 0.125, s=S, t=T)
+            w = M.sum_for(lambda t: cost[2, t] * x[2, 1] - t, t=T)          # one column, folded left to right
+            out[lowering] = (v, w, (2 * w + v) <= 3)
+        finally:
+            M.LOWERING = True
+    for a, b in zip(out[False][:2], out[True][:2]):
+        assert a.canonical == b.canonical and a.nrow == b.nrow == 1 and a.indexable == b.indexable
+        assert a.add.tobytes() == b.add.tobytes()
+        fa, fb = M._fold(a.t_row, a.t_col, a.t_val), M._fold(b.t_row, b.t_col, b.t_val)
+        assert all(np.array_equal(p, q) for p, q in zip(fa[:2], fb[:2])) and fa[2].tobytes() == fb[2].tobytes()
+    ca, cb = out[False][2], out[True][2]
+    assert ca.rhs.tobytes() == cb.rhs.tobytes() and ca.t_val.tobytes() == cb.t_val.tobytes()
+
+
+def test_untraceable_bodies_fall_back_and_errors_surface_from_the_eager_path():
+    S, T, _ = _sets()
+    lp = M.easylp()
+    x = lp.var("x", S, T)
+    lut = {s: float(s) for s in S}
+    f = M.for_(lambda s: lut[s] * x[s, 1] <= 1, s=S)                  # dict lookup needs the value of s
+    assert isinstance(f, M.ForSplit)
+    f = M.for_(lambda s: x[s, ] <= 1, s=S)                            # multi-row atoms
+    assert isinstance(f, M.ForSplit)
+    f = M.for_(lambda s: x[s, 1] * 2 + x[s, 1] <= 1, s=S)             # fine: two groups on one column
+    assert isinstance(f, lower.LoweredFor)
+    with pytest.raises(M.EasyLpError):
+        M.for_(lambda s: x[s + 3, 1] <= 1, s=S)                       # subscript out of bounds: the eager `[` reports it
+    with pytest.raises(M.EasyLpError):
+        M.for_(lambda s: x[s, 1] * x[s, 2] <= 1, s=S)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_device_expansion_and_assembly_equal_eager(name):
+    e, l = _build(name, False), _build(name, True)
+    rows, cols, vals, packed, m, _ = _lowered_parts(l)
+    r1, c1, v1, g1 = L.expand_terms(packed)
+    r2, c2, v2, g2 = lower_ref.expand(packed)
+    assert np.array_equal(r1, r2) and np.array_equal(c1, c2) and v1.tobytes() == v2.tobytes() and np.array_equal(g1, g2)
+    rp0, ci0, vv0 = e._csr()
+    rp, ci, vv = l._csr()
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and np.asarray(vv).tobytes() == np.asarray(vv0).tobytes()
+
+
+@pytest.mark.gpu
+def test_c2_lowered_build_is_bit_exact_and_fast():
+    """BASELINE config 2 through the DSL: one trace per constraint family instead of 180 000 body evaluations"""
+    import time
+    from oracle import gen
+    S = T = 300
+    p = gen.transport(S, T, seed=0)
+    src, snk = list(range(1, S + 1)), list(range(1, T + 1))
+    t0 = time.perf_counter()
+    lp = M.easylp()
+    x = lp.var("x", src, snk, lower=0)
+    cost = M.parameter(p["cost"].ravel(order="F"), src, snk)
+    supply, demand = M.parameter(p["supply"], src), M.parameter(p["demand"], snk)
+    lp.min(M.sum_for(lambda s, t: cost[s, t] * x[s, t], s=src, t=snk))
+    lp.con(make=M.for_(lambda s: M.sum_for(lambda t: x[s, t], t=snk) <= supply[s], s=src),
+           sell=M.for_(lambda t: M.sum_for(lambda s: x[s, t], s=src) >= demand[t], t=snk))
+    rp, ci, v = lp._csr()
+    dt = time.perf_counter() - t0
+    assert all(isinstance(b, lower.LoweredCon) for b in lp._blocks)
+    assert np.array_equal(rp, p["row_ptr"]) and np.array_equal(ci, p["col_idx"]) and np.asarray(v).tobytes() == p["vals"].tobytes()
+    assert lp.objective_fun.tobytes() == p["c"].tobytes()
+    assert lp.constraint.rhs.tobytes() == p["rhs"].tobytes()
+    assert dt < 2.0, f"lowered C2 build took {dt:.2f} s"
