@@ -447,6 +447,49 @@ def bench_assembly(args, L, p):
                                  "passes move ~32 B per term each, so the real traffic is ~8x the algorithmic bytes"}}
 
 
+def bench_lowering(args, L):
+    """BASELINE config 2 (transport 300 x 300) written with for + sum_for.  `eager` evaluates the body once
+    per atom / grid row on the host (the reference's interpreter loop, R/utils.R:50-53,405-408) and ships 180 000 terms;
+    `lowered` traces each body once and lets the device expand the index-set families (elp_assemble_lowered).  Both
+    must give the generator's canonical CSR bit for bit."""
+    from easylp_b200 import model as M
+    S = T = 300
+    p = gen.transport(S, T, seed=0)
+    src, snk = list(range(1, S + 1)), list(range(1, T + 1))
+
+    def build(lowering):
+        M.LOWERING = lowering
+        try:
+            t0 = time.perf_counter()
+            lp = M.easylp()
+            x = lp.var("x", src, snk, lower=0)
+            cost = M.parameter(p["cost"].ravel(order="F"), src, snk)
+            supply, demand = M.parameter(p["supply"], src), M.parameter(p["demand"], snk)
+            lp.min(M.sum_for(lambda s, t: cost[s, t] * x[s, t], s=src, t=snk))
+            lp.con(make=M.for_(lambda s: M.sum_for(lambda t: x[s, t], t=snk) <= supply[s], s=src),
+                   sell=M.for_(lambda t: M.sum_for(lambda s: x[s, t], s=src) >= demand[t], t=snk))
+            t1 = time.perf_counter()
+            rp, ci, v = lp._csr()
+            c = lp.objective_fun
+            t2 = time.perf_counter()
+        finally:
+            M.LOWERING = True
+        exact = bool(np.array_equal(rp, p["row_ptr"]) and np.array_equal(ci, p["col_idx"])
+                     and np.asarray(v).tobytes() == p["vals"].tobytes() and c.tobytes() == p["c"].tobytes()
+                     and lp.constraint.rhs.tobytes() == p["rhs"].tobytes())
+        st = lp.assembly_stats
+        return dict(host_s=t1 - t0, assemble_s=t2 - t1, total_s=t2 - t0, device_ms=st.solve_ms, bit_exact=exact,
+                    h2d_bytes=int(st.h2d_bytes), gpu_launches=int(st.kernel_launches))
+
+    build(True)                                     # warm-up (workspace, module load)
+    low = build(True)
+    eag = build(False)
+    return {"metric": "model_build_s", "unit": "s", "higher_is_better": False,
+            "workload": "C2: transport 300 x 300 (90 000 vars, 600 rows, 180 000 nnz) through for_/sum_for, objective via sum_for",
+            "value": low["total_s"], "lowered": low, "eager": eag, "speedup": eag["total_s"] / low["total_s"],
+            "gpu_launches": low["gpu_launches"]}
+
+
 # ------------------------------------------------------------------------------------------------
 def make_problem(args):
     w = args.workload
@@ -549,6 +592,8 @@ def main():
             asm = bench_assembly(args, L, p)
             res["assembly"] = asm
             res["gpu_launches"] += asm["gpu_launches"] * args.steps
+            if dist.rank == 0:
+                res["lowering"] = bench_lowering(args, L)
         if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_pdlp_baseline(p, args.cpu_sample_iters, threads)
     if dist.rank == 0:

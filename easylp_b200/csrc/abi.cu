@@ -271,9 +271,10 @@ static int64_t check_family(const elp_term_family& f, int64_t n_itab, int64_t n_
         ELP_REQUIRE(count < (1ll << 40), "lowered: family too large");
         if (f.extent[l] > 0) {
             ELP_REQUIRE(f.col_tab[l] < 0 || f.col_tab[l] + f.extent[l] <= n_itab, "lowered: column table outside itab");
+            ELP_REQUIRE(f.row_tab[l] < 0 || f.row_tab[l] + f.extent[l] <= n_itab, "lowered: row table outside itab");
             ELP_REQUIRE(f.coef_stride[l] >= 0 && f.row_stride[l] >= 0, "lowered: negative stride");
             coef_max += f.coef_stride[l] * (int64_t)(f.extent[l] - 1);
-            row_max += (int64_t)f.row_stride[l] * (f.extent[l] - 1);
+            if (f.row_tab[l] < 0) row_max += (int64_t)f.row_stride[l] * (f.extent[l] - 1);   // table rows: checked by the assembly (out-of-range terms are reported)
         }
     }
     ELP_REQUIRE(count == f.count, "lowered: family count %lld is not the product of its extents (%lld)", (long long)f.count, (long long)count);

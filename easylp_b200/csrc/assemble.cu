@@ -96,7 +96,7 @@ __global__ void asm_expand_family(const elp_term_family f, const int32_t* __rest
         const int32_t e = f.extent[l];
         const int32_t p = (int32_t)(rem % e);
         rem /= e;
-        r += f.row_stride[l] * p;
+        r += (f.row_tab[l] >= 0) ? itab[f.row_tab[l] + p] : f.row_stride[l] * p;
         if (f.col_tab[l] >= 0) c += itab[f.col_tab[l] + p];
         ci += f.coef_stride[l] * p;
     }

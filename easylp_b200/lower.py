@@ -135,18 +135,23 @@ class SymIndex(Coef):
             raise NotLowerable()
 
 
-def _evaluate(c: Coef, axes: dict, ndim: int) -> np.ndarray:
-    """value of the scalar over the loop grid: shape has the loop's extent on the axes it depends on, 1 elsewhere"""
+def _evaluate(c: Coef, axes: dict, ndim: int, expand=None) -> np.ndarray:
+    """value of the scalar over the loop grid: shape has the loop's extent on the axes it depends on, 1 elsewhere.
+    `expand[uid]`: positions of that loop's values along its axis when the axis is a fused (parent, ragged) loop."""
     one = (1,) * ndim
+    expand = expand or {}
     if c.kind == "const":
         return np.full(one, c.a)
     if c.kind == "idx":
         s = c.a
         if not s.numeric or s.uid not in axes:
             raise NotLowerable()
+        vals = np.asarray(s.seq, dtype=float)
+        if s.uid in expand:
+            vals = vals[expand[s.uid]]
         shape = list(one)
-        shape[axes[s.uid]] = len(s.seq)
-        return np.asarray(s.seq, dtype=float).reshape(shape)
+        shape[axes[s.uid]] = vals.size
+        return vals.reshape(shape)
     if c.kind == "param":
         idx = []
         for s in c.b:
@@ -156,19 +161,24 @@ def _evaluate(c: Coef, axes: dict, ndim: int) -> np.ndarray:
                 sym, tab = s
                 if sym.uid not in axes:
                     raise NotLowerable()
+                t = tab.astype(np.int64)
+                if sym.uid in expand:
+                    t = t[expand[sym.uid]]
                 shape = list(one)
-                shape[axes[sym.uid]] = len(sym.seq)
-                idx.append(tab.astype(np.int64).reshape(shape))
+                shape[axes[sym.uid]] = t.size
+                idx.append(t.reshape(shape))
         return np.asarray(c.a[tuple(np.broadcast_arrays(*idx))], dtype=float)
     if c.kind == "neg":
-        return -_evaluate(c.a, axes, ndim)
+        return -_evaluate(c.a, axes, ndim, expand)
     if c.kind == "bin":
-        a, b = _evaluate(c.a, axes, ndim), _evaluate(c.b, axes, ndim)
+        a, b = _evaluate(c.a, axes, ndim, expand), _evaluate(c.b, axes, ndim, expand)
         with np.errstate(all="ignore"):
             return a + b if c.op == "+" else a - b if c.op == "-" else a * b if c.op == "*" else a / b
     if c.kind == "sumover":
         # `Sum(*cells)`: add <- add + cell.add, cell after cell in double (model.Sum); first name fastest = last axis
         loops = c.b                                     # slowest first: they become the trailing axes
+        if expand or any(getattr(l, "ragged", None) for l in loops):
+            raise NotLowerable()                        # constants summed over a ragged set: not traced
         ax2 = dict(axes)
         for i, l in enumerate(loops):
             ax2[l.uid] = ndim + i
@@ -381,6 +391,37 @@ def has_symbolic(key):
     return any(isinstance(k, Coef) for k in key)
 
 
+# ---- ragged index sets ---------------------------------------------------------------------------------
+class RaggedSeq:
+    """`out[[v]]` with a symbolic v: one list of values per value of the enclosing loop variable"""
+
+    def __init__(self, parent: SymIndex, lists):
+        self.parent, self.lists = parent, [list(x) for x in lists]
+
+
+class IndexSets:
+    """A list of index sets keyed by the values of another index (R: a named list, `out[[v]]`), e.g. the arcs that
+    leave node v.  `sets[v]` is the plain list when v is a value; inside a for/sum_for trace it stands for all of
+    them at once, so `for (v in V) sum_for(a = out[[v]], ...)` lowers to one family over the (v, a) pairs."""
+
+    def __init__(self, mapping):
+        self.map = {k: list(v) for k, v in dict(mapping).items()}
+
+    def __getitem__(self, key):
+        if isinstance(key, Coef):
+            sym, off = key.as_subscript()
+            if off:
+                raise NotLowerable()
+            try:
+                return RaggedSeq(sym, [self.map[v] for v in sym.seq])
+            except (KeyError, TypeError):
+                raise NotLowerable()
+        return self.map[key]
+
+    def __len__(self):
+        return len(self.map)
+
+
 # ---- sum_for -----------------------------------------------------------------------------------------
 def _sum_group(cell: SymExpr, loops):
     """`do.call(sum, cells)`: every cell is folded on its own first (sum.lp_var), then the cells are added in grid
@@ -398,7 +439,16 @@ def try_sum_for(body, index):
     """Returns a SymExpr (inside an enclosing trace), a materialised lp_var (top level), or None = take the eager path."""
     names = list(index)
     try:
-        syms = {k: SymIndex(k, index[k]) for k in names}
+        syms = {}
+        for k in names:
+            seq = index[k]
+            if isinstance(seq, RaggedSeq):              # one set per value of an enclosing loop: a fused (parent, k) loop
+                if any(len(x) == 0 for x in seq.lists):
+                    return None                         # an empty sum is an error in the eager path
+                syms[k] = SymIndex(k, [v for x in seq.lists for v in x])
+                syms[k].ragged = (seq.parent, np.asarray([len(x) for x in seq.lists], dtype=np.int64))
+            else:
+                syms[k] = SymIndex(k, seq)
         cell = body(**syms)
         if not isinstance(cell, SymExpr):
             return None
@@ -408,6 +458,8 @@ def try_sum_for(body, index):
         expr = _sum_group(cell, loops)
         free = expr.syms()
         if all(u in {l.uid for l in loops} for u in free):
+            if any(getattr(l, "ragged", None) for l in loops):
+                return None
             first = body(**{k: index_first(index[k]) for k in names})       # metadata of the eager result
             return _materialise(expr, loops, first)
         return expr
@@ -518,12 +570,39 @@ def build_block(low: LoweredFor) -> LoweredCon:
         rstride[i] = s
         s *= len(outer[i].seq)
     families, groups, offset = [], [], 0
+    outer_ext = [len(l.seq) for l in outer]
     for g in low.con.groups:
-        loops = outer + list(g.loops)
-        if len(loops) > MAX_LOOPS:
+        # the loop nest of this group's families, slowest first.  A ragged `sum_for` index (one set per value of an
+        # outer loop) is fused with that outer loop into ONE trailing loop over the (parent, value) pairs: rows and
+        # columns come from tables over the pairs.  Outer loops may be reordered freely (rows are computed, not
+        # counted); the order of the terms INSIDE a row — the sum_for grid order — is what the fold depends on.
+        rag = [l for l in g.loops if getattr(l, "ragged", None)]
+        expand, fused = {}, None
+        if rag:
+            if len(rag) != 1 or g.loops[-1] is not rag[0]:
+                raise NotLowerable()
+            fused = rag[0]
+            parent, counts = fused.ragged
+            if parent.uid not in o_axes or counts.size != len(parent.seq):
+                raise NotLowerable()
+            ppos = np.repeat(np.arange(len(parent.seq), dtype=np.int64), counts)
+            expand = {parent.uid: ppos}
+            nest = [l for l in outer if l.uid != parent.uid] + list(g.loops[:-1])
+            axes = {l.uid: i for i, l in enumerate(nest)}
+            axes[parent.uid] = axes[fused.uid] = len(nest)
+            ext = [len(l.seq) for l in nest] + [len(fused.seq)]
+            row_stride = [rstride[o_axes[l.uid]] if l.uid in o_axes else 0 for l in nest] + [0]
+            row_tabs = [None] * len(nest) + [(ppos * rstride[o_axes[parent.uid]]).astype(_I)]
+            nest_uids = [[l.uid] for l in nest] + [[parent.uid, fused.uid]]
+        else:
+            nest = outer + list(g.loops)
+            axes = {l.uid: i for i, l in enumerate(nest)}
+            ext = [len(l.seq) for l in nest]
+            row_stride = rstride + [0] * len(g.loops)
+            row_tabs = [None] * len(nest)
+            nest_uids = [[l.uid] for l in nest]
+        if len(ext) > MAX_LOOPS:
             raise NotLowerable()
-        axes = {l.uid: i for i, l in enumerate(loops)}
-        ext = [len(l.seq) for l in loops]
         cells = int(np.prod(ext))
         posts = []
         for k in g.post:
@@ -533,8 +612,7 @@ def build_block(low: LoweredFor) -> LoweredCon:
             v = _evaluate(k, o_axes, len(outer))
             if not np.all(np.isfinite(v)):
                 raise NotLowerable()
-            posts.append(np.broadcast_to(v, [len(l.seq) for l in outer]).reshape(-1).astype(float) if v.size > 1
-                         else v.reshape(-1).astype(float))
+            posts.append(np.broadcast_to(v, outer_ext).reshape(-1).astype(float) if v.size > 1 else v.reshape(-1).astype(float))
         groups.append(posts)
         for ti, t in enumerate(g.terms):
             if any(u not in axes for u in t.tabs):
@@ -542,17 +620,26 @@ def build_block(low: LoweredFor) -> LoweredCon:
             free = t.coef.syms({})
             if any(u not in axes for u in free):
                 raise NotLowerable()
-            v = _evaluate(t.coef, axes, len(loops))
+            v = _evaluate(t.coef, axes, len(ext), expand)
             if not np.all(np.isfinite(v)):
                 raise NotLowerable()
-            cstride, st = [0] * len(loops), 1
-            for i in range(len(loops) - 1, -1, -1):
+            cstride, st = [0] * len(ext), 1
+            for i in range(len(ext) - 1, -1, -1):
                 if v.shape[i] > 1:
                     cstride[i] = st
                     st *= v.shape[i]
+            col_tabs = []
+            for uids in nest_uids:
+                tab = None
+                for u in uids:
+                    if u in t.tabs:
+                        tu = t.tabs[u][1].astype(np.int64)
+                        if u in expand:
+                            tu = tu[expand[u]]
+                        tab = tu if tab is None else tab + tu
+                col_tabs.append(None if tab is None else tab.astype(_I))
             families.append(dict(count=cells, out_offset=offset + ti, out_stride=len(g.terms), group=len(groups) - 1,
-                                 extent=ext, row_stride=rstride + [0] * len(g.loops), col0=t.col0,
-                                 col_tabs=[t.tabs[l.uid][1] if l.uid in t.tabs else None for l in loops],
+                                 extent=ext, row_stride=row_stride, row_tabs=row_tabs, col0=t.col0, col_tabs=col_tabs,
                                  coef=np.ascontiguousarray(v, dtype=float).reshape(-1), coef_stride=cstride))
         offset += cells * len(g.terms)
     return LoweredCon(nrow, low.con.op, rhs, families, groups, outer)
@@ -561,7 +648,8 @@ def build_block(low: LoweredFor) -> LoweredCon:
 # ---- packing for the C ABI ---------------------------------------------------------------------------
 class TermFamily(C.Structure):
     _fields_ = [("count", C.c_int64), ("out_offset", C.c_int64), ("coef_tab", C.c_int64),
-                ("col_tab", C.c_int64 * MAX_LOOPS), ("coef_stride", C.c_int64 * MAX_LOOPS),
+                ("col_tab", C.c_int64 * MAX_LOOPS), ("row_tab", C.c_int64 * MAX_LOOPS),
+                ("coef_stride", C.c_int64 * MAX_LOOPS),
                 ("extent", C.c_int32 * MAX_LOOPS), ("row_stride", C.c_int32 * MAX_LOOPS),
                 ("out_stride", C.c_int32), ("group", C.c_int32), ("n_loops", C.c_int32), ("row0", C.c_int32),
                 ("col0", C.c_int32), ("reserved", C.c_int32)]
@@ -598,13 +686,14 @@ def pack(blocks_with_rows):
             nd += f["coef"].size
             for l in range(len(f["extent"])):
                 t.extent[l], t.row_stride[l], t.coef_stride[l] = f["extent"][l], f["row_stride"][l], f["coef_stride"][l]
-                tab = f["col_tabs"][l]
-                if tab is None:
-                    t.col_tab[l] = -1
-                else:
-                    t.col_tab[l] = ni
-                    itab.append(tab)
-                    ni += tab.size
+                for key, dst in (("col_tabs", t.col_tab), ("row_tabs", t.row_tab)):
+                    tab = f[key][l]
+                    if tab is None:
+                        dst[l] = -1
+                    else:
+                        dst[l] = ni
+                        itab.append(tab)
+                        ni += tab.size
             fams.append(t)
         stream += blk.n_terms
     if len(groups) > 65535:

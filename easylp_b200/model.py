@@ -146,6 +146,13 @@ class Param:
         return float(out.ravel()[0]) if out.size == 1 else out.squeeze()
 
 
+def index_sets(mapping):
+    """A list of index sets keyed by the values of another index — R: a named list used as `out[[v]]`, e.g. the arcs
+    leaving node v.  Indexing with a value gives the plain list; inside a for/sum_for trace `sets[v]` stands for all of
+    them, so `for (v in V) sum_for(a = out[[v]], ...)` lowers to one family over the (v, a) pairs (lower.py)."""
+    return _lower.IndexSets(mapping)
+
+
 def parameter(x, *sets, byrow=False, **named):
     sets = list(sets) + list(named.values())
     if not sets:

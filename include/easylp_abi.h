@@ -134,6 +134,9 @@ typedef struct elp_term_family {
     int64_t out_offset;                     /* position of the family's first term in the lowered stream */
     int64_t coef_tab;                       /* offset of the coefficient table in dtab */
     int64_t col_tab[ELP_MAX_LOOPS];         /* per loop: offset in itab of its column-offset table, -1 = none */
+    int64_t row_tab[ELP_MAX_LOOPS];         /* per loop: offset in itab of a row-offset table, -1 = use row_stride.  A ragged
+                                               index set (`sum_for(a = out[[v]], ...)`) is one loop over the (v, a) pairs
+                                               whose rows and columns both come from tables. */
     int64_t coef_stride[ELP_MAX_LOOPS];     /* per loop: stride in the coefficient table (0 = independent) */
     int32_t extent[ELP_MAX_LOOPS];          /* loops slowest first */
     int32_t row_stride[ELP_MAX_LOOPS];      /* per loop: contribution of one step to the row index */

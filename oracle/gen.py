@@ -205,7 +205,8 @@ def mcnf(K=50, gw=100, gh=200, extra_arcs=20_600, seed=0):
     sense = np.concatenate([np.full(K * nodes, EQ), np.full(narcs, LE)]).astype(np.int8)
     c = np.tile(cost, K)
     return dict(m=m, n=n, row_ptr=row_ptr.astype(np.int32), col_idx=cols.astype(np.int32), vals=vals,
-                sense=sense, rhs=rhs, c=c, lb=np.zeros(n), ub=np.full(n, np.inf), maximize=False)
+                sense=sense, rhs=rhs, c=c, lb=np.zeros(n), ub=np.full(n, np.inf), maximize=False,
+                K=K, nodes=nodes, narcs=narcs, tails=tails, heads=heads, cost=cost, cap=cap, src=src, dst=dst, dem=dem)
 
 
 def term_stream(p, dup_frac=0.05, seed=0):

@@ -27,7 +27,7 @@ def expand(packed):
             for l in range(nl - 1, -1, -1):
                 p = rem % ext[l]
                 rem //= ext[l]
-                r += f.row_stride[l] * p
+                r += int(itab[f.row_tab[l] + p]) if f.row_tab[l] >= 0 else f.row_stride[l] * p
                 if f.col_tab[l] >= 0:
                     c += int(itab[f.col_tab[l] + p])
                 ci += f.coef_stride[l] * p
