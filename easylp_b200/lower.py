@@ -288,13 +288,18 @@ class SymExpr:
         return self._scale(inv, lambda a, _kk: Coef("bin", a, k, "/"))
 
     __rtruediv__ = __pow__ = __rpow__ = __mod__ = __floordiv__ = __invert__ = __abs__ = _refuse
-    __bool__ = __len__ = __iter__ = __getitem__ = _refuse
+    __bool__ = __iter__ = __getitem__ = _refuse
+
+    def __len__(self):
+        return 1
 
     def _plus(self, o, sign):
         if isinstance(o, SymExpr):
             # a + (b + c) adds the FOLDED pair (b + c).  That is the left fold a + b + c only if no entry receives both
             # b and c, which is certain when they sit on different variables (disjoint column ranges).
             blocks = [{t.block for t in g.terms} for g in o.groups]
+            if len(blocks) > 1 and any(None in b_ for b_ in blocks):
+                raise NotLowerable()                    # rows of aliases may share columns with anything
             if any(blocks[i] & blocks[j] for i in range(len(blocks)) for j in range(i)):
                 raise NotLowerable()
             og = o.groups if sign > 0 else [g.mapped(lambda c: Coef("neg", c)) for g in o.groups]
@@ -354,37 +359,128 @@ class SymCon:
     __bool__ = _refuse
 
 
+class SymVec:
+    """`x[f, ]`: the rows of a raw variable along its sliced dimensions (one entry with coefficient 1 per row).  Only
+    what `sum(x[f, ])`, `mean(x[f, ])` and a scalar factor need is traced."""
+    __array_ufunc__ = None
+    __hash__ = None
+
+    def __init__(self, term: Term, implicit):
+        self.term, self.implicit = term, list(implicit)      # implicit loops in dimension order (first fastest)
+
+    def __len__(self):
+        return int(np.prod([len(l.seq) for l in self.implicit]))
+
+    def _scaled(self, k):
+        if not isinstance(k, Coef) and not _is_number(k):
+            raise NotLowerable()                             # vectors recycle row-wise: not traced
+        k = Coef.wrap(k)
+        t = self.term
+        return SymVec(Term(t.block, t.col0, t.tabs, Coef("bin", t.coef, k, "*")), self.implicit)
+
+    def __mul__(self, k): return self._scaled(k)
+    __rmul__ = __mul__
+
+    def __truediv__(self, k):
+        if not isinstance(k, Coef) and not _is_number(k):
+            raise NotLowerable()
+        return self._scaled(Coef("bin", Coef("const", 1.0), Coef.wrap(k), "/"))
+
+    def __neg__(self):
+        t = self.term
+        return SymVec(Term(t.block, t.col0, t.tabs, Coef("neg", t.coef)), self.implicit)
+
+    def as_sum(self):
+        """sum.lp_var of the rows = colSums: every column occurs in one row only, so each column sum is its entry"""
+        return SymExpr([Group(tuple(reversed(self.implicit)), [self.term], [])])
+
+    __add__ = __radd__ = __sub__ = __rsub__ = __rtruediv__ = __pow__ = __getitem__ = __iter__ = __bool__ = _refuse
+    __le__ = __ge__ = __lt__ = __gt__ = __eq__ = __ne__ = _refuse
+
+
+def sym_sum(x, *dots):
+    """sum.lp_var (R/methods.R:244-257) on traced arguments: every argument is folded on its own, then `Reduce('+')`"""
+    parts = []
+    for a in (x,) + tuple(dots):
+        if isinstance(a, SymVec):
+            parts.append(a.as_sum())
+        elif isinstance(a, SymExpr) or isinstance(a, Coef) or _is_number(a):
+            parts.append(a)
+        else:
+            raise NotLowerable()
+    if not isinstance(parts[0], SymExpr):
+        raise NotLowerable()
+    acc = parts[0]
+    for p_ in parts[1:]:
+        acc = acc._plus(p_, +1)
+    return acc
+
+
+def is_traced(*xs):
+    return any(isinstance(x, (SymVec, SymExpr)) for x in xs)
+
+
 def var_getitem(x, key):
-    """`x[s, t]` with symbolic subscripts on a raw variable block -> one entry with coefficient 1 (R/methods.R:48-69)"""
+    """`x[s, t]` with symbolic subscripts (R/methods.R:48-69).  On a raw variable block: one entry with coefficient 1,
+    or — with empty subscripts, `x[f, ]` — a SymVec.  On any other indexable variable (an alias, `rowSums(x)`, ...): the
+    row picked by ONE loop variable, as a fused (loop value, entry of that row) family."""
     from . import model
-    if not (getattr(x, "raw", False) and x.indexable and x.has_dim and x.ind.size == x.nrow):
+    if not (x.indexable and x.has_dim and x.ind.size == x.nrow):
         raise NotLowerable()
     ind = x.ind
     if len(key) != ind.ndim:
         raise NotLowerable()
-    col0 = int(ind.flat[0]) - 1
-    if not np.array_equal(x.t_col, ind.flatten(order="F") - 1):
-        raise NotLowerable()
-    stride, tabs = 1, {}
+    raw = bool(getattr(x, "raw", False)) and np.array_equal(x.t_col, ind.flatten(order="F") - 1)
+    base = int(ind.flat[0]) - 1 if raw else 0
+    stride, tabs, implicit = 1, {}, []
     for d, k in enumerate(key):
         names = x.dimnames[d] if x.dimnames is not None else None
         if isinstance(k, Coef):
             sym, off = k.as_subscript()
-            tab = _subscript_table(ind.shape[d], names, sym, off) * _I(stride)
+            tab = _subscript_table(ind.shape[d], names, sym, off).astype(np.int64) * stride
             if sym.uid in tabs:
                 tab = tabs[sym.uid][1] + tab
-            tabs[sym.uid] = (sym, tab.astype(_I))
+            tabs[sym.uid] = (sym, tab)
+        elif k is None or (isinstance(k, slice) and k == slice(None)):
+            if not raw:
+                raise NotLowerable()
+            sym = SymIndex(f"_dim{d + 1}", range(1, ind.shape[d] + 1))
+            tabs[sym.uid] = (sym, np.arange(ind.shape[d], dtype=np.int64) * stride)
+            implicit.append(sym)
         elif _is_number(k) or isinstance(k, (str, np.str_)):
             try:
-                col0 += stride * int(model._positions((ind.shape[d],), [names] if names is not None else None, None, (k,))[0][0])
+                base += stride * int(model._positions((ind.shape[d],), [names] if names is not None else None, None, (k,))[0][0])
             except model.EasyLpError:
                 raise NotLowerable()
         else:
-            raise NotLowerable()                        # vectors, slices: a multi-row result
+            raise NotLowerable()                        # vectors of subscripts: not traced
         stride *= ind.shape[d]
-    if not tabs:
-        raise NotLowerable()                            # fully concrete: the eager `[` answers
-    return SymExpr([Group((), [Term(id(x), col0, tabs, Coef("const", 1.0))], [])])
+    if len(tabs) == len(implicit):
+        raise NotLowerable()                            # no loop variable involved: the eager `[` answers
+    if raw:
+        tabs = {u: (sy, t.astype(_I)) for u, (sy, t) in tabs.items()}
+        term = Term(id(x), base, tabs, Coef("const", 1.0))
+        return SymVec(term, implicit) if implicit else SymExpr([Group((), [term], [])])
+    # a row of a canonical multi-entry variable, chosen by one loop variable
+    if len(tabs) != 1:
+        raise NotLowerable()
+    (parent, rowtab), = tabs.values()
+    rowpos = rowtab + base
+    xc = x.copy()._canon()
+    ptr = np.asarray(xc._row_ptr(), dtype=np.int64)
+    counts = ptr[rowpos + 1] - ptr[rowpos]
+    total = int(counts.sum())
+    if total == 0:
+        raise NotLowerable()
+    src = np.repeat(ptr[rowpos] - np.r_[0, np.cumsum(counts)[:-1]], counts) + np.arange(total, dtype=np.int64)
+    e = SymIndex("_entry", range(total))
+    e.ragged = (parent, counts)
+    term = Term(None, 0, {e.uid: (e, np.asarray(xc.t_col)[src].astype(_I))},
+                Coef("param", np.asarray(xc.t_val, dtype=float)[src], [(e, np.arange(total, dtype=_I))]))
+    add = None
+    if np.any(np.asarray(x.add) != 0.0):
+        add = Coef("param", np.asarray(x.add, dtype=float), [(parent, rowpos.astype(_I))])
+    return SymExpr([Group((e,), [term], [])], add)
 
 
 def has_symbolic(key):

@@ -485,6 +485,8 @@ def compare(e1, op, e2):
 def Sum(x, *dots):
     """sum.lp_var (R/methods.R:244-257): each argument is column-summed on its own, then `Reduce("+")`.
     The Reduce is left PENDING as a term list in argument order — the device assembly folds it."""
+    if _lower.is_traced(x, *dots):            # inside a for/sum_for trace (lower.py)
+        return _lower.sym_sum(x, *dots)
     if not _is_var(x):
         if any(_is_var(d) for d in dots):
             raise EasyLpError("invalid 'type' (list) of argument")
@@ -530,6 +532,8 @@ def _sorted_by_col(col, val):
 
 
 def mean(x):
+    if _lower.is_traced(x):
+        return Sum(x) / len(x)
     if not _is_var(x):
         return float(np.mean(_as_vec(x)))
     return Sum(x) / len(x)

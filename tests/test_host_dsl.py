@@ -57,10 +57,14 @@ def test_term_lists_fold_to_the_reference_matrix(name, lowering):
 
 
 def test_some_reference_models_are_lowered():
-    """test-forsplit.R / test-constraints.R / test-investments.R write rows the trace accepts; aliases (`ext[m]`),
-    slices (`x[f, ]`) and data-dependent ranges keep the per-atom evaluation"""
-    lowered = {n for n in models.ALL if any(isinstance(b, lower.LoweredCon) for b in _build(n, True)._blocks)}
-    assert {"forsplit", "constraints", "investments_assembly"} <= lowered, lowered
+    """the reference's own models (test-DOP.R, test-aliases.R, test-forsplit.R, test-constraints.R, the vignettes'
+    transport problem) write rows the trace accepts: `sum(x[f, ])`, `sum_for`, alias rows `ext[m]`; vector atoms
+    (`x[, b, 2] >= 1`) and data-dependent ranges (`for (q in (p+1):n)`) keep the per-atom evaluation"""
+    blocks = {n: _build(n, True)._blocks for n in models.ALL}
+    lowered = {n for n, b in blocks.items() if any(isinstance(x, lower.LoweredCon) for x in b)}
+    assert {"dop", "aliases", "forsplit", "constraints", "transport_vignette", "transport_sum_for",
+            "investments_assembly"} <= lowered, lowered
+    assert all(isinstance(x, lower.LoweredCon) for x in blocks["dop"])
 
 
 def _constraints_lp():

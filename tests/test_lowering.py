@@ -64,6 +64,22 @@ def m_shifted_and_named(lp):
             "": M.for_(lambda h: M.sum_for(lambda p: mk[p, h + 1], p=P) <= 10 * h, h=H[:-1])}
 
 
+def m_slices_and_aliases(lp):
+    """`sum(x[f, ])` / `mean(x[, m])` slices, rows of aliases (`rowSums(x)[f]`), both scaled and combined"""
+    S, T, rng = _sets()
+    x = lp.var("x", S, T, lower=0)
+    z = lp.var("z", S, T, [1, 2])
+    made, sold = M.rowSums(x), M.colSums(x)
+    w = M.rowSums(x * M.parameter(rng.normal(size=20), S, T)) + 0.5          # an alias with coefficients and constants
+    cap, dem = M.parameter(rng.uniform(5, 9, len(S)), S), M.parameter(rng.uniform(1, 3, len(T)), T)
+    return dict(a1=M.for_(lambda s: M.Sum(x[s, :]) <= cap[s], s=S),
+                a2=M.for_(lambda t: M.mean(x[:, t]) * 3 >= dem[t], t=T),
+                a3=M.for_(lambda s: made[s] <= cap[s], s=S),
+                a4=M.for_(lambda t: 2 * sold[t] - M.Sum(0.5 * x[:, t], z[1, t, :]) >= dem[t] / 3, t=T),
+                a5=M.for_(lambda s: w[s] / 7 - x[s, 1] == s, s=S),
+                a6=M.for_(lambda s, t: M.Sum(z[s, t, :]) <= x[s, t], s=S, t=T))
+
+
 def m_mixed(lp):
     """lowered blocks between eager ones: vector rows, a body the trace refuses (python `if` on the index)"""
     S, T, rng = _sets()
@@ -104,7 +120,7 @@ def m_network(lp):
     return mcnf_dsl(lp, gen.mcnf(K=3, gw=4, gh=3, extra_arcs=6, seed=1))
 
 
-MODELS = dict(network=m_network, transport=m_transport, coefficients=m_coefficients, repeated=m_repeated_columns,
+MODELS = dict(slices=m_slices_and_aliases, network=m_network, transport=m_transport, coefficients=m_coefficients, repeated=m_repeated_columns,
               shifted=m_shifted_and_named, mixed=m_mixed)
 
 
@@ -147,7 +163,7 @@ def _lowered_parts(lp):
     return rows, cols, vals, lower.pack(low), int(offs[-1]), len(low)
 
 
-EXPECT_LOWERED = dict(network=2, transport=2, coefficients=3, repeated=4, shifted=2, mixed=2)
+EXPECT_LOWERED = dict(slices=6, network=2, transport=2, coefficients=3, repeated=4, shifted=2, mixed=2)
 
 
 @pytest.mark.parametrize("name", sorted(MODELS))
