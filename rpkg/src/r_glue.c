@@ -208,6 +208,121 @@ SEXP easylp_solve_batch(SEXP A, SEXP b, SEXP c, SEXP lower, SEXP upper, SEXP dir
     return out;
 }
 
+/* Element `name` of a named R list, or R_NilValue. */
+static SEXP list_get(SEXP lst, const char* name) {
+    SEXP nm = Rf_getAttrib(lst, R_NamesSymbol);
+    if (nm == R_NilValue) return R_NilValue;
+    for (R_xlen_t i = 0; i < XLENGTH(lst); ++i)
+        if (!strcmp(CHAR(STRING_ELT(nm, i)), name)) return VECTOR_ELT(lst, i);
+    return R_NilValue;
+}
+
+/* .Call("easylp_assemble_lowered", term_row, term_col, term_val, families, groups, m, n)
+ * The lowered assembly (include/easylp_abi.h, "(1b)"): `for (v in seq) body` / `sum_for(i = I, body)` whose body the R
+ * side recognised with substitute() as affine in indexed variables arrive as FAMILIES instead of expanded terms.
+ *   families: list of lists with integer scalars `out_offset`, `out_stride`, `group` (1-based), `row0` (1-based),
+ *             `col0` (1-based), integer vectors `extent`, `row_stride`, `coef_stride` (one entry per loop, slowest first),
+ *             lists `col_tab` / `row_tab` (per loop an integer vector of 0-based offsets, or NULL) and a double vector
+ *             `coef`.
+ *   groups:   list of lists with `row0` (1-based) and `mul`, a list of double vectors (length 1 = scalar, else one
+ *             multiplier per row of the block); group 1 is the plain group of the explicit terms.
+ * Returns list(row_ptr, col_idx, vals) like easylp_assemble_csr. */
+SEXP easylp_assemble_lowered(SEXP term_row, SEXP term_col, SEXP term_val, SEXP families, SEXP groups, SEXP m_, SEXP n_) {
+    const int64_t T = (int64_t)XLENGTH(term_val);
+    const int32_t m = Rf_asInteger(m_), n = Rf_asInteger(n_);
+    if (XLENGTH(term_row) != T || XLENGTH(term_col) != T) Rf_error("term vectors differ in length");
+    const int32_t nf = (int32_t)XLENGTH(families), ng = (int32_t)XLENGTH(groups);
+    /* pass 1: table sizes */
+    int64_t ni = 0, nd = 0, total = 0;
+    for (int32_t f = 0; f < nf; ++f) {
+        SEXP F = VECTOR_ELT(families, f);
+        SEXP ext = list_get(F, "extent"), ct = list_get(F, "col_tab"), rt = list_get(F, "row_tab");
+        const R_xlen_t nl = XLENGTH(ext);
+        if (nl > ELP_MAX_LOOPS) Rf_error("family %d has %d loops (max %d)", f + 1, (int)nl, ELP_MAX_LOOPS);
+        int64_t cnt = 1;
+        for (R_xlen_t l = 0; l < nl; ++l) {
+            cnt *= INTEGER(ext)[l];
+            if (ct != R_NilValue && VECTOR_ELT(ct, l) != R_NilValue) ni += XLENGTH(VECTOR_ELT(ct, l));
+            if (rt != R_NilValue && VECTOR_ELT(rt, l) != R_NilValue) ni += XLENGTH(VECTOR_ELT(rt, l));
+        }
+        nd += XLENGTH(list_get(F, "coef"));
+        total += cnt;
+    }
+    for (int32_t g = 0; g < ng; ++g) {
+        SEXP mul = list_get(VECTOR_ELT(groups, g), "mul");
+        if (mul != R_NilValue) for (R_xlen_t k = 0; k < XLENGTH(mul); ++k) nd += XLENGTH(VECTOR_ELT(mul, k));
+    }
+    elp_term_family* fam = (elp_term_family*)R_alloc((size_t)(nf > 0 ? nf : 1), sizeof(elp_term_family));
+    elp_fold_group* grp = (elp_fold_group*)R_alloc((size_t)(ng > 0 ? ng : 1), sizeof(elp_fold_group));
+    int32_t* itab = (int32_t*)R_alloc((size_t)(ni > 0 ? ni : 1), sizeof(int32_t));
+    double* dtab = (double*)R_alloc((size_t)(nd > 0 ? nd : 1), sizeof(double));
+    /* pass 2: pack */
+    int64_t pi = 0, pd = 0;
+    for (int32_t g = 0; g < ng; ++g) {
+        SEXP G = VECTOR_ELT(groups, g), mul = list_get(G, "mul");
+        memset(&grp[g], 0, sizeof grp[g]);
+        grp[g].row0 = Rf_asInteger(list_get(G, "row0")) - 1;
+        grp[g].n_mul = mul == R_NilValue ? 0 : (int32_t)XLENGTH(mul);
+        if (grp[g].n_mul > ELP_MAX_GROUP_MUL) Rf_error("group %d has too many multipliers", g + 1);
+        for (int32_t k = 0; k < grp[g].n_mul; ++k) {
+            SEXP v = VECTOR_ELT(mul, k);
+            grp[g].mul_tab[k] = pd;
+            grp[g].mul_per_row[k] = XLENGTH(v) > 1;
+            memcpy(dtab + pd, REAL(v), (size_t)XLENGTH(v) * sizeof(double));
+            pd += XLENGTH(v);
+        }
+    }
+    for (int32_t f = 0; f < nf; ++f) {
+        SEXP F = VECTOR_ELT(families, f);
+        SEXP ext = list_get(F, "extent"), rs = list_get(F, "row_stride"), cs = list_get(F, "coef_stride");
+        SEXP ct = list_get(F, "col_tab"), rt = list_get(F, "row_tab"), coef = list_get(F, "coef");
+        elp_term_family* t = &fam[f];
+        memset(t, 0, sizeof *t);
+        t->n_loops = (int32_t)XLENGTH(ext);
+        t->out_offset = (int64_t)Rf_asReal(list_get(F, "out_offset"));
+        t->out_stride = Rf_asInteger(list_get(F, "out_stride"));
+        t->group = Rf_asInteger(list_get(F, "group")) - 1;
+        t->row0 = Rf_asInteger(list_get(F, "row0")) - 1;
+        t->col0 = Rf_asInteger(list_get(F, "col0")) - 1;
+        t->coef_tab = pd;
+        memcpy(dtab + pd, REAL(coef), (size_t)XLENGTH(coef) * sizeof(double));
+        pd += XLENGTH(coef);
+        t->count = 1;
+        for (int32_t l = 0; l < t->n_loops; ++l) {
+            t->extent[l] = INTEGER(ext)[l];
+            t->row_stride[l] = INTEGER(rs)[l];
+            t->coef_stride[l] = INTEGER(cs)[l];
+            t->count *= t->extent[l];
+            t->col_tab[l] = t->row_tab[l] = -1;
+            SEXP c = ct == R_NilValue ? R_NilValue : VECTOR_ELT(ct, l);
+            SEXP r = rt == R_NilValue ? R_NilValue : VECTOR_ELT(rt, l);
+            if (c != R_NilValue) { t->col_tab[l] = pi; memcpy(itab + pi, INTEGER(c), (size_t)XLENGTH(c) * sizeof(int32_t)); pi += XLENGTH(c); }
+            if (r != R_NilValue) { t->row_tab[l] = pi; memcpy(itab + pi, INTEGER(r), (size_t)XLENGTH(r) * sizeof(int32_t)); pi += XLENGTH(r); }
+        }
+    }
+    const int64_t cap = T + total > 0 ? T + total : 1;
+    int32_t* row = zero_based(term_row);
+    int32_t* col = zero_based(term_col);
+    int32_t* col_out = (int32_t*)R_alloc((size_t)cap, sizeof(int32_t));
+    double* val_out = (double*)R_alloc((size_t)cap, sizeof(double));
+    SEXP row_ptr = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)m + 1));
+    int64_t nnz = 0;
+    const int rc = elp_assemble_lowered(T, row, col, REAL(term_val), nf, fam, ni, itab, nd, dtab, ng, grp, m, n,
+                                        (int32_t*)INTEGER(row_ptr), col_out, val_out, cap, &nnz, NULL);
+    if (rc) { UNPROTECT(1); elp_fail("easylp_assemble_lowered"); }
+    SEXP col_idx = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz));
+    SEXP vals = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
+    for (int64_t i = 0; i < nnz; ++i) INTEGER(col_idx)[i] = col_out[i] + 1;
+    if (nnz) memcpy(REAL(vals), val_out, (size_t)nnz * sizeof(double));
+    const char* names[] = {"row_ptr", "col_idx", "vals"};
+    SEXP out = PROTECT(named_list(3, names));
+    SET_VECTOR_ELT(out, 0, row_ptr);
+    SET_VECTOR_ELT(out, 1, col_idx);
+    SET_VECTOR_ELT(out, 2, vals);
+    UNPROTECT(4);
+    return out;
+}
+
 /* .Call("easylp_device_count") */
 SEXP easylp_device_count(void) {
     int32_t k = 0;
@@ -217,6 +332,7 @@ SEXP easylp_device_count(void) {
 
 static const R_CallMethodDef call_methods[] = {
     {"easylp_assemble_csr", (DL_FUNC)&easylp_assemble_csr, 5},
+    {"easylp_assemble_lowered", (DL_FUNC)&easylp_assemble_lowered, 7},
     {"easylp_solve_lp", (DL_FUNC)&easylp_solve_lp, 10},
     {"easylp_check_feasible", (DL_FUNC)&easylp_check_feasible, 7},
     {"easylp_solve_batch", (DL_FUNC)&easylp_solve_batch, 8},
