@@ -291,13 +291,30 @@ static int64_t stage_lowered(int64_t n_terms, const int32_t* term_row, const int
                              int64_t n_dtab, const double* dtab, int32_t n_groups, const elp_fold_group* groups, int32_t m,
                              AsmIo* io_out, AsmLowered* lo_out, cudaStream_t st) {
     ELP_REQUIRE(n_terms >= 0 && n_families >= 0 && n_itab >= 0 && n_dtab >= 0 && n_groups >= 0, "lowered: negative size");
-    int64_t total = 0, span = 0;
+    int64_t total = 0;
+    std::vector<int> order;
     for (int i = 0; i < n_families; ++i) {
         const int64_t cnt = check_family(families[i], n_itab, n_dtab, n_groups, m);
         total += cnt;
-        if (cnt > 0) span = std::max(span, families[i].out_offset + (cnt - 1) * families[i].out_stride + 1);
+        if (cnt > 0) order.push_back(i);
     }
-    ELP_REQUIRE(span == total, "lowered: the families do not tile the stream (span %lld, terms %lld)", (long long)span, (long long)total);
+    // The families must tile the stream exactly: a group of k families with stride k interleaves the k body terms of
+    // each cell over one region; regions follow one another without holes or overlap (every slot is written once).
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return families[a].out_offset < families[b].out_offset; });
+    int64_t pos = 0;
+    for (size_t i = 0; i < order.size();) {
+        const elp_term_family& f = families[order[i]];
+        const int k = f.out_stride;
+        bool ok = f.out_offset == pos && i + (size_t)k <= order.size();
+        for (int t = 0; ok && t < k; ++t) {
+            const elp_term_family& g = families[order[i + t]];
+            ok = g.out_offset == pos + t && g.out_stride == k && g.count == f.count;
+        }
+        ELP_REQUIRE(ok, "lowered: the families do not tile the stream (at position %lld)", (long long)pos);
+        pos += f.count * k;
+        i += (size_t)k;
+    }
+    ELP_REQUIRE(pos == total, "lowered: the families do not tile the stream (%lld of %lld slots)", (long long)pos, (long long)total);
     ELP_REQUIRE(groups != nullptr || n_groups == 0 || n_groups == 65536, "lowered: groups missing");
     for (int g = 0; groups && g < n_groups; ++g) {
         ELP_REQUIRE(groups[g].n_mul >= 0 && groups[g].n_mul <= ELP_MAX_GROUP_MUL, "lowered: group with %d multipliers", groups[g].n_mul);

@@ -262,6 +262,45 @@ def test_mcnf_through_the_dsl_is_the_generator_matrix(K, gw, gh, extra):
 
 
 @pytest.mark.gpu
+def test_lowered_abi_rejects_bad_descriptors():
+    """the C ABI checks the families against the table sizes and the matrix before any kernel reads them"""
+    l = _build("transport", True)
+    rows, cols, vals, packed, m, _ = _lowered_parts(l)
+    fam, n_fam, itab, dtab, grp, n_grp, n_low = packed
+
+    def call(packed_, m_=m, n_=l.nvar):
+        return L.assemble_lowered(rows, cols, vals, packed_, m_, n_)
+
+    call(packed)                                                      # the untouched descriptors are fine
+    old = fam[0].count
+    fam[0].count = old + 1                                            # count is not the product of the extents
+    with pytest.raises(L.ElpError, match="product of its extents"):
+        call(packed)
+    fam[0].count = old
+    old = fam[0].out_offset
+    fam[0].out_offset = old + 7                                       # the families no longer tile the stream
+    with pytest.raises(L.ElpError, match="tile the stream"):
+        call(packed)
+    fam[0].out_offset = old
+    with pytest.raises(L.ElpError, match="coefficient table outside"):
+        call((fam, n_fam, itab, dtab[:1], grp, n_grp, n_low))
+    with pytest.raises(L.ElpError, match="column table outside"):
+        call((fam, n_fam, itab[:3], dtab, grp, n_grp, n_low))
+    with pytest.raises(L.ElpError, match="rows outside the matrix"):
+        call(packed, m_=m - 1)
+    with pytest.raises(L.ElpError, match="outside"):                  # columns beyond n are caught by the assembly
+        call(packed, n_=l.nvar - 1)
+    old = fam[0].group
+    fam[0].group = n_grp                                              # a group that does not exist
+    with pytest.raises(L.ElpError, match="names group"):
+        call(packed)
+    fam[0].group = old
+    rp, ci, v, _ = call(packed)                                       # and the call still works afterwards
+    rp0, ci0, v0 = _build("transport", False)._csr()
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and v.tobytes() == np.asarray(v0).tobytes()
+
+
+@pytest.mark.gpu
 def test_c2_lowered_build_is_bit_exact_and_fast():
     """BASELINE config 2 through the DSL: one trace per constraint family instead of 180 000 body evaluations"""
     import time
