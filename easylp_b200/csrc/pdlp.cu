@@ -41,12 +41,6 @@ struct PdlpParams {   // device-resident; the host rewrites it between iteration
 
 constexpr int SPMV_THREADS = 256;             // block size of the setup-only helper kernels
 
-template <class Epi>
-__global__ void __launch_bounds__(256) apply_epi_kernel(int n, const double* __restrict__ g, Epi epi) {
-    const int j = blockIdx.x * 256 + threadIdx.x;
-    if (j < n) epi.apply(j, g[j], epi.preload_global(j), L2Hints{0, 0, 0});
-}
-
 // ---- epilogues of the SpMV (spmv.cuh): in(i) names the operand vectors the producer stages next to the
 // matrix stream, preload() picks this row's operands out of the stage, apply() runs after the row sum ------
 struct StoreEpi {
@@ -1348,12 +1342,11 @@ struct Pdlp {
         std::vector<cudaEvent_t> ev(2 * (size_t)reps + 1);
         for (auto& e : ev) ELP_CUDA(cudaEventCreate(&e));
         for (int i = 0; i < 3; ++i) { primal_step<false>(i, false); dual_step<false>(i, false); }
-        const bool b2b = env_int("ELP_PROBE_B2B", 0) != 0;      // experiment: the same kernel back to back
         for (int i = 0; i < reps; ++i) {
             ELP_CUDA(cudaEventRecord(ev[2 * i], st));
-            if (b2b && i >= reps / 2) dual_step<false>(i, false); else primal_step<false>(i, false);
+            primal_step<false>(i, false);
             ELP_CUDA(cudaEventRecord(ev[2 * i + 1], st));
-            if (b2b && i < reps / 2) primal_step<false>(i, false); else dual_step<false>(i, false);
+            dual_step<false>(i, false);
         }
         ELP_CUDA(cudaEventRecord(ev[2 * reps], st));
         ELP_CUDA(cudaStreamSynchronize(st));
