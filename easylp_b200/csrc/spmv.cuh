@@ -242,9 +242,40 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     }
 }
 
+// ---- long rows: one warp per row -----------------------------------------------------------------------
+// Matrices with few, long rows (the supply/demand rows of a transportation problem: 600 rows of 300 entries) give the
+// tile kernel above a handful of tiles for 148 SMs.  Here a warp owns a row (warp-strided, grid sized to the rows), the
+// lanes stride over its entries with plain streaming loads, and a butterfly sum (fixed order: deterministic) feeds the
+// same epilogue.  These matrices live in L2; the kernel is latency-bound, not bandwidth-bound.
+template <class Epi>
+__global__ void __launch_bounds__(128)
+spmv_rowwarp_kernel(int nrows, const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+                    const double* __restrict__ vec, Epi epi) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * 128 + threadIdx.x) >> 5, nw = (gridDim.x * 128) >> 5;
+    const L2Hints hints{0, 0, 0};
+    for (int r = gw; r < nrows; r += nw) {
+        const int a = __ldg(ptr + r), b = __ldg(ptr + r + 1);
+        typename Epi::Pre pre{};
+        if (lane == 0) pre = epi.preload_global(r);
+        double s0 = 0.0, s1 = 0.0;
+        int k = a + lane;
+        for (; k + 32 < b; k += 64) {                 // two independent chains per lane
+            const int c0 = ld_stream(idx + k), c1 = ld_stream(idx + k + 32);
+            const double v0 = ld_stream(val + k), v1 = ld_stream(val + k + 32);
+            s0 = fma(v0, __ldg(vec + c0), s0);
+            s1 = fma(v1, __ldg(vec + c1), s1);
+        }
+        if (k < b) s0 = fma(ld_stream(val + k), __ldg(vec + ld_stream(idx + k)), s0);
+        const double s = warp_sum(s0 + s1);
+        if (lane == 0) epi.apply(r, s, pre, hints);
+    }
+}
+
 // ---- launch plan ---------------------------------------------------------------------------------
 struct SpmvPlan {
     int L = 1, rpl = 1, cap = 256, ctas_per_sm = 6, ntiles = 0, nst = 2;
+    bool rowwarp = false;          // long rows: one warp per row (spmv_rowwarp_kernel)
     int rw() const { return 32 / L * rpl; }
 };
 
@@ -284,6 +315,9 @@ inline SpmvPlan plan_spmv(int64_t nnz, int nrows, int nin_max, int force_lanes =
     if (const int c = env_int("ELP_SPMV_CAP", 0)) cap = std::max(16, c / 4 * 4);
     p.cap = (int)cap;
     p.ntiles = ceil_div(nrows, rw);
+    // few long rows: the tiles of 32/L rows would not fill the machine; a warp per row does
+    p.rowwarp = force_lanes == 0 && avg >= 48.0 && p.ntiles < kNumSMs * 6 * SPMV_WARPS;
+    if (const char* e = getenv("ELP_SPMV_ROWWARP")) p.rowwarp = atoi(e) != 0 && force_lanes == 0;
     // residency: as many CTAs as 64 K registers allow (6 CTAs of 4 warps at 80 per thread, 3 at 160 for two rows per lane) inside 196 KB of shared memory.
     // Measured on B200: once the CTAs of an SM take more than the 196 KB carve-out step, the L1 left over
     // for the gathers is too small and the kernel slows down by ~30 %.
@@ -342,6 +376,13 @@ template <class Epi>
 void launch_spmv(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val, const double* vec,
                  const Epi& epi, cudaStream_t st) {
     if (nrows <= 0) return;
+    if constexpr (!Epi::SCATTER) {
+        if (p.rowwarp) {
+            const int grid = std::max(1, std::min(ceil_div(nrows, 4), kNumSMs * 16));
+            ELP_LAUNCH((spmv_rowwarp_kernel<Epi>), grid, 128, 0, st, nrows, ptr, idx, val, vec, epi);
+            return;
+        }
+    }
     switch (p.L) {
         case 1:  launch_spmv_l<1, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
         case 2:  launch_spmv_l<2, Epi>(p, nrows, ptr, idx, val, vec, epi, st); break;
