@@ -63,6 +63,10 @@ inline StoreEpi store_epi(double* out) { StoreEpi e; e.out = out; return e; }
 struct PeerOut {
     double* p[8];
     int n;          // 0: single destination (the local pointer of the epilogue)
+    // mask[j] bit r: rank r gathers entry j of this block (its matrix block references it).  Entries nobody else reads
+    // stay at home: on structured LPs (multi-commodity flow: a row block touches the columns of its own commodities)
+    // most of the exchange disappears.  nullptr = every rank gets every entry.
+    const unsigned char* mask;
 };
 
 // primal half of T(z) + reflection + Halpern combine.  g = (A'y)_j
@@ -102,8 +106,10 @@ struct PrimalEpi {
         const double xpj = fmin(fmax(p.x - tau * (p.c - g), p.l), p.u);
         const double xb = 2.0 * xpj - p.x;
         if (!CHECK && peers.n > 0) {
+            const unsigned mk = peers.mask ? peers.mask[j] : 0xffu;
 #pragma unroll 8
-            for (int r = 0; r < peers.n; ++r) peers.p[r][j] = xb;
+            for (int r = 0; r < peers.n; ++r)
+                if ((mk >> r) & 1u) peers.p[r][j] = xb;
         } else {
             st_out(xbar + j, xb, h, true);
         }
@@ -162,8 +168,10 @@ struct DualEpi {
             const double w = (k + 1.0) / (k + 2.0);
             const double yn = w * (2.0 * ypi - p.y) + (1.0 - w) * p.y0;
             if (peers.n > 0) {
+                const unsigned mk = peers.mask ? peers.mask[i] : 0xffu;
 #pragma unroll 8
-                for (int r = 0; r < peers.n; ++r) peers.p[r][i] = yn;
+                for (int r = 0; r < peers.n; ++r)
+                    if ((mk >> r) & 1u) peers.p[r][i] = yn;
             } else {
                 st_out(y + i, yn, h, true);
             }
@@ -558,6 +566,22 @@ __global__ void k_peer_wait(const unsigned long long* __restrict__ my_row, int n
     __threadfence_system();
 }
 
+// ---- which entries of the gathered vectors does each rank read? (sparse peer exchange) ------------------------
+__global__ void k_mark_used(uint32_t nnz, const int* __restrict__ idx, unsigned char* __restrict__ used) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) used[idx[i]] = 1;                       // same value from every writer
+}
+// mask[j] = sum over ranks r of used_r[first + j] << r, own bit always set (the local kernels read the local copy)
+__global__ void k_build_mask(int count, int first, size_t stride, int nranks, int rank, const unsigned char* __restrict__ used_all,
+                             unsigned char* __restrict__ mask, unsigned long long* __restrict__ sent) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    unsigned mk = 1u << rank;
+    for (int r = 0; r < nranks; ++r) mk |= (used_all[(size_t)r * stride + first + j] ? 1u : 0u) << r;
+    mask[j] = (unsigned char)mk;
+    atomicAdd(sent, (unsigned long long)(__popc(mk) - 1));
+}
+
 // ---- kernels of the one-off exchange that builds each rank's column block of A ---------------------
 __global__ void k_shift_idx(uint32_t nnz, int* __restrict__ idx, int offset) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -633,6 +657,8 @@ struct Pdlp {
     PeerOut x_out{}, y_out{};            // peers' xbar_full + n0, y_full + rank*mb
     PeerFlags xflags{}, yflags{};
     DevBuf<unsigned long long> flags;    // [2][8] flag rows (x, y) + [4] epochs/expectations
+    DevBuf<unsigned char> xmask, ymask;  // sparse exchange: which ranks gather entry j of my x-bar / y block
+    double exch_frac_x = 1.0, exch_frac_y = 1.0;   // fraction of the dense (N-1)-copy exchange that is actually sent
     std::vector<void*> ipc_opened;
     DevBuf<double> partials, scal;                              // scal: 2*NACC
     DevBuf<PdlpParams> params;
@@ -704,6 +730,7 @@ struct Pdlp {
             return;
         }
         x_out.n = y_out.n = N;
+        x_out.mask = y_out.mask = nullptr;
         for (int r = 0; r < N; ++r) {
             x_out.p[r] = xs[r] + n0;
             y_out.p[r] = ys[r] + (size_t)rank * mb;
@@ -711,6 +738,46 @@ struct Pdlp {
             yflags.row[r] = fs[r] + 8;
         }
         p2p = true;
+        if (env_int("ELP_PDLP_SPARSE_EXCHANGE", 1)) build_exchange_masks();
+    }
+    // Every rank marks the columns its row block references (K2 gathers x-bar there) and the rows its column block
+    // references (K1 gathers y there); the marks are all-gathered and each rank keeps, for the entries it PRODUCES, the
+    // set of ranks that read them.  The epilogues then store an entry only into those ranks' copies.
+    void build_exchange_masks() {
+        const size_t sx = (size_t)N * nb, sy = (size_t)N * mb;
+        DevBuf<unsigned char> used_x((size_t)N * sx), used_y((size_t)N * sy);
+        DevBuf<unsigned long long> sent(2);
+        used_x.zero(st); used_y.zero(st); sent.zero(st);
+        if (nnz > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnz, 256), 256, 0, st, (uint32_t)nnz, csr_idx.p, used_x.p + (size_t)rank * sx);
+        if (nnzc > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnzc, 256), 256, 0, st, (uint32_t)nnzc, csc_idx.p, used_y.p + (size_t)rank * sy);
+        comm_allgather_bytes(used_x.p, sx, st);
+        comm_allgather_bytes(used_y.p, sy, st);
+        xmask.alloc((size_t)std::max(nl, 1)); ymask.alloc((size_t)std::max(m, 1));
+        if (nl > 0) ELP_LAUNCH(k_build_mask, grid1(nl), 256, 0, st, nl, n0, sx, N, rank, used_x.p, xmask.p, sent.p);
+        if (m > 0) ELP_LAUNCH(k_build_mask, grid1(m), 256, 0, st, m, rank * mb, sy, N, rank, used_y.p, ymask.p, sent.p + 1);
+        unsigned long long h[2] = {0, 0};
+        ELP_CUDA(cudaMemcpyAsync(h, sent.p, sizeof h, cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        exch_frac_x = nl > 0 ? (double)h[0] / ((double)nl * (N - 1)) : 1.0;
+        exch_frac_y = m > 0 ? (double)h[1] / ((double)m * (N - 1)) : 1.0;
+        // all ranks take the same decision.  The masks cost a byte load and a predicate per store, and NVLink moves
+        // partial lines almost as dearly as full ones, so scattered savings do not pay: measured at N = 2, 60 % kept
+        // (C5) -> 4 % slower, 92-100 % kept (C4) -> 3 % slower; at N = 8, 23 % kept in long runs (C5) -> 1.9x faster.
+        // Random matrices keep 1 - exp(-nnz_local / n) (C4 at N = 8: 46 %, scattered) and stay on the dense stores.
+        double tot[4] = {(double)h[0] + (double)h[1], ((double)nl + (double)m) * (N - 1), 0, 0};
+        ELP_CUDA(cudaMemcpyAsync(scal.p, tot, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        comm_allreduce_sum(scal.p, 2, st);
+        ELP_CUDA(cudaMemcpyAsync(tot, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        const double kept = tot[1] > 0 ? tot[0] / tot[1] : 1.0;
+        const bool use = env_int("ELP_PDLP_SPARSE_EXCHANGE", 1) == 2 || kept < 0.40;
+        if (use) {
+            x_out.mask = xmask.p;
+            y_out.mask = ymask.p;
+        }
+        if (opt.verbose > 0 || env_int("ELP_PDLP_DEBUG", 0))
+            fprintf(stderr, "[pdlp] rank %d sparse exchange: x-bar %.1f %%, y %.1f %% of the dense peer stores; all ranks %.1f %% -> %s\n",
+                    rank, 100.0 * exch_frac_x, 100.0 * exch_frac_y, 100.0 * kept, use ? "masked stores" : "dense stores");
     }
     void barrier_stream() {              // all ranks have finished everything they queued before this point
         if (N > 1) comm_allreduce_sum(scal.p + NACC, 1, st);
@@ -1089,7 +1156,7 @@ struct Pdlp {
             return;
         }
         const bool direct = !CHECK && exchange && p2p;
-        PrimalEpi<CHECK> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, direct ? x_out : PeerOut{}};
+        PrimalEpi<CHECK> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, direct ? x_out : PeerOut{{}, 0, nullptr}};
         launch_spmv(plan_c, nl, csc_ptr.p, csc_idx.p, csc_val.p, y_full.p, epi, st);
         if (!exchange) return;
         if (direct) {
@@ -1102,12 +1169,12 @@ struct Pdlp {
     template <bool CHECK>
     void dual_step(int it, bool exchange = true) {
         if (!CHECK && scatter) {            // A x-bar + dual update, then g += val * y_new over the row's entries
-            DualEpi<false, true> epi{gcol.p, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, PeerOut{}};
+            DualEpi<false, true> epi{gcol.p, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, PeerOut{{}, 0, nullptr}};
             launch_spmv(plan_s, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
             return;
         }
         const bool direct = !CHECK && exchange && p2p;
-        DualEpi<CHECK> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, direct ? y_out : PeerOut{}};
+        DualEpi<CHECK> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, direct ? y_out : PeerOut{{}, 0, nullptr}};
         launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
         if (!exchange || CHECK) return;                      // a check iteration does not change y here
         if (direct) {
