@@ -49,7 +49,8 @@ class Stats(C.Structure):
 ABI_SYMBOLS = [
     "elp_version", "elp_last_error", "elp_device_count", "elp_set_device", "elp_default_options",
     "elp_status_string", "elp_kernel_launches", "elp_release_workspace", "elp_assemble_csr", "elp_assemble_lowered",
-    "elp_expand_terms", "elp_solve_lp", "elp_solve_batch",
+    "elp_expand_terms", "elp_model_assemble", "elp_model_dims", "elp_model_csr", "elp_model_solve", "elp_model_destroy",
+    "elp_solve_lp", "elp_solve_batch",
     "elp_batch_create", "elp_batch_run", "elp_batch_fetch", "elp_batch_destroy", "elp_spmv",
     "elp_check_feasible", "elp_pdlp_create", "elp_pdlp_run", "elp_pdlp_reset", "elp_pdlp_solution",
     "elp_pdlp_probe_spmv", "elp_pdlp_probe_step", "elp_pdlp_transpose", "elp_pdlp_destroy", "elp_comm_unique_id", "elp_comm_init", "elp_comm_size",
@@ -175,6 +176,61 @@ def assemble_lowered(term_row, term_col, term_val, packed, m: int, n: int):
                                       C.byref(nnz), C.byref(st)))
     k = nnz.value
     return row_ptr, col_idx[:k].copy(), vals[:k].copy(), st
+
+
+class Model:
+    """Device-resident canonical CSR of one model (elp_model_*): assembled from explicit terms and/or index-set families,
+    solved without the matrix crossing PCIe again, copied back only when the host asks for it."""
+
+    def __init__(self, term_row, term_col, term_val, packed, m: int, n: int):
+        fam, n_fam, itab, dtab, grp, n_grp, _n_low = packed
+        term_row, term_col = _i32(term_row), _i32(term_col)
+        term_val = _f64(term_val)
+        self.m, self.n = int(m), int(n)
+        self._h = C.c_void_p()
+        nnz = C.c_int64(0)
+        self.stats = Stats()
+        _check(lib().elp_model_assemble(C.c_int64(term_row.size), _p(term_row), _p(term_col), _p(term_val), C.c_int32(n_fam),
+                                        fam, C.c_int64(itab.size), _p(itab), C.c_int64(dtab.size), _p(dtab),
+                                        C.c_int32(n_grp), grp, C.c_int32(m), C.c_int32(n), C.byref(self._h),
+                                        C.byref(nnz), C.byref(self.stats)))
+        self.nnz = nnz.value
+
+    def csr(self):
+        row_ptr = np.zeros(self.m + 1, np.int32)
+        col_idx = np.zeros(max(self.nnz, 1), np.int32)
+        vals = np.zeros(max(self.nnz, 1), np.float64)
+        _check(lib().elp_model_csr(self._h, _p(row_ptr), _p(col_idx), _p(vals)))
+        return row_ptr, col_idx[:self.nnz], vals[:self.nnz]
+
+    def solve(self, sense, rhs, c, lb, ub, maximize=False, options: Options | None = None):
+        n, m = self.n, self.m
+        rhs, c = _f64(rhs), _f64(c)
+        lb, ub = _f64(lb, (n,)), _f64(ub, (n,))
+        sense = _i8(sense)
+        x = np.zeros(n)
+        y = np.zeros(max(m, 1))
+        status = C.c_int32(-1)
+        obj = C.c_double(np.nan)
+        st = Stats()
+        _check(lib().elp_model_solve(self._h, _p(sense), _p(rhs), _p(c), C.c_int32(1 if maximize else 0), _p(lb), _p(ub),
+                                     C.byref(options) if options is not None else None, C.byref(status), C.byref(obj),
+                                     _p(x), _p(y), C.byref(st)))
+        return LpResult(status.value, obj.value, x, y[:m], st)
+
+    def __deepcopy__(self, memo):         # a clone of the model rebuilds its own device copy (`$clone()`, SURVEY 8b)
+        return None
+
+    def close(self):
+        if self._h:
+            lib().elp_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def expand_terms(packed):

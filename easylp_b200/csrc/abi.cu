@@ -35,7 +35,7 @@ int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_co
                             const double* d_dtab = nullptr);
 Pdlp* pdlp_create(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
                   const int8_t* sense, const double* rhs, const double* c, int maximize, const double* lb,
-                  const double* ub, const elp_options& opt, bool dist, elp_stats* stats);
+                  const double* ub, const elp_options& opt, bool dist, elp_stats* stats, int64_t nnz_device = -1);
 void pdlp_run(Pdlp* p, int max_new_iters, elp_stats* stats);
 void pdlp_reset(Pdlp* p);
 void pdlp_solution(Pdlp* p, double* x, double* y, double* obj);
@@ -448,6 +448,37 @@ static void solve_small(int32_t m, int32_t n, const int32_t* row_ptr, const int3
     }
 }
 
+// PDLP on one GPU.  nnz_device >= 0: the CSR arrays are device pointers (elp_model_*).
+static void solve_large(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                        int64_t nnz_device, const int8_t* sense, const double* rhs, const double* c, int32_t maximize,
+                        const double* lb, const double* ub, const elp_options& o, int32_t* status, double* objval,
+                        double* x, double* y, elp_stats* stats) {
+    WallTimer wall;
+    bool bad_bounds = false;
+    for (int j = 0; j < n; ++j) if (lb[j] > ub[j]) { bad_bounds = true; break; }
+    elp_stats s1;
+    memset(&s1, 0, sizeof s1);
+    Pdlp* p = pdlp_create(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, false, &s1, nnz_device);
+    try {
+        elp_stats s2;
+        memset(&s2, 0, sizeof s2);
+        if (!bad_bounds) pdlp_run(p, 0, &s2);
+        pdlp_solution(p, x, y, objval);
+        *status = bad_bounds ? ELP_STATUS_INFEASIBLE : s2.status;
+        if (*status == ELP_STATUS_UNBOUNDED) *objval = maximize ? INFINITY : -INFINITY;
+        if (stats) {
+            *stats = s2;
+            stats->status = *status;
+            stats->setup_ms = s1.setup_ms;
+            stats->total_ms = wall.ms();
+        }
+    } catch (...) {
+        pdlp_destroy(p);
+        throw;
+    }
+    pdlp_destroy(p);
+}
+
 int elp_solve_lp(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
                  const int8_t* sense, const double* rhs, const double* c, int32_t maximize, const double* lb,
                  const double* ub, const elp_options* opt, int32_t* status, double* objval, double* x, double* y,
@@ -461,35 +492,119 @@ int elp_solve_lp(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* co
     if (method == ELP_METHOD_AUTO)   // size rule, not a backend switch: does the dense tableau fit in one SM?
         method = (simplex_smem_bytes(m, n) <= 200 * 1024) ? ELP_METHOD_SIMPLEX : ELP_METHOD_PDLP;
     // any block with lower > upper forces "unfeasible" (R/class.R:297-298); both solvers also detect it
-    if (method == ELP_METHOD_SIMPLEX) {
+    if (method == ELP_METHOD_SIMPLEX)
         solve_small(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
-    } else {
-        WallTimer wall;
-        bool bad_bounds = false;
-        for (int j = 0; j < n; ++j) if (lb[j] > ub[j]) { bad_bounds = true; break; }
-        elp_stats s1;
-        memset(&s1, 0, sizeof s1);
-        Pdlp* p = pdlp_create(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, false, &s1);
-        try {
-            elp_stats s2;
-            memset(&s2, 0, sizeof s2);
-            if (!bad_bounds) pdlp_run(p, 0, &s2);
-            pdlp_solution(p, x, y, objval);
-            *status = bad_bounds ? ELP_STATUS_INFEASIBLE : s2.status;
-            if (*status == ELP_STATUS_UNBOUNDED) *objval = maximize ? INFINITY : -INFINITY;
-            if (stats) {
-                *stats = s2;
-                stats->status = *status;
-                stats->setup_ms = s1.setup_ms;
-                stats->total_ms = wall.ms();
-                stats->kernel_launches += 0;
-            }
-        } catch (...) {
-            pdlp_destroy(p);
-            throw;
+    else
+        solve_large(m, n, row_ptr, col_idx, vals, -1, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
+    ELP_CATCH
+}
+
+/* ---- device-resident model: assembled once, solved (and re-solved) without the CSR crossing PCIe again ---- */
+struct Model {
+    int32_t m = 0, n = 0;
+    int64_t nnz = 0;
+    DevBuf<int32_t> ptr, idx;
+    DevBuf<double> val;
+};
+
+int elp_model_assemble(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
+                       int32_t n_families, const elp_term_family* families, int64_t n_itab, const int32_t* itab,
+                       int64_t n_dtab, const double* dtab, int32_t n_groups, const elp_fold_group* groups, int32_t m,
+                       int32_t n, elp_model** out, int64_t* nnz_out, elp_stats* stats) {
+    ELP_TRY
+    require_device();
+    WallTimer wall;
+    const int64_t l0 = g_launches.load();
+    ELP_REQUIRE(m >= 0 && n >= 0 && out, "elp_model_assemble: bad arguments");
+    cudaStream_t st = 0;
+    cudaEvent_t e0, e1;
+    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    AsmIo io; AsmLowered lo;
+    ELP_CUDA(cudaEventRecord(e0, st));
+    const int64_t T = stage_lowered(n_terms, term_row, term_col, term_val, n_families, families, n_itab, itab, n_dtab, dtab,
+                                    n_groups, groups, m, &io, &lo, st);
+    const int64_t nnz = assemble_csr_device(T, io.row, io.col, io.val, m, n, io.out_ptr, io.out_col, io.out_val, st,
+                                            lo.grp, lo.groups, lo.dtab);
+    auto* h = new Model();
+    try {
+        h->m = m; h->n = n; h->nnz = nnz;
+        h->ptr.alloc((size_t)m + 1); h->idx.alloc((size_t)std::max<int64_t>(nnz, 1)); h->val.alloc((size_t)std::max<int64_t>(nnz, 1));
+        ELP_CUDA(cudaMemcpyAsync(h->ptr.p, io.out_ptr, ((size_t)m + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        if (nnz) {
+            ELP_CUDA(cudaMemcpyAsync(h->idx.p, io.out_col, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+            ELP_CUDA(cudaMemcpyAsync(h->val.p, io.out_val, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
         }
-        pdlp_destroy(p);
+        ELP_CUDA(cudaEventRecord(e1, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete h;
+        throw;
     }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *out = reinterpret_cast<elp_model*>(h);
+    if (nnz_out) *nnz_out = nnz;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->solve_ms = ms;
+        stats->total_ms = wall.ms();
+        stats->kernel_launches = g_launches.load() - l0;
+        stats->iterations = (int32_t)std::min<int64_t>(T, 0x7fffffff);
+        stats->h2d_bytes = n_terms * 16 + n_itab * 4 + n_dtab * 8 + (int64_t)n_groups * (int64_t)sizeof(elp_fold_group);
+    }
+    ELP_CATCH
+}
+
+int elp_model_dims(const elp_model* hh, int32_t* m, int32_t* n, int64_t* nnz) {
+    ELP_TRY
+    auto* h = reinterpret_cast<const Model*>(hh);
+    ELP_REQUIRE(h, "elp_model_dims: null handle");
+    if (m) *m = h->m;
+    if (n) *n = h->n;
+    if (nnz) *nnz = h->nnz;
+    ELP_CATCH
+}
+
+int elp_model_csr(const elp_model* hh, int32_t* row_ptr, int32_t* col_idx, double* vals) {
+    ELP_TRY
+    auto* h = reinterpret_cast<const Model*>(hh);
+    ELP_REQUIRE(h && row_ptr, "elp_model_csr: bad arguments");
+    cudaStream_t st = 0;
+    ELP_CUDA(cudaMemcpyAsync(row_ptr, h->ptr.p, ((size_t)h->m + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (h->nnz && col_idx) ELP_CUDA(cudaMemcpyAsync(col_idx, h->idx.p, (size_t)h->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (h->nnz && vals) ELP_CUDA(cudaMemcpyAsync(vals, h->val.p, (size_t)h->nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ELP_CUDA(cudaStreamSynchronize(st));
+    ELP_CATCH
+}
+
+int elp_model_solve(const elp_model* hh, const int8_t* sense, const double* rhs, const double* c, int32_t maximize,
+                    const double* lb, const double* ub, const elp_options* opt, int32_t* status, double* objval, double* x,
+                    double* y, elp_stats* stats) {
+    ELP_TRY
+    require_device();
+    auto* h = reinterpret_cast<const Model*>(hh);
+    ELP_REQUIRE(h && status && objval && x && c && lb && ub, "elp_model_solve: bad arguments");
+    ELP_REQUIRE(h->n > 0, "Problem contains no variables.");
+    const elp_options o = effective_options(opt);
+    int method = o.method;
+    if (method == ELP_METHOD_AUTO)
+        method = (simplex_smem_bytes(h->m, h->n) <= 200 * 1024) ? ELP_METHOD_SIMPLEX : ELP_METHOD_PDLP;
+    if (method == ELP_METHOD_SIMPLEX) {          // a tableau that fits one SM: the few KB of CSR go through the host path
+        std::vector<int32_t> rp((size_t)h->m + 1), ci((size_t)std::max<int64_t>(h->nnz, 1));
+        std::vector<double> v((size_t)std::max<int64_t>(h->nnz, 1));
+        ELP_REQUIRE(elp_model_csr(hh, rp.data(), ci.data(), v.data()) == 0, "%s", g_last_error.c_str());
+        solve_small(h->m, h->n, rp.data(), ci.data(), v.data(), sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
+    } else {
+        solve_large(h->m, h->n, h->ptr.p, h->idx.p, h->val.p, h->nnz, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y,
+                    stats);
+    }
+    ELP_CATCH
+}
+
+int elp_model_destroy(elp_model* hh) {
+    ELP_TRY
+    delete reinterpret_cast<Model*>(hh);
     ELP_CATCH
 }
 

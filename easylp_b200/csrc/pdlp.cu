@@ -853,7 +853,8 @@ struct Pdlp {
     // ---- setup ---------------------------------------------------------------------------------
     void setup(int m_, int n_, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
                const int8_t* sense, const double* rhs, const double* c_h, int maximize_, const double* lb,
-               const double* ub, const elp_options& o, bool dist_) {
+               const double* ub, const elp_options& o, bool dist_, int64_t nnz_device = -1) {
+        // nnz_device >= 0: row_ptr / col_idx / vals are DEVICE arrays (a model assembled by elp_model_assemble)
         m = m_; n = n_; maximize = maximize_ != 0; opt = o;
         WallTimer dbg_t;
         const bool dbg = getenv("ELP_PDLP_DEBUG") != nullptr;
@@ -866,7 +867,7 @@ struct Pdlp {
         N = dist ? comm().nranks : 1;
         rank = dist ? comm().rank : 0;
         ELP_REQUIRE(m >= 0 && n > 0, "pdlp: bad shape %d x %d", m, n);
-        nnz = m > 0 ? row_ptr[m] : 0;
+        nnz = nnz_device >= 0 ? nnz_device : (m > 0 ? row_ptr[m] : 0);
         ELP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         partials.alloc((size_t)RED_BLOCKS * NACC); scal.alloc(2 * NACC); params.alloc(1);
         partials.zero(st);
@@ -898,12 +899,22 @@ struct Pdlp {
                                   &xaux_full, &y_full, &yaux_full})
             b->zero(st);
 
-        if (m == 0) { int z = 0; csr_ptr.upload(&z, 1, st); }
-        else csr_ptr.upload(row_ptr, m + 1, st);
-        csr_idx.upload(col_idx, nnz, st);
-        csr_val.upload(vals, nnz, st);
+        if (nnz_device >= 0) {
+            ELP_CUDA(cudaStreamSynchronize(0));           // the assembly ran on the default stream
+            ELP_CUDA(cudaMemcpyAsync(csr_ptr.p, row_ptr, ((size_t)m + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+            if (nnz) {
+                ELP_CUDA(cudaMemcpyAsync(csr_idx.p, col_idx, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, st));
+                ELP_CUDA(cudaMemcpyAsync(csr_val.p, vals, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            }
+        } else {
+            if (m == 0) { int z = 0; csr_ptr.upload(&z, 1, st); }
+            else csr_ptr.upload(row_ptr, m + 1, st);
+            csr_idx.upload(col_idx, nnz, st);
+            csr_val.upload(vals, nnz, st);
+            h2d += (int64_t)(m + 1) * 4 + nnz * 12;
+        }
         c.upload(c_h + n0, nl, st); l.upload(lb + n0, nl, st); u.upload(ub + n0, nl, st);
-        h2d += (int64_t)(m + 1) * 4 + nnz * 12 + (int64_t)nl * 24;
+        h2d += (int64_t)nl * 24;
         {
             DevBuf<int8_t> sense_d(std::max(m, 1));
             DevBuf<double> rhs_d(std::max(m, 1));
@@ -1456,11 +1467,11 @@ struct Pdlp {
 // ---- entry points used by abi.cu -----------------------------------------------------------------
 Pdlp* pdlp_create(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
                   const int8_t* sense, const double* rhs, const double* c, int maximize, const double* lb,
-                  const double* ub, const elp_options& opt, bool dist, elp_stats* stats) {
+                  const double* ub, const elp_options& opt, bool dist, elp_stats* stats, int64_t nnz_device) {
     WallTimer t;
     auto* p = new Pdlp();
     try {
-        p->setup(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, opt, dist);
+        p->setup(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, opt, dist, nnz_device);
     } catch (...) {
         delete p;
         throw;

@@ -749,7 +749,8 @@ class easylp:
         self.pointer = None                  # reference: lpSolveAPI handle (R/class.R:66); here: last elp_stats
         self.messages = []
         self._blocks = []
-        self._cache = None
+        self._model = None                   # device-resident CSR (elp_model handle), rebuilt whenever the rows change
+        self._cache_csr = None
         self._n_var = 0
         self._dir = "min"
         self._sol = np.zeros(0)
@@ -849,25 +850,41 @@ class easylp:
         return self
 
     # ---- device assembly ---------------------------------------------------------------------------
+    def _device_model(self):
+        """the model's canonical CSR, assembled on the device and KEPT there (elp_model_assemble): eager blocks hand over
+        their term lists, lowered blocks their index-set families; `$solve()` runs on this handle, `_csr()` copies it back"""
+        if self._model is None:
+            offs = np.cumsum([0] + [b.nrow for b in self._blocks])
+            m = int(offs[-1])
+            eager = [(b, o) for b, o in zip(self._blocks, offs) if not isinstance(b, _lower.LoweredCon)]
+            lowered = [(b, int(o)) for b, o in zip(self._blocks, offs) if isinstance(b, _lower.LoweredCon)]
+            rows = np.concatenate([b.t_row + o for b, o in eager]) if eager else np.zeros(0, _I)
+            cols = np.concatenate([b.t_col for b, _ in eager]) if eager else np.zeros(0, _I)
+            vals = np.concatenate([b.t_val for b, _ in eager]) if eager else np.zeros(0)
+            self._model = _lib.Model(rows, cols, vals, _lower.pack(lowered), m, self._n_var)
+            self.assembly_stats = self._model.stats
+        return self._model
+
+    @property
+    def _cache(self):
+        return self._cache_csr
+
+    @_cache.setter
+    def _cache(self, value):                 # every `self._cache = None` of the methods below also drops the device copy
+        self._cache_csr = value
+        if value is None and getattr(self, "_model", None) is not None:
+            self._model.close()
+            self._model = None
+
     def _csr(self):
-        """canonical CSR of `constraint$mat`, assembled by elp_assemble_csr (sort + ordered fold + scan + scatter)"""
+        """canonical CSR of `constraint$mat` on the host: sort + ordered fold + scan + scatter ran on the device
+        (elp_model_assemble); this copies the result back once"""
         if self._cache is None:
             m = sum(b.nrow for b in self._blocks)
             if m == 0:
                 self._cache = (np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
             else:
-                offs = np.cumsum([0] + [b.nrow for b in self._blocks])
-                eager = [(b, o) for b, o in zip(self._blocks, offs) if not isinstance(b, _lower.LoweredCon)]
-                lowered = [(b, int(o)) for b, o in zip(self._blocks, offs) if isinstance(b, _lower.LoweredCon)]
-                rows = np.concatenate([b.t_row + o for b, o in eager]) if eager else np.zeros(0, _I)
-                cols = np.concatenate([b.t_col for b, _ in eager]) if eager else np.zeros(0, _I)
-                vals = np.concatenate([b.t_val for b, _ in eager]) if eager else np.zeros(0)
-                if lowered:
-                    rp, ci, v, self.assembly_stats = _lib.assemble_lowered(rows, cols, vals, _lower.pack(lowered), m,
-                                                                           self._n_var)
-                else:
-                    rp, ci, v, self.assembly_stats = _lib.assemble_csr(rows, cols, vals, m, self._n_var)
-                self._cache = (rp, ci, v)
+                self._cache = self._device_model().csr()
         return self._cache
 
     # ---- $min / $max  R/class.R:230-246, 509-531 ---------------------------------------------------
@@ -954,12 +971,16 @@ class easylp:
                 opt.transpose = {"auto": 0, "gather": 1, "scatter": 2}[v] if isinstance(v, str) else int(v)
             else:
                 warnings.warn(f"lp.control option '{k}' has no meaning on the GPU path and is ignored")
-        rp, ci, v = self._csr()
-        m = rp.size - 1
+        m = sum(b.nrow for b in self._blocks)
         lb, ub = self._bounds()
         sense = np.array([_SENSE[d] for d in self.constraint.dir], dtype=np.int8)
-        r = _lib.solve_lp(m, self._n_var, rp, ci, v, sense, self.constraint.rhs, self.objective_fun, lb, ub,
-                          maximize=self._dir == "max", options=opt)
+        if m > 0:       # the matrix stays in HBM between `$con()` and `$solve()`
+            r = self._device_model().solve(sense, self.constraint.rhs, self.objective_fun, lb, ub,
+                                           maximize=self._dir == "max", options=opt)
+        else:
+            rp, ci, v = self._csr()
+            r = _lib.solve_lp(m, self._n_var, rp, ci, v, sense, self.constraint.rhs, self.objective_fun, lb, ub,
+                              maximize=self._dir == "max", options=opt)
         self._objval = float(large_to_infinity([r.objval])[0])
         self._sol = large_to_infinity(r.x)
         self._stat = r.status_string

@@ -166,6 +166,23 @@ int elp_assemble_lowered(int64_t n_terms, const int32_t* term_row, const int32_t
 int elp_expand_terms(int32_t n_families, const elp_term_family* families, int64_t n_itab, const int32_t* itab,
                      int64_t n_dtab, const double* dtab, int32_t* row, int32_t* col, double* val, int32_t* group);
 
+/* ---- (1c) device-resident model: the handle SURVEY 8b asks for (an R external pointer with a finalizer, treated as a
+ * rebuildable cache).  elp_model_assemble = elp_assemble_lowered that KEEPS the canonical CSR in HBM; elp_model_solve =
+ * elp_solve_lp on that CSR, so `$con()` ... `$solve()` moves the matrix over PCIe at most once (descriptors or terms
+ * in, nothing out); elp_model_csr copies it back when the host wants `constraint$mat`. */
+typedef struct elp_model elp_model;
+int elp_model_assemble(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
+                       int32_t n_families, const elp_term_family* families,
+                       int64_t n_itab, const int32_t* itab, int64_t n_dtab, const double* dtab,
+                       int32_t n_groups, const elp_fold_group* groups,
+                       int32_t m, int32_t n, elp_model** out, int64_t* nnz_out /* may be NULL */, elp_stats* stats /* may be NULL */);
+int elp_model_dims(const elp_model* h, int32_t* m, int32_t* n, int64_t* nnz);
+int elp_model_csr(const elp_model* h, int32_t* row_ptr /* m+1 */, int32_t* col_idx /* nnz */, double* vals /* nnz */);
+int elp_model_solve(const elp_model* h, const int8_t* sense, const double* rhs, const double* c, int32_t maximize,
+                    const double* lb, const double* ub, const elp_options* opt /* may be NULL */,
+                    int32_t* status, double* objval, double* x /* n */, double* y /* m, may be NULL */, elp_stats* stats);
+int elp_model_destroy(elp_model* h);
+
 /* ---- (2) one LP: replaces make.lp/set.objfn/lp.control/set.bounds/add.constraint/solve/
  *      get.objective/get.variables  (R/class.R:260-278) ------------------------------------- */
 int elp_solve_lp(int32_t m, int32_t n,

@@ -262,6 +262,73 @@ def test_mcnf_through_the_dsl_is_the_generator_matrix(K, gw, gh, extra):
 
 
 @pytest.mark.gpu
+def test_device_resident_model_is_the_host_path():
+    """elp_model_*: the CSR assembled on the device is the one elp_assemble_csr returns, and solving on the handle gives what
+    elp_solve_lp gives on the copied-back CSR (PDLP is deterministic: same iterations, same doubles)"""
+    from oracle import gen
+    p = gen.sparse_planted(3000, seed=4)
+    r, c, v = gen.term_stream(p, 0.1, 1)
+    rp0, ci0, v0, _ = L.assemble_csr(r, c, v, p["m"], p["n"])
+    h = L.Model(r, c, v, lower.pack([]), p["m"], p["n"])
+    rp, ci, vv = h.csr()
+    assert h.nnz == ci0.size and np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and vv.tobytes() == v0.tobytes()
+    for method in (L.METHOD_PDLP, L.METHOD_AUTO):
+        opt = L.default_options(method=method)
+        a = h.solve(p["sense"], p["rhs"], p["c"], p["lb"], p["ub"], options=opt)
+        b = L.solve_lp(p["m"], p["n"], rp0, ci0, v0, p["sense"], p["rhs"], p["c"], p["lb"], p["ub"], options=opt)
+        assert a.status == b.status == 0 and a.stats.iterations == b.stats.iterations
+        assert a.objval == b.objval and a.x.tobytes() == b.x.tobytes() and a.y.tobytes() == b.y.tobytes()
+    h.close()
+    # a small model goes through the simplex kernel from the handle as well
+    q = gen.readme_lp()
+    h = L.Model(np.repeat(np.arange(q["m"]), np.diff(q["row_ptr"])), q["col_idx"], q["vals"], lower.pack([]), q["m"], q["n"])
+    a = h.solve(q["sense"], q["rhs"], q["c"], q["lb"], q["ub"], maximize=True)
+    assert a.status == 0 and abs(a.objval - 2.0) <= 1e-12 and a.stats.method_used == L.METHOD_SIMPLEX
+
+
+@pytest.mark.gpu
+def test_clone_and_uncon_rebuild_the_device_model():
+    lp = M.easylp()
+    x = lp.var("x", [1, 2, 3, 4], lower=0)
+    lp.max(M.Sum(x))
+    lp.con(cap=M.for_(lambda i: x[i] <= i, i=[1, 2, 3, 4]), tot=lambda: M.Sum(x) <= 7)
+    lp.solve()
+    assert lp.status == "optimal" and abs(lp.objective_value - 7.0) <= 1e-9
+    cl = lp.clone()
+    assert cl._model is None and lp._model is not None          # the clone owns no device memory until it needs it
+    cl.uncon("tot")
+    cl.solve()
+    assert abs(cl.objective_value - 10.0) <= 1e-9
+    lp.solve()
+    assert abs(lp.objective_value - 7.0) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_config5_from_the_dsl_to_the_optimum():
+    """BASELINE config 5 end to end the way a user writes it: for/sum_for -> one trace -> device expansion + assembly ->
+    PDLP on the device-resident CSR (the matrix never visits the host)"""
+    import time
+    from oracle import gen
+    p = gen.mcnf()
+    t0 = time.perf_counter()
+    lp = M.easylp()
+    lp.con(**mcnf_dsl(lp, p))
+    t1 = time.perf_counter()
+    lp.solve(gpu_method="pdlp")
+    t2 = time.perf_counter()
+    assert lp._cache is None                                     # nobody asked for the CSR on the host
+    # the same LP handed over as the generator's CSR: same matrix bit for bit, deterministic solver -> same doubles
+    r0 = L.solve_lp(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], p["sense"], p["rhs"], p["c"], p["lb"], p["ub"],
+                    options=L.default_options(method=L.METHOD_PDLP))
+    assert lp.status == "optimal" and r0.status == 0 and lp.objective_value_raw == r0.objval
+    assert lp.pointer.iterations == r0.stats.iterations
+    st = lp.pointer
+    assert st.rel_primal_res <= 1e-6 and st.rel_dual_res <= 1e-6 and st.rel_gap <= 1e-6
+    print(f"config 5 through the DSL: build {t1 - t0:.2f} s, assemble + solve {t2 - t1:.2f} s "
+          f"({st.iterations} iterations, {st.solve_ms:.0f} ms in the PDHG loop)")
+
+
+@pytest.mark.gpu
 def test_lowered_abi_rejects_bad_descriptors():
     """the C ABI checks the families against the table sizes and the matrix before any kernel reads them"""
     l = _build("transport", True)
