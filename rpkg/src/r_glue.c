@@ -91,6 +91,33 @@ SEXP easylp_assemble_csr(SEXP term_row, SEXP term_col, SEXP term_val, SEXP m_, S
     return out;
 }
 
+/* list(status, objval, x, y, stats) of a solve; x and y are PROTECTed by the caller */
+static SEXP solve_result(int32_t status, double objval, SEXP x, SEXP y, const elp_stats* st) {
+    const char* snames[] = {"method", "iterations", "restarts", "rel_primal_res", "rel_dual_res", "rel_gap",
+                            "setup_ms", "solve_ms", "kernel_launches", "h2d_bytes", "d2h_bytes"};
+    SEXP stats = PROTECT(named_list(11, snames));
+    SET_VECTOR_ELT(stats, 0, Rf_ScalarInteger(st->method_used));
+    SET_VECTOR_ELT(stats, 1, Rf_ScalarInteger(st->iterations));
+    SET_VECTOR_ELT(stats, 2, Rf_ScalarInteger(st->restarts));
+    SET_VECTOR_ELT(stats, 3, Rf_ScalarReal(st->rel_primal_res));
+    SET_VECTOR_ELT(stats, 4, Rf_ScalarReal(st->rel_dual_res));
+    SET_VECTOR_ELT(stats, 5, Rf_ScalarReal(st->rel_gap));
+    SET_VECTOR_ELT(stats, 6, Rf_ScalarReal(st->setup_ms));
+    SET_VECTOR_ELT(stats, 7, Rf_ScalarReal(st->solve_ms));
+    SET_VECTOR_ELT(stats, 8, Rf_ScalarReal((double)st->kernel_launches));
+    SET_VECTOR_ELT(stats, 9, Rf_ScalarReal((double)st->h2d_bytes));
+    SET_VECTOR_ELT(stats, 10, Rf_ScalarReal((double)st->d2h_bytes));
+    const char* names[] = {"status", "objval", "x", "y", "stats"};
+    SEXP out = PROTECT(named_list(5, names));
+    SET_VECTOR_ELT(out, 0, Rf_ScalarInteger(status));
+    SET_VECTOR_ELT(out, 1, Rf_ScalarReal(objval));
+    SET_VECTOR_ELT(out, 2, x);
+    SET_VECTOR_ELT(out, 3, y);
+    SET_VECTOR_ELT(out, 4, stats);
+    UNPROTECT(2);
+    return out;
+}
+
 static void fill_options(elp_options* opt, SEXP control) {
     /* `control`: named list built by `$solve(...)` from the arguments it used to forward to lp.control()
      * (R/class.R:262): timeout, epsilon, verbose are mapped; gpu.* are additive. */
@@ -132,28 +159,8 @@ SEXP easylp_solve_lp(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP dir, SEXP rhs, 
                                 Rf_asLogical(maximize) ? 1 : 0, REAL(lower), REAL(upper), &opt, &status, &objval,
                                 REAL(x), m > 0 ? REAL(y) : NULL, &st);
     if (rc) { UNPROTECT(2); elp_fail("easylp_solve_lp"); }
-    const char* snames[] = {"method", "iterations", "restarts", "rel_primal_res", "rel_dual_res", "rel_gap",
-                            "setup_ms", "solve_ms", "kernel_launches", "h2d_bytes", "d2h_bytes"};
-    SEXP stats = PROTECT(named_list(11, snames));
-    SET_VECTOR_ELT(stats, 0, Rf_ScalarInteger(st.method_used));
-    SET_VECTOR_ELT(stats, 1, Rf_ScalarInteger(st.iterations));
-    SET_VECTOR_ELT(stats, 2, Rf_ScalarInteger(st.restarts));
-    SET_VECTOR_ELT(stats, 3, Rf_ScalarReal(st.rel_primal_res));
-    SET_VECTOR_ELT(stats, 4, Rf_ScalarReal(st.rel_dual_res));
-    SET_VECTOR_ELT(stats, 5, Rf_ScalarReal(st.rel_gap));
-    SET_VECTOR_ELT(stats, 6, Rf_ScalarReal(st.setup_ms));
-    SET_VECTOR_ELT(stats, 7, Rf_ScalarReal(st.solve_ms));
-    SET_VECTOR_ELT(stats, 8, Rf_ScalarReal((double)st.kernel_launches));
-    SET_VECTOR_ELT(stats, 9, Rf_ScalarReal((double)st.h2d_bytes));
-    SET_VECTOR_ELT(stats, 10, Rf_ScalarReal((double)st.d2h_bytes));
-    const char* names[] = {"status", "objval", "x", "y", "stats"};
-    SEXP out = PROTECT(named_list(5, names));
-    SET_VECTOR_ELT(out, 0, Rf_ScalarInteger(status));
-    SET_VECTOR_ELT(out, 1, Rf_ScalarReal(objval));
-    SET_VECTOR_ELT(out, 2, x);
-    SET_VECTOR_ELT(out, 3, y);
-    SET_VECTOR_ELT(out, 4, stats);
-    UNPROTECT(4);
+    SEXP out = solve_result(status, objval, x, y, &st);
+    UNPROTECT(2);
     return out;
 }
 
@@ -227,14 +234,22 @@ static SEXP list_get(SEXP lst, const char* name) {
  *   groups:   list of lists with `row0` (1-based) and `mul`, a list of double vectors (length 1 = scalar, else one
  *             multiplier per row of the block); group 1 is the plain group of the explicit terms.
  * Returns list(row_ptr, col_idx, vals) like easylp_assemble_csr. */
-SEXP easylp_assemble_lowered(SEXP term_row, SEXP term_col, SEXP term_val, SEXP families, SEXP groups, SEXP m_, SEXP n_) {
-    const int64_t T = (int64_t)XLENGTH(term_val);
-    const int32_t m = Rf_asInteger(m_), n = Rf_asInteger(n_);
-    if (XLENGTH(term_row) != T || XLENGTH(term_col) != T) Rf_error("term vectors differ in length");
-    const int32_t nf = (int32_t)XLENGTH(families), ng = (int32_t)XLENGTH(groups);
-    /* pass 1: table sizes */
-    int64_t ni = 0, nd = 0, total = 0;
-    for (int32_t f = 0; f < nf; ++f) {
+typedef struct {
+    elp_term_family* fam;
+    elp_fold_group* grp;
+    int32_t* itab;
+    double* dtab;
+    int32_t nf, ng;
+    int64_t ni, nd, total;
+} packed_families;
+
+/* R lists of families / groups -> the ABI's structs and pooled tables (R_alloc memory: reclaimed by R) */
+static packed_families pack_families(SEXP families, SEXP groups) {
+    packed_families P;
+    P.nf = (int32_t)XLENGTH(families);
+    P.ng = (int32_t)XLENGTH(groups);
+    P.ni = P.nd = P.total = 0;
+    for (int32_t f = 0; f < P.nf; ++f) {           /* pass 1: table sizes */
         SEXP F = VECTOR_ELT(families, f);
         SEXP ext = list_get(F, "extent"), ct = list_get(F, "col_tab"), rt = list_get(F, "row_tab");
         const R_xlen_t nl = XLENGTH(ext);
@@ -242,41 +257,40 @@ SEXP easylp_assemble_lowered(SEXP term_row, SEXP term_col, SEXP term_val, SEXP f
         int64_t cnt = 1;
         for (R_xlen_t l = 0; l < nl; ++l) {
             cnt *= INTEGER(ext)[l];
-            if (ct != R_NilValue && VECTOR_ELT(ct, l) != R_NilValue) ni += XLENGTH(VECTOR_ELT(ct, l));
-            if (rt != R_NilValue && VECTOR_ELT(rt, l) != R_NilValue) ni += XLENGTH(VECTOR_ELT(rt, l));
+            if (ct != R_NilValue && VECTOR_ELT(ct, l) != R_NilValue) P.ni += XLENGTH(VECTOR_ELT(ct, l));
+            if (rt != R_NilValue && VECTOR_ELT(rt, l) != R_NilValue) P.ni += XLENGTH(VECTOR_ELT(rt, l));
         }
-        nd += XLENGTH(list_get(F, "coef"));
-        total += cnt;
+        P.nd += XLENGTH(list_get(F, "coef"));
+        P.total += cnt;
     }
-    for (int32_t g = 0; g < ng; ++g) {
+    for (int32_t g = 0; g < P.ng; ++g) {
         SEXP mul = list_get(VECTOR_ELT(groups, g), "mul");
-        if (mul != R_NilValue) for (R_xlen_t k = 0; k < XLENGTH(mul); ++k) nd += XLENGTH(VECTOR_ELT(mul, k));
+        if (mul != R_NilValue) for (R_xlen_t k = 0; k < XLENGTH(mul); ++k) P.nd += XLENGTH(VECTOR_ELT(mul, k));
     }
-    elp_term_family* fam = (elp_term_family*)R_alloc((size_t)(nf > 0 ? nf : 1), sizeof(elp_term_family));
-    elp_fold_group* grp = (elp_fold_group*)R_alloc((size_t)(ng > 0 ? ng : 1), sizeof(elp_fold_group));
-    int32_t* itab = (int32_t*)R_alloc((size_t)(ni > 0 ? ni : 1), sizeof(int32_t));
-    double* dtab = (double*)R_alloc((size_t)(nd > 0 ? nd : 1), sizeof(double));
-    /* pass 2: pack */
-    int64_t pi = 0, pd = 0;
-    for (int32_t g = 0; g < ng; ++g) {
+    P.fam = (elp_term_family*)R_alloc((size_t)(P.nf > 0 ? P.nf : 1), sizeof(elp_term_family));
+    P.grp = (elp_fold_group*)R_alloc((size_t)(P.ng > 0 ? P.ng : 1), sizeof(elp_fold_group));
+    P.itab = (int32_t*)R_alloc((size_t)(P.ni > 0 ? P.ni : 1), sizeof(int32_t));
+    P.dtab = (double*)R_alloc((size_t)(P.nd > 0 ? P.nd : 1), sizeof(double));
+    int64_t pi = 0, pd = 0;                        /* pass 2: pack */
+    for (int32_t g = 0; g < P.ng; ++g) {
         SEXP G = VECTOR_ELT(groups, g), mul = list_get(G, "mul");
-        memset(&grp[g], 0, sizeof grp[g]);
-        grp[g].row0 = Rf_asInteger(list_get(G, "row0")) - 1;
-        grp[g].n_mul = mul == R_NilValue ? 0 : (int32_t)XLENGTH(mul);
-        if (grp[g].n_mul > ELP_MAX_GROUP_MUL) Rf_error("group %d has too many multipliers", g + 1);
-        for (int32_t k = 0; k < grp[g].n_mul; ++k) {
+        memset(&P.grp[g], 0, sizeof P.grp[g]);
+        P.grp[g].row0 = Rf_asInteger(list_get(G, "row0")) - 1;
+        P.grp[g].n_mul = mul == R_NilValue ? 0 : (int32_t)XLENGTH(mul);
+        if (P.grp[g].n_mul > ELP_MAX_GROUP_MUL) Rf_error("group %d has too many multipliers", g + 1);
+        for (int32_t k = 0; k < P.grp[g].n_mul; ++k) {
             SEXP v = VECTOR_ELT(mul, k);
-            grp[g].mul_tab[k] = pd;
-            grp[g].mul_per_row[k] = XLENGTH(v) > 1;
-            memcpy(dtab + pd, REAL(v), (size_t)XLENGTH(v) * sizeof(double));
+            P.grp[g].mul_tab[k] = pd;
+            P.grp[g].mul_per_row[k] = XLENGTH(v) > 1;
+            memcpy(P.dtab + pd, REAL(v), (size_t)XLENGTH(v) * sizeof(double));
             pd += XLENGTH(v);
         }
     }
-    for (int32_t f = 0; f < nf; ++f) {
+    for (int32_t f = 0; f < P.nf; ++f) {
         SEXP F = VECTOR_ELT(families, f);
         SEXP ext = list_get(F, "extent"), rs = list_get(F, "row_stride"), cs = list_get(F, "coef_stride");
         SEXP ct = list_get(F, "col_tab"), rt = list_get(F, "row_tab"), coef = list_get(F, "coef");
-        elp_term_family* t = &fam[f];
+        elp_term_family* t = &P.fam[f];
         memset(t, 0, sizeof *t);
         t->n_loops = (int32_t)XLENGTH(ext);
         t->out_offset = (int64_t)Rf_asReal(list_get(F, "out_offset"));
@@ -285,7 +299,7 @@ SEXP easylp_assemble_lowered(SEXP term_row, SEXP term_col, SEXP term_val, SEXP f
         t->row0 = Rf_asInteger(list_get(F, "row0")) - 1;
         t->col0 = Rf_asInteger(list_get(F, "col0")) - 1;
         t->coef_tab = pd;
-        memcpy(dtab + pd, REAL(coef), (size_t)XLENGTH(coef) * sizeof(double));
+        memcpy(P.dtab + pd, REAL(coef), (size_t)XLENGTH(coef) * sizeof(double));
         pd += XLENGTH(coef);
         t->count = 1;
         for (int32_t l = 0; l < t->n_loops; ++l) {
@@ -296,20 +310,14 @@ SEXP easylp_assemble_lowered(SEXP term_row, SEXP term_col, SEXP term_val, SEXP f
             t->col_tab[l] = t->row_tab[l] = -1;
             SEXP c = ct == R_NilValue ? R_NilValue : VECTOR_ELT(ct, l);
             SEXP r = rt == R_NilValue ? R_NilValue : VECTOR_ELT(rt, l);
-            if (c != R_NilValue) { t->col_tab[l] = pi; memcpy(itab + pi, INTEGER(c), (size_t)XLENGTH(c) * sizeof(int32_t)); pi += XLENGTH(c); }
-            if (r != R_NilValue) { t->row_tab[l] = pi; memcpy(itab + pi, INTEGER(r), (size_t)XLENGTH(r) * sizeof(int32_t)); pi += XLENGTH(r); }
+            if (c != R_NilValue) { t->col_tab[l] = pi; memcpy(P.itab + pi, INTEGER(c), (size_t)XLENGTH(c) * sizeof(int32_t)); pi += XLENGTH(c); }
+            if (r != R_NilValue) { t->row_tab[l] = pi; memcpy(P.itab + pi, INTEGER(r), (size_t)XLENGTH(r) * sizeof(int32_t)); pi += XLENGTH(r); }
         }
     }
-    const int64_t cap = T + total > 0 ? T + total : 1;
-    int32_t* row = zero_based(term_row);
-    int32_t* col = zero_based(term_col);
-    int32_t* col_out = (int32_t*)R_alloc((size_t)cap, sizeof(int32_t));
-    double* val_out = (double*)R_alloc((size_t)cap, sizeof(double));
-    SEXP row_ptr = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)m + 1));
-    int64_t nnz = 0;
-    const int rc = elp_assemble_lowered(T, row, col, REAL(term_val), nf, fam, ni, itab, nd, dtab, ng, grp, m, n,
-                                        (int32_t*)INTEGER(row_ptr), col_out, val_out, cap, &nnz, NULL);
-    if (rc) { UNPROTECT(1); elp_fail("easylp_assemble_lowered"); }
+    return P;
+}
+
+static SEXP csr_list(SEXP row_ptr, const int32_t* col_out, const double* val_out, int64_t nnz) {
     SEXP col_idx = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz));
     SEXP vals = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
     for (int64_t i = 0; i < nnz; ++i) INTEGER(col_idx)[i] = col_out[i] + 1;
@@ -319,7 +327,96 @@ SEXP easylp_assemble_lowered(SEXP term_row, SEXP term_col, SEXP term_val, SEXP f
     SET_VECTOR_ELT(out, 0, row_ptr);
     SET_VECTOR_ELT(out, 1, col_idx);
     SET_VECTOR_ELT(out, 2, vals);
-    UNPROTECT(4);
+    UNPROTECT(3);
+    return out;
+}
+
+SEXP easylp_assemble_lowered(SEXP term_row, SEXP term_col, SEXP term_val, SEXP families, SEXP groups, SEXP m_, SEXP n_) {
+    const int64_t T = (int64_t)XLENGTH(term_val);
+    const int32_t m = Rf_asInteger(m_), n = Rf_asInteger(n_);
+    if (XLENGTH(term_row) != T || XLENGTH(term_col) != T) Rf_error("term vectors differ in length");
+    const packed_families P = pack_families(families, groups);
+    const int64_t cap = T + P.total > 0 ? T + P.total : 1;
+    int32_t* row = zero_based(term_row);
+    int32_t* col = zero_based(term_col);
+    int32_t* col_out = (int32_t*)R_alloc((size_t)cap, sizeof(int32_t));
+    double* val_out = (double*)R_alloc((size_t)cap, sizeof(double));
+    SEXP row_ptr = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)m + 1));
+    int64_t nnz = 0;
+    const int rc = elp_assemble_lowered(T, row, col, REAL(term_val), P.nf, P.fam, P.ni, P.itab, P.nd, P.dtab, P.ng, P.grp, m, n,
+                                        (int32_t*)INTEGER(row_ptr), col_out, val_out, cap, &nnz, NULL);
+    if (rc) { UNPROTECT(1); elp_fail("easylp_assemble_lowered"); }
+    SEXP out = csr_list(row_ptr, col_out, val_out, nnz);
+    UNPROTECT(1);
+    return out;
+}
+
+/* ---- device-resident model (include/easylp_abi.h "(1c)"): an external pointer whose finalizer frees the HBM copy.
+ * The R object treats it as a rebuildable cache: `$clone()` and saveRDS() drop it, the next `$solve()` re-assembles. ---- */
+static void model_finalizer(SEXP ptr) {
+    elp_model* h = (elp_model*)R_ExternalPtrAddr(ptr);
+    if (h) { elp_model_destroy(h); R_ClearExternalPtr(ptr); }
+}
+
+static elp_model* model_of(SEXP ptr) {
+    elp_model* h = (elp_model*)R_ExternalPtrAddr(ptr);
+    if (!h) Rf_error("the device copy of this model is gone (cloned or restored object): call $con()/$solve() again");
+    return h;
+}
+
+/* .Call("easylp_model_assemble", term_row, term_col, term_val, families, groups, m, n) -> external pointer */
+SEXP easylp_model_assemble(SEXP term_row, SEXP term_col, SEXP term_val, SEXP families, SEXP groups, SEXP m_, SEXP n_) {
+    const int64_t T = (int64_t)XLENGTH(term_val);
+    const int32_t m = Rf_asInteger(m_), n = Rf_asInteger(n_);
+    if (XLENGTH(term_row) != T || XLENGTH(term_col) != T) Rf_error("term vectors differ in length");
+    const packed_families P = pack_families(families, groups);
+    elp_model* h = NULL;
+    const int rc = elp_model_assemble(T, zero_based(term_row), zero_based(term_col), REAL(term_val), P.nf, P.fam, P.ni, P.itab,
+                                      P.nd, P.dtab, P.ng, P.grp, m, n, &h, NULL, NULL);
+    if (rc) elp_fail("easylp_model_assemble");
+    SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, model_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* .Call("easylp_model_csr", model) -> list(row_ptr, col_idx, vals): `constraint$mat` for printing / inspection */
+SEXP easylp_model_csr(SEXP model) {
+    elp_model* h = model_of(model);
+    int32_t m = 0, n = 0;
+    int64_t nnz = 0;
+    if (elp_model_dims(h, &m, &n, &nnz)) elp_fail("easylp_model_csr");
+    int32_t* col_out = (int32_t*)R_alloc((size_t)(nnz > 0 ? nnz : 1), sizeof(int32_t));
+    double* val_out = (double*)R_alloc((size_t)(nnz > 0 ? nnz : 1), sizeof(double));
+    SEXP row_ptr = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)m + 1));
+    if (elp_model_csr(h, (int32_t*)INTEGER(row_ptr), col_out, val_out)) { UNPROTECT(1); elp_fail("easylp_model_csr"); }
+    SEXP out = csr_list(row_ptr, col_out, val_out, nnz);
+    UNPROTECT(1);
+    return out;
+}
+
+/* .Call("easylp_model_solve", model, dir, rhs, objective_fun, maximize, lower, upper, control): `$solve()` on the
+ * device-resident matrix; same result list as easylp_solve_lp. */
+SEXP easylp_model_solve(SEXP model, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize, SEXP lower, SEXP upper, SEXP control) {
+    elp_model* h = model_of(model);
+    int32_t m = 0, n = 0;
+    if (elp_model_dims(h, &m, &n, NULL)) elp_fail("easylp_model_solve");
+    if (XLENGTH(cost) != n || XLENGTH(lower) != n || XLENGTH(upper) != n) Rf_error("objective/bounds must have one entry per variable");
+    if (XLENGTH(dir) != m || XLENGTH(rhs) != m) Rf_error("dir/rhs must have one entry per constraint");
+    elp_options opt;
+    fill_options(&opt, control);
+    int8_t* sense = sense_codes(dir, 0);
+    SEXP x = PROTECT(Rf_allocVector(REALSXP, n));
+    SEXP y = PROTECT(Rf_allocVector(REALSXP, m));
+    int32_t status = 0;
+    double objval = 0.0;
+    elp_stats st;
+    memset(&st, 0, sizeof st);
+    const int rc = elp_model_solve(h, sense, REAL(rhs), REAL(cost), Rf_asLogical(maximize) ? 1 : 0, REAL(lower), REAL(upper),
+                                   &opt, &status, &objval, REAL(x), m > 0 ? REAL(y) : NULL, &st);
+    if (rc) { UNPROTECT(2); elp_fail("easylp_model_solve"); }
+    SEXP out = solve_result(status, objval, x, y, &st);
+    UNPROTECT(2);
     return out;
 }
 
@@ -333,6 +430,9 @@ SEXP easylp_device_count(void) {
 static const R_CallMethodDef call_methods[] = {
     {"easylp_assemble_csr", (DL_FUNC)&easylp_assemble_csr, 5},
     {"easylp_assemble_lowered", (DL_FUNC)&easylp_assemble_lowered, 7},
+    {"easylp_model_assemble", (DL_FUNC)&easylp_model_assemble, 7},
+    {"easylp_model_csr", (DL_FUNC)&easylp_model_csr, 1},
+    {"easylp_model_solve", (DL_FUNC)&easylp_model_solve, 8},
     {"easylp_solve_lp", (DL_FUNC)&easylp_solve_lp, 10},
     {"easylp_check_feasible", (DL_FUNC)&easylp_check_feasible, 7},
     {"easylp_solve_batch", (DL_FUNC)&easylp_solve_batch, 8},

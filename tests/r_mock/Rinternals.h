@@ -37,4 +37,9 @@ SEXP Rf_ScalarInteger(int);
 SEXP Rf_ScalarReal(double);
 void Rf_error(const char*, ...) __attribute__((noreturn));
 char* R_alloc(size_t, int);
+SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
+void* R_ExternalPtrAddr(SEXP);
+void R_ClearExternalPtr(SEXP);
+typedef void (*R_CFinalizer_t)(SEXP);
+void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
 #endif
