@@ -580,6 +580,12 @@ __global__ void k_build_mask(int count, int first, size_t stride, int nranks, in
     for (int r = 0; r < nranks; ++r) mk |= (used_all[(size_t)r * stride + first + j] ? 1u : 0u) << r;
     mask[j] = (unsigned char)mk;
     atomicAdd(sent, (unsigned long long)(__popc(mk) - 1));
+    if ((j & 3) == 0) {          // the same count per 32-byte line (4 entries): what the links actually carry
+        unsigned line = mk;
+        for (int q = 1; q < 4 && j + q < count; ++q)
+            for (int r = 0; r < nranks; ++r) line |= (used_all[(size_t)r * stride + first + j + q] ? 1u : 0u) << r;
+        atomicAdd(sent + 2, (unsigned long long)(__popc(line | (1u << rank)) - 1));
+    }
 }
 
 // ---- kernels of the one-off exchange that builds each rank's column block of A ---------------------
@@ -746,7 +752,7 @@ struct Pdlp {
     void build_exchange_masks() {
         const size_t sx = (size_t)N * nb, sy = (size_t)N * mb;
         DevBuf<unsigned char> used_x((size_t)N * sx), used_y((size_t)N * sy);
-        DevBuf<unsigned long long> sent(2);
+        DevBuf<unsigned long long> sent(4);      // entries x-bar, entries y, 32-byte lines (both), unused
         used_x.zero(st); used_y.zero(st); sent.zero(st);
         if (nnz > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnz, 256), 256, 0, st, (uint32_t)nnz, csr_idx.p, used_x.p + (size_t)rank * sx);
         if (nnzc > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnzc, 256), 256, 0, st, (uint32_t)nnzc, csc_idx.p, used_y.p + (size_t)rank * sy);
@@ -755,28 +761,29 @@ struct Pdlp {
         xmask.alloc((size_t)std::max(nl, 1)); ymask.alloc((size_t)std::max(m, 1));
         if (nl > 0) ELP_LAUNCH(k_build_mask, grid1(nl), 256, 0, st, nl, n0, sx, N, rank, used_x.p, xmask.p, sent.p);
         if (m > 0) ELP_LAUNCH(k_build_mask, grid1(m), 256, 0, st, m, rank * mb, sy, N, rank, used_y.p, ymask.p, sent.p + 1);
-        unsigned long long h[2] = {0, 0};
+        // (k_build_mask adds its line count to sent[+2]: the y launch starts at sent + 1, so lines of y land in sent[3])
+        unsigned long long h[4] = {0, 0, 0, 0};
         ELP_CUDA(cudaMemcpyAsync(h, sent.p, sizeof h, cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         exch_frac_x = nl > 0 ? (double)h[0] / ((double)nl * (N - 1)) : 1.0;
         exch_frac_y = m > 0 ? (double)h[1] / ((double)m * (N - 1)) : 1.0;
-        // all ranks take the same decision.  The masks cost a byte load and a predicate per store, and NVLink moves
-        // partial lines almost as dearly as full ones, so scattered savings do not pay: measured at N = 2, 60 % kept
-        // (C5) -> 4 % slower, 92-100 % kept (C4) -> 3 % slower; at N = 8, 23 % kept in long runs (C5) -> 1.9x faster.
-        // Random matrices keep 1 - exp(-nnz_local / n) (C4 at N = 8: 46 %, scattered) and stay on the dense stores.
-        double tot[4] = {(double)h[0] + (double)h[1], ((double)nl + (double)m) * (N - 1), 0, 0};
+        // all ranks take the same decision.  The masks cost a byte load and a predicate per store, and the links move
+        // partial 32-byte lines as dearly as full ones, so the decision is taken on LINES kept: measured at N = 2, 60 %
+        // kept (C5) -> 4 % slower, 92-100 % (C4) -> 3 % slower; at N = 8, 23 % kept in long runs (C5) -> 1.9x faster.
+        // A random matrix keeps 1 - exp(-nnz_local / n) of the entries (C4 at N = 8: 46 %) but 91 % of the lines.
+        double tot[4] = {(double)h[2] + (double)h[3], ((double)((nl + 3) / 4) + (double)((m + 3) / 4)) * (N - 1), 0, 0};
         ELP_CUDA(cudaMemcpyAsync(scal.p, tot, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
         comm_allreduce_sum(scal.p, 2, st);
         ELP_CUDA(cudaMemcpyAsync(tot, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         const double kept = tot[1] > 0 ? tot[0] / tot[1] : 1.0;
-        const bool use = env_int("ELP_PDLP_SPARSE_EXCHANGE", 1) == 2 || kept < 0.40;
+        const bool use = env_int("ELP_PDLP_SPARSE_EXCHANGE", 1) == 2 || kept < 0.50;
         if (use) {
             x_out.mask = xmask.p;
             y_out.mask = ymask.p;
         }
         if (opt.verbose > 0 || env_int("ELP_PDLP_DEBUG", 0))
-            fprintf(stderr, "[pdlp] rank %d sparse exchange: x-bar %.1f %%, y %.1f %% of the dense peer stores; all ranks %.1f %% -> %s\n",
+            fprintf(stderr, "[pdlp] rank %d sparse exchange: x-bar %.1f %%, y %.1f %% of the dense peer stores; 32-byte lines, all ranks %.1f %% -> %s\n",
                     rank, 100.0 * exch_frac_x, 100.0 * exch_frac_y, 100.0 * kept, use ? "masked stores" : "dense stores");
     }
     void barrier_stream() {              // all ranks have finished everything they queued before this point
