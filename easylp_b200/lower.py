@@ -356,6 +356,7 @@ class SymExpr:
 class SymCon:
     def __init__(self, groups, op, rhs):
         self.groups, self.op, self.rhs = groups, op, rhs
+        self.row_loops = []          # vector atoms: the loops over the rows of ONE atom, slowest first
     __bool__ = _refuse
 
 
@@ -395,7 +396,21 @@ class SymVec:
         return SymExpr([Group(tuple(reversed(self.implicit)), [self.term], [])])
 
     __add__ = __radd__ = __sub__ = __rsub__ = __rtruediv__ = __pow__ = __getitem__ = __iter__ = __bool__ = _refuse
-    __le__ = __ge__ = __lt__ = __gt__ = __eq__ = __ne__ = _refuse
+
+    def _cmp(self, op, o):
+        """`x[, b, 2] >= 1`: one row per entry of the slice (R/methods.R:200-225 with a recycled scalar rhs)"""
+        if not isinstance(o, Coef) and not _is_number(o):
+            raise NotLowerable()                             # vector right-hand sides: not traced
+        con = SymCon([Group((), [self.term], [])], op, Coef.wrap(o))
+        con.row_loops = list(reversed(self.implicit))        # rows of the atom: first sliced dimension fastest
+        return con
+
+    def __le__(self, o): return self._cmp("<=", o)
+    def __ge__(self, o): return self._cmp(">=", o)
+    def __lt__(self, o): return self._cmp("<", o)
+    def __gt__(self, o): return self._cmp(">", o)
+    def __eq__(self, o): return self._cmp("==", o)
+    def __ne__(self, o): raise NotLowerable()
 
 
 def sym_sum(x, *dots):
@@ -621,7 +636,7 @@ def try_for(body, index):
             return None
         low = LoweredFor(loops, r)
         free = SymExpr(r.groups, r.rhs).syms()
-        if all(u in {l.uid for l in loops} for u in free):
+        if all(u in {l.uid for l in loops + r.row_loops} for u in free):
             low.block = build_block(low)                # top level: descriptors now, so failures fall back here
         return low
     except Exception:
@@ -631,9 +646,10 @@ def try_for(body, index):
 class LoweredCon:
     """A block of constraint rows kept as families (the lowered twin of model.lp_con)."""
 
-    def __init__(self, nrow, dir_, rhs, families, groups, loops):
+    def __init__(self, nrow, dir_, rhs, families, groups, loops, rows_per_atom=1):
         self.nrow, self._dir, self.rhs = nrow, dir_, rhs
         self.families, self.groups, self.loops = families, groups, loops
+        self.rows_per_atom = rows_per_atom              # > 1: vector atoms (`x[, b, 2] >= 1`), rows named atom[k]
         self.init_name, self.head = "", "["             # head: the row names up to the first loop ("make[", "hi[i=1,")
         self.n_terms = int(sum(f["count"] for f in families))
 
@@ -649,12 +665,16 @@ class LoweredCon:
     def rownames(self):                                 # flatten_for_split + name_constraint (R/utils.R:66-94,154-165)
         from . import model
         parts = [[f"{l.name}={model._chr(v)}" for v in l.seq] for l in self.loops]
-        return [f"{self.head}{','.join(p)}]" for p in itertools.product(*parts)]
+        atoms = [f"{self.head}{','.join(p)}]" for p in itertools.product(*parts)]
+        if self.rows_per_atom == 1:
+            return atoms
+        return [f"{a}[{k}]" for a in atoms for k in range(1, self.rows_per_atom + 1)]
 
 
 def build_block(low: LoweredFor) -> LoweredCon:
     """Families of one lowered block, rows numbered from 0 (easylp._csr places the block)."""
-    outer = low.loops
+    for_loops = low.loops
+    outer = low.loops + list(low.con.row_loops)         # a vector atom's own rows vary fastest
     nrow = int(np.prod([len(l.seq) for l in outer]))
     o_axes = {l.uid: i for i, l in enumerate(outer)}
     rhs = np.broadcast_to(_evaluate(low.con.rhs, o_axes, len(outer)), [len(l.seq) for l in outer]).reshape(-1).astype(float)
@@ -738,7 +758,8 @@ def build_block(low: LoweredFor) -> LoweredCon:
                                  extent=ext, row_stride=row_stride, row_tabs=row_tabs, col0=t.col0, col_tabs=col_tabs,
                                  coef=np.ascontiguousarray(v, dtype=float).reshape(-1), coef_stride=cstride))
         offset += cells * len(g.terms)
-    return LoweredCon(nrow, low.con.op, rhs, families, groups, outer)
+    per_atom = int(np.prod([len(l.seq) for l in low.con.row_loops])) if low.con.row_loops else 1
+    return LoweredCon(nrow, low.con.op, rhs, families, groups, for_loops, per_atom)
 
 
 # ---- packing for the C ABI ---------------------------------------------------------------------------

@@ -77,7 +77,9 @@ def m_slices_and_aliases(lp):
                 a3=M.for_(lambda s: made[s] <= cap[s], s=S),
                 a4=M.for_(lambda t: 2 * sold[t] - M.Sum(0.5 * x[:, t], z[1, t, :]) >= dem[t] / 3, t=T),
                 a5=M.for_(lambda s: w[s] / 7 - x[s, 1] == s, s=S),
-                a6=M.for_(lambda s, t: M.Sum(z[s, t, :]) <= x[s, t], s=S, t=T))
+                a6=M.for_(lambda s, t: M.Sum(z[s, t, :]) <= x[s, t], s=S, t=T),
+                a7=M.for_(lambda t: z[:, t, 2] >= 1 + t, t=T),                          # vector atoms: one row per entry
+                a8=M.for_(lambda s: -2 * z[s, :, :] <= dem[1] * s, s=S))
 
 
 def m_mixed(lp):
@@ -163,7 +165,7 @@ def _lowered_parts(lp):
     return rows, cols, vals, lower.pack(low), int(offs[-1]), len(low)
 
 
-EXPECT_LOWERED = dict(slices=6, network=2, transport=2, coefficients=3, repeated=4, shifted=2, mixed=2)
+EXPECT_LOWERED = dict(slices=8, network=2, transport=2, coefficients=3, repeated=4, shifted=2, mixed=2)
 
 
 @pytest.mark.parametrize("name", sorted(MODELS))
