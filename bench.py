@@ -116,9 +116,13 @@ def ncu_traffic(key):
     capture of this same workload (profiles/r1_ncu_traffic.json); None when no capture is on file."""
     try:
         with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
-            return int(json.load(f)[key]["dram_bytes"])
+            t = json.load(f)
+        for k in (key + "_gather", key):          # the latest capture of the gather kernels, else the first one
+            if k in t:
+                return int(t[k]["dram_bytes"])
     except (OSError, KeyError, ValueError):
-        return None
+        pass
+    return None
 
 
 def pdlp_bytes(m, n, nnz):

@@ -13,7 +13,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeasylp_b200.so")
+# ELP_LIB_PATH: another build of the same library (A/B runs of two kernel versions in one GPU call); default in-tree
+LIB_PATH = os.environ.get("ELP_LIB_PATH") or os.path.join(_HERE, "libeasylp_b200.so")
 
 LE, GE, EQ = 0, 1, 2
 STATUS_OPTIMAL, STATUS_INFEASIBLE, STATUS_UNBOUNDED, STATUS_NUMFAILURE, STATUS_TIMEOUT = 0, 2, 3, 5, 7
