@@ -53,28 +53,71 @@ extern thread_local std::string g_last_error;
         ELP_CUDA(cudaGetLastError());                                              \
     } while (0)
 
+// One device allocation handed out in pieces.  cudaMalloc / cudaFree cost 2-13 ms PER CALL on a B200 box whatever the
+// size (scripts/malloc_probe.cu: 1.2 GB in one piece 2 + 6 ms), and a PDLP handle used to make ~60 of them.  While an
+// ArenaScope is active on the calling thread, DevBuf::alloc takes its memory from the arena (256-byte aligned, never
+// returned piecewise; the arena is freed as a whole by its owner) and falls back to cudaMalloc when the arena is full.
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    Arena() = default;
+    Arena(const Arena&) = delete;
+    Arena& operator=(const Arena&) = delete;
+    ~Arena() { release(); }
+    void reserve(size_t bytes) {
+        release();
+        if (bytes && cudaMalloc(&base, bytes) == cudaSuccess) cap = bytes;
+        else { base = nullptr; cap = 0; cudaGetLastError(); }      // no arena: every buffer gets its own allocation
+    }
+    void* take(size_t bytes) {
+        const size_t at = (used + 255) & ~(size_t)255;
+        if (!base || at + bytes > cap) return nullptr;
+        used = at + bytes;
+        return base + at;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        base = nullptr; cap = used = 0;
+    }
+};
+inline thread_local Arena* g_arena = nullptr;
+struct ArenaScope {
+    Arena* prev;
+    explicit ArenaScope(Arena* a) : prev(g_arena) { g_arena = a; }
+    ~ArenaScope() { g_arena = prev; }
+    ArenaScope(const ArenaScope&) = delete;
+    ArenaScope& operator=(const ArenaScope&) = delete;
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;            // false: a piece of an Arena (freed with it)
     DevBuf() = default;
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; o.owned = true; }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; o.owned = true; }
         return *this;
     }
     ~DevBuf() { release(); }
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) ELP_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        if (!count) return;
+        if (g_arena) {
+            p = static_cast<T*>(g_arena->take(count * sizeof(T)));
+            if (p) { owned = false; return; }
+        }
+        ELP_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        owned = true;
     }
     void release() {
-        if (p) cudaFree(p);
-        p = nullptr; n = 0;
+        if (p && owned) cudaFree(p);
+        p = nullptr; n = 0; owned = true;
     }
     void upload(const T* host, size_t count, cudaStream_t s = 0) {
         if (count) ELP_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));

@@ -640,6 +640,9 @@ __global__ void k_merge_cols(int nranks, int nb, const uint32_t* __restrict__ le
 //   check travel in one 16-double allreduce.
 // ------------------------------------------------------------------------------------------------
 struct Pdlp {
+    // single GPU: every persistent buffer of the handle is a piece of `arena` (one cudaMalloc / cudaFree instead of ~40),
+    // the temporaries of the setup pieces of `scratch` (freed when the setup is over).  Declared first: destroyed last.
+    Arena arena, scratch;
     int N = 1, rank = 0;
     int m = 0, mb = 0;          // local rows, padded rows per rank
     int n = 0, nb = 0, n0 = 0, nl = 0;   // global columns, columns per rank, my first column, my column count
@@ -876,6 +879,11 @@ struct Pdlp {
         ELP_REQUIRE(m >= 0 && n > 0, "pdlp: bad shape %d x %d", m, n);
         nnz = nnz_device >= 0 ? nnz_device : (m > 0 ? row_ptr[m] : 0);
         ELP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (N == 1 && env_int("ELP_PDLP_ARENA", 1)) {   // (peer-mapped buffers of the distributed path need their own allocations)
+            arena.reserve((size_t)24 * nnz + (size_t)4 * (m + n) + (size_t)8 * ((size_t)10 * n + (size_t)9 * m) + (2u << 20));
+            scratch.reserve((size_t)52 * nnz + (size_t)16 * ((size_t)n + m) + (8u << 20));
+        }
+        ArenaScope persistent(arena.base ? &arena : nullptr);
         partials.alloc((size_t)RED_BLOCKS * NACC); scal.alloc(2 * NACC); params.alloc(1);
         partials.zero(st);
         // block sizes: multiples of 4 keep every block 32-byte aligned (16-byte-granular bulk copies)
@@ -923,6 +931,7 @@ struct Pdlp {
         c.upload(c_h + n0, nl, st); l.upload(lb + n0, nl, st); u.upload(ub + n0, nl, st);
         h2d += (int64_t)nl * 24;
         {
+            ArenaScope tmp(scratch.base ? &scratch : g_arena);
             DevBuf<int8_t> sense_d(std::max(m, 1));
             DevBuf<double> rhs_d(std::max(m, 1));
             sense_d.upload(sense, m, st); rhs_d.upload(rhs, m, st);
@@ -975,12 +984,15 @@ struct Pdlp {
         setup_peer_stores();
         reset();
         mark("reset");
+        ELP_CUDA(cudaStreamSynchronize(st));
+        scratch.release();                           // the setup's temporaries, in one cudaFree
     }
 
     // CSC of my column block over all rows, row ids in the padded y_full layout.  Every rank transposes its own row
     // block with the stable radix sort that backs the assembly, then the column slices travel to their owners in
     // one grouped send/recv and are merged source by source (= ascending global row).
     void build_column_block() {
+        ArenaScope tmp(scratch.base ? &scratch : g_arena);       // temporaries; the CSC arrays below go to the handle's arena
         // ---- local transpose: CSC of my row block over all n columns ----------------------------------
         DevBuf<int> lptr((size_t)n + 1), lidx(std::max<int64_t>(nnz, 1));
         DevBuf<double> lval(std::max<int64_t>(nnz, 1));
@@ -1002,6 +1014,7 @@ struct Pdlp {
         }
         if (N == 1) {
             nnzc = nnz;
+            ArenaScope keep(arena.base ? &arena : nullptr);
             csc_ptr.alloc((size_t)nl + 1 + SPMV_PTR_PAD); csc_idx.alloc(nnzc + SPMV_PAD); csc_val.alloc(nnzc + SPMV_PAD);
             csc_ptr.zero(st); csc_idx.zero(st); csc_val.zero(st);
             ELP_CUDA(cudaMemcpyAsync(csc_ptr.p, lptr.p, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -1065,6 +1078,7 @@ struct Pdlp {
     }
 
     void scale_problem() {
+        ArenaScope tmp(scratch.base ? &scratch : g_arena);
         const int ruiz = opt.ruiz_iters >= 0 ? opt.ruiz_iters : 10;
         // dr_full = yaux_full (padded row layout), dc_full = xaux_full (flat column layout) during scaling
         double* dr_full = yaux_full.p;
