@@ -410,6 +410,10 @@ static void solve_small(int32_t m, int32_t n, const int32_t* row_ptr, const int3
     const int64_t l0 = g_launches.load();
     cudaStream_t st = 0;
     const int64_t nnz = m > 0 ? row_ptr[m] : 0;
+    // a dozen small buffers: one allocation (cudaMalloc costs milliseconds per call, more than this whole solve)
+    Arena arena;
+    arena.reserve((size_t)8 * ((size_t)std::max(m, 1) * n + 2 * (size_t)std::max<int64_t>(nnz, 1) + 4 * (size_t)std::max(m, 1) + 5 * (size_t)n) + 16 * 512);
+    ArenaScope scope(arena.base ? &arena : nullptr);
     DevBuf<int> ptr((size_t)m + 1), idx(std::max<int64_t>(nnz, 1));
     DevBuf<double> val(std::max<int64_t>(nnz, 1)), A((size_t)std::max(m, 1) * n), b(std::max(m, 1)), cd(n), lbd(n), ubd(n),
         obj(1), xd(n), yd(std::max(m, 1));

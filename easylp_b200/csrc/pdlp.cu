@@ -1530,6 +1530,9 @@ void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, con
     cudaStream_t st = 0;
     const int64_t nnz = m > 0 ? row_ptr[m] : 0;
     if (m == 0) return;
+    Arena arena;                 // eight buffers, one allocation
+    arena.reserve((size_t)12 * (nnz + SPMV_PAD) + (size_t)8 * std::max(n, 1) + (size_t)30 * (m + 8) + 16 * 512);
+    ArenaScope scope(arena.base ? &arena : nullptr);
     DevBuf<int> ptr(m + 1 + SPMV_PTR_PAD), idx(nnz + SPMV_PAD);
     DevBuf<double> val(nnz + SPMV_PAD), xd(std::max(n, 1)), od(m);
     idx.zero(st); val.zero(st); ptr.zero(st);
