@@ -40,6 +40,29 @@ easylp_assemble <- function(term_row, term_col, term_val, nrow, ncol) {
           as.integer(nrow), as.integer(ncol))
 }
 
+# Lowered assembly (include/easylp_abi.h "(1b)"): explicit terms plus the FAMILIES that for_split()/sum_for() record
+# when their body, evaluated once with symbolic loop variables, is affine in indexed variables (the executable
+# specification of that trace is easylp_b200/lower.py; see INTEGRATION.md).  `families` / `groups` are the lists
+# rpkg/src/r_glue.c::pack_families documents.
+easylp_assemble_lowered <- function(term_row, term_col, term_val, families, groups, nrow, ncol) {
+    .Call("easylp_assemble_lowered", as.integer(term_row), as.integer(term_col), as.double(term_val),
+          families, groups, as.integer(nrow), as.integer(ncol))
+}
+
+# Device-resident model: the same assembly, but the canonical CSR stays in HBM behind an external pointer (with a
+# finalizer).  `$con()`/`$uncon()`/`$var()` set `private$model <- NULL`; `$solve()` builds it on demand and solves
+# on it, so the matrix crosses PCIe at most once (as descriptors or terms) between `$con()` and the solution.
+# A cloned or readRDS-restored object holds a NULL pointer: the glue raises, and easylp_model() rebuilds.
+easylp_model <- function(self, private) {
+    if (is.null(private$model)) {
+        t <- private$terms                 # list(row, col, val, families, groups) kept by the sparse term-list DSL
+        private$model <- .Call("easylp_model_assemble", as.integer(t$row), as.integer(t$col), as.double(t$val),
+                               t$families, t$groups, length(self$constraint$rhs), private$n_var)
+    }
+    private$model
+}
+easylp_model_csr <- function(model) .Call("easylp_model_csr", model)     # constraint$mat for printing / inspection
+
 # Replacement for the body of easylp$solve (R/class.R:251-302).  `self`/`private` are the R6 bindings.
 easylp_solve_impl <- function(self, private, ...) {
     if (private$n_var == 0L)
@@ -57,13 +80,22 @@ easylp_solve_impl <- function(self, private, ...) {
         warning("lp.control option '", k, "' has no meaning on the GPU path and is ignored")
     control <- control[intersect(names(control), known)]
 
-    csr <- if (!is.null(self$constraint$csr)) self$constraint$csr else easylp_dense_to_csr(self$constraint$mat)
     lower <- unlist(lapply(self$variables, function(x) rep(x$bound[1L], length(x$ind))))
     upper <- unlist(lapply(self$variables, function(x) rep(x$bound[2L], length(x$ind))))
 
-    res <- .Call("easylp_solve_lp", as.integer(csr$row_ptr), as.integer(csr$col_idx), as.double(csr$vals),
-                 as.character(self$constraint$dir), as.double(self$constraint$rhs), as.double(self$objective_fun),
-                 private$dir == "max", as.double(lower), as.double(upper), control)
+    res <- if (!is.null(private$terms)) {
+        # sparse term-list DSL: solve on the device-resident matrix (rebuilt if the pointer did not survive a clone)
+        solve_on <- function() .Call("easylp_model_solve", easylp_model(self, private), as.character(self$constraint$dir),
+                                     as.double(self$constraint$rhs), as.double(self$objective_fun), private$dir == "max",
+                                     as.double(lower), as.double(upper), control)
+        tryCatch(solve_on(), error = function(e) { private$model <- NULL; solve_on() })
+    } else {
+        # smallest drop-in: the reference's dense constraint$mat, converted on the host
+        csr <- easylp_dense_to_csr(self$constraint$mat)
+        .Call("easylp_solve_lp", as.integer(csr$row_ptr), as.integer(csr$col_idx), as.double(csr$vals),
+              as.character(self$constraint$dir), as.double(self$constraint$rhs), as.double(self$objective_fun),
+              private$dir == "max", as.double(lower), as.double(upper), control)
+    }
 
     private$objval <- res$objval |> large_to_infinity()
     private$sol[] <- res$x |> large_to_infinity()
@@ -77,7 +109,7 @@ easylp_solve_impl <- function(self, private, ...) {
 
 # Replacement for private$feasible (R/class.R:533-540): mat %*% sol + compare_tol on the device.
 easylp_feasible_impl <- function(self, private, tol = 2e-8) {
-    csr <- if (!is.null(self$constraint$csr)) self$constraint$csr else easylp_dense_to_csr(self$constraint$mat)
+    csr <- if (!is.null(private$terms)) easylp_model_csr(easylp_model(self, private)) else easylp_dense_to_csr(self$constraint$mat)
     stopifnot(length(csr$row_ptr) > 1L)
     nam <- self$constraint$rownames
     if (is.null(nam)) nam <- rownames(self$constraint$mat)
