@@ -20,18 +20,18 @@ struct AsmIo {
 AsmIo asm_io_buffers(size_t T, size_t m);
 void asm_workspace_release();
 struct AsmLowered {
-    uint16_t* grp;
+    int32_t* grp;
     int32_t* itab;
     double* dtab;
     elp_fold_group* groups;
 };
 AsmLowered asm_lowered_buffers(size_t T, size_t n_itab, size_t n_dtab, size_t n_groups);
 void asm_expand_families(int n_families, const elp_term_family* fam, const int32_t* d_itab, const double* d_dtab,
-                         int64_t stream_offset, int32_t* d_row, int32_t* d_col, double* d_val, uint16_t* d_grp,
+                         int64_t stream_offset, int32_t* d_row, int32_t* d_col, double* d_val, int32_t* d_grp,
                          cudaStream_t st);
 int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_col, const double* d_val, int32_t m,
                             int32_t n, int32_t* d_row_ptr, int32_t* d_col_idx, double* d_vals, cudaStream_t st,
-                            const uint16_t* d_grp = nullptr, const elp_fold_group* d_groups = nullptr,
+                            const int32_t* d_grp = nullptr, const elp_fold_group* d_groups = nullptr,
                             const double* d_dtab = nullptr);
 Pdlp* pdlp_create(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
                   const int8_t* sense, const double* rhs, const double* c, int maximize, const double* lb,
@@ -262,7 +262,7 @@ int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* te
 // checks a family against the table sizes and returns the number of terms it emits
 static int64_t check_family(const elp_term_family& f, int64_t n_itab, int64_t n_dtab, int32_t n_groups, int32_t m) {
     ELP_REQUIRE(f.n_loops >= 0 && f.n_loops <= ELP_MAX_LOOPS, "lowered: family with %d loops (max %d)", f.n_loops, ELP_MAX_LOOPS);
-    ELP_REQUIRE(f.group >= 0 && f.group < std::max(n_groups, 1) && f.group < 65536, "lowered: family names group %d of %d", f.group, n_groups);
+    ELP_REQUIRE(f.group >= 0 && f.group < std::max(n_groups, 1), "lowered: family names group %d of %d", f.group, n_groups);
     ELP_REQUIRE(f.out_stride >= 1 && f.out_offset >= 0, "lowered: bad stream placement");
     int64_t count = 1, coef_max = f.coef_tab, row_max = f.row0;
     for (int l = 0; l < f.n_loops; ++l) {
@@ -289,7 +289,10 @@ static int64_t check_family(const elp_term_family& f, int64_t n_itab, int64_t n_
 static int64_t stage_lowered(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
                              int32_t n_families, const elp_term_family* families, int64_t n_itab, const int32_t* itab,
                              int64_t n_dtab, const double* dtab, int32_t n_groups, const elp_fold_group* groups, int32_t m,
-                             AsmIo* io_out, AsmLowered* lo_out, cudaStream_t st) {
+                             AsmIo* io_out, AsmLowered* lo_out, cudaStream_t st, bool rows_unbounded = false) {
+    // rows_unbounded: the caller only wants the stream (elp_expand_terms): no row limit, no row_ptr staging
+    const int32_t m_alloc = rows_unbounded ? 0 : m;
+    if (rows_unbounded) m = 0x7fffffff;
     ELP_REQUIRE(n_terms >= 0 && n_families >= 0 && n_itab >= 0 && n_dtab >= 0 && n_groups >= 0, "lowered: negative size");
     int64_t total = 0;
     std::vector<int> order;
@@ -315,7 +318,7 @@ static int64_t stage_lowered(int64_t n_terms, const int32_t* term_row, const int
         i += (size_t)k;
     }
     ELP_REQUIRE(pos == total, "lowered: the families do not tile the stream (%lld of %lld slots)", (long long)pos, (long long)total);
-    ELP_REQUIRE(groups != nullptr || n_groups == 0 || n_groups == 65536, "lowered: groups missing");
+    ELP_REQUIRE(groups != nullptr || n_groups == 0 || n_groups == 0x7fffffff, "lowered: groups missing");
     for (int g = 0; groups && g < n_groups; ++g) {
         ELP_REQUIRE(groups[g].n_mul >= 0 && groups[g].n_mul <= ELP_MAX_GROUP_MUL, "lowered: group with %d multipliers", groups[g].n_mul);
         for (int k = 0; k < groups[g].n_mul; ++k)
@@ -323,13 +326,13 @@ static int64_t stage_lowered(int64_t n_terms, const int32_t* term_row, const int
     }
     const size_t T = (size_t)(n_terms + total);
     ELP_REQUIRE(T < 0xffffffffull, "lowered: too many terms");
-    const AsmIo io = asm_io_buffers(std::max<size_t>(T, 1), (size_t)m);
+    const AsmIo io = asm_io_buffers(std::max<size_t>(T, 1), (size_t)m_alloc);
     const AsmLowered lo = asm_lowered_buffers(T, (size_t)n_itab, (size_t)n_dtab, groups ? (size_t)n_groups : 0);
     if (n_terms) {
         ELP_CUDA(cudaMemcpyAsync(io.row, term_row, (size_t)n_terms * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         ELP_CUDA(cudaMemcpyAsync(io.col, term_col, (size_t)n_terms * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         ELP_CUDA(cudaMemcpyAsync(io.val, term_val, (size_t)n_terms * sizeof(double), cudaMemcpyHostToDevice, st));
-        ELP_CUDA(cudaMemsetAsync(lo.grp, 0, (size_t)n_terms * sizeof(uint16_t), st));
+        ELP_CUDA(cudaMemsetAsync(lo.grp, 0, (size_t)n_terms * sizeof(int32_t), st));
     }
     if (n_itab) ELP_CUDA(cudaMemcpyAsync(lo.itab, itab, (size_t)n_itab * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (n_dtab) ELP_CUDA(cudaMemcpyAsync(lo.dtab, dtab, (size_t)n_dtab * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -389,15 +392,13 @@ int elp_expand_terms(int32_t n_families, const elp_term_family* families, int64_
     cudaStream_t st = 0;
     AsmIo io; AsmLowered lo;
     const int64_t T = stage_lowered(0, nullptr, nullptr, nullptr, n_families, families, n_itab, itab, n_dtab, dtab,
-                                    65536, nullptr, 0x7fffffff, &io, &lo, st);
+                                    0x7fffffff, nullptr, 0, &io, &lo, st, true);
     if (T) {
-        std::vector<uint16_t> g16((size_t)T);
         ELP_CUDA(cudaMemcpyAsync(row, io.row, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaMemcpyAsync(col, io.col, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaMemcpyAsync(val, io.val, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, st));
-        ELP_CUDA(cudaMemcpyAsync(g16.data(), lo.grp, (size_t)T * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        if (group) ELP_CUDA(cudaMemcpyAsync(group, lo.grp, (size_t)T * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
-        if (group) for (int64_t i = 0; i < T; ++i) group[i] = g16[(size_t)i];
     }
     ELP_CATCH
 }

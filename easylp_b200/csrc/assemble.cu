@@ -57,7 +57,7 @@ __device__ __forceinline__ double asm_finish_group(double gs, uint32_t g, uint32
     return gs;
 }
 __global__ void asm_segment_fold_grouped(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
-                                         const double* __restrict__ val, const uint16_t* __restrict__ grp,
+                                         const double* __restrict__ val, const int32_t* __restrict__ grp,
                                          const elp_fold_group* __restrict__ groups, const double* __restrict__ dtab,
                                          uint32_t T, uint32_t n, double* __restrict__ sums, uint32_t* __restrict__ keep) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,12 +66,12 @@ __global__ void asm_segment_fold_grouped(const uint64_t* __restrict__ keys, cons
     if (i > 0 && keys[i - 1] == k) { keep[i] = 0; return; }
     const uint32_t row = (uint32_t)(k / n);
     uint32_t p = perm[i];
-    uint32_t g = grp[p];
+    uint32_t g = (uint32_t)grp[p];
     double gs = val[p], acc = 0.0;
     bool have = false;
     for (uint32_t j = i + 1; j < T && keys[j] == k; ++j) {
         p = perm[j];
-        const uint32_t gj = grp[p];
+        const uint32_t gj = (uint32_t)grp[p];
         if (gj == g) { gs = __dadd_rn(gs, val[p]); continue; }
         gs = asm_finish_group(gs, g, row, groups, dtab);
         if (gs != 0.0) { acc = have ? __dadd_rn(acc, gs) : gs; have = true; }
@@ -87,7 +87,7 @@ __global__ void asm_segment_fold_grouped(const uint64_t* __restrict__ keys, cons
 // the column offset and the coefficient index, write the term at its place in the stream.
 __global__ void asm_expand_family(const elp_term_family f, const int32_t* __restrict__ itab, const double* __restrict__ dtab,
                                   int32_t* __restrict__ row, int32_t* __restrict__ col, double* __restrict__ val,
-                                  uint16_t* __restrict__ grp) {
+                                  int32_t* __restrict__ grp) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= f.count) return;
     int64_t rem = idx, ci = f.coef_tab;
@@ -101,7 +101,7 @@ __global__ void asm_expand_family(const elp_term_family f, const int32_t* __rest
         ci += f.coef_stride[l] * p;
     }
     const int64_t pos = f.out_offset + idx * f.out_stride;
-    row[pos] = r; col[pos] = c; val[pos] = dtab[ci]; grp[pos] = (uint16_t)f.group;
+    row[pos] = r; col[pos] = c; val[pos] = dtab[ci]; grp[pos] = f.group;
 }
 
 __global__ void asm_compact(const uint64_t* __restrict__ keys, const double* __restrict__ sums,
@@ -150,7 +150,7 @@ struct AsmWorkspace {
     DevBuf<int32_t> in_row, in_col, out_ptr, out_col;
     DevBuf<double> in_val, out_val;
     // lowered assembly: fold groups of the stream, descriptor tables
-    DevBuf<uint16_t> in_grp;
+    DevBuf<int32_t> in_grp;
     DevBuf<int32_t> itab;
     DevBuf<double> dtab;
     DevBuf<elp_fold_group> groups;
@@ -179,7 +179,7 @@ struct AsmIo {
     double *val, *out_val;
 };
 struct AsmLowered {
-    uint16_t* grp;
+    int32_t* grp;
     int32_t* itab;
     double* dtab;
     elp_fold_group* groups;
@@ -197,7 +197,7 @@ AsmLowered asm_lowered_buffers(size_t T, size_t n_itab, size_t n_dtab, size_t n_
     return AsmLowered{w.in_grp.p, w.itab.p, w.dtab.p, w.groups.p};
 }
 void asm_expand_families(int n_families, const elp_term_family* fam, const int32_t* d_itab, const double* d_dtab,
-                         int64_t stream_offset, int32_t* d_row, int32_t* d_col, double* d_val, uint16_t* d_grp,
+                         int64_t stream_offset, int32_t* d_row, int32_t* d_col, double* d_val, int32_t* d_grp,
                          cudaStream_t st) {
     for (int i = 0; i < n_families; ++i) {
         elp_term_family f = fam[i];
@@ -211,7 +211,7 @@ void asm_expand_families(int n_families, const elp_term_family* fam, const int32
 // Returns nnz (synchronises the stream once to read it back).
 int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_col, const double* d_val, int32_t m,
                             int32_t n, int32_t* d_row_ptr, int32_t* d_col_idx, double* d_vals, cudaStream_t st,
-                            const uint16_t* d_grp, const elp_fold_group* d_groups, const double* d_dtab) {
+                            const int32_t* d_grp, const elp_fold_group* d_groups, const double* d_dtab) {
     ELP_REQUIRE(m >= 0 && n >= 0, "assemble: negative shape");
     if (T == 0 || m == 0) {
         ELP_LAUNCH(asm_empty_row_ptr, ceil_div((int64_t)m + 1, 256), 256, 0, st, d_row_ptr, (uint32_t)m);

@@ -685,6 +685,8 @@ def build_block(low: LoweredFor) -> LoweredCon:
     for i in range(len(outer) - 1, -1, -1):
         rstride[i] = s
         s *= len(outer[i].seq)
+    if len(low.con.groups) > 256:
+        raise NotLowerable()                            # hundreds of separate addends per row: the eager path copes better
     families, groups, offset = [], [], 0
     outer_ext = [len(l.seq) for l in outer]
     for g in low.con.groups:
@@ -813,8 +815,6 @@ def pack(blocks_with_rows):
                         ni += tab.size
             fams.append(t)
         stream += blk.n_terms
-    if len(groups) > 65535:
-        raise NotLowerable()
     fam_arr = (TermFamily * max(len(fams), 1))(*fams)
     grp_arr = (FoldGroup * len(groups))(*groups)
     itab = np.concatenate(itab).astype(_I) if itab else np.zeros(0, _I)
