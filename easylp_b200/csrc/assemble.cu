@@ -51,9 +51,10 @@ __global__ void asm_segment_fold(const uint64_t* __restrict__ keys, const uint32
 __device__ __forceinline__ double asm_finish_group(double gs, uint32_t g, uint32_t row, const elp_fold_group* __restrict__ groups,
                                                    const double* __restrict__ dtab) {
     if (g == 0) return gs;
-    const elp_fold_group G = groups[g];
-    for (int k = 0; k < G.n_mul; ++k)
-        gs = __dmul_rn(gs, dtab[G.mul_tab[k] + (G.mul_per_row[k] ? (int64_t)(row - (uint32_t)G.row0) : 0)]);
+    const elp_fold_group* G = groups + g;          // read in place: a local copy of the struct would live on the stack
+    const int n_mul = G->n_mul;
+    for (int k = 0; k < n_mul; ++k)
+        gs = __dmul_rn(gs, dtab[G->mul_tab[k] + (G->mul_per_row[k] ? (int64_t)(row - (uint32_t)G->row0) : 0)]);
     return gs;
 }
 __global__ void asm_segment_fold_grouped(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
