@@ -145,3 +145,19 @@ def test_random_bodies_lower_exactly_or_fall_back():
         assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0), seed
         assert v.tobytes() == v0.tobytes(), seed
     assert lowered >= len(SEEDS) // 3, (lowered, failed)
+
+
+@pytest.mark.gpu
+def test_random_bodies_on_the_device():
+    """the same random bodies through elp_model_assemble: lowered families expanded and folded on the device against
+    the eager term lists folded on the device"""
+    checked = 0
+    for seed in range(60):
+        e, l = build(seed, False), build(seed, True)
+        if not any(isinstance(b, lower.LoweredCon) for b in l._blocks):
+            continue
+        a, b = e._csr(), l._csr()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), seed
+        assert np.asarray(a[2]).tobytes() == np.asarray(b[2]).tobytes(), seed
+        checked += 1
+    assert checked >= 30
