@@ -32,3 +32,22 @@ def test_registered_routines_match_their_definitions():
         sig = re.search(r"SEXP %s\(([^)]*)\)" % name, src).group(1)
         got = 0 if sig.strip() == "void" else sig.count("SEXP")
         assert got == nargs, (name, got, nargs)
+
+
+def test_r_side_calls_only_registered_routines():
+    """every .Call("easylp_...") in rpkg/R/gpu_solve.R names a routine of the registration table, with the right arity"""
+    src = open(GLUE).read()
+    table = dict((n, int(k)) for n, k in re.findall(r'\{"(easylp_\w+)",\s*\(DL_FUNC\)&\w+,\s*(\d+)\}', src))
+    r_src = open(os.path.join(ROOT, "rpkg", "R", "gpu_solve.R")).read()
+    calls = re.findall(r'\.Call\("(easylp_\w+)"', r_src)
+    assert calls and set(calls) <= set(table), set(calls) - set(table)
+    # arity: count top-level commas of each call's argument list
+    for m in re.finditer(r'\.Call\("(easylp_\w+)"', r_src):
+        i, depth, args = m.end(), 1, 0
+        while depth:
+            ch = r_src[i]
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            args += ch == "," and depth == 1
+            i += 1
+        assert args == table[m.group(1)], (m.group(1), args, table[m.group(1)])
