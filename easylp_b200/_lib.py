@@ -50,7 +50,7 @@ class Stats(C.Structure):
 ABI_SYMBOLS = [
     "elp_version", "elp_last_error", "elp_device_count", "elp_set_device", "elp_default_options",
     "elp_status_string", "elp_kernel_launches", "elp_release_workspace", "elp_assemble_csr", "elp_assemble_lowered",
-    "elp_expand_terms", "elp_model_assemble", "elp_model_dims", "elp_model_csr", "elp_model_solve", "elp_model_destroy",
+    "elp_expand_terms", "elp_model_assemble", "elp_model_dims", "elp_model_csr", "elp_model_solve", "elp_model_destroy", "elp_model_pdlp_create",
     "elp_solve_lp", "elp_solve_batch",
     "elp_batch_create", "elp_batch_run", "elp_batch_fetch", "elp_batch_destroy", "elp_spmv",
     "elp_check_feasible", "elp_pdlp_create", "elp_pdlp_run", "elp_pdlp_reset", "elp_pdlp_solution",
@@ -218,6 +218,22 @@ class Model:
                                      C.byref(options) if options is not None else None, C.byref(status), C.byref(obj),
                                      _p(x), _p(y), C.byref(st)))
         return LpResult(status.value, obj.value, x, y[:m], st)
+
+    def pdlp(self, sense, rhs, c, lb, ub, maximize=False, options: Options | None = None) -> "Pdlp":
+        """a PDLP handle on this device-resident matrix (run it in chunks with .run(k), as the R glue does)"""
+        n = self.n
+        rhs, c = _f64(rhs), _f64(c)
+        lb, ub = _f64(lb, (n,)), _f64(ub, (n,))
+        sense = _i8(sense)
+        h = Pdlp.__new__(Pdlp)
+        h.m, h.n = self.m, self.n
+        h._h = C.c_void_p()
+        h.setup_stats = Stats()
+        h._keep = (sense, rhs, c, lb, ub)
+        _check(lib().elp_model_pdlp_create(self._h, _p(sense), _p(rhs), _p(c), C.c_int32(1 if maximize else 0), _p(lb),
+                                           _p(ub), C.byref(options) if options is not None else None, C.byref(h._h),
+                                           C.byref(h.setup_stats)))
+        return h
 
     def __deepcopy__(self, memo):         # a clone of the model rebuilds its own device copy (`$clone()`, SURVEY 8b)
         return None

@@ -782,6 +782,19 @@ int elp_pdlp_create(int32_t m_local, int32_t n, const int32_t* row_ptr, const in
         pdlp_create(m_local, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, dist != 0, stats));
     ELP_CATCH
 }
+int elp_model_pdlp_create(const elp_model* hh, const int8_t* sense, const double* rhs, const double* c, int32_t maximize,
+                          const double* lb, const double* ub, const elp_options* opt, elp_pdlp** out, elp_stats* stats) {
+    ELP_TRY
+    require_device();
+    auto* h = reinterpret_cast<const Model*>(hh);
+    ELP_REQUIRE(h && out && c && lb && ub, "elp_model_pdlp_create: bad arguments");
+    ELP_REQUIRE(h->n > 0, "Problem contains no variables.");
+    if (stats) memset(stats, 0, sizeof *stats);
+    const elp_options o = effective_options(opt);
+    *out = reinterpret_cast<elp_pdlp*>(pdlp_create(h->m, h->n, h->ptr.p, h->idx.p, h->val.p, sense, rhs, c, maximize, lb, ub, o,
+                                                   false, stats, h->nnz));
+    ELP_CATCH
+}
 int elp_pdlp_run(elp_pdlp* h, int32_t max_new_iters, elp_stats* stats) {
     ELP_TRY
     ELP_REQUIRE(h, "null handle");

@@ -245,6 +245,12 @@ int elp_pdlp_probe_spmv(elp_pdlp* h, int32_t reps, double* ms_csr, double* ms_cs
 int elp_pdlp_probe_step(elp_pdlp* h, int32_t reps, double* ms_primal, double* ms_dual);
 int elp_pdlp_transpose(elp_pdlp* h, int32_t* mode);   /* the ELP_TRANSPOSE_* the plain iterations of this handle use */
 int elp_pdlp_destroy(elp_pdlp* h);
+/* A PDLP handle on a device-resident model (elp_model_assemble): the CSR is copied device-to-device.  With
+ * elp_pdlp_run(h, k) in a loop the caller regains control every k iterations — the R glue checks for user interrupts
+ * there — and the result is the one elp_model_solve returns. */
+int elp_model_pdlp_create(const elp_model* model, const int8_t* sense, const double* rhs, const double* c,
+                          int32_t maximize, const double* lb, const double* ub, const elp_options* opt,
+                          elp_pdlp** out, elp_stats* stats);
 
 /* ---- multi-GPU plumbing (one process per GPU; NCCL resolved with dlopen at first use) -------- */
 #define ELP_UNIQUE_ID_BYTES 128

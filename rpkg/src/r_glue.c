@@ -395,6 +395,8 @@ SEXP easylp_model_csr(SEXP model) {
     return out;
 }
 
+static void check_interrupt(void* unused) { (void)unused; R_CheckUserInterrupt(); }
+
 /* .Call("easylp_model_solve", model, dir, rhs, objective_fun, maximize, lower, upper, control): `$solve()` on the
  * device-resident matrix; same result list as easylp_solve_lp. */
 SEXP easylp_model_solve(SEXP model, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize, SEXP lower, SEXP upper, SEXP control) {
@@ -412,8 +414,30 @@ SEXP easylp_model_solve(SEXP model, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize
     double objval = 0.0;
     elp_stats st;
     memset(&st, 0, sizeof st);
-    const int rc = elp_model_solve(h, sense, REAL(rhs), REAL(cost), Rf_asLogical(maximize) ? 1 : 0, REAL(lower), REAL(upper),
-                                   &opt, &status, &objval, REAL(x), m > 0 ? REAL(y) : NULL, &st);
+    int rc;
+    if (opt.method == ELP_METHOD_PDLP) {
+        /* a long first-order solve: run it in chunks and let the user interrupt between them.
+         * R_CheckUserInterrupt() would longjmp past our cleanup, so it runs under R_ToplevelExec. */
+        elp_pdlp* p = NULL;
+        rc = elp_model_pdlp_create(h, sense, REAL(rhs), REAL(cost), Rf_asLogical(maximize) ? 1 : 0, REAL(lower), REAL(upper),
+                                   &opt, &p, &st);
+        const double setup_ms = st.setup_ms;
+        int interrupted = 0;
+        while (!rc && !interrupted) {
+            rc = elp_pdlp_run(p, 4096, &st);
+            if (rc || st.status != ELP_STATUS_TIMEOUT || (opt.max_iter > 0 && st.iterations >= opt.max_iter)) break;
+            interrupted = !R_ToplevelExec(check_interrupt, NULL);
+        }
+        if (!rc && !interrupted) rc = elp_pdlp_solution(p, REAL(x), m > 0 ? REAL(y) : NULL, &objval);
+        status = st.status;
+        st.setup_ms = setup_ms;
+        if (p) elp_pdlp_destroy(p);
+        if (interrupted) { UNPROTECT(2); Rf_error("easylp$solve interrupted after %d PDHG iterations", st.iterations); }
+        if (!rc && status == ELP_STATUS_UNBOUNDED) objval = Rf_asLogical(maximize) ? R_PosInf : R_NegInf;
+    } else {
+        rc = elp_model_solve(h, sense, REAL(rhs), REAL(cost), Rf_asLogical(maximize) ? 1 : 0, REAL(lower), REAL(upper),
+                             &opt, &status, &objval, REAL(x), m > 0 ? REAL(y) : NULL, &st);
+    }
     if (rc) { UNPROTECT(2); elp_fail("easylp_model_solve"); }
     SEXP out = solve_result(status, objval, x, y, &st);
     UNPROTECT(2);

@@ -37,6 +37,9 @@ SEXP Rf_ScalarInteger(int);
 SEXP Rf_ScalarReal(double);
 void Rf_error(const char*, ...) __attribute__((noreturn));
 char* R_alloc(size_t, int);
+extern double R_PosInf, R_NegInf;
+void R_CheckUserInterrupt(void);
+Rboolean R_ToplevelExec(void (*fun)(void*), void* data);
 SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
 void* R_ExternalPtrAddr(SEXP);
 void R_ClearExternalPtr(SEXP);

@@ -283,6 +283,18 @@ def test_device_resident_model_is_the_host_path():
         b = L.solve_lp(p["m"], p["n"], rp0, ci0, v0, p["sense"], p["rhs"], p["c"], p["lb"], p["ub"], options=opt)
         assert a.status == b.status == 0 and a.stats.iterations == b.stats.iterations
         assert a.objval == b.objval and a.x.tobytes() == b.x.tobytes() and a.y.tobytes() == b.y.tobytes()
+    # chunked solve on the same device matrix (what the R glue does to stay interruptible): same iterate, same doubles
+    ph = h.pdlp(p["sense"], p["rhs"], p["c"], p["lb"], p["ub"], options=L.default_options(method=L.METHOD_PDLP))
+    chunks = 0
+    while True:
+        st = ph.run(1000)
+        chunks += 1
+        if st.status != L.STATUS_TIMEOUT or chunks > 500:
+            break
+    xs, ys, objs = ph.solution()
+    ph.close()
+    assert chunks > 1 and st.status == 0 and st.iterations == a.stats.iterations
+    assert objs == a.objval and xs.tobytes() == a.x.tobytes() and ys.tobytes() == a.y.tobytes()
     h.close()
     # a small model goes through the simplex kernel from the handle as well
     q = gen.readme_lp()
