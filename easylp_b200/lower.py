@@ -130,9 +130,12 @@ class SymIndex(Coef):
         self.name, self.seq, self.uid = name, list(seq), next(_uid)
         if not self.seq:
             raise NotLowerable()
-        self.numeric = all(_is_number(v) for v in self.seq)
-        if not self.numeric and not all(isinstance(v, (str, np.str_)) for v in self.seq):
-            raise NotLowerable()
+        if len(self.seq) > 256 and type(self.seq[0]) in (int, float) and np.asarray(self.seq).dtype.kind in "iuf":
+            self.numeric = True                         # long numeric ranges: one vectorised check instead of a Python loop
+        else:
+            self.numeric = all(_is_number(v) for v in self.seq)
+            if not self.numeric and not all(isinstance(v, (str, np.str_)) for v in self.seq):
+                raise NotLowerable()
 
 
 def _evaluate(c: Coef, axes: dict, ndim: int, expand=None) -> np.ndarray:
