@@ -55,3 +55,25 @@ def test_no_cpu_fallback():
         L.solve_lp(0, 1, [0], [], [], [], [], [1.0], [0.0], [1.0])
     with pytest.raises(L.ElpError):
         L.solve_batch(np.ones((1, 1, 1)), np.ones((1, 1)), np.ones((1, 1)), None, None, None)
+    from easylp_b200 import lower
+    empty = lower.pack([])
+    with pytest.raises(L.ElpError, match="no CUDA device"):
+        L.assemble_lowered(np.zeros(1, np.int32), np.zeros(1, np.int32), np.ones(1), empty, 1, 1)
+    with pytest.raises(L.ElpError, match="no CUDA device"):
+        L.expand_terms(empty)
+    with pytest.raises(L.ElpError, match="no CUDA device"):
+        L.Model(np.zeros(1, np.int32), np.zeros(1, np.int32), np.ones(1), empty, 1, 1)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="this test pins the no-GPU behaviour")
+def test_the_host_dsl_cannot_solve_without_the_device():
+    """the product path through the R6 mirror: building terms is host work, folding and solving are not"""
+    from easylp_b200 import model as M
+    lp = M.easylp()
+    x, y = lp.var("x"), lp.var("y")
+    lp.max(x + y)
+    lp.con(x + 2 * y <= 3, y >= 3 * x - 2)
+    with pytest.raises(L.ElpError, match="no CUDA device"):
+        lp.solve()
+    with pytest.raises(L.ElpError, match="no CUDA device"):
+        lp.constraint.mat
