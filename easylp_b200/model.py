@@ -49,6 +49,10 @@ class EasyLpError(Exception):
     """stop() in the reference."""
 
 
+def _identity(v):
+    return v
+
+
 def message(text, sink=None):
     """R's message(): to stderr, and recorded on the model so tests can expect it."""
     print(text, file=sys.stderr)
@@ -764,6 +768,11 @@ class easylp:
     def clone(self):
         return copy.deepcopy(self)
 
+    def __getstate__(self):                 # pickling = saveRDS(): the device copy is a rebuildable cache, never state
+        state = dict(self.__dict__)
+        state["_model"] = None
+        return state
+
     # ---- $var  R/class.R:85-179 ------------------------------------------------------------------
     def var(self, name, *sets, integer=False, binary=False, lower=-np.inf, upper=np.inf, **named):
         if not isinstance(name, str):
@@ -903,7 +912,7 @@ class easylp:
         if transform is not None:           # identity cannot decrease; skip the 64-point probe (and the assembly)
             lo, up = self._objective_bounds(self.objective_fun, self.objective_add)
             _warn_decreasing_transformation(transform, lo, up)
-        self.objective_transform = transform if transform is not None else (lambda v: v)
+        self.objective_transform = transform if transform is not None else _identity
         self.reset_solution()
         return self
 

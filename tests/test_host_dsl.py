@@ -67,6 +67,29 @@ def test_some_reference_models_are_lowered():
     assert all(isinstance(x, lower.LoweredCon) for x in blocks["dop"])
 
 
+def test_pickle_and_clone_drop_the_device_handle():
+    """the device-resident model is a rebuildable cache — `$clone()` and saveRDS()/pickle never carry it"""
+    import pickle
+
+    class FakeHandle:                       # stands for _lib.Model: not picklable, must not be copied
+        def __reduce__(self):
+            raise TypeError("a device pointer cannot be pickled")
+
+        def __deepcopy__(self, memo):
+            return None
+
+        def close(self):
+            pass
+
+    lp = _build("readme")
+    lp._model = FakeHandle()
+    back = pickle.loads(pickle.dumps(lp))
+    assert back._model is None and back.constraint.rownames == lp.constraint.rownames
+    assert back.constraint.rhs.tobytes() == lp.constraint.rhs.tobytes()
+    assert lp.clone()._model is None and lp._model is not None
+    lp._model = None
+
+
 def _constraints_lp():
     lp = _build("constraints")
     return lp, lp["x"], lp["y"]
