@@ -161,3 +161,66 @@ def test_random_bodies_on_the_device():
         assert np.asarray(a[2]).tobytes() == np.asarray(b[2]).tobytes(), seed
         checked += 1
     assert checked >= 30
+
+
+# ---- two loop variables: row order (first index outermost), row names, coefficient tables over both -----------
+def node2(rng, env, depth):
+    """(s, t) -> a one-row expression"""
+    c = rng.integers(0, 9 if depth > 0 else 5)
+    v = (env.x, env.z)[int(rng.integers(0, 2))]
+    if c == 0:
+        return lambda s, t: v[s, t]
+    if c == 1:
+        return lambda s, t: env.y[s]
+    if c == 2:
+        return lambda s, t: M.sum_for(lambda u: env.a[u, t] * v[u, t], u=S)
+    if c == 3:
+        return lambda s, t: env.a[s, t] * v[s, t] / env.w[t]
+    if c == 4:
+        j = int(rng.integers(1, len(T) + 1))
+        return lambda s, t: v[s, j] * (t + s / 2)
+    sub = node2(rng, env, depth - 1)
+    if c == 5:
+        return lambda s, t: env.k[s] * sub(s, t)
+    if c == 6:
+        return lambda s, t: sub(s, t) - env.w[t]
+    other = node2(rng, env, depth - 1)
+    if c == 7:
+        return lambda s, t: sub(s, t) + other(s, t)
+    return lambda s, t: sub(s, t) - other(s, t)
+
+
+def build2(seed, lowering, nested):
+    rng = np.random.default_rng(10_000 + seed)
+    old = M.LOWERING
+    M.LOWERING = lowering
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            env = Env(rng)
+            lhs = node2(rng, env, 2)
+            body = lambda s, t: lhs(s, t) <= env.a[s, t] + s      # noqa: E731
+            if nested:
+                env.lp.con(c=M.for_(lambda s: M.for_(lambda t: body(s, t), t=T), s=S))
+            else:
+                env.lp.con(M.for_(body, s=S, t=T))                 # unnamed: rows "[s=1,t=1]", ...
+            return env.lp
+    finally:
+        M.LOWERING = old
+
+
+@pytest.mark.parametrize("nested", [False, True])
+def test_random_bodies_over_two_indices(nested):
+    lowered = 0
+    for seed in range(150):
+        e, l = build2(seed, False, nested), build2(seed, True, nested)
+        assert e.constraint.rownames == l.constraint.rownames, seed
+        assert e.constraint.names == l.constraint.names, seed
+        assert e.constraint.rhs.tobytes() == l.constraint.rhs.tobytes(), seed
+        if not any(isinstance(b, lower.LoweredCon) for b in l._blocks):
+            continue
+        lowered += 1
+        rp0, ci0, v0, _ = model_fold(e)
+        rp, ci, v, _ = model_fold(l)
+        assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and v.tobytes() == v0.tobytes(), seed
+    assert lowered >= 75
