@@ -237,10 +237,11 @@ class Term:
 
 
 class Group:
-    __slots__ = ("loops", "terms", "post")
+    __slots__ = ("loops", "terms", "post", "from_slice")
 
     def __init__(self, loops, terms, post):
         self.loops, self.terms, self.post = tuple(loops), list(terms), list(post)
+        self.from_slice = False      # the loops are the rows of one slice (`sum(x[f, ])`): every column occurs once
 
     def mapped(self, f):
         return Group(self.loops, [Term(t.block, t.col0, t.tabs, f(t.coef)) for t in self.terms], self.post)
@@ -396,7 +397,9 @@ class SymVec:
 
     def as_sum(self):
         """sum.lp_var of the rows = colSums: every column occurs in one row only, so each column sum is its entry"""
-        return SymExpr([Group(tuple(reversed(self.implicit)), [self.term], [])])
+        g = Group(tuple(reversed(self.implicit)), [self.term], [])
+        g.from_slice = True
+        return SymExpr([g])
 
     __add__ = __radd__ = __sub__ = __rsub__ = __rtruediv__ = __pow__ = __getitem__ = __iter__ = __bool__ = _refuse
 
@@ -540,6 +543,12 @@ class IndexSets:
 def _sum_group(cell: SymExpr, loops):
     """`do.call(sum, cells)`: every cell is folded on its own first (sum.lp_var), then the cells are added in grid
     order.  With one bare group whose entries sit on distinct variables the per-cell fold is the identity."""
+    if len(cell.groups) == 1 and getattr(cell.groups[0], "from_slice", False) and not cell.groups[0].post:
+        # the cell is `sum` of a slice (`tdm[, m] * k[m]`): its own fold is the identity (every column once), so the
+        # slice's rows simply become the fastest loops of this sum
+        g = cell.groups[0]
+        add = Coef("sumover", cell.add, tuple(loops)) if cell.add is not None else None
+        return SymExpr([Group(tuple(loops) + g.loops, g.terms, [])], add)
     if any(g.loops or g.post for g in cell.groups):
         raise NotLowerable()                            # a sum of sums folds three levels deep
     terms = [t for g in cell.groups for t in g.terms]   # `a + b` inside the cell: entries of different variables
@@ -564,6 +573,8 @@ def try_sum_for(body, index):
             else:
                 syms[k] = SymIndex(k, seq)
         cell = body(**syms)
+        if isinstance(cell, SymVec):                    # `sum_for(m = M, tdm[, m] * k[m])`: every cell is summed first
+            cell = cell.as_sum()
         if not isinstance(cell, SymExpr):
             return None
         loops = [syms[k] for k in reversed(names)]      # slowest first; the first name is the fastest (R/utils.R:402)
@@ -575,7 +586,7 @@ def try_sum_for(body, index):
             if any(getattr(l, "ragged", None) for l in loops):
                 return None
             first = body(**{k: index_first(index[k]) for k in names})       # metadata of the eager result
-            return _materialise(expr, loops, first)
+            return _materialise(expr, list(expr.groups[0].loops), first)
         return expr
     except Exception:
         return None
