@@ -82,7 +82,8 @@ def m_slices_and_aliases(lp):
                 a5=M.for_(lambda s: w[s] / 7 - x[s, 1] == s, s=S),
                 a6=M.for_(lambda s, t: M.Sum(z[s, t, :]) <= x[s, t], s=S, t=T),
                 a7=M.for_(lambda t: z[:, t, 2] >= 1 + t, t=T),                          # vector atoms: one row per entry
-                a8=M.for_(lambda s: -2 * z[s, :, :] <= dem[1] * s, s=S))
+                a8=M.for_(lambda s: -2 * z[s, :, :] <= dem[1] * s, s=S),
+                a9=M.for_(lambda s: M.sum_for(lambda t: z[s, t, :] * dem[t], t=T) / 2 <= cap[s], s=S))   # cells that are slices
 
 
 def m_mixed(lp):
@@ -168,7 +169,7 @@ def _lowered_parts(lp):
     return rows, cols, vals, lower.pack(low), int(offs[-1]), len(low)
 
 
-EXPECT_LOWERED = dict(slices=8, network=2, transport=2, coefficients=3, repeated=6, shifted=2, mixed=2)
+EXPECT_LOWERED = dict(slices=9, network=2, transport=2, coefficients=3, repeated=6, shifted=2, mixed=2)
 
 
 @pytest.mark.parametrize("name", sorted(MODELS))
