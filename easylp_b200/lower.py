@@ -32,6 +32,7 @@ _I = np.int32
 MAX_LOOPS = 6
 MAX_GROUP_MUL = 4
 _uid = itertools.count(1)
+_depth = 0          # > 0 while the body of an enclosing for / sum_for is being traced
 
 
 class NotLowerable(Exception):
@@ -241,10 +242,12 @@ class Group:
 
     def __init__(self, loops, terms, post):
         self.loops, self.terms, self.post = tuple(loops), list(terms), list(post)
-        self.from_slice = False      # the loops are the rows of one slice (`sum(x[f, ])`): every column occurs once
+        self.from_slice = False      # a canonical row — `sum(x[f, ])`, a row of an alias: every column occurs at most once
 
     def mapped(self, f):
-        return Group(self.loops, [Term(t.block, t.col0, t.tabs, f(t.coef)) for t in self.terms], self.post)
+        g = Group(self.loops, [Term(t.block, t.col0, t.tabs, f(t.coef)) for t in self.terms], self.post)
+        g.from_slice = self.from_slice
+        return g
 
 
 class SymExpr:
@@ -272,8 +275,8 @@ class SymExpr:
         if len(self.groups) != 1:
             raise NotLowerable()                        # (a + b) * k scales the folded sum of both: three levels
         g = self.groups[0]
-        if not g.loops and len(g.terms) == 1 and not g.post:
-            ng = g.mapped(lambda c: Coef("bin", c, k, "*"))                     # coef * k on the one entry
+        if ((not g.loops and len(g.terms) == 1) or g.from_slice) and not g.post:
+            ng = g.mapped(lambda c: Coef("bin", c, k, "*"))                     # coef * k, entry by entry (no entry repeats)
         else:
             ng = Group(g.loops, g.terms, g.post + [k])                          # multiplies the folded sum
             if len(ng.post) > MAX_GROUP_MUL:
@@ -501,7 +504,9 @@ def var_getitem(x, key):
     add = None
     if np.any(np.asarray(x.add) != 0.0):
         add = Coef("param", np.asarray(x.add, dtype=float), [(parent, rowpos.astype(_I))])
-    return SymExpr([Group((e,), [term], [])], add)
+    g = Group((e,), [term], [])
+    g.from_slice = True
+    return SymExpr([g], add)
 
 
 def has_symbolic(key):
@@ -572,7 +577,12 @@ def try_sum_for(body, index):
                 syms[k].ragged = (seq.parent, np.asarray([len(x) for x in seq.lists], dtype=np.int64))
             else:
                 syms[k] = SymIndex(k, seq)
-        cell = body(**syms)
+        global _depth
+        _depth += 1
+        try:
+            cell = body(**syms)
+        finally:
+            _depth -= 1
         if isinstance(cell, SymVec):                    # `sum_for(m = M, tdm[, m] * k[m])`: every cell is summed first
             cell = cell.as_sum()
         if not isinstance(cell, SymExpr):
@@ -581,13 +591,15 @@ def try_sum_for(body, index):
         if len(loops) > MAX_LOOPS:
             return None
         expr = _sum_group(cell, loops)
+        if _depth > 0:
+            return expr                                 # inside an enclosing trace (even if no outer index is used here)
         free = expr.syms()
-        if all(u in {l.uid for l in loops} for u in free):
-            if any(getattr(l, "ragged", None) for l in loops):
-                return None
-            first = body(**{k: index_first(index[k]) for k in names})       # metadata of the eager result
-            return _materialise(expr, list(expr.groups[0].loops), first)
-        return expr
+        if any(u not in {l.uid for l in loops} for u in free):
+            return None                                 # a loop variable that nobody binds: cannot happen at top level
+        if any(getattr(l, "ragged", None) for l in expr.groups[0].loops):
+            return None                                 # ragged pairs are only expanded on the device
+        first = body(**{k: index_first(index[k]) for k in names})           # metadata of the eager result
+        return _materialise(expr, list(expr.groups[0].loops), first)
     except Exception:
         return None
 
@@ -642,7 +654,12 @@ def try_for(body, index):
     names = list(index)
     try:
         syms = {k: SymIndex(k, index[k]) for k in names}
-        r = body(**syms)
+        global _depth
+        _depth += 1
+        try:
+            r = body(**syms)
+        finally:
+            _depth -= 1
         loops = [syms[k] for k in names]                # first index outermost (model.for_)
         if isinstance(r, LoweredFor):
             loops, r = loops + r.loops, r.con
@@ -715,16 +732,23 @@ def build_block(low: LoweredFor) -> LoweredCon:
                 raise NotLowerable()
             fused = rag[0]
             parent, counts = fused.ragged
-            if parent.uid not in o_axes or counts.size != len(parent.seq):
+            if counts.size != len(parent.seq):
                 raise NotLowerable()
             ppos = np.repeat(np.arange(len(parent.seq), dtype=np.int64), counts)
             expand = {parent.uid: ppos}
-            nest = [l for l in outer if l.uid != parent.uid] + list(g.loops[:-1])
+            if parent.uid in o_axes:                    # one set per value of a `for` index: rows come from a table
+                nest = [l for l in outer if l.uid != parent.uid] + list(g.loops[:-1])
+                row_stride = [rstride[o_axes[l.uid]] if l.uid in o_axes else 0 for l in nest] + [0]
+                row_tabs = [None] * len(nest) + [(ppos * rstride[o_axes[parent.uid]]).astype(_I)]
+            elif len(g.loops) >= 2 and g.loops[-2] is parent:   # ... of the fastest `sum_for` index: all inside one row
+                nest = outer + list(g.loops[:-2])
+                row_stride = rstride + [0] * (len(g.loops) - 2) + [0]
+                row_tabs = [None] * (len(nest) + 1)
+            else:
+                raise NotLowerable()
             axes = {l.uid: i for i, l in enumerate(nest)}
             axes[parent.uid] = axes[fused.uid] = len(nest)
             ext = [len(l.seq) for l in nest] + [len(fused.seq)]
-            row_stride = [rstride[o_axes[l.uid]] if l.uid in o_axes else 0 for l in nest] + [0]
-            row_tabs = [None] * len(nest) + [(ppos * rstride[o_axes[parent.uid]]).astype(_I)]
             nest_uids = [[l.uid] for l in nest] + [[parent.uid, fused.uid]]
         else:
             nest = outer + list(g.loops)

@@ -83,7 +83,9 @@ def m_slices_and_aliases(lp):
                 a6=M.for_(lambda s, t: M.Sum(z[s, t, :]) <= x[s, t], s=S, t=T),
                 a7=M.for_(lambda t: z[:, t, 2] >= 1 + t, t=T),                          # vector atoms: one row per entry
                 a8=M.for_(lambda s: -2 * z[s, :, :] <= dem[1] * s, s=S),
-                a9=M.for_(lambda s: M.sum_for(lambda t: z[s, t, :] * dem[t], t=T) / 2 <= cap[s], s=S))   # cells that are slices
+                a9=M.for_(lambda s: M.sum_for(lambda t: z[s, t, :] * dem[t], t=T) / 2 <= cap[s], s=S),   # cells that are slices
+                a10=M.for_(lambda t: M.sum_for(lambda s: w[s] * cap[s] - 0.5, s=S) - 3 * x[1, t] >= dem[t], t=T),     # alias rows as cells
+                a11=M.for_(lambda t: M.sum_for(lambda s, u: (sold[u] + 1) / cap[s], u=T, s=S) <= t, t=T))
 
 
 def m_mixed(lp):
@@ -169,7 +171,7 @@ def _lowered_parts(lp):
     return rows, cols, vals, lower.pack(low), int(offs[-1]), len(low)
 
 
-EXPECT_LOWERED = dict(slices=9, network=2, transport=2, coefficients=3, repeated=6, shifted=2, mixed=2)
+EXPECT_LOWERED = dict(slices=11, network=2, transport=2, coefficients=3, repeated=6, shifted=2, mixed=2)
 
 
 @pytest.mark.parametrize("name", sorted(MODELS))
