@@ -859,6 +859,12 @@ class easylp:
         return self
 
     # ---- device assembly ---------------------------------------------------------------------------
+    def _dir_codes(self, table):
+        """int8 code of every row's direction; lowered blocks have one direction for all their rows"""
+        parts = [np.full(b.nrow, table[b._dir], dtype=np.int8) if isinstance(b, _lower.LoweredCon)
+                 else np.array([table[d] for d in b.dir], dtype=np.int8) for b in self._blocks]
+        return np.concatenate(parts) if parts else np.zeros(0, np.int8)
+
     def _device_model(self):
         """the model's canonical CSR, assembled on the device and KEPT there (elp_model_assemble): eager blocks hand over
         their term lists, lowered blocks their index-set families; `$solve()` runs on this handle, `_csr()` copies it back"""
@@ -982,7 +988,7 @@ class easylp:
                 warnings.warn(f"lp.control option '{k}' has no meaning on the GPU path and is ignored")
         m = sum(b.nrow for b in self._blocks)
         lb, ub = self._bounds()
-        sense = np.array([_SENSE[d] for d in self.constraint.dir], dtype=np.int8)
+        sense = self._dir_codes(_SENSE)
         if m > 0:       # the matrix stays in HBM between `$con()` and `$solve()`
             r = self._device_model().solve(sense, self.constraint.rhs, self.objective_fun, lb, ub,
                                            maximize=self._dir == "max", options=opt)
@@ -1008,7 +1014,7 @@ class easylp:
         m = rp.size - 1
         if m <= 0:
             raise EasyLpError("nrow(mat) > 0L is not TRUE")
-        strict = np.array([_STRICT[d] for d in self.constraint.dir], dtype=np.int8)
+        strict = self._dir_codes(_STRICT)
         sol = np.where(np.isfinite(self._sol), self._sol, 0.0) if not np.all(np.isfinite(self._sol)) else self._sol
         feas = _lib.check_feasible(m, self._n_var, rp, ci, v, sol, strict, self.constraint.rhs, tol)
         if not feas.all():

@@ -192,6 +192,12 @@ def test_lowered_blocks_equal_eager_blocks(name):
     assert vv.tobytes() == vv0.tobytes()
 
 
+def test_direction_codes_of_mixed_blocks():
+    l = _build("mixed", True)
+    assert l._dir_codes(M._SENSE).tolist() == [M._SENSE[d] for d in l.constraint.dir]
+    assert l._dir_codes(M._STRICT).tolist() == [M._STRICT[d] for d in l.constraint.dir]
+
+
 def test_top_level_sum_for_is_the_eager_pending_list():
     """outside a `for`, sum_for returns an ordinary lp_var: the same pending terms, emitted in one vectorised pass"""
     S, T, rng = _sets()
