@@ -668,7 +668,9 @@ def try_for(body, index):
         low = LoweredFor(loops, r)
         free = SymExpr(r.groups, r.rhs).syms()
         if all(u in {l.uid for l in loops + r.row_loops} for u in free):
-            low.block = build_block(low)                # top level: descriptors now, so failures fall back here
+            low.block = build_block(low)                # descriptors now, so failures fall back here
+        elif _depth == 0:
+            return None                                 # a loop variable nobody binds, at top level: not ours
         return low
     except Exception:
         return None
