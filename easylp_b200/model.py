@@ -1071,12 +1071,18 @@ class easylp:
         out = {}
         for k, (name, c) in enumerate([(None, c) for c in unnamed] + list(named.items()), 1):
             if callable(c):
+                global LOWERING
+                keep, LOWERING = LOWERING, False         # `$test` shows the evaluated atoms: no lowering here
                 try:
                     c = c()
                 except Exception as e:       # tryCatch(..., error = identity)
                     c = e
+                finally:
+                    LOWERING = keep
             if isinstance(c, ForSplit):
                 c = [a for _, a in flatten_for_split(c, name or "")]
+            elif isinstance(c, _lower.LoweredFor):       # evaluated by the caller with lowering on: the block of rows
+                c = c.block
             out[name or k] = c
         return out
 
