@@ -20,15 +20,16 @@ S, T = [1, 2, 3, 4], [1, 2, 3]
 
 
 class Env:
-    def __init__(self, rng):
-        self.lp = M.easylp()
+    def __init__(self, rng, api=M):
+        self.api = api                   # easylp_b200.model (term lists) or oracle.dsl_ref (the reference's dense arithmetic)
+        self.lp = api.easylp()
         self.x = self.lp.var("x", S, T)
         self.y = self.lp.var("y", S)
         self.z = self.lp.var("z", S, T)
-        self.a = M.parameter(np.round(rng.normal(size=len(S) * len(T)), 3), S, T)
-        self.w = M.parameter(np.round(rng.uniform(0.5, 2.0, len(T)), 3), T)
-        self.k = M.parameter(np.round(rng.uniform(-2.0, 2.0, len(S)), 3), S)
-        self.alias = M.rowSums(self.x * self.a) + 0.25
+        self.a = api.parameter(np.round(rng.normal(size=len(S) * len(T)), 3), S, T)
+        self.w = api.parameter(np.round(rng.uniform(0.5, 2.0, len(T)), 3), T)
+        self.k = api.parameter(np.round(rng.uniform(-2.0, 2.0, len(S)), 3), S)
+        self.alias = api.rowSums(self.x * self.a) + 0.25
 
 
 def scalar(rng, env):
@@ -77,10 +78,10 @@ def node(rng, env, depth):
         return lambda s: v[s, j]
     if c == 2:
         f = cell(rng, env)
-        return lambda s: M.sum_for(lambda t: f(s, t), t=T)
+        return lambda s: env.api.sum_for(lambda t: f(s, t), t=T)
     if c == 3:
         v = (env.x, env.z)[int(rng.integers(0, 2))]
-        return lambda s: M.Sum(v[s, :])
+        return lambda s: env.api.Sum(v[s, :])
     if c == 4:
         return lambda s: env.alias[s]
     sub = node(rng, env, depth - 1)
@@ -101,20 +102,20 @@ def node(rng, env, depth):
     return lambda s: sub(s) - other(s)
 
 
-def build(seed, lowering):
+def build(seed, lowering, api=M):
     rng = np.random.default_rng(seed)
     old = M.LOWERING
     M.LOWERING = lowering
     try:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            env = Env(rng)
+            env = Env(rng, api)
             lhs = node(rng, env, 3)
             rhs = scalar(rng, env) if rng.random() < 0.6 else node(rng, env, 1)
             op = ("<=", ">=", "==")[int(rng.integers(0, 3))]
             body = (lambda s: lhs(s) <= rhs(s)) if op == "<=" else (lambda s: lhs(s) >= rhs(s)) if op == ">=" else \
                 (lambda s: lhs(s) == rhs(s))
-            env.lp.con(c=M.for_(body, s=S))
+            env.lp.con(c=api.for_(body, s=S))
             return env.lp
     finally:
         M.LOWERING = old
@@ -145,6 +146,27 @@ def test_random_bodies_lower_exactly_or_fall_back():
         assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0), seed
         assert v.tobytes() == v0.tobytes(), seed
     assert lowered >= len(SEEDS) // 3, (lowered, failed)
+
+
+def test_random_bodies_against_the_dense_reference_arithmetic():
+    """the same random bodies evaluated by the dense restatement of the reference's R arithmetic (oracle/dsl_ref.py):
+    its `constraint$mat` must be what the lowered families fold to — the trace is pinned to the reference's matrix
+    algebra, not only to this repo's own term-list evaluation"""
+    from oracle import dsl_ref
+    checked = 0
+    for seed in range(120):
+        try:
+            d = build(seed, False, api=dsl_ref).canonical()
+        except dsl_ref.RError:
+            continue
+        l = build(seed, True)
+        rp, ci, v, _ = model_fold(l)
+        assert np.array_equal(rp, d["row_ptr"]) and np.array_equal(ci, d["col_idx"]), seed
+        assert v.tobytes() == d["vals"].tobytes(), seed
+        assert l.constraint.rhs.tobytes() == d["rhs"].tobytes() and l.constraint.dir == d["dir"], seed
+        assert l.constraint.rownames == d["rownames"], seed
+        checked += any(isinstance(b, lower.LoweredCon) for b in l._blocks)
+    assert checked >= 60
 
 
 @pytest.mark.gpu
