@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the driver's measurement contract for the EasyLP B200 solve path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pdlp|batch|transport]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pdlp|batch|transport|mcnf]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -11,6 +11,9 @@ cols, ~20M nnz) — the configuration whose SpMV roofline north_star sets the ta
 complete solve from the initial iterate to the 1e-6 relative KKT tolerance, so `ms_per_step` IS the
 time-to-1e-6-gap.  The batched-simplex number (config 3: 200k dense 20x30 LPs) rides in the same line under
 `"batch"` with its own value / e2e / roofline / cpu_baseline; `--workload batch` makes it the primary.
+At N = 1 two more sub-lines ride along: `"assembly"` (device CSR assembly of a 21 M-term stream of config 4's matrix,
+checked bit-exact) and `"lowering"` (config 2 built through for/sum_for: per-atom evaluation vs one trace + device
+expansion, both checked bit-exact).  `--workload mcnf|transport` make configs 5 / 2 the timed PDLP workload.
 
 Timing: device time comes from CUDA events recorded by the library on the stream its kernels run on
 (elp_stats.solve_ms); under torchrun the MAX over ranks is taken.  Inputs (2 x 240 MB of matrix per
