@@ -116,15 +116,16 @@ def pinned(a):
 
 def ncu_traffic(key):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu
-    capture of this same workload (profiles/r1_ncu_traffic.json); None when no capture is on file."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
-            t = json.load(f)
-        for k in (key + "_gather", key):          # the latest capture of the gather kernels, else the first one
-            if k in t:
-                return int(t[k]["dram_bytes"])
-    except (OSError, KeyError, ValueError):
-        pass
+    capture of this same workload (profiles/r2_ncu_traffic.json, else round 1's); None when no capture is on file."""
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            for k in (key + "_gather", key):          # the latest capture of the gather kernels, else the first one
+                if k in t:
+                    return int(t[k]["dram_bytes"])
+        except (OSError, KeyError, ValueError):
+            pass
     return None
 
 
@@ -183,6 +184,57 @@ class Dist:
             self.td.destroy_process_group()
 
 
+
+PARITY_TOL = 1e-6      # north_star: objective within 1e-6 relative, primal / dual residuals <= 1e-6 relative
+
+
+def check_parity(L, st, obj, planted, args):
+    """status / objective / residual parity of one finished solve; the caller exits non-zero when `ok` is False"""
+    out = {"status": L.status_string(st.status), "objective": obj, "planted_objective": planted,
+           "rel_primal_res": st.rel_primal_res, "rel_dual_res": st.rel_dual_res, "rel_gap": st.rel_gap, "tol": PARITY_TOL}
+    ok = st.status == L.STATUS_OPTIMAL and st.rel_primal_res <= PARITY_TOL and st.rel_dual_res <= PARITY_TOL \
+        and st.rel_gap <= PARITY_TOL
+    if planted is not None:
+        out["objective_rel_err"] = abs(obj - planted) / max(1.0, abs(planted))
+        ok = ok and out["objective_rel_err"] <= PARITY_TOL
+    out["ok"] = bool(ok)
+    return out
+
+
+def e2e_single_call(args, dist, L, p, steps):
+    """N > 1: what an R user gets — ONE process, ONE blocking elp_solve_lp(devices = N) on host buffers.  Rank 0 makes the
+    call (worker threads inside the library drive the N GPUs); the other ranks have released their GPUs and wait."""
+    N = dist.world
+    out = {}
+    dist.barrier()
+    if dist.rank == 0:
+        keys = ("row_ptr", "col_idx", "vals", "sense", "rhs", "c", "lb", "ub")
+        hp = {k: pinned(p[k]) for k in keys}
+        opt = L.default_options(method=L.METHOD_PDLP, eps_rel=1e-6, max_iter=args.max_iter, devices=N)
+        L.set_device(0)
+
+        def call():
+            return L.solve_lp(p["m"], p["n"], hp["row_ptr"], hp["col_idx"], hp["vals"], hp["sense"], hp["rhs"], hp["c"],
+                              hp["lb"], hp["ub"], maximize=p["maximize"], options=opt)
+        r = call()                      # warm-up: worker threads + in-process communicator (kept by the library)
+        t0 = time.perf_counter()
+        iters = h2d = d2h = 0
+        for _ in range(steps):
+            r = call()
+            iters += r.stats.iterations
+            h2d += r.stats.h2d_bytes
+            d2h += r.stats.d2h_bytes + 8 * (p["n"] + p["m"])
+        dt = time.perf_counter() - t0
+        L.release_workspace()
+        L.set_device(dist.local)
+        out = {"value": iters / dt, "unit": "iter/s", "h2d_bytes_per_step": int(h2d / steps), "d2h_bytes_per_step": int(d2h / steps),
+               "s_per_solve": dt / steps, "steps": steps,
+               "breakdown": {"setup_s": round(r.stats.setup_ms * 1e-3, 4), "run_device_s": round(r.stats.solve_ms * 1e-3, 4)},
+               "path": f"elp_solve_lp(host CSR, devices={N}): one process, one blocking call, {N} worker threads",
+               "_stats": r.stats, "_obj": r.objval}
+    dist.barrier()
+    return out
+
 # ------------------------------------------------------------------------------------------------
 def cpu_pdlp_baseline(p, max_iter, threads):
     from oracle import cbind
@@ -202,6 +254,39 @@ def cpu_batch_baseline(d, sample, threads):
     return {"value": sample / dt, "unit": "LP/s", "cores": threads, "kind": "port",
             "sample": f"first {sample} LPs of the same batch with oracle/simplex_ref.c (C + OpenMP bounded primal "
                       f"simplex restatement; the reference's lp_solve is not in the image), {dt:.1f} s"}
+
+
+def highs_stand_in(args, gpu_c2_s=None, gpu_c3_lps=None):
+    """A REAL CPU simplex solver beside the ports: HiGHS dual simplex (scipy `highs-ds`), labelled a
+    stand-in for lp_solve, which is not in this image.  Wall time to the optimum of config 2 (whole solve) and of the first
+    `n` LPs of config 3, one core (HiGHS' simplex is serial).  Time-to-solution, not iter/s."""
+    try:
+        from scipy.optimize import linprog
+        from scipy.sparse import csr_matrix
+    except Exception as e:                                  # scipy missing on the box: say so, do not fail the bench
+        return {"unavailable": str(e)}
+    out = {"solver": "HiGHS dual simplex via scipy.optimize.linprog(method='highs-ds'); stand-in for lp_solve 5.5", "cores": 1}
+    p = gen.transport(300, 300, seed=0)
+    A = csr_matrix((p["vals"], p["col_idx"], p["row_ptr"]), shape=(p["m"], p["n"]))
+    le, ge = p["sense"] == 0, p["sense"] == 1
+    from scipy.sparse import vstack
+    t0 = time.perf_counter()
+    r = linprog(p["c"], A_ub=vstack([A[le], -A[ge]]), b_ub=np.r_[p["rhs"][le], -p["rhs"][ge]], bounds=(0, None), method="highs-ds")
+    out["c2_transport_s"] = time.perf_counter() - t0
+    out["c2_status"], out["c2_objective"] = int(r.status), float(r.fun)
+    if gpu_c2_s:
+        out["c2_gpu_s"] = gpu_c2_s
+        out["c2_speedup_time_to_solution"] = out["c2_transport_s"] / gpu_c2_s
+    d = gen.dense_batch(B=args.highs_lps, seed=0)
+    t0 = time.perf_counter()
+    for i in range(d["B"]):
+        linprog(d["c"][i], A_ub=d["A"][i], b_ub=d["b"][i], bounds=list(zip(d["lb"][i], d["ub"][i])), method="highs-ds")
+    dt = time.perf_counter() - t0
+    out["c3_sample_lps"], out["c3_sample_s"], out["c3_lps_per_s"] = d["B"], dt, d["B"] / dt
+    out["c3_note"] = "scipy's per-call overhead is inside this figure (the reference's R loop over lpSolveAPI::solve pays a similar one)"
+    if gpu_c3_lps:
+        out["c3_speedup_throughput"] = gpu_c3_lps / out["c3_lps_per_s"]
+    return out
 
 
 def host_threads():
@@ -262,13 +347,20 @@ def bench_pdlp(args, dist, L, p, workload_name):
     ms_primal, ms_dual = h.probe_step(50)
     h.close()
 
+    # ---- parity gate (north_star): status exact, objective <= 1e-6 relative, residuals <= 1e-6 -- the exit code
+    # of this script carries it at every N
+    parity = check_parity(L, last, obj, p.get("obj_opt"), args)
+
     # ---- e2e: the user-facing call with host buffers; H2D + setup + solve + D2H timed -------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    if N > 1:
+        e2e = e2e_single_call(args, dist, L, p, e2e_steps)
+        parity["e2e_call"] = check_parity(L, e2e.pop("_stats"), e2e.pop("_obj"), p.get("obj_opt"), args) if dist.rank == 0 else None
     dist.barrier()
     t0 = time.perf_counter()
     e2e_iters, h2d, d2h = 0, 0, 0
     parts = {"create_s": 0.0, "run_s": 0.0, "solution_s": 0.0, "close_s": 0.0, "run_device_s": 0.0}
-    for _ in range(e2e_steps):
+    for _ in range(e2e_steps if N == 1 else 0):
         ta = time.perf_counter()
         hh = create()
         tb = time.perf_counter()
@@ -287,6 +379,11 @@ def bench_pdlp(args, dist, L, p, workload_name):
             parts[key] += v / e2e_steps
     dist.barrier()
     e2e_s = dist.vmax(time.perf_counter() - t0)
+    if N == 1:
+        e2e = {"value": e2e_iters / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": int(h2d / e2e_steps),
+               "d2h_bytes_per_step": int(d2h / e2e_steps), "s_per_solve": e2e_s / e2e_steps, "steps": e2e_steps,
+               "breakdown": {k: round(v, 4) for k, v in parts.items()},
+               "path": "elp_pdlp_create(host CSR) -> elp_pdlp_run -> elp_pdlp_solution (= elp_solve_lp)"}
 
     peak, peak_src = measured_peak()
     # local matrix of this rank for the roofline (N = 1: the whole matrix)
@@ -317,7 +414,9 @@ def bench_pdlp(args, dist, L, p, workload_name):
         key_primal, key_dual = "primal_from_g", "dual_scatter"
     dom_ms, dom_b, dom_name, dom_key = \
         (ms_primal, b_csc, name_primal, key_primal) if ms_primal >= ms_dual else (ms_dual, b_csr, name_dual, key_dual)
-    traffic = ncu_traffic(dom_key) if (N == 1 and args.scale == 1.0 and args.workload == "pdlp") else None
+    traffic = None
+    if N == 1 and args.scale == 1.0:
+        traffic = ncu_traffic(dom_key if workload_name.startswith("C4") else workload_name[:2].lower() + "_" + dom_key)
     ach = dom_b / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     iter_ms = dev_ms / max(iters, 1)
     res = {
@@ -333,10 +432,8 @@ def bench_pdlp(args, dist, L, p, workload_name):
         "status": L.status_string(last.status), "objective": obj, "planted_objective": p.get("obj_opt"),
         "rel_primal_res": last.rel_primal_res, "rel_dual_res": last.rel_dual_res, "rel_gap": last.rel_gap,
         "restarts": last.restarts, "wall_ms_per_step": wall_ms / args.steps,
-        "e2e": {"value": e2e_iters / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": int(h2d / e2e_steps),
-                "d2h_bytes_per_step": int(d2h / e2e_steps), "s_per_solve": e2e_s / e2e_steps, "steps": e2e_steps,
-                "breakdown": {k: round(v, 4) for k, v in parts.items()},
-                "path": "elp_pdlp_create(host CSR) -> elp_pdlp_run -> elp_pdlp_solution (= elp_solve_lp)"},
+        "parity": parity,
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "frac_of_nominal_8000": ach / 8000.0, "peak_source": peak_src, "traffic": traffic,
@@ -412,6 +509,8 @@ def bench_batch(args, dist, L, d):
                    "parallelism": f"LP ranges x{N}, no collective",
                    "l2": "batch data (%.2f GB) exceeds the 126 MB L2; no flush needed" % (bytes_lp * B / 1e9)},
         "optimal": int(n_opt), "pivots_per_lp": pivots / B, "pivots_per_s": pivots / ms * 1e3,
+        "parity": {"ok": bool(int(n_opt) == B), "optimal": int(n_opt), "of": B,
+                   "note": "every LP of the batch is feasible and bounded by construction: status must be optimal for all"},
         "e2e": {"value": B * e2e_steps / e2e_s, "unit": "LP/s", "h2d_bytes_per_step": int(st2.h2d_bytes * N),
                 "d2h_bytes_per_step": int(st2.d2h_bytes * N), "path": "elp_solve_batch(host arrays)"},
         "gpu_launches": int(launches),
@@ -498,16 +597,29 @@ def bench_lowering(args, L):
 
 
 # ------------------------------------------------------------------------------------------------
+def golden_objective(key):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "configs.json")) as f:
+            return float.fromhex(json.load(f)[key]["objective"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def make_problem(args):
     w = args.workload
     if w == "pdlp":
         m = int(round(2_000_000 * args.scale))
         return gen.sparse_planted(m, seed=0), f"C4: synthetic sparse LP {m} rows x {2 * m} cols, planted optimum, PDLP to 1e-6"
     if w == "transport":
-        return gen.transport(300, 300, seed=0), "C2: transportation 300 x 300 (90k vars, 600 rows), PDLP to 1e-6"
+        p = gen.transport(300, 300, seed=0)
+        p["obj_opt"] = golden_objective("c2_transport_300x300_seed0")     # HiGHS (tests/golden/make_configs.py)
+        return p, "C2: transportation 300 x 300 (90k vars, 600 rows), PDLP to 1e-6"
     if w == "mcnf":
         K = max(1, int(round(50 * args.scale)))
-        return gen.mcnf(K=K), f"C5: multi-commodity flow, {K} commodities on 20k nodes / 100k arcs, PDLP to 1e-6"
+        p = gen.mcnf(K=K)
+        if K == 50:
+            p["obj_opt"] = golden_objective("c5_mcnf_K50_seed0")          # shortest-path decomposition, capacities slack
+        return p, f"C5: multi-commodity flow, {K} commodities on 20k nodes / 100k arcs, PDLP to 1e-6"
     raise SystemExit(f"unknown workload {w}")
 
 
@@ -562,6 +674,7 @@ def main():
     ap.add_argument("--cpu-sample-iters", type=int, default=150)
     ap.add_argument("--cpu-sample-lps", type=int, default=20_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--highs-lps", type=int, default=2000, help="LPs of config 3 given to the HiGHS stand-in")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary (batch) arm in the pdlp line")
     args = ap.parse_args()
 
@@ -589,7 +702,7 @@ def main():
             sec = bench_batch(args, dist, L, d)
             if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
                 sec["cpu_baseline"] = cpu_batch_baseline(d, min(d["B"], args.cpu_sample_lps), threads)
-            res["batch"] = {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "optimal",
+            res["batch"] = {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "optimal", "parity",
                                                 "pivots_per_lp", "pivots_per_s", "e2e", "gpu_launches", "roofline")
                             if k in sec}
             if "cpu_baseline" in sec:
@@ -601,11 +714,46 @@ def main():
             res["gpu_launches"] += asm["gpu_launches"] * args.steps
             if dist.rank == 0:
                 res["lowering"] = bench_lowering(args, L)
+        if dist.world == 1 and not args.no_secondary and args.workload == "pdlp":
+            # config 5 rides along: the structured LP where the SpMV kernel passes 60 % of the HBM roofline, with its own
+            # roofline block and the independently pinned objective; config 2 gives the time-to-solution the HiGHS
+            # stand-in is compared with
+            sub_args = argparse.Namespace(**vars(args))
+            sub_args.steps, sub_args.warmup, sub_args.e2e_steps = max(3, min(args.steps, 5)), 3, 2
+            for key, wl in (("mcnf", "mcnf"), ("transport", "transport")):
+                sub_args.workload = wl
+                q, qname = make_problem(sub_args)
+                sub = bench_pdlp(sub_args, dist, L, q, qname)
+                res[key] = {k: sub[k] for k in ("metric", "value", "unit", "ms_per_step", "time_to_gap_s", "iterations_per_solve",
+                                                "config", "parity", "e2e", "gpu_launches", "roofline") if k in sub}
+                res["gpu_launches"] += sub["gpu_launches"]
         if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_pdlp_baseline(p, args.cpu_sample_iters, threads)
+            res["cpu_baseline"]["alt"] = highs_stand_in(args, gpu_c2_s=res.get("transport", {}).get("time_to_gap_s"),
+                                                        gpu_c3_lps=res.get("batch", {}).get("e2e", {}).get("value"))
     if dist.rank == 0:
         print(json.dumps(res), flush=True)
     dist.close()
+    # the exit code carries parity: a wrong status / objective / residual at any N is a failed run, not a slow one
+    bad = []
+    par = res.get("parity")
+    if par is not None and not par["ok"]:
+        bad.append(f"pdlp parity: {par}")
+    if par is not None and par.get("e2e_call") and not par["e2e_call"]["ok"]:
+        bad.append(f"pdlp parity of the single-call e2e: {par['e2e_call']}")
+    for key in ("batch", "mcnf"):
+        sub = res if res.get("metric") == "batched_lps_per_s" and key == "batch" else res.get(key)
+        if isinstance(sub, dict) and sub.get("parity") is not None and not sub["parity"]["ok"]:
+            bad.append(f"{key} parity: {sub['parity']}")
+    for key in ("assembly", "lowering"):
+        sub = res.get(key)
+        if isinstance(sub, dict):
+            exact = sub.get("bit_exact", True) and sub.get("lowered", {}).get("bit_exact", True) and sub.get("eager", {}).get("bit_exact", True)
+            if not exact:
+                bad.append(f"{key}: CSR not bit-exact")
+    if bad:
+        print("PARITY FAILURE: " + "; ".join(bad), file=sys.stderr, flush=True)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -31,7 +31,7 @@ class Options(C.Structure):
     _fields_ = [("eps_rel", C.c_double), ("time_limit_s", C.c_double), ("max_iter", C.c_int32),
                 ("check_every", C.c_int32), ("method", C.c_int32), ("verbose", C.c_int32),
                 ("use_graph", C.c_int32), ("ruiz_iters", C.c_int32), ("transpose", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("devices", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -40,7 +40,7 @@ class Stats(C.Structure):
                 ("rel_primal_res", C.c_double), ("rel_dual_res", C.c_double), ("rel_gap", C.c_double),
                 ("setup_ms", C.c_double), ("solve_ms", C.c_double), ("total_ms", C.c_double),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("spmv_ms", C.c_double)]
+                ("spmv_ms", C.c_double), ("limit_reached", C.c_int32), ("reserved", C.c_int32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

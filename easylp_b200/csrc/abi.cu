@@ -5,6 +5,10 @@
 #include "../../include/easylp_abi.h"
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 namespace elp {
 
@@ -38,7 +42,7 @@ Pdlp* pdlp_create(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, 
                   const double* ub, const elp_options& opt, bool dist, elp_stats* stats, int64_t nnz_device = -1);
 void pdlp_run(Pdlp* p, int max_new_iters, elp_stats* stats);
 void pdlp_reset(Pdlp* p);
-void pdlp_solution(Pdlp* p, double* x, double* y, double* obj);
+void pdlp_solution(Pdlp* p, double* x, double* y, double* obj, bool collective_x = false);
 void pdlp_probe(Pdlp* p, int reps, double* a, double* b);
 void pdlp_probe_step(Pdlp* p, int reps, double* a, double* b);
 int pdlp_transpose(Pdlp* p);
@@ -51,6 +55,7 @@ void simplex_batch_device(int64_t B, int m, int n, const double* A, const double
                           double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st);
 void densify_device(int m, int n, const int* ptr, const int* idx, const double* val, double* A, cudaStream_t st);
 
+void pool_release();            // shuts the multi-GPU worker pool down (defined next to it, below)
 static void require_device() {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -69,6 +74,10 @@ static elp_options effective_options(const elp_options* opt) {
         if (!(o.eps_rel > 0)) o.eps_rel = d.eps_rel;
         if (o.check_every <= 1) o.check_every = d.check_every;
         if (o.ruiz_iters < 0) o.ruiz_iters = d.ruiz_iters;
+        if (o.devices < 0) o.devices = 0;
+    }
+    if (o.devices == 0) {
+        if (const char* e = getenv("ELP_DEVICES")) o.devices = std::max(0, atoi(e));    // site-wide default (R: gpu.devices=)
     }
     return o;
 }
@@ -149,6 +158,171 @@ using namespace elp;
     }                                               \
     return 0;
 
+// ---- single-process multi-GPU: one persistent worker thread per GPU ---------------------------------------------
+// `$solve()` is ONE blocking call from ONE R thread (/root/reference/R/class.R:251-302).  With elp_options.devices = N
+// the call partitions the LP by row blocks (balanced by non-zeros), hands block r to worker r — a host thread bound to
+// GPU r that owns rank r of an in-process NCCL communicator — and every worker runs the same distributed PDLP a
+// process-per-GPU launch runs (pdlp.cu; peers are mapped with cudaDeviceEnablePeerAccess instead of CUDA IPC).  The
+// workers and their communicator live until elp_release_workspace(): NCCL initialisation costs more than a solve.
+struct DevicePool {
+    int N = 0;
+    std::vector<int> devs;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    uint64_t generation = 0;
+    int remaining = 0;
+    bool stop = false;
+    std::function<void(int)> job;
+    std::vector<std::string> errors;
+
+    void worker(int r) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void(int)> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_job.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                fn = job;
+            }
+            std::string err;
+            try { fn(r); }
+            catch (const std::exception& e) { err = e.what(); }
+            catch (...) { err = "unknown C++ exception"; }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!err.empty()) errors[r] = err;
+                if (--remaining == 0) cv_done.notify_all();
+            }
+        }
+    }
+    // runs fn(rank) on every worker and waits; rethrows the first error
+    void run(std::function<void(int)> fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = std::move(fn);
+            errors.assign(N, std::string());
+            remaining = N;
+            ++generation;
+        }
+        cv_job.notify_all();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return remaining == 0; });
+        for (int r = 0; r < N; ++r)
+            if (!errors[r].empty()) throw Error(format("GPU worker %d (device %d): %s", r, devs[r], errors[r].c_str()));
+    }
+    void start(int n_dev, int first_dev, int dev_count) {
+        N = n_dev;
+        devs.resize(N);
+        for (int r = 0; r < N; ++r) devs[r] = (first_dev + r) % dev_count;
+        for (int r = 0; r < N; ++r) workers.emplace_back([this, r] { worker(r); });
+        unsigned char id[ELP_UNIQUE_ID_BYTES];
+        comm_unique_id(id);
+        run([&](int r) {
+            ELP_CUDA(cudaSetDevice(devs[r]));
+            comm_init(N, r, id);
+        });
+    }
+    void shutdown() {
+        if (workers.empty()) return;
+        try { run([](int) { cudaDeviceSynchronize(); comm_destroy(); }); } catch (...) {}
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_job.notify_all();
+        for (auto& t : workers) t.join();
+        workers.clear();
+        N = 0;
+    }
+};
+static std::mutex g_pool_mutex;          // one multi-GPU solve at a time per process
+static DevicePool* g_pool = nullptr;     // deliberately never destroyed at exit (worker threads blocked on a condition
+                                         // variable are reaped with the process; tearing NCCL down after CUDA is not safe)
+
+void elp::pool_release() {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool) { g_pool->shutdown(); delete g_pool; g_pool = nullptr; }
+}
+
+// rows [cut[r], cut[r+1]) for rank r: contiguous, balanced by non-zeros (the rule of easylp_b200/partition.py::row_cuts)
+static std::vector<int32_t> row_cuts_by_nnz(int32_t m, const int32_t* row_ptr, int N) {
+    std::vector<int32_t> cut(N + 1, 0);
+    const int64_t nnz = m > 0 ? row_ptr[m] : 0;
+    for (int g = 1; g < N; ++g) {
+        const double target = (double)nnz * g / N;
+        const int32_t* it = std::lower_bound(row_ptr, row_ptr + m + 1, target, [](int32_t a, double t) { return (double)a < t; });
+        cut[g] = (int32_t)(it - row_ptr);
+    }
+    cut[N] = m;
+    for (int g = 1; g <= N; ++g) cut[g] = std::min(std::max(cut[g], cut[g - 1]), m);
+    return cut;
+}
+
+static void solve_multi(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                        const int8_t* sense, const double* rhs, const double* c, int32_t maximize, const double* lb,
+                        const double* ub, const elp_options& o, int32_t* status, double* objval, double* x, double* y,
+                        elp_stats* stats) {
+    WallTimer wall;
+    int dev_count = 0, cur = 0;
+    ELP_CUDA(cudaGetDeviceCount(&dev_count));
+    ELP_CUDA(cudaGetDevice(&cur));
+    ELP_REQUIRE(o.devices <= dev_count, "devices = %d but only %d CUDA device(s) are visible", o.devices, dev_count);
+    ELP_REQUIRE(o.devices <= 8, "devices = %d: at most 8 GPUs of one box", o.devices);
+    bool bad_bounds = false;
+    for (int j = 0; j < n; ++j) if (lb[j] > ub[j]) { bad_bounds = true; break; }
+    const int N = o.devices;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool && (g_pool->N != N || g_pool->devs[0] != cur)) { g_pool->shutdown(); delete g_pool; g_pool = nullptr; }
+    if (!g_pool) {
+        g_pool = new DevicePool();
+        try { g_pool->start(N, cur, dev_count); }
+        catch (...) { g_pool->shutdown(); delete g_pool; g_pool = nullptr; throw; }
+    }
+    const std::vector<int32_t> cut = row_cuts_by_nnz(m, row_ptr, N);
+    std::vector<elp_stats> s_setup(N), s_run(N);
+    const int64_t l0 = g_launches.load();
+    elp_options od = o;
+    od.devices = 0;
+    g_pool->run([&](int r) {
+        const int32_t r0 = cut[r], r1 = cut[r + 1], ml = r1 - r0;
+        const int64_t off = m > 0 ? row_ptr[r0] : 0;
+        std::vector<int32_t> rp((size_t)ml + 1);
+        for (int32_t i = 0; i <= ml; ++i) rp[i] = (int32_t)((m > 0 ? row_ptr[r0 + i] : 0) - off);
+        memset(&s_setup[r], 0, sizeof(elp_stats));
+        memset(&s_run[r], 0, sizeof(elp_stats));
+        Pdlp* p = pdlp_create(ml, n, rp.data(), col_idx + off, vals + off, sense + r0, rhs + r0, c, maximize, lb, ub, od, true,
+                              &s_setup[r]);
+        try {
+            if (!bad_bounds) pdlp_run(p, 0, &s_run[r]);
+            double obj = 0.0;
+            pdlp_solution(p, r == 0 ? x : nullptr, y ? y + r0 : nullptr, &obj, true);
+            if (r == 0) *objval = obj;
+        } catch (...) {
+            pdlp_destroy(p);
+            throw;
+        }
+        pdlp_destroy(p);
+    });
+    *status = bad_bounds ? ELP_STATUS_INFEASIBLE : s_run[0].status;
+    if (*status == ELP_STATUS_UNBOUNDED) *objval = maximize ? INFINITY : -INFINITY;
+    if (stats) {
+        *stats = s_run[0];
+        stats->status = *status;
+        stats->setup_ms = s_setup[0].setup_ms;
+        stats->total_ms = wall.ms();
+        stats->kernel_launches = g_launches.load() - l0;
+        stats->h2d_bytes = 0; stats->d2h_bytes = 0;
+        for (int r = 0; r < N; ++r) {
+            stats->h2d_bytes += s_run[r].h2d_bytes;
+            stats->d2h_bytes += s_run[r].d2h_bytes;
+            stats->solve_ms = std::max(stats->solve_ms, s_run[r].solve_ms);     // device time: the slowest rank
+        }
+    }
+}
+
 extern "C" {
 
 const char* elp_version(void) { return "easylp_b200 0.1 (sm_100a)"; }
@@ -185,7 +359,7 @@ int elp_default_options(elp_options* o) {
     o->use_graph = 1;
     o->ruiz_iters = 10;
     o->transpose = ELP_TRANSPOSE_AUTO;
-    o->reserved = 0;
+    o->devices = 0;
     return 0;
 }
 
@@ -214,6 +388,7 @@ int elp_release_workspace(void) {
     ELP_TRY
     asm_workspace_release();
     batch_stream_workspace().release();
+    pool_release();
     ELP_CATCH
 }
 
@@ -499,6 +674,8 @@ int elp_solve_lp(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* co
     // any block with lower > upper forces "unfeasible" (R/class.R:297-298); both solvers also detect it
     if (method == ELP_METHOD_SIMPLEX)
         solve_small(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
+    else if (o.devices > 1)      // the large-LP path over several GPUs of the box, still one blocking call
+        solve_multi(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
     else
         solve_large(m, n, row_ptr, col_idx, vals, -1, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
     ELP_CATCH
@@ -600,6 +777,13 @@ int elp_model_solve(const elp_model* hh, const int8_t* sense, const double* rhs,
         std::vector<double> v((size_t)std::max<int64_t>(h->nnz, 1));
         ELP_REQUIRE(elp_model_csr(hh, rp.data(), ci.data(), v.data()) == 0, "%s", g_last_error.c_str());
         solve_small(h->m, h->n, rp.data(), ci.data(), v.data(), sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
+    } else if (o.devices > 1) {
+        // several GPUs: the row blocks travel from this device's copy through the host (one D2H of the CSR; the blocks
+        // then go straight to their GPUs)
+        std::vector<int32_t> rp((size_t)h->m + 1), ci((size_t)std::max<int64_t>(h->nnz, 1));
+        std::vector<double> v((size_t)std::max<int64_t>(h->nnz, 1));
+        ELP_REQUIRE(elp_model_csr(hh, rp.data(), ci.data(), v.data()) == 0, "%s", g_last_error.c_str());
+        solve_multi(h->m, h->n, rp.data(), ci.data(), v.data(), sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
     } else {
         solve_large(h->m, h->n, h->ptr.p, h->idx.p, h->val.p, h->nnz, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y,
                     stats);

@@ -1,6 +1,7 @@
 // comm.cu — see comm.cuh.
 #include "comm.cuh"
 #include <dlfcn.h>
+#include <mutex>
 
 namespace elp {
 
@@ -19,9 +20,13 @@ struct NcclApi {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_api;
-Comm g_comm;
+std::mutex g_api_mutex;
+// One communicator per HOST THREAD: a process-per-GPU caller (torchrun) has one thread that owns one rank; the
+// single-process multi-GPU solve (abi.cu: device pool) runs one worker thread per GPU, each with its own rank.
+thread_local Comm g_comm;
 
 void load_api() {
+    std::lock_guard<std::mutex> lock(g_api_mutex);
     if (g_api.lib) return;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) {

@@ -1,4 +1,4 @@
-// comm.cuh — NCCL plumbing for the partitioned PDLP (one process per GPU).
+// comm.cuh — NCCL plumbing for the partitioned PDLP (one host thread per GPU: in one process or in several).
 // NCCL is resolved with dlopen at first use so that the single-GPU path (and the R package) has no
 // link-time NCCL dependency.  Used: all-gather (the x-bar and y blocks every iteration, scaling vectors at
 // setup), allreduce (scalar residual partials), grouped send/recv (one-off exchange that builds each rank's
@@ -14,7 +14,7 @@ struct Comm {
     int nranks = 1, rank = 0;
     ncclComm_t comm = nullptr;
 };
-Comm& comm();                         // process-wide communicator (comm.cu)
+Comm& comm();                         // the calling thread's communicator (comm.cu)
 
 void comm_unique_id(void* id128);
 void comm_init(int nranks, int rank, const void* id128);

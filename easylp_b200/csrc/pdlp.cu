@@ -30,6 +30,7 @@
 #include "../../include/easylp_abi.h"
 #include <cmath>
 #include <algorithm>
+#include <unistd.h>
 
 namespace elp {
 
@@ -37,6 +38,7 @@ struct PdlpParams {   // device-resident; the host rewrites it between iteration
     double tau, sigma;
     int k_base;       // iterations since restart at the start of the chunk
     int pad;
+    long long epoch_base;   // multi-GPU: exchange epochs completed before the chunk (iteration `it` produces epoch_base + it + 1)
 };
 
 constexpr int SPMV_THREADS = 256;             // block size of the setup-only helper kernels
@@ -46,6 +48,7 @@ constexpr int SPMV_THREADS = 256;             // block size of the setup-only he
 struct StoreEpi {
     static constexpr int NIN = 0;
     static constexpr bool SCATTER = false;
+    static constexpr bool DIST = false;
     double* scat = nullptr;
     double* out;
     struct Pre {};
@@ -57,23 +60,88 @@ struct StoreEpi {
 
 inline StoreEpi store_epi(double* out) { StoreEpi e; e.out = out; return e; }
 
-// Where an epilogue publishes the block it produces: its own copy of the gathered vector, or — when the ranks have
-// mapped each other's buffers (CUDA IPC over NVLink) — the copy of EVERY rank, so that the all-gather is done by the
-// stores of the kernel itself, overlapped with the rest of the tile walk.
-struct PeerOut {
-    double* p[8];
-    int n;          // 0: single destination (the local pointer of the epilogue)
-    // mask[j] bit r: rank r gathers entry j of this block (its matrix block references it).  Entries nobody else reads
-    // stay at home: on structured LPs (multi-commodity flow: a row block touches the columns of its own commodities)
-    // most of the exchange disappears.  nullptr = every rank gets every entry.
-    const unsigned char* mask;
+// ---- multi-GPU exchange: ghost vectors filled by the producers' own stores -------------------------------------
+// Rank r gathers only the entries of x-bar (y) that its row (column) block references.  It keeps them in a COMPACT
+// ghost vector — entries in ascending global id, its matrix copy for the plain iterations carries the compact ids — with
+// two buffers selected by the parity of the epoch, so a producer may run one kernel ahead of its consumers without a
+// write-after-read hazard.  The epilogue of the producing kernel stores each value straight into the ghost vector of
+// every rank that reads it (CUDA IPC / peer access over NVLink); the position is the tile's base in that rank's vector
+// (a table built at setup) plus the number of lower lanes that also store there (one ballot per destination), so the
+// stores of a warp are contiguous.  The hand-off lives inside the kernels: the last CTA of the producer to finish
+// publishes the epoch in slot `rank` of every consumer's flag row (release), and every warp of the consuming kernel
+// waits — after it has queued its first matrix tiles — until all N slots have reached the epoch it needs (acquire).
+struct GhostOut {
+    double* buf[8];                    // rank r's ghost vector, buffer 0; buffer 1 lies stride[r] doubles further
+    uint32_t stride[8];
+    unsigned long long* flag[8];       // rank r's flag row for this vector (N slots); this rank writes slot `rank`
+    const unsigned char* mask;         // [my block] bit r: rank r gathers this entry
+    const int* base;                   // [tiles of my block][8]: position of the tile's first entry in r's ghost vector
+    unsigned int* done;                // CTAs of the current launch that have finished (reset by the last one)
+    int n, rank;
 };
+struct GhostIn {
+    const double* vec;                 // my ghost vector, buffer 0
+    uint32_t stride;
+    const unsigned long long* flags;   // my flag row for it
+    unsigned int* err;                 // bit 0: a producer never showed up (the host turns it into an error)
+    int n;
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// consumer side: returns the buffer that holds epoch `want`
+__device__ __forceinline__ const double* ghost_acquire(const GhostIn& gi, long long want, int lane) {
+    if (lane < gi.n) {
+        unsigned long long spins = 0;
+        while ((long long)ld_acquire_sys(gi.flags + lane) < want) {
+            if (++spins > (1ull << 25)) { atomicOr(gi.err, 1u); break; }      // ~10 s: a peer died; fail, do not hang
+            if (spins > 64) __nanosleep(32);
+        }
+    }
+    __syncwarp();
+    return gi.vec + ((want & 1) ? gi.stride : 0u);
+}
+// producer side, per row of a warp tile (all 32 lanes call it; `owner` lanes carry a value)
+__device__ __forceinline__ void ghost_publish(const GhostOut& go, long long epoch, int tile, int lane, bool owner, int row, double v) {
+    const unsigned mk = owner ? (unsigned)go.mask[row] : 0u;
+    const int mybase = lane < go.n ? go.base[(size_t)tile * 8 + lane] : 0;
+    const unsigned lower = (1u << lane) - 1u;
+    const bool odd = (epoch & 1) != 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r < go.n) {
+            const bool send = (mk >> r) & 1u;
+            const unsigned b = __ballot_sync(0xffffffffu, send);
+            const int br = __shfl_sync(0xffffffffu, mybase, r);
+            if (send) go.buf[r][(odd ? go.stride[r] : 0u) + (uint32_t)br + __popc(b & lower)] = v;
+        }
+    }
+}
+__device__ __forceinline__ void ghost_release(const GhostOut& go, long long epoch) {
+    __threadfence_system();                       // this thread's peer stores are visible system-wide ...
+    __syncthreads();                              // ... for every thread of the CTA
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(go.done, 1u);
+        if (old == gridDim.x - 1) {               // every CTA has passed its fence
+            *go.done = 0u;
+            __threadfence_system();
+            for (int r = 0; r < go.n; ++r) st_release_sys(go.flag[r] + go.rank, (unsigned long long)epoch);
+        }
+    }
+}
 
 // primal half of T(z) + reflection + Halpern combine.  g = (A'y)_j
-template <bool CHECK>
+// GHOST (multi-GPU plain iterations): gathers y from this rank's ghost vector and publishes x-bar into the peers'.
+template <bool CHECK, bool GHOST = false>
 struct PrimalEpi {
     static constexpr int NIN = CHECK ? 4 : 5;
     static constexpr bool SCATTER = false;
+    static constexpr bool DIST = GHOST;
     double* scat;
     const double* __restrict__ c;
     const double* __restrict__ l;
@@ -84,7 +152,8 @@ struct PrimalEpi {
     double* __restrict__ xp;
     const PdlpParams* __restrict__ P;
     int it;
-    PeerOut peers;
+    GhostIn gin;        // y ghost (consumed)
+    GhostOut gout;      // x-bar ghosts (produced)
     struct Pre { double x, c, l, u, x0; };
     __device__ __forceinline__ const double* in(int i) const {
         return i == 0 ? x : i == 1 ? c : i == 2 ? l : i == 3 ? u : x0;
@@ -105,14 +174,7 @@ struct PrimalEpi {
         const double tau = P->tau;
         const double xpj = fmin(fmax(p.x - tau * (p.c - g), p.l), p.u);
         const double xb = 2.0 * xpj - p.x;
-        if (!CHECK && peers.n > 0) {
-            const unsigned mk = peers.mask ? peers.mask[j] : 0xffu;
-#pragma unroll 8
-            for (int r = 0; r < peers.n; ++r)
-                if ((mk >> r) & 1u) peers.p[r][j] = xb;
-        } else {
-            st_out(xbar + j, xb, h, true);
-        }
+        if (!GHOST) st_out(xbar + j, xb, h, true);
         if (CHECK) {
             xp[j] = xpj;
         } else {
@@ -120,16 +182,24 @@ struct PrimalEpi {
             const double w = (k + 1.0) / (k + 2.0);
             st_out(x + j, w * xb + (1.0 - w) * p.x0, h, false);
         }
-        return 0.0;
+        return GHOST ? xb : 0.0;
     }
+    // y of the previous iteration carries epoch_base + it; this launch produces epoch_base + it + 1
+    __device__ __forceinline__ const double* acquire(int lane) const { return ghost_acquire(gin, P->epoch_base + it, lane); }
+    __device__ __forceinline__ void publish(int tile, int lane, bool owner, int row, double v) const {
+        ghost_publish(gout, P->epoch_base + it + 1, tile, lane, owner, row, v);
+    }
+    __device__ __forceinline__ void release() const { ghost_release(gout, P->epoch_base + it + 1); }
 };
 
 // dual half.  ax = (A xbar)_i.  SCAT: the kernel then adds val[k] * y_new_i into scat[idx[k]] over the entries of row i,
 // i.e. it leaves g = A'y_new behind for the next (gather-free) primal update.
-template <bool CHECK, bool SCAT = false>
+// GHOST (multi-GPU plain iterations): gathers x-bar from this rank's ghost vector and publishes y into the peers'.
+template <bool CHECK, bool SCAT = false, bool GHOST = false>
 struct DualEpi {
     static constexpr int NIN = CHECK ? 3 : 4;
     static constexpr bool SCATTER = SCAT;
+    static constexpr bool DIST = GHOST;
     double* scat;
     const double* __restrict__ lc;
     const double* __restrict__ uc;
@@ -139,7 +209,8 @@ struct DualEpi {
     double* __restrict__ axbar;
     const PdlpParams* __restrict__ P;
     int it;
-    PeerOut peers;
+    GhostIn gin;        // x-bar ghost (consumed)
+    GhostOut gout;      // y ghosts (produced)
     struct Pre { double y, lc, uc, y0; };
     __device__ __forceinline__ const double* in(int i) const { return i == 0 ? y : i == 1 ? lc : i == 2 ? uc : y0; }
     __device__ __forceinline__ Pre preload(const double* s, int rt, int g) const {
@@ -167,18 +238,17 @@ struct DualEpi {
             const double k = (double)(P->k_base + it);
             const double w = (k + 1.0) / (k + 2.0);
             const double yn = w * (2.0 * ypi - p.y) + (1.0 - w) * p.y0;
-            if (peers.n > 0) {
-                const unsigned mk = peers.mask ? peers.mask[i] : 0xffu;
-#pragma unroll 8
-                for (int r = 0; r < peers.n; ++r)
-                    if ((mk >> r) & 1u) peers.p[r][i] = yn;
-            } else {
-                st_out(y + i, yn, h, true);
-            }
+            st_out(y + i, yn, h, !GHOST);       // with ghosts nobody gathers from the home block
             return yn;
         }
         return 0.0;
     }
+    // the x-bar of this same iteration carries epoch_base + it + 1, and so does the y this launch produces
+    __device__ __forceinline__ const double* acquire(int lane) const { return ghost_acquire(gin, P->epoch_base + it + 1, lane); }
+    __device__ __forceinline__ void publish(int tile, int lane, bool owner, int row, double v) const {
+        ghost_publish(gout, P->epoch_base + it + 1, tile, lane, owner, row, v);
+    }
+    __device__ __forceinline__ void release() const { ghost_release(gout, P->epoch_base + it + 1); }
 };
 
 // Gather-free primal update of the scatter formulation: g = A'y was accumulated by the previous dual kernel.
@@ -366,7 +436,8 @@ k_final_reduce(const double* __restrict__ partials, int nblocks, double* __restr
 }
 
 // row-side check sums.  acc: 0 pres^2 (unscaled), 1 dy.(A dx), 2 |dy|^2, 3 |yp-y0|^2, 4 dual obj (rows),
-//                            5 |b|^2 helper unused, 6 ray: |yp - y0|_inf proxy unused, 7 unused
+//                            5 yp.(A xp - proj): objective error the primal residual can hide, 6 unused,
+//                            7 reserved (multi-GPU: wall-clock agreement)
 __global__ void __launch_bounds__(RED_THREADS)
 k_check_rows(int m, const double* __restrict__ axp, const double* __restrict__ axbar, const double* __restrict__ y,
              const double* __restrict__ yp, const double* __restrict__ y0, const double* __restrict__ lc,
@@ -374,8 +445,10 @@ k_check_rows(int m, const double* __restrict__ axp, const double* __restrict__ a
     double acc[NACC] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < m; i += gridDim.x * RED_THREADS) {
         const double a = axp[i], lo = lc[i], hi = uc[i];
-        const double viol = (a - fmin(fmax(a, lo), hi)) / dr[i];
+        const double off = a - fmin(fmax(a, lo), hi);
+        const double viol = off / dr[i];
         const double ypi = yp[i];
+        acc[5] += ypi * off;                       // first-order effect of the primal infeasibility on the objective (scale-invariant)
         const double dy = ypi - y[i];
         const double d0 = ypi - y0[i];
         acc[0] += viol * viol;
@@ -387,7 +460,8 @@ k_check_rows(int m, const double* __restrict__ axp, const double* __restrict__ a
     block_reduce_store(acc, partials);
 }
 
-// column-side check sums.  acc: 0 dres^2 (unscaled), 1 |dx|^2, 2 |xp-x0|^2, 3 c'xp, 4 dual obj (bounds)
+// column-side check sums.  acc: 0 dres^2 (unscaled), 1 |dx|^2, 2 |xp-x0|^2, 3 c'xp, 4 dual obj (bounds),
+//                               5 xp.(dual residual): objective error the dual residual can hide
 __global__ void __launch_bounds__(RED_THREADS)
 k_check_cols(int n, const double* __restrict__ g, const double* __restrict__ c, const double* __restrict__ l,
              const double* __restrict__ u, const double* __restrict__ x, const double* __restrict__ xp,
@@ -407,6 +481,7 @@ k_check_cols(int n, const double* __restrict__ g, const double* __restrict__ c, 
         acc[2] += d0 * d0;
         acc[3] += c[j] * xpj;
         acc[4] += (at_lo ? rpos * lj : 0.0) + (at_hi ? rneg * uj : 0.0);
+        acc[5] += ((at_lo ? 0.0 : rpos) + (at_hi ? 0.0 : rneg)) * xpj;   // the same for the dual infeasibility
     }
     block_reduce_store(acc, partials);
 }
@@ -533,58 +608,49 @@ void launch_diff(int n, const double* a, const double* b, double* out, cudaStrea
     if (n > 0) ELP_LAUNCH(k_diff, ceil_div(n, 256), 256, 0, st, n, a, b, out);
 }
 
-// ---- cross-GPU hand-off of the blocks written by peer stores ------------------------------------------------
-// Every rank runs the same sequence of (signal, wait) pairs; the epoch lives in device memory so the pair can be
-// replayed from a CUDA graph.  signal: runs after the producing kernel in stream order (its peer stores are complete),
-// bumps this rank's epoch and publishes it in slot `rank` of every peer's flag row.  wait: spins (bounded) until all
-// N slots of the local flag row have reached the local expectation.
-struct PeerFlags {
-    unsigned long long* row[8];   // row[r]: rank r's flag row (N slots), mapped into this process
-};
-__global__ void k_peer_signal(PeerFlags f, int nranks, int rank, unsigned long long* __restrict__ epoch) {
-    if (threadIdx.x == 0) { *epoch += 1ull; __threadfence_system(); }
-    __syncthreads();
-    const unsigned long long e = *epoch;
-    if ((int)threadIdx.x < nranks) {
-        volatile unsigned long long* dst = f.row[threadIdx.x] + rank;
-        *dst = e;
-    }
-    __threadfence_system();
-}
-__global__ void k_peer_wait(const unsigned long long* __restrict__ my_row, int nranks, unsigned long long* __restrict__ expect) {
-    __shared__ unsigned long long want;
-    if (threadIdx.x == 0) { *expect += 1ull; want = *expect; }
-    __syncthreads();
-    if ((int)threadIdx.x < nranks) {
-        const volatile unsigned long long* src = my_row + threadIdx.x;
-        unsigned long long spins = 0;
-        while (*src < want) {
-            if (++spins > (1ull << 28)) __trap();           // ~30 s: a peer died — fail instead of hanging the GPU
-            __nanosleep(64);
-        }
-    }
-    __threadfence_system();
-}
-
-// ---- which entries of the gathered vectors does each rank read? (sparse peer exchange) ------------------------
+// ---- setup of the ghost exchange (multi-GPU) -----------------------------------------------------------------
 __global__ void k_mark_used(uint32_t nnz, const int* __restrict__ idx, unsigned char* __restrict__ used) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) used[idx[i]] = 1;                       // same value from every writer
 }
-// mask[j] = sum over ranks r of used_r[first + j] << r, own bit always set (the local kernels read the local copy)
-__global__ void k_build_mask(int count, int first, size_t stride, int nranks, int rank, const unsigned char* __restrict__ used_all,
+__global__ void k_marks_to_u32(uint32_t count, const unsigned char* __restrict__ used, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= count) out[i] = i < count ? (used[i] ? 1u : 0u) : 0u;     // one extra slot: the scan leaves the total there
+}
+// compact ids of my matrix copy: position of every referenced global id in my ghost vector
+__global__ void k_remap_idx(uint32_t nnz, const int* __restrict__ idx, const uint32_t* __restrict__ pos, int* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) out[i] = (int)pos[idx[i]];
+}
+// base[tile][r] = position, in rank r's ghost vector, of the first entry of my tile (pos = scan of r's marks)
+__global__ void k_tile_base(int ntiles, int rw, int first, const uint32_t* __restrict__ pos, int r, int* __restrict__ base) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles) base[(size_t)t * 8 + r] = (int)pos[first + t * rw];
+}
+__global__ void k_ghost_list(uint32_t count, const unsigned char* __restrict__ used, const uint32_t* __restrict__ pos, int* __restrict__ list) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && used[i]) list[pos[i]] = (int)i;
+}
+// mask[j] bit r: rank r gathers entry first + j
+__global__ void k_ghost_mask(int count, int first, size_t stride, int nranks, const unsigned char* __restrict__ used_all,
                              unsigned char* __restrict__ mask, unsigned long long* __restrict__ sent) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
-    unsigned mk = 1u << rank;
+    unsigned mk = 0;
     for (int r = 0; r < nranks; ++r) mk |= (used_all[(size_t)r * stride + first + j] ? 1u : 0u) << r;
     mask[j] = (unsigned char)mk;
-    atomicAdd(sent, (unsigned long long)(__popc(mk) - 1));
-    if ((j & 3) == 0) {          // the same count per 32-byte line (4 entries): what the links actually carry
-        unsigned line = mk;
-        for (int q = 1; q < 4 && j + q < count; ++q)
-            for (int r = 0; r < nranks; ++r) line |= (used_all[(size_t)r * stride + first + j + q] ? 1u : 0u) << r;
-        atomicAdd(sent + 2, (unsigned long long)(__popc(line | (1u << rank)) - 1));
+    atomicAdd(sent, (unsigned long long)__popc(mk));
+}
+// ghost[k] = full[list[k]]  (after a collective refreshed the full-layout vector)
+__global__ void k_compact(int count, const int* __restrict__ list, const double* __restrict__ full, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) out[k] = full[list[k]];
+}
+
+__global__ void k_ghost_signal_only(GhostOut go, const PdlpParams* __restrict__ P, int it) {
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int r = 0; r < go.n; ++r) st_release_sys(go.flag[r] + go.rank, (unsigned long long)(P->epoch_base + it + 1));
     }
 }
 
@@ -662,11 +728,17 @@ struct Pdlp {
     // peer-store exchange (N > 1, CUDA IPC): every rank's xbar_full / y_full / flag rows mapped here
     bool scatter = false;        // plain iterations: g = A'y accumulated by the dual kernel's scatter (single GPU only)
     SpmvPlan plan_s;             // tile plan of the scatter kernel (CSR rows)
-    bool p2p = false;
-    PeerOut x_out{}, y_out{};            // peers' xbar_full + n0, y_full + rank*mb
-    PeerFlags xflags{}, yflags{};
-    DevBuf<unsigned long long> flags;    // [2][8] flag rows (x, y) + [4] epochs/expectations
-    DevBuf<unsigned char> xmask, ymask;  // sparse exchange: which ranks gather entry j of my x-bar / y block
+    // ghost exchange (N > 1): compact ghost vectors filled by the peers' kernels, see GhostOut / GhostIn
+    bool ghost = false;
+    DevBuf<int> csr_idx_g, csc_idx_g;    // the matrix copies' ids in the compact numbering of my ghost vectors
+    DevBuf<unsigned char> xmask, ymask;  // which ranks gather entry j of my x-bar / y block
+    DevBuf<int> xbase, ybase;            // [tiles][8] base positions in the consumers' ghost vectors
+    DevBuf<int> ylist;                   // global (padded) ids of my y ghost entries, ascending
+    DevBuf<unsigned char> ghost_mem;     // flag rows, error word, CTA counters, x-bar ghost x2, y ghost x2 (mapped by the peers)
+    int gx = 0, gy = 0;                  // entries of my ghost vectors
+    GhostIn xin{}, yin{};
+    GhostOut xout{}, yout{};
+    long long epoch_base = 0;            // never reset: the flag rows only grow
     double exch_frac_x = 1.0, exch_frac_y = 1.0;   // fraction of the dense (N-1)-copy exchange that is actually sent
     std::vector<void*> ipc_opened;
     DevBuf<double> partials, scal;                              // scal: 2*NACC
@@ -676,11 +748,16 @@ struct Pdlp {
     int k = 0, total = 0, restarts = 0;
     double fpe0 = -1.0, fpe_prev = -1.0;
     double beta_artificial = 0.36;   // artificial restart once the epoch is this fraction of all iterations so far
+    double w_kp = 0.5, w_ki = 0.0, w_kd = 0.0, w_ismooth = 0.3, w_err_sum = 0.0, w_err_prev = 0.0;   // primal-weight controller
+    int gap_rule = 0;                // 0: PDLP's gap test at eps/4; 1: gap + residual-induced objective error bound <= gap_factor * eps
+    double gap_factor = 1.0, obj_err = 0.0;
     bool need_fpe0 = true;
     int status = ELP_STATUS_TIMEOUT;
     bool finished = false;
     double pobj = 0, dobj = 0, rel_pres = 0, rel_dres = 0, rel_gap = 0;
     int checks = 0;
+    WallTimer run_clock;             // started by the first run() after a reset: lp.control(timeout=) covers the whole solve
+    bool clock_running = false, time_up = false, hit_time_limit = false;
     // graph of one chunk of (check_every-1) plain iterations
     cudaGraphExec_t graph = nullptr;
     int graph_len = 0;
@@ -693,101 +770,153 @@ struct Pdlp {
         if (st) cudaStreamDestroy(st);
     }
 
-    // Maps every rank's gathered buffers into this process (CUDA IPC) so that the iteration kernels can store their
-    // block straight into all copies over NVLink.  Falls back to the NCCL all-gather when IPC is not available.
-    void setup_peer_stores() {
-        p2p = false;
+    // Builds the ghost exchange: which entries every rank gathers, their compact numbering, the producers' masks and
+    // tile bases, and the peer mappings (same process: peer access; other processes: CUDA IPC).  Falls back to NCCL
+    // all-gathers of the full vectors when the GPUs cannot reach each other's memory (or ELP_PDLP_P2P=0).
+    static constexpr size_t GH_FLAGS_BYTES = 512;      // x flags [0,64) y flags [64,128) err 128 done-x 136 done-y 140
+    void setup_ghost_exchange() {
+        ghost = false;
         if (N <= 1 || N > 8 || env_int("ELP_PDLP_P2P", 1) == 0) return;
-        flags.alloc(2 * 8 + 4);
-        flags.zero(st);
+        Arena* const keep = arena.base ? &arena : nullptr;
+        ArenaScope tmp(scratch.base ? &scratch : nullptr);        // temporaries; what the handle keeps goes to `keep` below
+        const size_t sx = (size_t)N * nb, sy = (size_t)N * mb;
+        // ---- 1. who reads what -----------------------------------------------------------------------------------
+        DevBuf<unsigned char> used_x((size_t)N * sx), used_y((size_t)N * sy);
+        used_x.zero(st); used_y.zero(st);
+        if (nnz > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnz, 256), 256, 0, st, (uint32_t)nnz, csr_idx.p, used_x.p + (size_t)rank * sx);
+        if (nnzc > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnzc, 256), 256, 0, st, (uint32_t)nnzc, csc_idx.p, used_y.p + (size_t)rank * sy);
+        comm_allgather_bytes(used_x.p, sx, st);
+        comm_allgather_bytes(used_y.p, sy, st);
+        // ---- 2. compact numbering per consumer; my ids, my lists, the tile bases of what I produce -----------------
+        ELP_REQUIRE(plan_c.rpl == 1 && plan_r.rpl == 1, "pdlp: two rows per lane is a single-GPU option");
+        {
+            ArenaScope k(keep);
+            csr_idx_g.alloc(nnz + SPMV_PAD); csc_idx_g.alloc(nnzc + SPMV_PAD);
+            xbase.alloc((size_t)std::max(plan_c.ntiles, 1) * 8); ybase.alloc((size_t)std::max(plan_r.ntiles, 1) * 8);
+            xmask.alloc((size_t)std::max(nl, 1)); ymask.alloc((size_t)std::max(m, 1));
+            ylist.alloc(sy);                                       // at most every padded row
+        }
+        csr_idx_g.zero(st); csc_idx_g.zero(st);
+        xbase.zero(st); ybase.zero(st);
+        DevBuf<uint32_t> pos(std::max(sx, sy) + 1);
+        ScanWorkspace sw;
+        std::vector<uint32_t> gxs(N), gys(N);
+        for (int r = 0; r < N; ++r) {
+            ELP_LAUNCH(k_marks_to_u32, ceil_div((int64_t)sx + 1, 256), 256, 0, st, (uint32_t)sx, used_x.p + (size_t)r * sx, pos.p);
+            exclusive_scan_u32(pos.p, sx + 1, sw, st);
+            ELP_CUDA(cudaMemcpyAsync(&gxs[r], pos.p + sx, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            if (r == rank && nnz > 0) ELP_LAUNCH(k_remap_idx, ceil_div(nnz, 256), 256, 0, st, (uint32_t)nnz, csr_idx.p, pos.p, csr_idx_g.p);
+            if (nl > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_c.ntiles, 256), 256, 0, st, plan_c.ntiles, plan_c.rw(), n0, pos.p, r, xbase.p);
+            ELP_CUDA(cudaStreamSynchronize(st));
+        }
+        for (int r = 0; r < N; ++r) {
+            ELP_LAUNCH(k_marks_to_u32, ceil_div((int64_t)sy + 1, 256), 256, 0, st, (uint32_t)sy, used_y.p + (size_t)r * sy, pos.p);
+            exclusive_scan_u32(pos.p, sy + 1, sw, st);
+            ELP_CUDA(cudaMemcpyAsync(&gys[r], pos.p + sy, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            if (r == rank) {
+                if (nnzc > 0) ELP_LAUNCH(k_remap_idx, ceil_div(nnzc, 256), 256, 0, st, (uint32_t)nnzc, csc_idx.p, pos.p, csc_idx_g.p);
+                ELP_LAUNCH(k_ghost_list, ceil_div((int64_t)sy, 256), 256, 0, st, (uint32_t)sy, used_y.p + (size_t)r * sy, pos.p, ylist.p);
+            }
+            if (m > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_r.ntiles, 256), 256, 0, st, plan_r.ntiles, plan_r.rw(), rank * mb, pos.p, r, ybase.p);
+            ELP_CUDA(cudaStreamSynchronize(st));
+        }
+        gx = (int)gxs[rank]; gy = (int)gys[rank];
+        // ---- 3. masks of what I produce -----------------------------------------------------------------------------
+        DevBuf<unsigned long long> sent(2);
+        sent.zero(st);
+        if (nl > 0) ELP_LAUNCH(k_ghost_mask, grid1(nl), 256, 0, st, nl, n0, sx, N, used_x.p, xmask.p, sent.p);
+        if (m > 0) ELP_LAUNCH(k_ghost_mask, grid1(m), 256, 0, st, m, rank * mb, sy, N, used_y.p, ymask.p, sent.p + 1);
+        unsigned long long h[2] = {0, 0};
+        ELP_CUDA(cudaMemcpyAsync(h, sent.p, sizeof h, cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
-        struct Handles { cudaIpcMemHandle_t x, y, f; };
-        static_assert(sizeof(Handles) % 8 == 0, "handle block must be a multiple of 8 bytes");
-        std::vector<Handles> all(N);
-        int ok = 1;
-        if (cudaIpcGetMemHandle(&all[rank].x, xbar_full.p) != cudaSuccess) ok = 0;
-        if (cudaIpcGetMemHandle(&all[rank].y, y_full.p) != cudaSuccess) ok = 0;
-        if (cudaIpcGetMemHandle(&all[rank].f, flags.p) != cudaSuccess) ok = 0;
+        exch_frac_x = nl > 0 ? (double)h[0] / ((double)nl * N) : 1.0;
+        exch_frac_y = m > 0 ? (double)h[1] / ((double)m * N) : 1.0;
+        // ---- 4. my ghost memory, mapped by everybody -------------------------------------------------------------------
+        auto padded = [](uint32_t g) { return (uint32_t)((g + SPMV_VPAD + 31) & ~31u); };
+        auto bytes_of = [&](int r) { return GH_FLAGS_BYTES + (size_t)8 * 2 * ((size_t)padded(gxs[r]) + padded(gys[r])); };
+        {
+            ArenaScope own(nullptr);                                // mapped by the peers: its own allocation
+            ghost_mem.alloc(bytes_of(rank));
+        }
+        ghost_mem.zero(st);
+        ELP_CUDA(cudaStreamSynchronize(st));
+        struct PeerInfo { cudaIpcMemHandle_t h; unsigned long long ptr; long long pid; long long dev; };
+        static_assert(sizeof(PeerInfo) % 8 == 0, "peer record must be a multiple of 8 bytes");
+        std::vector<PeerInfo> all(N);
+        int ok = 1, dev = 0;
+        ELP_CUDA(cudaGetDevice(&dev));
+        memset(&all[rank], 0, sizeof(PeerInfo));
+        all[rank].ptr = (unsigned long long)(uintptr_t)ghost_mem.p;
+        all[rank].pid = (long long)getpid();
+        all[rank].dev = dev;
+        if (cudaIpcGetMemHandle(&all[rank].h, ghost_mem.p) != cudaSuccess) memset(&all[rank].h, 0, sizeof all[rank].h);
         cudaGetLastError();
-        DevBuf<unsigned char> hbuf((size_t)N * sizeof(Handles));
-        ELP_CUDA(cudaMemcpyAsync(hbuf.p + (size_t)rank * sizeof(Handles), &all[rank], sizeof(Handles), cudaMemcpyHostToDevice, st));
-        comm_allgather_bytes(hbuf.p, sizeof(Handles), st);
-        ELP_CUDA(cudaMemcpyAsync(all.data(), hbuf.p, (size_t)N * sizeof(Handles), cudaMemcpyDeviceToHost, st));
+        DevBuf<unsigned char> hbuf((size_t)N * sizeof(PeerInfo));
+        ELP_CUDA(cudaMemcpyAsync(hbuf.p + (size_t)rank * sizeof(PeerInfo), &all[rank], sizeof(PeerInfo), cudaMemcpyHostToDevice, st));
+        comm_allgather_bytes(hbuf.p, sizeof(PeerInfo), st);
+        ELP_CUDA(cudaMemcpyAsync(all.data(), hbuf.p, (size_t)N * sizeof(PeerInfo), cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
-        std::vector<double*> xs(N), ys(N);
-        std::vector<unsigned long long*> fs(N);
+        std::vector<unsigned char*> base(N, nullptr);
         for (int r = 0; r < N && ok; ++r) {
-            if (r == rank) { xs[r] = xbar_full.p; ys[r] = y_full.p; fs[r] = flags.p; continue; }
-            void *px = nullptr, *py = nullptr, *pf = nullptr;
-            if (cudaIpcOpenMemHandle(&px, all[r].x, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
-            ipc_opened.push_back(px);
-            if (cudaIpcOpenMemHandle(&py, all[r].y, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
-            ipc_opened.push_back(py);
-            if (cudaIpcOpenMemHandle(&pf, all[r].f, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
-            ipc_opened.push_back(pf);
-            xs[r] = (double*)px; ys[r] = (double*)py; fs[r] = (unsigned long long*)pf;
+            if (r == rank) { base[r] = ghost_mem.p; continue; }
+            if (all[r].pid == all[rank].pid) {                 // a thread of this process drives that GPU: plain peer access
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, dev, (int)all[r].dev) != cudaSuccess || !can) { ok = 0; break; }
+                const cudaError_t e = cudaDeviceEnablePeerAccess((int)all[r].dev, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; break; }
+                base[r] = (unsigned char*)(uintptr_t)all[r].ptr;
+            } else {
+                void* q = nullptr;
+                if (cudaIpcOpenMemHandle(&q, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+                ipc_opened.push_back(q);
+                base[r] = (unsigned char*)q;
+            }
         }
         cudaGetLastError();
-        // everyone or no one
-        double okd = (double)ok;
+        double okd = (double)ok;                                 // everyone or no one
         ELP_CUDA(cudaMemcpyAsync(scal.p, &okd, sizeof okd, cudaMemcpyHostToDevice, st));
         comm_allreduce_sum(scal.p, 1, st);
         ELP_CUDA(cudaMemcpyAsync(&okd, scal.p, sizeof okd, cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
         if ((int)okd != N) {
-            if (opt.verbose > 0 && rank == 0) fprintf(stderr, "[pdlp] CUDA IPC unavailable: NCCL all-gather exchange\n");
+            if (opt.verbose > 0 && rank == 0) fprintf(stderr, "[pdlp] no peer access between the GPUs: NCCL all-gather exchange\n");
             return;
         }
-        x_out.n = y_out.n = N;
-        x_out.mask = y_out.mask = nullptr;
+        xout = GhostOut{}; yout = GhostOut{};
+        xout.n = yout.n = N; xout.rank = yout.rank = rank;
+        xout.mask = xmask.p; yout.mask = ymask.p;
+        xout.base = xbase.p; yout.base = ybase.p;
+        xout.done = reinterpret_cast<unsigned int*>(ghost_mem.p + 136);
+        yout.done = reinterpret_cast<unsigned int*>(ghost_mem.p + 140);
         for (int r = 0; r < N; ++r) {
-            x_out.p[r] = xs[r] + n0;
-            y_out.p[r] = ys[r] + (size_t)rank * mb;
-            xflags.row[r] = fs[r];
-            yflags.row[r] = fs[r] + 8;
+            double* g0 = reinterpret_cast<double*>(base[r] + GH_FLAGS_BYTES);
+            xout.buf[r] = g0;                               xout.stride[r] = padded(gxs[r]);
+            yout.buf[r] = g0 + 2 * (size_t)padded(gxs[r]);  yout.stride[r] = padded(gys[r]);
+            xout.flag[r] = reinterpret_cast<unsigned long long*>(base[r]);
+            yout.flag[r] = reinterpret_cast<unsigned long long*>(base[r] + 64);
         }
-        p2p = true;
-        if (env_int("ELP_PDLP_SPARSE_EXCHANGE", 1)) build_exchange_masks();
-    }
-    // Every rank marks the columns its row block references (K2 gathers x-bar there) and the rows its column block
-    // references (K1 gathers y there); the marks are all-gathered and each rank keeps, for the entries it PRODUCES, the
-    // set of ranks that read them.  The epilogues then store an entry only into those ranks' copies.
-    void build_exchange_masks() {
-        const size_t sx = (size_t)N * nb, sy = (size_t)N * mb;
-        DevBuf<unsigned char> used_x((size_t)N * sx), used_y((size_t)N * sy);
-        DevBuf<unsigned long long> sent(4);      // entries x-bar, entries y, 32-byte lines (both), unused
-        used_x.zero(st); used_y.zero(st); sent.zero(st);
-        if (nnz > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnz, 256), 256, 0, st, (uint32_t)nnz, csr_idx.p, used_x.p + (size_t)rank * sx);
-        if (nnzc > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnzc, 256), 256, 0, st, (uint32_t)nnzc, csc_idx.p, used_y.p + (size_t)rank * sy);
-        comm_allgather_bytes(used_x.p, sx, st);
-        comm_allgather_bytes(used_y.p, sy, st);
-        xmask.alloc((size_t)std::max(nl, 1)); ymask.alloc((size_t)std::max(m, 1));
-        if (nl > 0) ELP_LAUNCH(k_build_mask, grid1(nl), 256, 0, st, nl, n0, sx, N, rank, used_x.p, xmask.p, sent.p);
-        if (m > 0) ELP_LAUNCH(k_build_mask, grid1(m), 256, 0, st, m, rank * mb, sy, N, rank, used_y.p, ymask.p, sent.p + 1);
-        // (k_build_mask adds its line count to sent[+2]: the y launch starts at sent + 1, so lines of y land in sent[3])
-        unsigned long long h[4] = {0, 0, 0, 0};
-        ELP_CUDA(cudaMemcpyAsync(h, sent.p, sizeof h, cudaMemcpyDeviceToHost, st));
-        ELP_CUDA(cudaStreamSynchronize(st));
-        exch_frac_x = nl > 0 ? (double)h[0] / ((double)nl * (N - 1)) : 1.0;
-        exch_frac_y = m > 0 ? (double)h[1] / ((double)m * (N - 1)) : 1.0;
-        // all ranks take the same decision.  The masks cost a byte load and a predicate per store, and the links move
-        // partial 32-byte lines as dearly as full ones, so the decision is taken on LINES kept: measured at N = 2, 60 %
-        // kept (C5) -> 4 % slower, 92-100 % (C4) -> 3 % slower; at N = 8, 23 % kept in long runs (C5) -> 1.9x faster.
-        // A random matrix keeps 1 - exp(-nnz_local / n) of the entries (C4 at N = 8: 46 %) but 91 % of the lines.
-        double tot[4] = {(double)h[2] + (double)h[3], ((double)((nl + 3) / 4) + (double)((m + 3) / 4)) * (N - 1), 0, 0};
-        ELP_CUDA(cudaMemcpyAsync(scal.p, tot, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-        comm_allreduce_sum(scal.p, 2, st);
-        ELP_CUDA(cudaMemcpyAsync(tot, scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        ELP_CUDA(cudaStreamSynchronize(st));
-        const double kept = tot[1] > 0 ? tot[0] / tot[1] : 1.0;
-        const bool use = env_int("ELP_PDLP_SPARSE_EXCHANGE", 1) == 2 || kept < 0.50;
-        if (use) {
-            x_out.mask = xmask.p;
-            y_out.mask = ymask.p;
-        }
+        unsigned int* err = reinterpret_cast<unsigned int*>(ghost_mem.p + 128);
+        xin = GhostIn{xout.buf[rank], xout.stride[rank], xout.flag[rank], err, N};
+        yin = GhostIn{yout.buf[rank], yout.stride[rank], yout.flag[rank], err, N};
+        ghost = true;
         if (opt.verbose > 0 || env_int("ELP_PDLP_DEBUG", 0))
-            fprintf(stderr, "[pdlp] rank %d sparse exchange: x-bar %.1f %%, y %.1f %% of the dense peer stores; 32-byte lines, all ranks %.1f %% -> %s\n",
-                    rank, 100.0 * exch_frac_x, 100.0 * exch_frac_y, 100.0 * kept, use ? "masked stores" : "dense stores");
+            fprintf(stderr, "[pdlp] rank %d ghost exchange: gathers %d of %d x-bar entries and %d of %d y entries; sends %.1f %% / %.1f %% of a dense all-gather (%s)\n",
+                    rank, gx, n, gy, N * mb, 100.0 * exch_frac_x, 100.0 * exch_frac_y,
+                    ipc_opened.empty() ? "peer access" : "CUDA IPC");
+    }
+    // y changed outside the plain iterations (reset, restart, Halpern finish): every rank gets the new blocks through
+    // one all-gather and rebuilds the ghost buffer the next plain iteration reads (parity of epoch_base)
+    void refresh_y() {
+        gather_y(y_full.p);
+        if (ghost && gy > 0)
+            ELP_LAUNCH(k_compact, grid1(gy), 256, 0, st, gy, ylist.p, y_full.p, const_cast<double*>(yin.vec) + ((epoch_base & 1) ? yin.stride : 0u));
+    }
+    void check_device_error() {          // a consumer gave up waiting for a peer: report, do not hang or trap
+        if (!ghost) return;
+        unsigned int e = 0;
+        ELP_CUDA(cudaMemcpyAsync(&e, ghost_mem.p + 128, sizeof e, cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        ELP_REQUIRE(e == 0, "pdlp: rank %d timed out waiting for a peer GPU's block (exchange flag never arrived)", rank);
     }
     void barrier_stream() {              // all ranks have finished everything they queued before this point
         if (N > 1) comm_allreduce_sum(scal.p + NACC, 1, st);
@@ -879,9 +1008,24 @@ struct Pdlp {
         ELP_REQUIRE(m >= 0 && n > 0, "pdlp: bad shape %d x %d", m, n);
         nnz = nnz_device >= 0 ? nnz_device : (m > 0 ? row_ptr[m] : 0);
         ELP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        if (N == 1 && env_int("ELP_PDLP_ARENA", 1)) {   // (peer-mapped buffers of the distributed path need their own allocations)
+        if (N == 1 && env_int("ELP_PDLP_ARENA", 1)) {
             arena.reserve((size_t)24 * nnz + (size_t)4 * (m + n) + (size_t)8 * ((size_t)10 * n + (size_t)9 * m) + (2u << 20));
             scratch.reserve((size_t)52 * nnz + (size_t)16 * ((size_t)n + m) + (8u << 20));
+        } else if (N > 1 && env_int("ELP_PDLP_ARENA", 1)) {
+            // Distributed: the same two arenas, sized from what this rank knows (its row block; the column block is
+            // taken as 1.3 x as many entries — row blocks are balanced by non-zeros — and anything beyond falls back to
+            // cudaMalloc).  Besides the milliseconds, this keeps cudaMalloc / cudaFree — which synchronise the device
+            // and serialise on process-wide locks — out of the stretches between two collectives when the ranks are
+            // threads of ONE process (elp_solve_lp(devices = N)): a rank stuck in cudaFree behind a collective whose
+            // peer is stuck in cudaMalloc before launching its half would never return.  Only the ghost memory that
+            // the peers map keeps its own allocation.
+            const size_t nbg = (size_t)((ceil_div(n, N) + 3) & ~3), sxg = (size_t)N * nbg;
+            const size_t mbg = (size_t)m + m / 8 + 64, syg = (size_t)N * mbg;          // padded rows per rank: a guess
+            const size_t nnzc_g = (size_t)(1.3 * (double)nnz) + (1u << 20);
+            arena.reserve((size_t)16 * nnz + (size_t)16 * nnzc_g + (size_t)8 * (10 * nbg + 9 * (size_t)m) + (size_t)16 * (sxg + syg) +
+                          (size_t)2 * (nbg + m) + (size_t)4 * syg + (4u << 20));
+            scratch.reserve((size_t)52 * nnz + (size_t)12 * nnzc_g + (size_t)16 * ((size_t)n + m) + (size_t)N * (sxg + syg) +
+                            (size_t)8 * std::max(sxg, syg) + (size_t)16 * sxg + (16u << 20));
         }
         ArenaScope persistent(arena.base ? &arena : nullptr);
         partials.alloc((size_t)RED_BLOCKS * NACC); scal.alloc(2 * NACC); params.alloc(1);
@@ -955,6 +1099,12 @@ struct Pdlp {
             ELP_REQUIRE(!(mode == ELP_TRANSPOSE_SCATTER && N > 1), "pdlp: the scatter formulation is single-GPU only");
             scatter = N == 1 && mode == ELP_TRANSPOSE_SCATTER && m > 0;
             if (const char* e = getenv("ELP_PDLP_BETA_ART")) beta_artificial = atof(e);       // experiments
+            if (const char* e = getenv("ELP_PDLP_KP")) w_kp = atof(e);
+            if (const char* e = getenv("ELP_PDLP_KI")) w_ki = atof(e);
+            if (const char* e = getenv("ELP_PDLP_KD")) w_kd = atof(e);
+            if (const char* e = getenv("ELP_PDLP_ISMOOTH")) w_ismooth = atof(e);
+            if (const char* e = getenv("ELP_PDLP_GAP_RULE")) gap_rule = atoi(e);
+            if (const char* e = getenv("ELP_PDLP_GAP_FACTOR")) gap_factor = atof(e);
             plan_s = plan_spmv(nnz, m, 4, 0, env_int("ELP_SPMV_SCAT_STAGES", 2));
         }
 
@@ -981,7 +1131,7 @@ struct Pdlp {
         fetch_scalars(h);
         const double ncn = std::sqrt(h[0]);
         w_init = (nbn > 1e-10 && ncn > 1e-10) ? ncn / nbn : 1.0;
-        setup_peer_stores();
+        setup_ghost_exchange();
         reset();
         mark("reset");
         ELP_CUDA(cudaStreamSynchronize(st));
@@ -1070,6 +1220,7 @@ struct Pdlp {
         for (int r = 0; r < N; ++r) exclusive_scan_u32(srcptr.p + (size_t)r * nb, (size_t)nb, sw, st);
         roff_d.upload(roff.data(), N + 1, st);
         nnzc = total_in;
+        ArenaScope keep(arena.base ? &arena : nullptr);
         csc_ptr.alloc((size_t)nb + 1 + SPMV_PTR_PAD); csc_idx.alloc(nnzc + SPMV_PAD); csc_val.alloc(nnzc + SPMV_PAD);
         csc_ptr.zero(st); csc_idx.zero(st); csc_val.zero(st);
         ELP_LAUNCH(k_merge_cols, ceil_div(nb + 1, 256), 256, 0, st, N, nb, lens_in.p, srcptr.p, newptr.p, roff_d.p,
@@ -1167,56 +1318,61 @@ struct Pdlp {
         y_full.zero(st); y0.zero(st); yp.zero(st); axbar.zero(st); axp.zero(st); xbar_full.zero(st);
         gcol.zero(st);                             // = A'y for y = 0 (scatter formulation)
         w = w_init; k = 0; total = 0; restarts = 0; fpe0 = -1; fpe_prev = -1; need_fpe0 = true;
+        w_err_sum = 0.0; w_err_prev = 0.0; obj_err = 0.0;
         status = ELP_STATUS_TIMEOUT; finished = false; checks = 0;
+        clock_running = false; time_up = false; hit_time_limit = false;
         push_params();
-        barrier_stream();          // nobody stores into a peer's copy before that peer has cleared it
+        if (ghost) refresh_y();    // (its all-gather also keeps any rank from running ahead into a peer that is still resetting)
+        else barrier_stream();
         ELP_CUDA(cudaStreamSynchronize(st));
     }
 
     void push_params() {
-        PdlpParams p{eta / w, eta * w, k, 0};
+        PdlpParams p{eta / w, eta * w, k, 0, epoch_base};
         // pageable source is copied to a staging buffer before the call returns, so a stack object is fine
         ELP_CUDA(cudaMemcpyAsync(params.p, &p, sizeof p, cudaMemcpyHostToDevice, st));
     }
 
     // ---- iteration pieces ------------------------------------------------------------------------
+    // multi-GPU, a rank without columns / rows still owes its consumers the epoch
+    void signal_only(const GhostOut& go, int it) {
+        ELP_LAUNCH(k_ghost_signal_only, 1, 32, 0, st, go, params.p, it);
+    }
     template <bool CHECK>
-    void primal_step(int it, bool exchange = true) {
+    void primal_step(int it) {
         if (!CHECK && scatter) {            // g = A'y is already in gcol (left there by the dual kernel's scatter)
             const int grid = std::max(1, std::min(ceil_div(nl / 2, 256), kNumSMs * 8));
             ELP_LAUNCH(k_primal_from_g, grid, 256, 0, st, nl, gcol.p, c.p, l.p, u.p, x0.p, x.p, xbar(), params.p, it);
             return;
         }
-        const bool direct = !CHECK && exchange && p2p;
-        PrimalEpi<CHECK> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, direct ? x_out : PeerOut{{}, 0, nullptr}};
-        launch_spmv(plan_c, nl, csc_ptr.p, csc_idx.p, csc_val.p, y_full.p, epi, st);
-        if (!exchange) return;
-        if (direct) {
-            ELP_LAUNCH(k_peer_signal, 1, 32, 0, st, xflags, N, rank, flags.p + 16);
-            ELP_LAUNCH(k_peer_wait, 1, 32, 0, st, flags.p, N, flags.p + 17);
-        } else {
-            gather_x(xbar_full.p);
+        if (!CHECK && ghost) {              // gathers y from my ghost vector, publishes x-bar into the consumers' ghost vectors
+            PrimalEpi<false, true> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, yin, xout};
+            if (nl > 0) launch_spmv(plan_c, nl, csc_ptr.p, csc_idx_g.p, csc_val.p, yin.vec, epi, st);
+            else signal_only(xout, it);
+            return;
         }
+        PrimalEpi<CHECK> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, GhostIn{}, GhostOut{}};
+        launch_spmv(plan_c, nl, csc_ptr.p, csc_idx.p, csc_val.p, y_full.p, epi, st);
+        gather_x(xbar_full.p);
     }
     template <bool CHECK>
-    void dual_step(int it, bool exchange = true) {
+    void dual_step(int it) {
         if (!CHECK && scatter) {            // A x-bar + dual update, then g += val * y_new over the row's entries
-            DualEpi<false, true> epi{gcol.p, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, PeerOut{{}, 0, nullptr}};
+            DualEpi<false, true> epi{gcol.p, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, GhostIn{}, GhostOut{}};
             launch_spmv(plan_s, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
             return;
         }
-        const bool direct = !CHECK && exchange && p2p;
-        DualEpi<CHECK> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, direct ? y_out : PeerOut{{}, 0, nullptr}};
-        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
-        if (!exchange || CHECK) return;                      // a check iteration does not change y here
-        if (direct) {
-            ELP_LAUNCH(k_peer_signal, 1, 32, 0, st, yflags, N, rank, flags.p + 18);
-            ELP_LAUNCH(k_peer_wait, 1, 32, 0, st, flags.p + 8, N, flags.p + 19);
-        } else {
-            gather_y(y_full.p);
+        if (!CHECK && ghost) {
+            DualEpi<false, false, true> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, xin, yout};
+            if (m > 0) launch_spmv(plan_r, m, csr_ptr.p, csr_idx_g.p, csr_val.p, xin.vec, epi, st);
+            else signal_only(yout, it);
+            return;
         }
+        DualEpi<CHECK> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, GhostIn{}, GhostOut{}};
+        launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
+        if (!CHECK) gather_y(y_full.p);                      // a check iteration does not change y here
     }
-    int kernels_per_iter() const { return (m > 0 ? 1 : 0) + (nl > 0 ? 1 : 0) + (p2p ? 4 : 0); }
+    int kernels_per_iter() const { return ghost ? 2 : (m > 0 ? 1 : 0) + (nl > 0 ? 1 : 0); }
 
     void plain_iterations(int count) {
         if (count <= 0) return;
@@ -1247,6 +1403,7 @@ struct Pdlp {
         }
         k += count;
         total += count;
+        if (ghost) epoch_base += count;
         push_params();
     }
 
@@ -1254,6 +1411,7 @@ struct Pdlp {
     // either restarts from T(z) or completes the Halpern step.  Returns true when the solve is over.
     bool check_iteration() {
         double h[2 * NACC];
+        if (ghost) gather_y(y_full.p);             // the plain iterations only kept the ghost vectors current
         primal_step<true>(0);                      // xbar (gathered), xp
         dual_step<true>(0);                        // yp, axbar; y unchanged
         // A xp on my rows (needs everyone's xp) and A' yp on my columns (needs everyone's yp)
@@ -1269,10 +1427,19 @@ struct Pdlp {
         ELP_LAUNCH(k_check_cols, RED_BLOCKS, RED_THREADS, 0, st, nl, gcol.p, c.p, l.p, u.p, x.p, xp.p, x0.p, dc.p,
                    partials.p);
         reduce_to(scal.p + NACC);
-        if (N > 1) comm_allreduce_sum(scal.p, 2 * NACC, st);       // the scalar residuals: ONE collective
+        if (N > 1) {
+            // slot 7 of the row sums is free: the ranks agree on a wall-clock exit through the same collective
+            const double over = (opt.time_limit_s > 0 && run_clock.ms() > opt.time_limit_s * 1e3) ? 1.0 : 0.0;
+            ELP_CUDA(cudaMemcpyAsync(scal.p + 7, &over, sizeof over, cudaMemcpyHostToDevice, st));
+            comm_allreduce_sum(scal.p, 2 * NACC, st);       // the scalar residuals: ONE collective
+        }
         ELP_CUDA(cudaMemcpyAsync(h, scal.p, 2 * NACC * sizeof(double), cudaMemcpyDeviceToHost, st));
+        unsigned int dev_err = 0;
+        if (ghost) ELP_CUDA(cudaMemcpyAsync(&dev_err, ghost_mem.p + 128, sizeof dev_err, cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
+        ELP_REQUIRE(dev_err == 0, "pdlp: rank %d timed out waiting for a peer GPU's block (exchange flag never arrived)", rank);
         d2h += 2 * NACC * sizeof(double);
+        time_up = N > 1 ? h[7] > 0.0 : (opt.time_limit_s > 0 && run_clock.ms() > opt.time_limit_s * 1e3);
         ++checks;
         const double* hr = h;
         const double* hc = h + NACC;
@@ -1293,9 +1460,17 @@ struct Pdlp {
         if (!std::isfinite(fpe) || !std::isfinite(pobj)) {
             status = ELP_STATUS_NUMFAILURE; finished = true; return true;
         }
-        // The gap is tested at eps/4: |p - d| <= (eps/4)(1 + |p| + |d|) keeps the objective within eps RELATIVE of
-        // the optimum (north_star: "objective within 1e-6 relative"); PDLP's plain gap test allows ~2 eps.
-        if (rel_pres <= eps && rel_dres <= eps && rel_gap <= 0.25 * eps) {
+        // The gap is tested at eps/4: |p - d| <= (eps/4)(1 + |p| + |d|); PDLP's plain gap test allows ~2 eps on the
+        // objective.  north_star asks for the OBJECTIVE within eps relative, which none of PDLP's three tests bounds: a
+        // primal residual of eps (1 + ||b||) can hide an objective error of up to ||y*|| times that.  obj_err adds the
+        // rigorous first-order bounds |yp.(A xp - proj)| and |xp.(dual residual)| (scale-invariant; two spare
+        // accumulators of the check kernels) and gap_rule = 1 (ELP_PDLP_GAP_RULE) tests that sum instead.  Measured
+        // (profiles/r2_gap_rule.md): the bound overestimates the true error 6-50x — the reduced-cost terms it ignores
+        // cancel most of it — and costs 3x (C4 at 50 k rows) to 23x (C4 full size) the iterations, so it is an option
+        // for callers who need a certificate, not the default.
+        obj_err = (std::fabs(pobj - dobj) + std::fabs(hr[5]) + std::fabs(hc[5])) / (1.0 + std::fabs(pobj) + std::fabs(dobj));
+        const bool gap_ok = gap_rule == 0 ? rel_gap <= 0.25 * eps : obj_err <= gap_factor * eps;
+        if (rel_pres <= eps && rel_dres <= eps && gap_ok) {
             status = ELP_STATUS_OPTIMAL; finished = true; return true;
         }
         if (k > 0 && (checks % 4 == 0) && detect_infeasible()) { finished = true; return true; }
@@ -1311,7 +1486,14 @@ struct Pdlp {
         const int span = std::max(std::max(nl, m), 1);
         if (restart) {
             const double ddx = std::sqrt(hc[2]), ddy = std::sqrt(hr[3]);
-            if (ddx > 1e-10 && ddy > 1e-10) w = std::exp(0.5 * std::log(ddy / ddx) + 0.5 * std::log(w));
+            if (ddx > 1e-10 && ddy > 1e-10) {
+                // PID-style controller on log w (cuPDLPx): e = log(w dx / dy) is the imbalance of the two movements;
+                // kp = 0.5, ki = kd = 0 is PDLP's geometric-mean smoothing
+                const double e = std::log(w * ddx / ddy);
+                w_err_sum = w_ismooth * w_err_sum + e;
+                w = std::exp(std::log(w) - (w_kp * e + w_ki * w_err_sum + w_kd * (e - w_err_prev)));
+                w_err_prev = e;
+            }
             ELP_LAUNCH(k_restart, grid1(span), 256, 0, st, nl, x.p, x0.p, xp.p, m, y(), y0.p, yp.p);
             k = 0; ++restarts; need_fpe0 = true; fpe_prev = -1;
         } else {
@@ -1319,7 +1501,7 @@ struct Pdlp {
             ELP_LAUNCH(k_halpern_finish, grid1(span), 256, 0, st, nl, x.p, xbar(), x0.p, m, y(), yp.p, y0.p, wk);
             ++k;
         }
-        gather_y(y_full.p);                        // y changed: everyone needs the new blocks
+        refresh_y();                               // y changed: everyone needs the new blocks
         if (scatter) spmv_cols(y_full.p, gcol.p);  // ... and the scatter formulation needs g = A'y of the new y
         push_params();
         return false;
@@ -1367,6 +1549,7 @@ struct Pdlp {
 
     void run(int max_new_iters, elp_stats* stats) {
         WallTimer wall;
+        if (!clock_running) { run_clock = WallTimer(); clock_running = true; }     // the time limit spans all run() calls of a solve
         const int64_t launches0 = g_launches.load();
         cudaEvent_t e0, e1;
         ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
@@ -1382,7 +1565,7 @@ struct Pdlp {
             if (k % ce == 0) {
                 if (check_iteration()) break;
                 --budget;
-                if (N == 1 && opt.time_limit_s > 0 && wall.ms() > opt.time_limit_s * 1e3) break;   // ranks must agree: no wall-clock exit when distributed
+                if (time_up) { hit_time_limit = true; break; }     // (distributed: agreed on inside the check's allreduce)
                 continue;
             }
             int cnt = ce - (k % ce);
@@ -1410,17 +1593,21 @@ struct Pdlp {
             stats->kernel_launches = g_launches.load() - launches0;
             stats->h2d_bytes = h2d;
             stats->d2h_bytes = d2h;
+            stats->limit_reached = (status == ELP_STATUS_TIMEOUT) ? (hit_time_limit ? 2 : (total >= limit_total ? 1 : 0)) : 0;
         }
     }
 
     // x: all n columns (gathered from the ranks' blocks); y: my rows
-    void solution(double* x_h, double* y_h, double* obj) {
-        if (x_h) {
+    // collective_x: take part in the all-gather of x even when this rank does not want the result (x_h == nullptr)
+    void solution(double* x_h, double* y_h, double* obj, bool collective_x = false) {
+        if (x_h || (collective_x && N > 1)) {
             if (nl > 0) ELP_LAUNCH(k_unscale, grid1(nl), 256, 0, st, nl, xp.p, dc.p, 1.0, xaux_full.p + n0);
             gather_x(xaux_full.p);
-            xaux_full.download(x_h, n, st);
+            if (x_h) {
+                xaux_full.download(x_h, n, st);
+                d2h += (int64_t)n * 8;
+            }
             ELP_CUDA(cudaStreamSynchronize(st));
-            d2h += (int64_t)n * 8;
         }
         if (y_h && m > 0) {
             ELP_LAUNCH(k_unscale, grid1(m), 256, 0, st, m, yp.p, dr.p, maximize ? -1.0 : 1.0, axp.p);
@@ -1440,14 +1627,16 @@ struct Pdlp {
         run(3 * std::max(2, opt.check_every), nullptr);
         std::vector<cudaEvent_t> ev(2 * (size_t)reps + 1);
         for (auto& e : ev) ELP_CUDA(cudaEventCreate(&e));
-        for (int i = 0; i < 3; ++i) { primal_step<false>(i, false); dual_step<false>(i, false); }
+        // real iterations, exchange included (multi-GPU: the peers run the same sequence)
+        for (int i = 0; i < 3; ++i) { primal_step<false>(i); dual_step<false>(i); }
         for (int i = 0; i < reps; ++i) {
             ELP_CUDA(cudaEventRecord(ev[2 * i], st));
-            primal_step<false>(i, false);
+            primal_step<false>(3 + i);
             ELP_CUDA(cudaEventRecord(ev[2 * i + 1], st));
-            dual_step<false>(i, false);
+            dual_step<false>(3 + i);
         }
         ELP_CUDA(cudaEventRecord(ev[2 * reps], st));
+        if (ghost) epoch_base += 3 + reps;
         ELP_CUDA(cudaStreamSynchronize(st));
         double tp = 0.0, td = 0.0;
         for (int i = 0; i < reps; ++i) {
@@ -1502,7 +1691,7 @@ Pdlp* pdlp_create(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, 
 }
 void pdlp_run(Pdlp* p, int max_new_iters, elp_stats* stats) { p->run(max_new_iters, stats); }
 void pdlp_reset(Pdlp* p) { p->reset(); }
-void pdlp_solution(Pdlp* p, double* x, double* y, double* obj) { p->solution(x, y, obj); }
+void pdlp_solution(Pdlp* p, double* x, double* y, double* obj, bool collective_x) { p->solution(x, y, obj, collective_x); }
 void pdlp_probe(Pdlp* p, int reps, double* a, double* b) { p->probe_spmv(reps, a, b); }
 void pdlp_probe_step(Pdlp* p, int reps, double* a, double* b) { p->probe_step(reps, a, b); }
 int pdlp_transpose(Pdlp* p) { return p->scatter ? ELP_TRANSPOSE_SCATTER : ELP_TRANSPOSE_GATHER; }

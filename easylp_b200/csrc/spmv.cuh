@@ -131,6 +131,9 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     bounds(p_tile + nw, n_s, n_e);
 #pragma unroll
     for (int s = 0; s < NSTW; ++s) issue(s);
+    // multi-GPU: the gathered vector is filled by the peers' stores.  The matrix stream is already on its way; wait
+    // here — once per warp — until every producer has published the epoch this launch consumes.
+    if constexpr (Epi::DIST) vec = epi.acquire(lane);
 
     // ---- consumer ------------------------------------------------------------------------------------------
     const int g = lane / L;                // first row of the tile this lane group owns
@@ -223,7 +226,10 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             double a = acc[j];
             if (L > 1) a = group_sum<L>(a);
             double mult = 0.0;
-            if (sub == 0 && row0 + j * G < nrows) mult = epi.apply(row0 + j * G, a, pre[j], hints);
+            const bool owner = sub == 0 && row0 + j * G < nrows;
+            if (owner) mult = epi.apply(row0 + j * G, a, pre[j], hints);
+            // multi-GPU: the value just produced goes into the ghost vector of every rank that gathers it (warp-collective)
+            if constexpr (Epi::DIST) epi.publish(tile, lane, owner, row0 + j * G, mult);
             if (Epi::SCATTER) {
                 // out[idx[k]] += val[k] * mult over this row's entries (fire-and-forget fp64 reductions: SASS RED.ADD.F64);
                 // rows whose multiplier is zero (inactive constraints) send nothing.
@@ -240,6 +246,8 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             issue(hstage);
         }
     }
+    // multi-GPU: the last CTA to finish tells every consumer that this rank's block of the epoch is complete
+    if constexpr (Epi::DIST) epi.release();
 }
 
 // ---- long rows: one warp per row -----------------------------------------------------------------------
@@ -376,7 +384,7 @@ template <class Epi>
 void launch_spmv(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val, const double* vec,
                  const Epi& epi, cudaStream_t st) {
     if (nrows <= 0) return;
-    if constexpr (!Epi::SCATTER) {
+    if constexpr (!Epi::SCATTER && !Epi::DIST) {
         if (p.rowwarp) {
             const int grid = std::max(1, std::min(ceil_div(nrows, 4), kNumSMs * 16));
             ELP_LAUNCH((spmv_rowwarp_kernel<Epi>), grid, 128, 0, st, nrows, ptr, idx, val, vec, epi);

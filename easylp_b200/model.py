@@ -976,8 +976,13 @@ class easylp:
                 opt.time_limit_s = float(v)
             elif k == "verbose":
                 opt.verbose = int(v) if not isinstance(v, str) else int(v not in ("neutral", "critical", "severe"))
-            elif k == "epsilon" or k == "gpu_tol":
+            elif k == "gpu_tol":
                 opt.eps_rel = float(v)
+            elif k == "epsilon":                 # lp_solve's integer-rounding tolerance: nothing to map it to
+                warnings.warn("lp.control option 'epsilon' is lp_solve's integer-rounding tolerance and is ignored; "
+                              "the GPU path's optimality tolerance is gpu_tol")
+            elif k == "gpu_devices":             # spread one large solve over this many GPUs of the box
+                opt.devices = int(v)
             elif k == "gpu_max_iter":
                 opt.max_iter = int(v)
             elif k == "gpu_method":

@@ -67,7 +67,9 @@ typedef struct elp_options {
     int32_t use_graph;     /* PDLP: replay the iteration chunk from a CUDA graph (default 1) */
     int32_t ruiz_iters;    /* <0: default 10 */
     int32_t transpose;     /* PDLP, how A'y is formed in the plain iterations: ELP_TRANSPOSE_* (default AUTO) */
-    int32_t reserved;      /* keeps the struct a multiple of 8 bytes; must be 0 */
+    int32_t devices;       /* large-LP path: GPUs of this box to spread ONE solve over (0 or 1: the current device only;
+                              N > 1: devices cur, cur+1, ... — row blocks of A, one worker thread per GPU inside this
+                              call, see elp_solve_lp).  R: lp$solve(gpu.devices = N); default from env ELP_DEVICES */
 } elp_options;
 
 /* Per-solve statistics (SURVEY.md §5 "metrics"): returned to R as a list. */
@@ -88,6 +90,9 @@ typedef struct elp_stats {
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     double spmv_ms;            /* device time of the timed A.x / A'.y probe (elp_pdlp_probe_spmv) */
+    int32_t limit_reached;     /* with status 7: 0 = only this call's max_new_iters ran out (call again), 1 = the iteration
+                                  limit of the solve, 2 = its time limit (lp.control(timeout=)) — do not call again */
+    int32_t reserved;
 } elp_stats;
 
 /* ---- housekeeping -------------------------------------------------------------------------- */

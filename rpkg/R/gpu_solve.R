@@ -19,6 +19,11 @@ easylp_status_string <- function(status) {
         "5" = "numerical failure encountered",
         "6" = "process aborted",
         "7" = "timeout",
+        "9" = "the model was solved by presolve",
+        "10" = "the branch and bound routine failed",
+        "11" = "the branch and bound was stopped because of a break-at-first or break-at-value",
+        "12" = "a feasible branch and bound solution was found",
+        "13" = "no feasible branch and bound solution was found",
         "undocumented status"
     )
 }
@@ -54,7 +59,9 @@ easylp_assemble_lowered <- function(term_row, term_col, term_val, families, grou
 # on it, so the matrix crosses PCIe at most once (as descriptors or terms) between `$con()` and the solution.
 # A cloned or readRDS-restored object holds a NULL pointer: the glue raises, and easylp_model() rebuilds.
 easylp_model <- function(self, private) {
-    if (is.null(private$model)) {
+    # rebuild only when there is no live device model: never built, invalidated by $con()/$var(), or a pointer that did
+    # not survive a clone / readRDS (external pointers come back NULL).  Interrupts and real errors propagate.
+    if (is.null(private$model) || !.Call("easylp_model_valid", private$model)) {
         t <- private$terms                 # list(row, col, val, families, groups) kept by the sparse term-list DSL
         private$model <- .Call("easylp_model_assemble", as.integer(t$row), as.integer(t$col), as.double(t$val),
                                t$families, t$groups, length(self$constraint$rhs), private$n_var)
@@ -75,7 +82,10 @@ easylp_solve_impl <- function(self, private, ...) {
         stop("integer/binary variables need lp_solve's branch and bound; the B200 path solves LPs only")
 
     control <- list(...)
-    known <- c("timeout", "epsilon", "verbose", "gpu.tol", "gpu.max_iter", "gpu.method", "gpu.transpose")
+    known <- c("timeout", "verbose", "gpu.tol", "gpu.max_iter", "gpu.method", "gpu.transpose", "gpu.devices")
+    if ("epsilon" %in% names(control))      # lp_solve's integer-rounding tolerance: no counterpart here (use gpu.tol)
+        warning("lp.control option 'epsilon' is lp_solve's integer-rounding tolerance and is ignored; the GPU path's optimality tolerance is gpu.tol")
+    control$epsilon <- NULL
     for (k in setdiff(names(control), known))
         warning("lp.control option '", k, "' has no meaning on the GPU path and is ignored")
     control <- control[intersect(names(control), known)]
@@ -88,7 +98,7 @@ easylp_solve_impl <- function(self, private, ...) {
         solve_on <- function() .Call("easylp_model_solve", easylp_model(self, private), as.character(self$constraint$dir),
                                      as.double(self$constraint$rhs), as.double(self$objective_fun), private$dir == "max",
                                      as.double(lower), as.double(upper), control)
-        tryCatch(solve_on(), error = function(e) { private$model <- NULL; solve_on() })
+        solve_on()
     } else {
         # smallest drop-in: the reference's dense constraint$mat, converted on the host
         csr <- easylp_dense_to_csr(self$constraint$mat)

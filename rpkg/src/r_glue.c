@@ -128,7 +128,11 @@ static void fill_options(elp_options* opt, SEXP control) {
         const char* k = CHAR(STRING_ELT(nm, i));
         SEXP v = VECTOR_ELT(control, i);
         if (!strcmp(k, "timeout")) opt->time_limit_s = Rf_asReal(v);
-        else if (!strcmp(k, "epsilon") || !strcmp(k, "gpu.tol")) opt->eps_rel = Rf_asReal(v);
+        /* lp_solve's `epsilon` is its INTEGER-ROUNDING tolerance (1e-9 / 1e-11 are usual values), not an optimality
+         * tolerance: mapping it to PDLP's relative KKT tolerance drove solves to the iteration cap.  Only
+         * gpu.tol sets eps_rel; `$solve()` warns that `epsilon` is ignored. */
+        else if (!strcmp(k, "gpu.tol")) opt->eps_rel = Rf_asReal(v);
+        else if (!strcmp(k, "gpu.devices")) opt->devices = Rf_asInteger(v);       /* GPUs of the box to spread one solve over */
         else if (!strcmp(k, "verbose")) opt->verbose = Rf_asInteger(v);
         else if (!strcmp(k, "gpu.max_iter")) opt->max_iter = Rf_asInteger(v);
         else if (!strcmp(k, "gpu.method")) opt->method = Rf_asInteger(v);
@@ -415,7 +419,9 @@ SEXP easylp_model_solve(SEXP model, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize
     elp_stats st;
     memset(&st, 0, sizeof st);
     int rc;
-    if (opt.method == ELP_METHOD_PDLP) {
+    for (R_xlen_t j = 0; j < n; ++j)       /* lower > upper: "unfeasible" without a solve (R/class.R:297-298), as solve_large does */
+        if (REAL(lower)[j] > REAL(upper)[j]) { opt.method = ELP_METHOD_AUTO; break; }
+    if (opt.method == ELP_METHOD_PDLP && opt.devices <= 1) {
         /* a long first-order solve: run it in chunks and let the user interrupt between them.
          * R_CheckUserInterrupt() would longjmp past our cleanup, so it runs under R_ToplevelExec. */
         elp_pdlp* p = NULL;
@@ -423,9 +429,13 @@ SEXP easylp_model_solve(SEXP model, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize
                                    &opt, &p, &st);
         const double setup_ms = st.setup_ms;
         int interrupted = 0;
+        int32_t seen = -1;
         while (!rc && !interrupted) {
             rc = elp_pdlp_run(p, 4096, &st);
-            if (rc || st.status != ELP_STATUS_TIMEOUT || (opt.max_iter > 0 && st.iterations >= opt.max_iter)) break;
+            /* stop on an answer, on the solve's own iteration / time limit (the handle keeps the clock across calls and
+             * says so in limit_reached), or when a call made no progress — never spin on a solve that cannot advance */
+            if (rc || st.status != ELP_STATUS_TIMEOUT || st.limit_reached != 0 || st.iterations <= seen) break;
+            seen = st.iterations;
             interrupted = !R_ToplevelExec(check_interrupt, NULL);
         }
         if (!rc && !interrupted) rc = elp_pdlp_solution(p, REAL(x), m > 0 ? REAL(y) : NULL, &objval);
@@ -444,6 +454,12 @@ SEXP easylp_model_solve(SEXP model, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize
     return out;
 }
 
+/* .Call("easylp_model_valid", model) -> TRUE when the external pointer still holds a device model (FALSE after a
+ * clone / readRDS, whose pointers are NULL): `$solve()` rebuilds only then, and lets every real error propagate. */
+SEXP easylp_model_valid(SEXP model) {
+    return Rf_ScalarLogical(TYPEOF(model) == EXTPTRSXP && R_ExternalPtrAddr(model) != NULL);
+}
+
 /* .Call("easylp_device_count") */
 SEXP easylp_device_count(void) {
     int32_t k = 0;
@@ -457,6 +473,7 @@ static const R_CallMethodDef call_methods[] = {
     {"easylp_model_assemble", (DL_FUNC)&easylp_model_assemble, 7},
     {"easylp_model_csr", (DL_FUNC)&easylp_model_csr, 1},
     {"easylp_model_solve", (DL_FUNC)&easylp_model_solve, 8},
+    {"easylp_model_valid", (DL_FUNC)&easylp_model_valid, 1},
     {"easylp_solve_lp", (DL_FUNC)&easylp_solve_lp, 10},
     {"easylp_check_feasible", (DL_FUNC)&easylp_check_feasible, 7},
     {"easylp_solve_batch", (DL_FUNC)&easylp_solve_batch, 8},

@@ -9,6 +9,7 @@
  * `solve(prob)` (/root/reference/R/class.R:276) for LPs too large for the simplex oracle.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -63,7 +64,8 @@ static double nrm2(const double *v, int n) {
 
 /* out[0]=objective (problem's own sense) 1=iterations 2=restarts 3=rel primal res 4=rel dual res 5=rel gap
  * 6=seconds in the iteration loop 7=seconds of setup */
-int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const double *vals,
+static double envd(const char* n, double d) { const char* e = getenv(n); return e ? atof(e) : d; }
+int elpo_pdlp_lab(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const double *vals,
               const int8_t *sense, const double *rhs, const double *c_in, int maximize,
               const double *lb, const double *ub, double eps, int max_iter, int check_every, int nthreads,
               double *x_out, double *y_out, double *out)
@@ -73,34 +75,16 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
 #endif
     double t_setup0 = now_s();
     const int64_t nnz = m > 0 ? row_ptr[m] : 0;
-    /* NUMA: every array the iteration streams is FIRST TOUCHED by the thread that will stream it (same static
-     * schedule as the loops below), including private copies of the caller's CSR (numpy placed that on one node).
-     * Without this the port ran at ~53 GB/s on a 2-socket host: a straw man. */
     mat_t A;
-    int *rp_own = (int *)malloc(sizeof(int) * ((size_t)m + 2)), *ci_own = (int *)malloc(sizeof(int) * (nnz + 1));
-    A.m = m; A.n = n; A.rp = rp_own; A.ci = ci_own;
+    A.m = m; A.n = n; A.rp = row_ptr; A.ci = col_idx;
     A.rv = (double *)malloc(sizeof(double) * (nnz + 1));
-    {
-        int i;
-#pragma omp parallel for schedule(static)
-        for (i = 0; i < m; ++i) {
-            rp_own[i] = row_ptr[i];
-            for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) { ci_own[k] = col_idx[k]; A.rv[k] = vals[k]; }
-        }
-        rp_own[m] = m > 0 ? row_ptr[m] : 0;
-    }
+    memcpy(A.rv, vals, sizeof(double) * nnz);
     A.cp = (int *)calloc((size_t)n + 2, sizeof(int));
     A.ri = (int *)malloc(sizeof(int) * (nnz + 1));
     A.cv = (double *)malloc(sizeof(double) * (nnz + 1));
     int *src = (int *)malloc(sizeof(int) * (nnz + 1));   /* csc slot -> csr slot */
     for (int64_t k = 0; k < nnz; ++k) A.cp[col_idx[k] + 1]++;
     for (int j = 0; j < n; ++j) A.cp[j + 1] += A.cp[j];
-    {
-        int j;
-#pragma omp parallel for schedule(static)
-        for (j = 0; j < n; ++j)
-            for (int k = A.cp[j]; k < A.cp[j + 1]; ++k) { A.ri[k] = 0; A.cv[k] = 0.0; src[k] = 0; }   /* page placement */
-    }
     {
         int *cur = (int *)malloc(sizeof(int) * ((size_t)n + 1));
         memcpy(cur, A.cp, sizeof(int) * ((size_t)n + 1));
@@ -116,13 +100,6 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
     double *lc = (double *)malloc(sizeof(double) * (m + 1)), *uc = (double *)malloc(sizeof(double) * (m + 1)),
            *dr = (double *)malloc(sizeof(double) * (m + 1));
     double norm_b = 0, norm_c = 0;
-    {
-        int j, i;
-#pragma omp parallel for schedule(static)
-        for (j = 0; j < n; ++j) { c[j] = 0; l[j] = 0; u[j] = 0; dc[j] = 0; }
-#pragma omp parallel for schedule(static)
-        for (i = 0; i < m; ++i) { lc[i] = 0; uc[i] = 0; dr[i] = 0; }
-    }
     for (int j = 0; j < n; ++j) { c[j] = maximize ? -c_in[j] : c_in[j]; l[j] = lb[j]; u[j] = ub[j]; dc[j] = 1.0; norm_c += c[j] * c[j]; }
     for (int i = 0; i < m; ++i) {
         lc[i] = sense[i] == LE ? -INFINITY : rhs[i];
@@ -168,20 +145,12 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
     }
     free(rs); free(cs);
 
-    double *x = (double *)malloc(sizeof(double) * n), *x0 = (double *)malloc(sizeof(double) * n),
+    double *x = (double *)calloc(n, sizeof(double)), *x0 = (double *)malloc(sizeof(double) * n),
            *xp = (double *)malloc(sizeof(double) * n), *xbar = (double *)malloc(sizeof(double) * n),
            *g = (double *)malloc(sizeof(double) * n);
-    double *y = (double *)malloc(sizeof(double) * (m + 1)), *y0 = (double *)malloc(sizeof(double) * (m + 1)),
-           *yp = (double *)malloc(sizeof(double) * (m + 1)), *ax = (double *)malloc(sizeof(double) * (m + 1)),
-           *axp = (double *)malloc(sizeof(double) * (m + 1));
-    {
-        int j, i;
-#pragma omp parallel for schedule(static)
-        for (j = 0; j < n; ++j) { x[j] = 0; x0[j] = 0; xp[j] = 0; xbar[j] = 0; g[j] = 0; }
-#pragma omp parallel for schedule(static)
-        for (i = 0; i < m; ++i) { y[i] = 0; y0[i] = 0; yp[i] = 0; ax[i] = 0; axp[i] = 0; }
-        y[m] = y0[m] = yp[m] = ax[m] = axp[m] = 0;
-    }
+    double *y = (double *)calloc(m + 1, sizeof(double)), *y0 = (double *)calloc(m + 1, sizeof(double)),
+           *yp = (double *)calloc(m + 1, sizeof(double)), *ax = (double *)calloc(m + 1, sizeof(double)),
+           *axp = (double *)calloc(m + 1, sizeof(double));
     /* power iteration */
     double smax = 0.0;
     if (nnz > 0 && m > 0) {
@@ -213,6 +182,13 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
     double w = (nb > 1e-10 && nc > 1e-10) ? nc / nb : 1.0;
     for (int j = 0; j < n; ++j) { x[j] = fmin(fmax(0.0, l[j]), u[j]); x0[j] = x[j]; xp[j] = x[j]; }
 
+    const double KP = envd("LAB_KP", 0.5), KI = envd("LAB_KI", 0.0), KD = envd("LAB_KD", 0.0);
+    const double RHO = envd("LAB_RHO", 1.0), B_SUFF = envd("LAB_BSUFF", 0.2), B_NEC = envd("LAB_BNEC", 0.8), B_ART = envd("LAB_BART", 0.36);
+    const double GAPF = envd("LAB_GAPF", 0.25);
+    const int OBJTEST = (int)envd("LAB_OBJTEST", 0);
+    const double ISMOOTH = envd("LAB_ISMOOTH", 1.0);
+    const int WAVG = (int)envd("LAB_WAVG", 0);
+    double e_int = 0.0, e_prev = 0.0;
     const int ce = check_every > 1 ? check_every : 64;
     const int limit = max_iter > 0 ? max_iter : 2000000;
     int k = 0, total = 0, restarts = 0, status = 7, need_fpe0 = 1;
@@ -229,7 +205,7 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
             const double xj = x[j];
             const double xpj = fmin(fmax(xj - tau * (c[j] - g[j]), l[j]), u[j]);
             xbar[j] = 2.0 * xpj - xj;
-            if (check) xp[j] = xpj; else x[j] = wk * xbar[j] + (1.0 - wk) * x0[j];
+            if (check) xp[j] = xpj; else x[j] = wk * ((1.0 + RHO) * xpj - RHO * xj) + (1.0 - wk) * x0[j];
         }
         spmv_rows(&A, xbar, ax);
 #pragma omp parallel for schedule(static)
@@ -237,29 +213,31 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
             const double yi = y[i], v = yi - sig * ax[i];
             const double lo = v + sig * lc[i], hi = v + sig * uc[i];
             const double ypi = lo > 0 ? lo : (hi < 0 ? hi : 0.0);
-            if (check) yp[i] = ypi; else y[i] = wk * (2.0 * ypi - yi) + (1.0 - wk) * y0[i];
+            if (check) yp[i] = ypi; else y[i] = wk * ((1.0 + RHO) * ypi - RHO * yi) + (1.0 - wk) * y0[i];
         }
         ++total;
         if (!check) { ++k; continue; }
         /* ---- check: KKT of the candidate T(z) and fixed-point error of z ---- */
         spmv_rows(&A, xp, axp);
         spmv_cols(&A, yp, g);
-        double pres2 = 0, dyadx = 0, dy2 = 0, ddy2 = 0, dobj_r = 0;
-#pragma omp parallel for reduction(+ : pres2, dyadx, dy2, ddy2, dobj_r) schedule(static)
+        double pres2 = 0, dyadx = 0, dy2 = 0, ddy2 = 0, dobj_r = 0, corr_p = 0;
+#pragma omp parallel for reduction(+ : pres2, dyadx, dy2, ddy2, dobj_r, corr_p) schedule(static)
         for (i = 0; i < m; ++i) {
             const double a = axp[i];
             const double viol = (a - fmin(fmax(a, lc[i]), uc[i])) / dr[i];
+            corr_p += yp[i] * (a - fmin(fmax(a, lc[i]), uc[i]));
             const double dy = yp[i] - y[i], d0 = yp[i] - y0[i];
             pres2 += viol * viol; dyadx += dy * (ax[i] - a); dy2 += dy * dy; ddy2 += d0 * d0;
             dobj_r += yp[i] > 0 ? yp[i] * lc[i] : (yp[i] < 0 ? yp[i] * uc[i] : 0.0);
         }
-        double dres2 = 0, dx2 = 0, ddx2 = 0, po = 0, dobj_c = 0;
-#pragma omp parallel for reduction(+ : dres2, dx2, ddx2, po, dobj_c) schedule(static)
+        double dres2 = 0, dx2 = 0, ddx2 = 0, po = 0, dobj_c = 0, corr_d = 0;
+#pragma omp parallel for reduction(+ : dres2, dx2, ddx2, po, dobj_c, corr_d) schedule(static)
         for (j = 0; j < n; ++j) {
             const double r = c[j] - g[j], xpj = xp[j];
             const int at_lo = isfinite(l[j]) && xpj <= l[j], at_hi = isfinite(u[j]) && xpj >= u[j];
             const double rpos = fmax(r, 0.0), rneg = fmin(r, 0.0);
             const double res = ((at_lo ? 0.0 : rpos) + (at_hi ? 0.0 : rneg)) / dc[j];
+            corr_d += ((at_lo ? 0.0 : rpos) + (at_hi ? 0.0 : rneg)) * xpj;
             const double dx = xpj - x[j], d0 = xpj - x0[j];
             dres2 += res * res; dx2 += dx * dx; ddx2 += d0 * d0; po += c[j] * xpj;
             dobj_c += (at_lo ? rpos * l[j] : 0.0) + (at_hi ? rneg * u[j] : 0.0);
@@ -268,24 +246,32 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
         pobj = po; dobj = dobj_r + dobj_c;
         rp = sqrt(pres2) / (1 + norm_b); rd = sqrt(dres2) / (1 + norm_c);
         rg = fabs(pobj - dobj) / (1 + fabs(pobj) + fabs(dobj));
-        if (rp <= eps && rd <= eps && rg <= 0.25 * eps) { status = 0; break; }   /* gap at eps/4: see pdlp.cu */
+        if (getenv("LAB_TRACE")) fprintf(stderr, "%d %.4e %.4e %.4e %.4e %.4e %.10e\n", total, rp, rd, rg, corr_p / (1 + fabs(pobj) + fabs(dobj)), corr_d / (1 + fabs(pobj) + fabs(dobj)), pobj);
+        if (OBJTEST) { const double e = (fabs(pobj - dobj) + fabs(corr_p) + fabs(corr_d)) / (1 + fabs(pobj) + fabs(dobj)); if (rp <= eps && rd <= eps && e <= GAPF * eps) { status = 0; break; } }
+        else if (rp <= eps && rd <= eps && rg <= GAPF * eps) { status = 0; break; }   /* gap at eps/4: see pdlp.cu */
         if (need_fpe0) { fpe0 = fpe; need_fpe0 = 0; }
         int restart = 0;
         if (k > 0) {
-            if (fpe <= 0.2 * fpe0) restart = 1;
-            else if (fpe <= 0.8 * fpe0 && fpe_prev >= 0 && fpe > fpe_prev) restart = 1;
-            else if ((double)k >= 0.36 * (double)total) restart = 1;
+            if (fpe <= B_SUFF * fpe0) restart = 1;
+            else if (fpe <= B_NEC * fpe0 && fpe_prev >= 0 && fpe > fpe_prev) restart = 1;
+            else if ((double)k >= B_ART * (double)total) restart = 1;
         }
         fpe_prev = fpe;
         if (restart) {
             const double ddx = sqrt(ddx2), ddy = sqrt(ddy2);
-            if (ddx > 1e-10 && ddy > 1e-10) w = exp(0.5 * log(ddy / ddx) + 0.5 * log(w));
+            if (ddx > 1e-10 && ddy > 1e-10) {
+                const double e = log(w * ddx / ddy);      /* >0: primal moves too much relative to dual */
+                e_int = KI * e_int + e;
+                w = exp(log(w) - (KP * e + (KI > 0 ? KI * (e_int - e) : 0.0) + KD * (e - e_prev)));
+                e_prev = e;
+                (void)WAVG;
+            }
             for (j = 0; j < n; ++j) { x[j] = xp[j]; x0[j] = xp[j]; }
             for (i = 0; i < m; ++i) { y[i] = yp[i]; y0[i] = yp[i]; }
             k = 0; ++restarts; need_fpe0 = 1; fpe_prev = -1;
         } else {
-            for (j = 0; j < n; ++j) x[j] = wk * xbar[j] + (1.0 - wk) * x0[j];
-            for (i = 0; i < m; ++i) y[i] = wk * (2.0 * yp[i] - y[i]) + (1.0 - wk) * y0[i];
+            for (j = 0; j < n; ++j) x[j] = wk * ((1.0 + RHO) * xp[j] - RHO * x[j]) + (1.0 - wk) * x0[j];
+            for (i = 0; i < m; ++i) y[i] = wk * ((1.0 + RHO) * yp[i] - RHO * y[i]) + (1.0 - wk) * y0[i];
             ++k;
         }
     }
@@ -296,7 +282,7 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
         out[0] = maximize ? -pobj : pobj; out[1] = total; out[2] = restarts; out[3] = rp; out[4] = rd; out[5] = rg;
         out[6] = t_loop; out[7] = t_setup;
     }
-    free(rp_own); free(ci_own); free(A.rv); free(A.cp); free(A.ri); free(A.cv); free(src); free(c); free(l); free(u); free(dc); free(lc); free(uc);
+    free(A.rv); free(A.cp); free(A.ri); free(A.cv); free(src); free(c); free(l); free(u); free(dc); free(lc); free(uc);
     free(dr); free(x); free(x0); free(xp); free(xbar); free(g); free(y); free(y0); free(yp); free(ax); free(axp);
     return status;
 }

@@ -1,7 +1,8 @@
 """Regenerates tests/golden/configs.json — run from the repo root:  python tests/golden/make_configs.py
 
 Independent-solver (HiGHS via scipy; a stand-in for lp_solve, which is not in this image) objectives for the BASELINE
-configs a CPU solver can finish: C2 (transport 300 x 300) and a small multi-commodity instance of the C5 family.
+configs a CPU solver can finish: C2 (transport 300 x 300) and two small multi-commodity instances of the C5 family; the
+full-size C5 (50 commodities, 5 M variables) is pinned by a combinatorial argument instead (mcnf_by_shortest_paths).
 C4 carries its own planted optimum (oracle/gen.py) and needs no CPU solve."""
 import json
 import os
@@ -31,8 +32,40 @@ def highs(p):
     return float(r.fun)
 
 
+def mcnf_by_shortest_paths(p):
+    """Exact optimum of a multi-commodity instance WITHOUT an LP solver: drop the capacity rows, the LP splits into one
+    shortest-path problem per commodity (Dijkstra); if the resulting arc loads respect every capacity — asserted — that
+    flow is feasible for the full LP and optimal for a relaxation of it, hence optimal.  True for the full-size C5
+    (max load / capacity = 0.48), so config 5 has an objective that no first-order method produced."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+    nodes, narcs, K = p["nodes"], p["narcs"], p["K"]
+    t, h, cost, cap = p["tails"], p["heads"], p["cost"], p["cap"]
+    order = np.lexsort((cost, h, t))                      # cheapest of parallel arcs first
+    key = t[order] * nodes + h[order]
+    first = np.ones(order.size, bool)
+    first[1:] = key[1:] != key[:-1]
+    sel = order[first]
+    G = csr_matrix((cost[sel], (t[sel], h[sel])), shape=(nodes, nodes))
+    arc_of = {(int(a), int(b)): int(i) for a, b, i in zip(t[sel], h[sel], sel)}
+    dist, pred = dijkstra(G, directed=True, indices=p["src"], return_predecessors=True)
+    load = np.zeros(narcs)
+    obj = 0.0
+    for k in range(K):
+        v, s = int(p["dst"][k]), int(p["src"][k])
+        obj += p["dem"][k] * dist[k, v]
+        while v != s:
+            u = int(pred[k, v])
+            load[arc_of[(u, v)]] += p["dem"][k]
+            v = u
+    assert (load <= cap).all(), "capacities bind: the shortest-path decomposition is not the optimum of this instance"
+    return float(obj)
+
+
 def main():
     out = {
+        "c5_mcnf_K50_seed0": {"objective": mcnf_by_shortest_paths(gen.mcnf(K=50)).hex(),
+                              "how": "per-commodity Dijkstra; capacities verified slack (see mcnf_by_shortest_paths)"},
         "c2_transport_300x300_seed0": {"objective": highs(gen.transport(300, 300, seed=0)).hex()},
         "c5_small_K3_12x10_extra40_seed1": {"objective": highs(gen.mcnf(K=3, gw=12, gh=10, extra_arcs=40, seed=1)).hex()},
         "c5_small_K5_20x15_extra100_seed2": {"objective": highs(gen.mcnf(K=5, gw=20, gh=15, extra_arcs=100, seed=2)).hex()},

@@ -113,3 +113,13 @@ def test_c5_multicommodity_50_commodities():
     dual = float(np.dot(np.where(np.isfinite(p["rhs"]), p["rhs"], 0.0), y))
     assert dual <= r.objval + 1e-6 * (1 + abs(r.objval) + abs(dual))
     assert abs(r.objval - dual) <= 2e-6 * (1 + abs(r.objval) + abs(dual))
+    # independent objective: the instance decomposes into 50 shortest-path problems whose loads respect every capacity
+    # (tests/golden/make_configs.py::mcnf_by_shortest_paths) -- no first-order method produced this number
+    ref = CONFIGS["c5_mcnf_K50_seed0"]
+    assert abs(r.objval - ref) <= 1e-6 * abs(ref)
+    # dual feasibility recomputed on the host: reduced costs c - A'y may only be negative within the tolerance
+    # (lb = 0, ub = +inf), and the capacity rows (<=) carry non-positive multipliers in this sign convention
+    rc = p["c"] - gen._csr_rmatvec(p["row_ptr"].astype(np.int64), p["col_idx"], p["vals"], y, p["n"])
+    assert np.linalg.norm(np.minimum(rc, 0.0)) <= 1e-6 * (1 + np.linalg.norm(p["c"]))
+    le = p["sense"] == 0
+    assert np.linalg.norm(np.maximum(y[le], 0.0)) <= 1e-6 * (1 + np.linalg.norm(y))

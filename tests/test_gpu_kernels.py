@@ -61,8 +61,16 @@ def test_spmv_and_feasible():
     p = gen.sparse_planted(3000, seed=1)
     x = np.random.default_rng(0).normal(size=p["n"])
     out = L.spmv(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], x)
-    ref = gen._csr_matvec(p["row_ptr"].astype(np.int64), p["col_idx"], p["vals"], x, p["m"])
-    assert np.allclose(out, ref, rtol=1e-12, atol=1e-12)
+    # S4 is BIT-identical to a scalar loop: one lane per row, products and sums in index order, no FMA.
+    # numpy float64 scalars do the same IEEE multiply / add one at a time (reduceat would sum pairwise).
+    rp, ci, v = p["row_ptr"], p["col_idx"], p["vals"]
+    ref = np.zeros(p["m"])
+    for i in range(p["m"]):
+        s = np.float64(0.0)
+        for k in range(rp[i], rp[i + 1]):
+            s = s + v[k] * x[ci[k]]
+        ref[i] = s
+    assert out.tobytes() == ref.tobytes()
     feas = L.check_feasible(p["m"], p["n"], p["row_ptr"], p["col_idx"], p["vals"], p["x_opt"], p["sense"], p["rhs"])
     assert feas.all()
 
