@@ -52,8 +52,11 @@ void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, con
 size_t simplex_smem_bytes(int m, int n);
 void simplex_batch_device(int64_t B, int m, int n, const double* A, const double* b, const double* c, const double* lb,
                           const double* ub, const int8_t* sense, int maximize, int max_pivots, int32_t* status,
-                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st);
+                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st, int shared_model = 0);
 void densify_device(int m, int n, const int* ptr, const int* idx, const double* val, double* A, cudaStream_t st);
+void solve_mip(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals, const int8_t* sense,
+               const double* rhs, const double* c, int32_t maximize, const double* lb, const double* ub,
+               const uint8_t* is_int, const elp_options& o, int32_t* status, double* objval, double* x, elp_stats* stats);
 
 void pool_release();            // shuts the multi-GPU worker pool down (defined next to it, below)
 static void require_device() {
@@ -678,6 +681,29 @@ int elp_solve_lp(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* co
         solve_multi(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
     else
         solve_large(m, n, row_ptr, col_idx, vals, -1, sense, rhs, c, maximize, lb, ub, o, status, objval, x, y, stats);
+    ELP_CATCH
+}
+
+int elp_solve_mip(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                  const int8_t* sense, const double* rhs, const double* c, int32_t maximize, const double* lb,
+                  const double* ub, const uint8_t* is_integer, const elp_options* opt, int32_t* status, double* objval,
+                  double* x, elp_stats* stats) {
+    ELP_TRY
+    require_device();
+    ELP_REQUIRE(n > 0, "Problem contains no variables.");   // R/class.R:253-254
+    ELP_REQUIRE(m >= 0 && status && objval && x && c && lb && ub && is_integer, "elp_solve_mip: bad arguments");
+    const elp_options o = effective_options(opt);
+    bool any = false, bad_bounds = false;
+    for (int j = 0; j < n; ++j) { any = any || is_integer[j] != 0; bad_bounds = bad_bounds || lb[j] > ub[j]; }
+    if (bad_bounds) {                                        // R/class.R:297-298
+        *status = ELP_STATUS_INFEASIBLE; *objval = 0.0;
+        for (int j = 0; j < n; ++j) x[j] = 0.0;
+        if (stats) { memset(stats, 0, sizeof *stats); stats->status = *status; stats->method_used = ELP_METHOD_SIMPLEX; }
+    } else if (!any) {                                       // no integer column after all: the plain LP path
+        solve_small(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, status, objval, x, nullptr, stats);
+    } else {
+        solve_mip(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, is_integer, o, status, objval, x, stats);
+    }
     ELP_CATCH
 }
 

@@ -45,12 +45,14 @@ constexpr int SPMV_THREADS = 256;             // block size of the setup-only he
 
 // ---- epilogues of the SpMV (spmv.cuh): in(i) names the operand vectors the producer stages next to the
 // matrix stream, preload() picks this row's operands out of the stage, apply() runs after the row sum ------
+struct NoRoute {};
 struct StoreEpi {
     static constexpr int NIN = 0;
     static constexpr bool SCATTER = false;
     static constexpr bool DIST = false;
     double* scat = nullptr;
     double* out;
+    using Route = NoRoute;
     struct Pre {};
     __device__ __forceinline__ const double* in(int) const { return nullptr; }
     __device__ __forceinline__ Pre preload(const double*, int, int) const { return Pre{}; }
@@ -106,10 +108,17 @@ __device__ __forceinline__ const double* ghost_acquire(const GhostIn& gi, long l
     __syncwarp();
     return gi.vec + ((want & 1) ? gi.stride : 0u);
 }
-// producer side, per row of a warp tile (all 32 lanes call it; `owner` lanes carry a value)
-__device__ __forceinline__ void ghost_publish(const GhostOut& go, long long epoch, int tile, int lane, bool owner, int row, double v) {
-    const unsigned mk = owner ? (unsigned)go.mask[row] : 0u;
-    const int mybase = lane < go.n ? go.base[(size_t)tile * 8 + lane] : 0;
+// producer side, per row of a warp tile (all 32 lanes call both; `owner` lanes carry a value)
+struct GhostRoute { unsigned mk; int base; };
+__device__ __forceinline__ GhostRoute ghost_route(const GhostOut& go, int tile, int lane, bool owner, int row) {
+    GhostRoute g;
+    g.mk = owner ? (unsigned)go.mask[row] : 0u;
+    g.base = lane < go.n ? go.base[(size_t)tile * 8 + lane] : 0;
+    return g;
+}
+__device__ __forceinline__ void ghost_publish(const GhostOut& go, long long epoch, const GhostRoute& rt, int lane, double v) {
+    const unsigned mk = rt.mk;
+    const int mybase = rt.base;
     const unsigned lower = (1u << lane) - 1u;
     const bool odd = (epoch & 1) != 0;
 #pragma unroll
@@ -123,9 +132,9 @@ __device__ __forceinline__ void ghost_publish(const GhostOut& go, long long epoc
     }
 }
 __device__ __forceinline__ void ghost_release(const GhostOut& go, long long epoch) {
-    __threadfence_system();                       // this thread's peer stores are visible system-wide ...
-    __syncthreads();                              // ... for every thread of the CTA
+    __syncthreads();                              // the CTA's peer stores happen before ...
     if (threadIdx.x == 0) {
+        __threadfence_system();                   // ... this (cumulative) fence makes them visible system-wide
         const unsigned old = atomicAdd(go.done, 1u);
         if (old == gridDim.x - 1) {               // every CTA has passed its fence
             *go.done = 0u;
@@ -154,6 +163,7 @@ struct PrimalEpi {
     int it;
     GhostIn gin;        // y ghost (consumed)
     GhostOut gout;      // x-bar ghosts (produced)
+    using Route = GhostRoute;
     struct Pre { double x, c, l, u, x0; };
     __device__ __forceinline__ const double* in(int i) const {
         return i == 0 ? x : i == 1 ? c : i == 2 ? l : i == 3 ? u : x0;
@@ -186,8 +196,9 @@ struct PrimalEpi {
     }
     // y of the previous iteration carries epoch_base + it; this launch produces epoch_base + it + 1
     __device__ __forceinline__ const double* acquire(int lane) const { return ghost_acquire(gin, P->epoch_base + it, lane); }
-    __device__ __forceinline__ void publish(int tile, int lane, bool owner, int row, double v) const {
-        ghost_publish(gout, P->epoch_base + it + 1, tile, lane, owner, row, v);
+    __device__ __forceinline__ Route route(int tile, int lane, bool owner, int row) const { return ghost_route(gout, tile, lane, owner, row); }
+    __device__ __forceinline__ void publish(const Route& rt, int lane, double v) const {
+        ghost_publish(gout, P->epoch_base + it + 1, rt, lane, v);
     }
     __device__ __forceinline__ void release() const { ghost_release(gout, P->epoch_base + it + 1); }
 };
@@ -211,6 +222,7 @@ struct DualEpi {
     int it;
     GhostIn gin;        // x-bar ghost (consumed)
     GhostOut gout;      // y ghosts (produced)
+    using Route = GhostRoute;
     struct Pre { double y, lc, uc, y0; };
     __device__ __forceinline__ const double* in(int i) const { return i == 0 ? y : i == 1 ? lc : i == 2 ? uc : y0; }
     __device__ __forceinline__ Pre preload(const double* s, int rt, int g) const {
@@ -245,8 +257,9 @@ struct DualEpi {
     }
     // the x-bar of this same iteration carries epoch_base + it + 1, and so does the y this launch produces
     __device__ __forceinline__ const double* acquire(int lane) const { return ghost_acquire(gin, P->epoch_base + it + 1, lane); }
-    __device__ __forceinline__ void publish(int tile, int lane, bool owner, int row, double v) const {
-        ghost_publish(gout, P->epoch_base + it + 1, tile, lane, owner, row, v);
+    __device__ __forceinline__ Route route(int tile, int lane, bool owner, int row) const { return ghost_route(gout, tile, lane, owner, row); }
+    __device__ __forceinline__ void publish(const Route& rt, int lane, double v) const {
+        ghost_publish(gout, P->epoch_base + it + 1, rt, lane, v);
     }
     __device__ __forceinline__ void release() const { ghost_release(gout, P->epoch_base + it + 1); }
 };

@@ -113,7 +113,8 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 simplex_batch_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, const double* __restrict__ bg,
                      const double* __restrict__ cg, const double* __restrict__ lbg, const double* __restrict__ ubg,
-                     const int8_t* __restrict__ senseg, int maximize, int max_pivots, int32_t* __restrict__ status_out,
+                     const int8_t* __restrict__ senseg, int maximize, int max_pivots, int shared_model,
+                     int32_t* __restrict__ status_out,
                      double* __restrict__ obj_out, double* __restrict__ x_out, double* __restrict__ y_out,
                      int32_t* __restrict__ pivots_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -139,12 +140,13 @@ simplex_batch_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, con
 
     const int64_t lp = blockIdx.x;
     if (lp >= B) return;
-    const double* A = Ag + lp * (int64_t)m * n;
-    const double* b = bg + lp * (int64_t)m;
-    const double* c = cg + lp * (int64_t)n;
+    const int64_t mlp = shared_model ? 0 : lp;      // branch and bound: every node shares A, b, c, sense; bounds differ
+    const double* A = Ag + mlp * (int64_t)m * n;
+    const double* b = bg + mlp * (int64_t)m;
+    const double* c = cg + mlp * (int64_t)n;
     const double* lb = lbg ? lbg + lp * (int64_t)n : nullptr;
     const double* ub = ubg ? ubg + lp * (int64_t)n : nullptr;
-    const int8_t* sense = senseg ? senseg + lp * (int64_t)m : nullptr;
+    const int8_t* sense = senseg ? senseg + mlp * (int64_t)m : nullptr;
 
     // ---- stage the LP: TMA bulk copies where alignment allows, cooperative loads otherwise ----------
     const size_t bytesA = (size_t)m * n * 8, bytesb = (size_t)m * 8, bytesn = (size_t)n * 8;
@@ -436,7 +438,7 @@ template <int MR, int CPL>
 __global__ void __launch_bounds__(SW_WARPS * 32)
 simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, const double* __restrict__ bg,
                     const double* __restrict__ cg, const double* __restrict__ lbg, const double* __restrict__ ubg,
-                    const int8_t* __restrict__ senseg, int maximize, int max_pivots, int use_tma,
+                    const int8_t* __restrict__ senseg, int maximize, int max_pivots, int shared_model, int use_tma,
                     int32_t* __restrict__ status_out, double* __restrict__ obj_out, double* __restrict__ x_out,
                     double* __restrict__ y_out, int32_t* __restrict__ pivots_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -467,8 +469,9 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
     uint32_t phase = 0;
 
     for (int64_t lp = gw; lp < B; lp += nw) {
-        const double* A = Ag + lp * (int64_t)m * n;
-        const int8_t* sense = senseg ? senseg + lp * (int64_t)m : nullptr;
+        const int64_t mlp = shared_model ? 0 : lp;  // branch and bound: every node shares A, b, c, sense; bounds differ
+        const double* A = Ag + mlp * (int64_t)m * n;
+        const int8_t* sense = senseg ? senseg + mlp * (int64_t)m : nullptr;
         // ---- tableau rows of A: one bulk copy per row, issued by the lanes in parallel ----------------
         if (use_tma && m > 0) {
             // generic-proxy writes to the tableau (previous LP) must be ordered before the async-proxy copies
@@ -491,7 +494,7 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             clo[c] = 0.0; chi[c] = 0.0; ccost[c] = 0.0; cxn[c] = 0.0; cstate[c] = ST_BASIC;
             if (col < n) {
                 const double l = lbg ? lbg[lp * (int64_t)n + col] : 0.0, u = ubg ? ubg[lp * (int64_t)n + col] : INFINITY;
-                const double cj = cg[lp * (int64_t)n + col];
+                const double cj = cg[mlp * (int64_t)n + col];
                 clo[c] = l; chi[c] = u;
                 ccost[c] = maximize ? -cj : cj;
                 if (l > u) bad = 1;
@@ -517,7 +520,7 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
         if (lane < MR) {
             double r = 0.0;
             if (lane < m) {
-                r = bg[lp * (int64_t)m + lane];
+                r = bg[mlp * (int64_t)m + lane];
                 const double* Ti = Ts + lane * NS;
                 for (int j = 0; j < n; ++j) r -= Ti[j] * xs[j];
             } else { blo[lane] = -INFINITY; bhi[lane] = INFINITY; bcost[lane] = 0.0; basis[lane] = -1; }
@@ -775,7 +778,8 @@ int simplex_pick_threads(int m, int n) {
 template <int MR, int CPL>
 static void simplex_warp_launch_inst(int64_t B, int m, int n, const double* A, const double* b, const double* c,
                                      const double* lb, const double* ub, const int8_t* sense, int maximize, int max_pivots,
-                                     int32_t* status, double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st) {
+                                     int32_t* status, double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st,
+                                     int shared_model) {
     auto kern = simplex_warp_kernel<MR, CPL>;
     const WarpSimplexLayout lay(MR, CPL);
     const size_t smem = (size_t)SW_WARPS * lay.total;
@@ -787,13 +791,14 @@ static void simplex_warp_launch_inst(int64_t B, int m, int n, const double* A, c
     const int use_tma = (n % 2 == 0) && al16(A) && env_flag("ELP_SIMPLEX_TMA", 1);   // 16-byte rows
     const int64_t want = (B + SW_WARPS - 1) / SW_WARPS;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * occ));
-    ELP_LAUNCH(kern, grid, SW_WARPS * 32, smem, st, B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, use_tma, status,
-               obj, x, y, pivots);
+    ELP_LAUNCH(kern, grid, SW_WARPS * 32, smem, st, B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, shared_model, use_tma,
+               status, obj, x, y, pivots);
 }
 
 static bool simplex_warp_launch(int64_t B, int m, int n, const double* A, const double* b, const double* c,
                                 const double* lb, const double* ub, const int8_t* sense, int maximize, int max_pivots,
-                                int32_t* status, double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st) {
+                                int32_t* status, double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st,
+                                int shared_model) {
     if (!env_flag("ELP_SIMPLEX_WARP", 1)) return false;
     const int N = m + n;
     if (m > 32 || N > 96) return false;
@@ -803,7 +808,7 @@ static bool simplex_warp_launch(int64_t B, int m, int n, const double* A, const 
 #define ELP_SW(MR_, CPL_)                                                                                              \
     if (mr == MR_ && cpl == CPL_) {                                                                                    \
         simplex_warp_launch_inst<MR_, CPL_>(B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, status, obj, x, y, \
-                                            pivots, st);                                                               \
+                                            pivots, st, shared_model);                                                 \
         return true;                                                                                                   \
     }
     ELP_SW(4, 1) ELP_SW(8, 1) ELP_SW(12, 1) ELP_SW(16, 1) ELP_SW(20, 1) ELP_SW(24, 1) ELP_SW(28, 1) ELP_SW(32, 1)
@@ -816,11 +821,11 @@ static bool simplex_warp_launch(int64_t B, int m, int n, const double* A, const 
 // all pointers are device pointers
 void simplex_batch_device(int64_t B, int m, int n, const double* A, const double* b, const double* c, const double* lb,
                           const double* ub, const int8_t* sense, int maximize, int max_pivots, int32_t* status,
-                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st) {
+                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st, int shared_model) {
     if (B <= 0) return;
     ELP_REQUIRE(n > 0 && m >= 0, "simplex: bad shape %d x %d", m, n);
     ELP_REQUIRE(B < 0x7fffffffll, "simplex: batch too large");
-    if (simplex_warp_launch(B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, status, obj, x, y, pivots, st)) return;
+    if (simplex_warp_launch(B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, status, obj, x, y, pivots, st, shared_model)) return;
     const size_t smem = simplex_smem_bytes(m, n);
     ELP_REQUIRE(smem <= 227 * 1024, "simplex: tableau of %d x %d needs %zu bytes of shared memory (max 227 KB)", m, n,
                 smem);
@@ -830,7 +835,7 @@ void simplex_batch_device(int64_t B, int m, int n, const double* A, const double
         ELP_CUDA(cudaFuncSetAttribute(simplex_batch_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                       (int)smem));                                                                \
         ELP_LAUNCH((simplex_batch_kernel<T>), (unsigned)B, T, smem, st, B, m, n, A, b, c, lb, ub, sense, maximize, \
-                   max_pivots, status, obj, x, y, pivots);                                                        \
+                   max_pivots, shared_model, status, obj, x, y, pivots);                                          \
     } while (0)
     if (threads == 32) ELP_SIMPLEX_LAUNCH(32);
     else if (threads == 64) ELP_SIMPLEX_LAUNCH(64);

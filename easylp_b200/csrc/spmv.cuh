@@ -148,6 +148,13 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
         int st[RPL], en[RPL], a0 = 0, a1 = 0;
         typename Epi::Pre pre[RPL];
         double acc[RPL];
+        // multi-GPU: who reads this tile's outputs and where they go — fetched now so that the latency of these two
+        // loads hides behind the gathers instead of sitting on the warp's critical path after the row sum
+        [[maybe_unused]] typename Epi::Route route[RPL];
+        if constexpr (Epi::DIST) {
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) route[j] = epi.route(tile, lane, sub == 0 && row0 + j * G < nrows, row0 + j * G);
+        }
 #pragma unroll
         for (int j = 0; j < RPL; ++j) { st[j] = 0; en[j] = 0; acc[j] = 0.0; pre[j] = typename Epi::Pre{}; }
         for (int piece = 0;; ++piece) {
@@ -229,7 +236,7 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             const bool owner = sub == 0 && row0 + j * G < nrows;
             if (owner) mult = epi.apply(row0 + j * G, a, pre[j], hints);
             // multi-GPU: the value just produced goes into the ghost vector of every rank that gathers it (warp-collective)
-            if constexpr (Epi::DIST) epi.publish(tile, lane, owner, row0 + j * G, mult);
+            if constexpr (Epi::DIST) epi.publish(route[j], lane, mult);
             if (Epi::SCATTER) {
                 // out[idx[k]] += val[k] * mult over this row's entries (fire-and-forget fp64 reductions: SASS RED.ADD.F64);
                 // rows whose multiplier is zero (inactive constraints) send nothing.

@@ -963,9 +963,6 @@ class easylp:
     def solve(self, **control):
         if self._n_var == 0:
             raise EasyLpError("Problem contains no variables.")
-        if self.any_integer():
-            raise EasyLpError("integer/binary variables need lp_solve's branch and bound; the B200 path solves LPs only "
-                              "(SURVEY.md §2 row 14)")
         if np.all(self.objective_fun == 0):
             raise EasyLpError("Must specify objective function.")
         if self._dir not in ("min", "max"):
@@ -994,7 +991,14 @@ class easylp:
         m = sum(b.nrow for b in self._blocks)
         lb, ub = self._bounds()
         sense = self._dir_codes(_SENSE)
-        if m > 0:       # the matrix stays in HBM between `$con()` and `$solve()`
+        if self.any_integer():
+            # set.type(prob, columns, "integer" | "binary") + lp_solve's branch and bound (R/class.R:264-276): the tree's
+            # frontiers go through the batched simplex kernel (csrc/mip.cu)
+            is_int = np.concatenate([np.repeat(bool(v.integer or v.binary), v.ind.size) for v in self.variables.values()])
+            rp, ci, v = self._csr()
+            r = _lib.solve_mip(m, self._n_var, rp, ci, v, sense, self.constraint.rhs, self.objective_fun, lb, ub, is_int,
+                               maximize=self._dir == "max", options=opt)
+        elif m > 0:       # the matrix stays in HBM between `$con()` and `$solve()`
             r = self._device_model().solve(sense, self.constraint.rhs, self.objective_fun, lb, ub,
                                            maximize=self._dir == "max", options=opt)
         else:

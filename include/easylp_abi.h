@@ -199,6 +199,21 @@ int elp_solve_lp(int32_t m, int32_t n,
                  int32_t* status, double* objval, double* x /* n */, double* y /* m, may be NULL */,
                  elp_stats* stats /* may be NULL */);
 
+/* ---- (2b) models with integer / binary variables: replaces `solve(prob)` after `set.type(prob, columns, "integer" |
+ *      "binary")` (R/class.R:264-276), i.e. lp_solve's branch and bound.  is_integer[j] != 0 marks an integer column (a
+ *      binary one is an integer column with bounds [0, 1], R/class.R:104-110).  The tree's open nodes share A, b, c and
+ *      differ in their bounds: every frontier is ONE launch of the batched simplex kernel (csrc/mip.cu).  Status codes as
+ *      lp_solve: 0 optimal, 2 unfeasible, 3 unbounded, 1 sub-optimal / 7 timeout when opt->max_iter (a NODE limit here) or
+ *      opt->time_limit_s stops the search with / without an incumbent.  stats->restarts = nodes solved,
+ *      stats->iterations = simplex pivots.  Models whose dense tableau does not fit one SM are refused. */
+int elp_solve_mip(int32_t m, int32_t n,
+                  const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                  const int8_t* sense, const double* rhs,
+                  const double* c, int32_t maximize,
+                  const double* lb, const double* ub, const uint8_t* is_integer /* n */,
+                  const elp_options* opt /* may be NULL */,
+                  int32_t* status, double* objval, double* x /* n */, elp_stats* stats /* may be NULL */);
+
 /* ---- (3) a batch of small dense LPs (BASELINE config 3; additive entry point) ---
  * A is [B][m][n] row-major, b [B][m], c [B][n], lb/ub [B][n] (NULL => 0 / +Inf), sense [B][m]
  * (NULL => all "<=").  One LP per CTA; outputs status[B], obj[B], x[B][n]. */

@@ -605,6 +605,23 @@ class easylp:
             self._join(name_constraint(c, name))
         return self
 
+    def associate(self, x, binary, max1=None, max0=None, min1=None, min0=None):   # R/class.R:332-358
+        """Dense restatement for a plain variable `x` (update_bounds of a variable is its own bound pair)."""
+        lo, up = x.bound
+        max1 = up if max1 is None else max1
+        max0 = lo if max0 is None else max0
+        min1 = lo if min1 is None else min1
+        min0 = lo if min0 is None else min0
+        if not all(np.isfinite(v) for v in (max1, max0, min1, min0)):
+            raise RError("is.finite(max1), is.finite(max0), is.finite(min1), is.finite(min0) are not all TRUE")
+        if not binary.binary:
+            warnings.warn("Variable is not binary.")
+        if max1 != up or max0 != up:
+            self.con(assoc_max=x <= max0 + (max1 - max0) * binary)
+        if min1 != lo or min0 != lo:
+            self.con(assoc_min=x >= min0 + (min1 - min0) * binary)
+        return self
+
     def uncon(self, name):           # R/class.R:308-316
         names = [name] if isinstance(name, str) else list(name)
         keep = np.array([n not in names for n in self.names], dtype=bool)
@@ -654,4 +671,6 @@ class easylp:
                     vals=np.concatenate(vals) if vals else np.zeros(0),
                     dir=list(self.dir), sense=sense, rhs=self.rhs.copy(), c=self.objective_fun.copy(),
                     objective_add=self.objective_add, lb=lb, ub=ub, maximize=self.direction == "max",
-                    names=list(self.names), rownames=list(self.rownames))
+                    names=list(self.names), rownames=list(self.rownames),
+                    is_integer=np.concatenate([np.repeat(bool(v.integer or v.binary), v.ind.size)
+                                               for v in self.variables.values()]).astype(np.uint8) if n else np.zeros(0, np.uint8))

@@ -78,8 +78,6 @@ easylp_solve_impl <- function(self, private, ...) {
         stop("Must specify objective function.")
     if (!is.element(private$dir, c("min", "max")))
         stop("Direction must be either 'min' or 'max'.")
-    if (self$any_integer())
-        stop("integer/binary variables need lp_solve's branch and bound; the B200 path solves LPs only")
 
     control <- list(...)
     known <- c("timeout", "verbose", "gpu.tol", "gpu.max_iter", "gpu.method", "gpu.transpose", "gpu.devices")
@@ -93,7 +91,15 @@ easylp_solve_impl <- function(self, private, ...) {
     lower <- unlist(lapply(self$variables, function(x) rep(x$bound[1L], length(x$ind))))
     upper <- unlist(lapply(self$variables, function(x) rep(x$bound[2L], length(x$ind))))
 
-    res <- if (!is.null(private$terms)) {
+    res <- if (self$any_integer()) {
+        # set.type(prob, columns, type) + lp_solve's branch and bound (R/class.R:264-276): the frontiers of the tree go
+        # through the batched simplex kernel (easylp_b200/csrc/mip.cu).  Binary columns carry the bounds [0, 1].
+        is_int <- unlist(lapply(self$variables, function(x) rep(x$integer || x$binary, length(x$ind))))
+        csr <- if (!is.null(private$terms)) easylp_model_csr(easylp_model(self, private)) else easylp_dense_to_csr(self$constraint$mat)
+        .Call("easylp_solve_mip", as.integer(csr$row_ptr), as.integer(csr$col_idx), as.double(csr$vals),
+              as.character(self$constraint$dir), as.double(self$constraint$rhs), as.double(self$objective_fun),
+              private$dir == "max", as.double(lower), as.double(upper), as.logical(is_int), control)
+    } else if (!is.null(private$terms)) {
         # sparse term-list DSL: solve on the device-resident matrix (rebuilt if the pointer did not survive a clone)
         solve_on <- function() .Call("easylp_model_solve", easylp_model(self, private), as.character(self$constraint$dir),
                                      as.double(self$constraint$rhs), as.double(self$objective_fun), private$dir == "max",

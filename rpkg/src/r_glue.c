@@ -168,6 +168,38 @@ SEXP easylp_solve_lp(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP dir, SEXP rhs, 
     return out;
 }
 
+/* .Call("easylp_solve_mip", row_ptr, col_idx, vals, dir, rhs, objective_fun, maximize, lower, upper, is_integer, control)
+ * Models with integer / binary variables: replaces set.type(prob, columns, type) + lp_solve's branch and bound behind
+ * solve(prob) (R/class.R:264-276).  is_integer: logical(n), TRUE for integer and binary columns (binary columns carry the
+ * bounds [0, 1], R/class.R:104-110).  Same result list as easylp_solve_lp (y is all zero: no duals for a MILP). */
+SEXP easylp_solve_mip(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize,
+                      SEXP lower, SEXP upper, SEXP is_integer, SEXP control) {
+    const int32_t m = (int32_t)XLENGTH(row_ptr) - 1, n = (int32_t)XLENGTH(cost);
+    if (XLENGTH(lower) != n || XLENGTH(upper) != n || XLENGTH(is_integer) != n)
+        Rf_error("bounds and types must have one entry per variable");
+    if (XLENGTH(dir) != m || XLENGTH(rhs) != m) Rf_error("dir/rhs must have one entry per constraint");
+    elp_options opt;
+    fill_options(&opt, control);
+    int8_t* sense = sense_codes(dir, 0);
+    int32_t* cols = zero_based(col_idx);
+    uint8_t* ii = (uint8_t*)R_alloc((size_t)(n > 0 ? n : 1), 1);
+    for (int32_t j = 0; j < n; ++j) ii[j] = LOGICAL(is_integer)[j] ? 1 : 0;
+    SEXP x = PROTECT(Rf_allocVector(REALSXP, n));
+    SEXP y = PROTECT(Rf_allocVector(REALSXP, m));
+    for (int32_t i = 0; i < m; ++i) REAL(y)[i] = 0.0;
+    int32_t status = 0;
+    double objval = 0.0;
+    elp_stats st;
+    memset(&st, 0, sizeof st);
+    const int rc = elp_solve_mip(m, n, (const int32_t*)INTEGER(row_ptr), cols, REAL(vals), sense, REAL(rhs), REAL(cost),
+                                 Rf_asLogical(maximize) ? 1 : 0, REAL(lower), REAL(upper), ii, &opt, &status, &objval,
+                                 REAL(x), &st);
+    if (rc) { UNPROTECT(2); elp_fail("easylp_solve_mip"); }
+    SEXP out = solve_result(status, objval, x, y, &st);
+    UNPROTECT(2);
+    return out;
+}
+
 /* .Call("easylp_check_feasible", row_ptr, col_idx, vals, sol, dir, rhs, tol) -> logical(m)
  * Replaces `lhs <- mat %*% sol` + compare_tol (R/class.R:533-540, R/utils.R:167-171). */
 SEXP easylp_check_feasible(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP sol, SEXP dir, SEXP rhs, SEXP tol) {
@@ -475,6 +507,7 @@ static const R_CallMethodDef call_methods[] = {
     {"easylp_model_solve", (DL_FUNC)&easylp_model_solve, 8},
     {"easylp_model_valid", (DL_FUNC)&easylp_model_valid, 1},
     {"easylp_solve_lp", (DL_FUNC)&easylp_solve_lp, 10},
+    {"easylp_solve_mip", (DL_FUNC)&easylp_solve_mip, 11},
     {"easylp_check_feasible", (DL_FUNC)&easylp_check_feasible, 7},
     {"easylp_solve_batch", (DL_FUNC)&easylp_solve_batch, 8},
     {"easylp_device_count", (DL_FUNC)&easylp_device_count, 0},

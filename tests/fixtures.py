@@ -24,12 +24,14 @@ def load_golden():
         g["col_idx"] = np.array(v["col_idx"], np.int32)
         g["objective_add"] = float.fromhex(v["objective_add"])
         g["sense"] = np.array([SENSE[d] for d in v["dir"]], np.int8)
-        if "highs" in v:
-            h = dict(v["highs"])
-            if "objective" in h:
-                h["objective"] = float.fromhex(h["objective"])
-                h["x"] = unhex(h["x"])
-            g["highs"] = h
+        for key in ("highs", "highs_milp"):           # continuous models / models with integer columns (branch and cut)
+            if key in v:
+                h = dict(v[key])
+                if "objective" in h:
+                    h["objective"] = float.fromhex(h["objective"])
+                    h["x"] = unhex(h["x"])
+                g[key] = h
+        g["is_integer"] = np.array(v.get("is_integer", [0] * v["n"]), np.uint8)
         out[name] = g
     return out
 

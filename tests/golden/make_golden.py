@@ -61,6 +61,25 @@ def highs(can):
     return out
 
 
+def highs_milp(can):
+    """integer / binary models: HiGHS branch and cut (scipy.optimize.milp), stand-in for lp_solve's branch and bound"""
+    from scipy.optimize import Bounds, LinearConstraint, milp
+    from scipy.sparse import csr_matrix
+    m, n = can["m"], can["n"]
+    A = csr_matrix((can["vals"], can["col_idx"], can["row_ptr"]), shape=(m, n))
+    sign = -1.0 if can["maximize"] else 1.0
+    lo = np.where(can["sense"] == 0, -np.inf, can["rhs"])
+    hi = np.where(can["sense"] == 1, np.inf, can["rhs"])
+    r = milp(sign * can["c"], constraints=LinearConstraint(A, lo, hi) if m else None, integrality=can["is_integer"].astype(int),
+             bounds=Bounds(can["lb"], can["ub"]))
+    status = {0: 0, 2: 2, 3: 3}.get(r.status, -1)
+    out = {"status": status}
+    if status == 0:
+        out["objective"] = float(sign * r.fun).hex()
+        out["x"] = hexes(r.x)
+    return out
+
+
 def main():
     warnings.simplefilter("ignore")
     out = {}
@@ -73,10 +92,10 @@ def main():
                    lb=hexes(can["lb"]), ub=hexes(can["ub"]), maximize=bool(can["maximize"]),
                    names=can["names"], rownames=can["rownames"],
                    integer=bool(any(v.integer or v.binary for v in lp.variables.values())))
-        if not rec["integer"]:
-            h = highs(can)
-            if h is not None:
-                rec["highs"] = h
+        rec["is_integer"] = [int(v) for v in can["is_integer"]]
+        h = highs(can) if not rec["integer"] else highs_milp(can)
+        if h is not None:
+            rec["highs_milp" if rec["integer"] else "highs"] = h
         out[name] = rec
     with open(os.path.join(HERE, "models.json"), "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)

@@ -158,8 +158,29 @@ def modified_indexed(api):
     return lp
 
 
+def cyingair(api):
+    """tests/testthat/test-cyingair.R:1-24 — binary + integer variables, `$associate`; the reference's test pins the
+    solution x = (0, 2, 3, 49), quin = (0, 1, 1, 1) (test-cyingair.R:27-30)"""
+    Avio = ["Jumbo", "Petit", "Mitja", "Gran"]
+    preu = [79, 67, 50, 35]
+    benefici = [5.8, 4.2, 3, 2.3]
+    lp = api.easylp()
+    quin = lp.var("quin", Avio, binary=True)
+    x = lp.var("x", Avio, integer=True, lower=0, upper=100)
+    lp.max(api.Sum(x * benefici))
+    lp.associate(x, quin, min1=1)
+    lp.con(tipus=api.Sum(quin) == 3,
+           r_pressupost=api.Sum(x * preu) <= 2000,
+           min_avions=api.Sum(x) >= 35,
+           no_mes_petits_que_mitjans=x["Petit"] <= x["Mitja"],
+           no_jumbo_i_grans=quin["Jumbo"] + quin["Gran"] <= 1,
+           quinze_percent=x["Jumbo"] <= 0.15 * api.Sum(x))
+    return lp
+
+
 def investments_assembly(api):
-    """tests/testthat/test-investments.R:1-41 — assembly only (binary variables: MIP is out of scope)"""
+    """tests/testthat/test-investments.R:1-41 — binary variables; the reference's test pins objective 469 and
+    x = (0, 0, 1, 1, 1, 0) (test-investments.R:45-46)"""
     Project, Year = list(range(1, 7)), list(range(1, 6))
     npv = api.parameter([141, 187, 121, 83, 265, 127], Project)
     budget = api.parameter([250, 75, 50, 50, 50], Year)
@@ -201,4 +222,5 @@ def duplicate_fold(api, seed=3):
 ALL = dict(readme=readme, dop=dop, unbounded=unbounded, rhs_variable=rhs_variable, infeasible_mean=infeasible_mean,
            constraints=constraints, forsplit=forsplit, aliases=aliases, transport_vignette=transport_vignette,
            transport_sum_for=lambda api: transport_vignette(api, True), modified=modified,
-           modified_indexed=modified_indexed, investments_assembly=investments_assembly, duplicate_fold=duplicate_fold)
+           modified_indexed=modified_indexed, investments_assembly=investments_assembly, duplicate_fold=duplicate_fold,
+           cyingair=cyingair)

@@ -11,6 +11,7 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 #define REALSXP 14
 #define STRSXP 16
 #define VECSXP 19
+#define EXTPTRSXP 22
 extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);
@@ -35,6 +36,8 @@ int Rf_asLogical(SEXP);
 double Rf_asReal(SEXP);
 SEXP Rf_ScalarInteger(int);
 SEXP Rf_ScalarReal(double);
+SEXP Rf_ScalarLogical(int);
+int TYPEOF(SEXP);
 void Rf_error(const char*, ...) __attribute__((noreturn));
 char* R_alloc(size_t, int);
 extern double R_PosInf, R_NegInf;

@@ -152,11 +152,14 @@ def test_solve_prechecks_keep_the_reference_messages():
         lp.solve()
 
 
-def test_integer_variables_are_rejected_by_the_gpu_solve():
-    # MIP is out of scope; the LP-only path must say so rather than relax silently
+def test_integer_variables_reach_the_branch_and_bound_entry_point():
+    # R/class.R:264-276: set.type + lp_solve's branch and bound; here elp_solve_mip (csrc/mip.cu).  Without a CUDA device
+    # the call fails loudly (no CPU fallback) instead of relaxing silently; the GPU run is tests/test_mip.py
+    from easylp_b200 import _lib
     lp = _build("investments_assembly")
-    with pytest.raises(M.EasyLpError, match="integer/binary"):
-        lp.solve()
+    if _lib.device_count() == 0:
+        with pytest.raises(_lib.ElpError, match="no CUDA device"):
+            lp.solve()
 
 
 def test_division_is_multiplication_by_the_reciprocal():
