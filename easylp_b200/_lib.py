@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "elp_version", "elp_last_error", "elp_device_count", "elp_set_device", "elp_default_options",
     "elp_status_string", "elp_kernel_launches", "elp_release_workspace", "elp_assemble_csr", "elp_assemble_lowered",
     "elp_expand_terms", "elp_model_assemble", "elp_model_dims", "elp_model_csr", "elp_model_solve", "elp_model_destroy", "elp_model_pdlp_create",
-    "elp_solve_lp", "elp_solve_mip", "elp_solve_batch",
+    "elp_solve_lp", "elp_solve_mip", "elp_sensitivity", "elp_solve_batch",
     "elp_batch_create", "elp_batch_run", "elp_batch_fetch", "elp_batch_destroy", "elp_spmv",
     "elp_check_feasible", "elp_pdlp_create", "elp_pdlp_run", "elp_pdlp_reset", "elp_pdlp_solution",
     "elp_pdlp_probe_spmv", "elp_pdlp_probe_step", "elp_pdlp_transpose", "elp_pdlp_destroy", "elp_comm_unique_id", "elp_comm_init", "elp_comm_size",
@@ -311,6 +311,26 @@ def solve_mip(m, n, row_ptr, col_idx, vals, sense, rhs, c, lb, ub, is_integer, m
                                C.byref(options) if options is not None else None,
                                C.byref(status), C.byref(obj), _p(x), C.byref(st)))
     return LpResult(status.value, obj.value, x, np.zeros(m), st)
+
+
+def sensitivity(m, n, row_ptr, col_idx, vals, sense, rhs, c, lb, ub, maximize=False, options: Options | None = None):
+    """elp_sensitivity: solve on the simplex path and range the objective coefficients and the right-hand sides.
+    Returns (status, objval, x, obj_from, obj_till, rhs_from, rhs_till, duals)."""
+    row_ptr, col_idx = _i32(row_ptr), _i32(col_idx)
+    vals, rhs, c = _f64(vals), _f64(rhs), _f64(c)
+    lb, ub = _f64(lb, (n,)), _f64(ub, (n,))
+    sense = _i8(sense)
+    if row_ptr.size == 0:
+        row_ptr = np.zeros(1, np.int32)
+    x, of, ot = np.zeros(n), np.zeros(n), np.zeros(n)
+    rf, rt, du = np.zeros(max(m, 1)), np.zeros(max(m, 1)), np.zeros(max(m, 1))
+    status = C.c_int32(-1)
+    obj = C.c_double(np.nan)
+    _check(lib().elp_sensitivity(C.c_int32(m), C.c_int32(n), _p(row_ptr), _p(col_idx), _p(vals), _p(sense), _p(rhs), _p(c),
+                                 C.c_int32(1 if maximize else 0), _p(lb), _p(ub),
+                                 C.byref(options) if options is not None else None, C.byref(status), C.byref(obj), _p(x),
+                                 _p(of), _p(ot), _p(rf), _p(rt), _p(du)))
+    return status.value, obj.value, x, of, ot, rf[:m], rt[:m], du[:m]
 
 
 def solve_batch(A, b, c, lb=None, ub=None, sense=None, maximize=False, options: Options | None = None, out=None):

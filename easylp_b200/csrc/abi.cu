@@ -52,8 +52,13 @@ void spmv_host(int m, int n, const int32_t* row_ptr, const int32_t* col_idx, con
 size_t simplex_smem_bytes(int m, int n);
 void simplex_batch_device(int64_t B, int m, int n, const double* A, const double* b, const double* c, const double* lb,
                           const double* ub, const int8_t* sense, int maximize, int max_pivots, int32_t* status,
-                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st, int shared_model = 0);
+                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st, int shared_model = 0,
+                          int32_t* basis = nullptr);
 void densify_device(int m, int n, const int* ptr, const int* idx, const double* val, double* A, cudaStream_t st);
+void sensitivity(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                 const int8_t* sense, const double* rhs, const double* c, int32_t maximize, const double* lb,
+                 const double* ub, const elp_options& o, int32_t* status, double* objval, double* x, double* obj_from,
+                 double* obj_till, double* rhs_from, double* rhs_till, double* duals);
 void solve_mip(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals, const int8_t* sense,
                const double* rhs, const double* c, int32_t maximize, const double* lb, const double* ub,
                const uint8_t* is_int, const elp_options& o, int32_t* status, double* objval, double* x, elp_stats* stats);
@@ -704,6 +709,21 @@ int elp_solve_mip(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* c
     } else {
         solve_mip(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, is_integer, o, status, objval, x, stats);
     }
+    ELP_CATCH
+}
+
+int elp_sensitivity(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                    const int8_t* sense, const double* rhs, const double* c, int32_t maximize, const double* lb,
+                    const double* ub, const elp_options* opt, int32_t* status, double* objval, double* x, double* obj_from,
+                    double* obj_till, double* rhs_from, double* rhs_till, double* duals) {
+    ELP_TRY
+    require_device();
+    ELP_REQUIRE(n > 0, "Problem contains no variables.");
+    ELP_REQUIRE(m >= 0 && status && objval && x && c && lb && ub && obj_from && obj_till && (m == 0 || (rhs_from && rhs_till && duals)),
+                "elp_sensitivity: bad arguments");
+    const elp_options o = effective_options(opt);
+    sensitivity(m, n, row_ptr, col_idx, vals, sense, rhs, c, maximize, lb, ub, o, status, objval, x, obj_from, obj_till, rhs_from,
+                rhs_till, duals);
     ELP_CATCH
 }
 

@@ -28,7 +28,8 @@ namespace elp {
 size_t simplex_smem_bytes(int m, int n);
 void simplex_batch_device(int64_t B, int m, int n, const double* A, const double* b, const double* c, const double* lb,
                           const double* ub, const int8_t* sense, int maximize, int max_pivots, int32_t* status,
-                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st, int shared_model);
+                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st, int shared_model,
+                          int32_t* basis = nullptr);
 void densify_device(int m, int n, const int* ptr, const int* idx, const double* val, double* A, cudaStream_t st);
 
 namespace {

@@ -53,6 +53,7 @@ struct StoreEpi {
     double* scat = nullptr;
     double* out;
     using Route = NoRoute;
+    using Stage = NoRoute;
     struct Pre {};
     __device__ __forceinline__ const double* in(int) const { return nullptr; }
     __device__ __forceinline__ Pre preload(const double*, int, int) const { return Pre{}; }
@@ -67,79 +68,148 @@ inline StoreEpi store_epi(double* out) { StoreEpi e; e.out = out; return e; }
 // ghost vector — entries in ascending global id, its matrix copy for the plain iterations carries the compact ids — with
 // two buffers selected by the parity of the epoch, so a producer may run one kernel ahead of its consumers without a
 // write-after-read hazard.  The epilogue of the producing kernel stores each value straight into the ghost vector of
-// every rank that reads it (CUDA IPC / peer access over NVLink); the position is the tile's base in that rank's vector
-// (a table built at setup) plus the number of lower lanes that also store there (one ballot per destination), so the
-// stores of a warp are contiguous.  The hand-off lives inside the kernels: the last CTA of the producer to finish
-// publishes the epoch in slot `rank` of every consumer's flag row (release), and every warp of the consuming kernel
-// waits — after it has queued its first matrix tiles — until all N slots have reached the epoch it needs (acquire).
+// every rank that reads it (peer access / CUDA IPC over NVLink); the position is the tile's base in that rank's vector
+// plus the number of lower lanes that also store there (one ballot per destination), so the stores of a warp are
+// contiguous.  Masks and bases of a tile form a 64-byte routing record that is staged with the tile by TMA.
+// The hand-off lives in the PROLOGUE of the consuming kernel.  Stream order makes everything this rank launched
+// before complete, so thread 0 of the kernel first publishes "my part of epoch E is done" in slot `rank` of every
+// rank's flag row (one system fence, N stores; no per-CTA fences, counters or extra launches: measured at N = 2 the
+// in-producer variant — fence + last-CTA counter in every CTA — cost 21 us per iteration), and one warp per CTA then
+// polls the local flag row until all N slots have reached E while the first matrix tiles are already on their way.
 struct GhostOut {
     double* buf[8];                    // rank r's ghost vector, buffer 0; buffer 1 lies stride[r] doubles further
     uint32_t stride[8];
-    unsigned long long* flag[8];       // rank r's flag row for this vector (N slots); this rank writes slot `rank`
-    const unsigned char* mask;         // [my block] bit r: rank r gathers this entry
-    const int* base;                   // [tiles of my block][8]: position of the tile's first entry in r's ghost vector
-    unsigned int* done;                // CTAs of the current launch that have finished (reset by the last one)
+    const uint32_t* route;             // [tiles of my block][SPMV_ROUTE_WORDS]: words 0-7 position of the tile's first entry
+                                       // in rank r's ghost vector, bytes 32-63 per row of the tile: bit r = rank r gathers it
     int n, rank;
+    int dbg;                           // measurement switches (ELP_GHOST_DEBUG): 1 no remote stores, 16 no routing
 };
 struct GhostIn {
     const double* vec;                 // my ghost vector, buffer 0
     uint32_t stride;
-    const unsigned long long* flags;   // my flag row for it
+    const unsigned long long* flags;   // my flag row for it (N slots)
+    unsigned long long* peer_flag[8];  // rank r's flag row for the same vector; this rank writes slot `rank`
     unsigned int* err;                 // bit 0: a producer never showed up (the host turns it into an error)
-    int n;
+    int n, rank;
+    int dbg;                           // 2 no wait, 4 no signal
 };
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+// flag store AFTER an explicit system fence: relaxed is enough (a st.release would repeat the fence per destination)
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// consumer side: returns the buffer that holds epoch `want`
+// consumer prologue: signal my part of epoch `want`, wait for everybody's; returns the buffer that holds the epoch
 __device__ __forceinline__ const double* ghost_acquire(const GhostIn& gi, long long want, int lane) {
-    if (lane < gi.n) {
-        unsigned long long spins = 0;
-        while ((long long)ld_acquire_sys(gi.flags + lane) < want) {
-            if (++spins > (1ull << 25)) { atomicOr(gi.err, 1u); break; }      // ~10 s: a peer died; fail, do not hang
-            if (spins > 64) __nanosleep(32);
-        }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !(gi.dbg & 4)) {
+        __threadfence_system();
+        for (int r = 0; r < gi.n; ++r) st_relaxed_sys(gi.peer_flag[r] + gi.rank, (unsigned long long)want);
     }
-    __syncwarp();
+    if (!(gi.dbg & 2) && (threadIdx.x >> 5) == 0 && lane < gi.n) {
+        unsigned long long spins = 0;
+        while ((long long)ld_volatile_u64(gi.flags + lane) < want) {
+            if (++spins > (1ull << 25)) { atomicOr(gi.err, 1u); break; }      // ~10 s: a peer died; fail, do not hang
+            if (spins > 16) __nanosleep(20);
+        }
+        __threadfence_system();                    // acquire: the gathers below are ordered behind the flags
+    }
+    __syncthreads();
     return gi.vec + ((want & 1) ? gi.stride : 0u);
 }
-// producer side, per row of a warp tile (all 32 lanes call both; `owner` lanes carry a value)
+// producer side.  A warp owns a contiguous range of tiles (spmv.cuh), so what it produces for rank r is ONE contiguous
+// run of r's ghost vector.  Values for remote ranks are collected in a 64-entry shared-memory ring per destination and
+// leave in stores of up to 32 consecutive doubles that END on a 256-byte boundary of the destination (after the first,
+// partial one every store is a full, aligned 256-byte line pair): NVLink moves full packets instead of one short,
+// misaligned packet per tile and destination — measured at N = 8, where the per-tile stores were packet-rate bound.
+// Lane r keeps the bookkeeping of destination r: entries appended, entries sent, the run's start in r's vector.
 struct GhostRoute { unsigned mk; int base; };
-__device__ __forceinline__ GhostRoute ghost_route(const GhostOut& go, int tile, int lane, bool owner, int row) {
+struct GhostStage {
+    double* ring;          // this warp's rings: [remote destination slot][SPMV_RING]
+    double* dst;           // lane r: start of my run in rank r's ghost vector (buffer of this epoch)
+    int cnt, sent;         // lane r: entries appended to / sent from the run
+    int phase;             // lane r: (absolute position of the run's start) mod 32, for the alignment of the stores
+    bool started;
+};
+__device__ __forceinline__ GhostRoute ghost_route(const GhostOut& go, const uint32_t* rec, int lane, bool owner, int row_in_tile) {
     GhostRoute g;
-    g.mk = owner ? (unsigned)go.mask[row] : 0u;
-    g.base = lane < go.n ? go.base[(size_t)tile * 8 + lane] : 0;
+    g.mk = owner ? (unsigned)reinterpret_cast<const unsigned char*>(rec)[32 + row_in_tile] : 0u;
+    g.base = (int)rec[lane & 7];
+    if (go.dbg & 16) g.mk = 0u;
     return g;
 }
-__device__ __forceinline__ void ghost_publish(const GhostOut& go, long long epoch, const GhostRoute& rt, int lane, double v) {
+__device__ __forceinline__ void ghost_stage_init(GhostStage& s, const GhostOut& go, unsigned char* rings, int warp, int lane) {
+    s.ring = reinterpret_cast<double*>(rings) + (size_t)warp * (go.n - 1) * SPMV_RING;
+    s.dst = nullptr; s.cnt = 0; s.sent = 0; s.phase = 0; s.started = false;
+}
+// sends [sent, upto) of destination r's run; warp-uniform arguments
+__device__ __forceinline__ void ghost_send(const GhostStage& s, int slot, int r, int from, int upto, int lane) {
+    const unsigned long long d = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)s.dst, r);
+    double* dp = reinterpret_cast<double*>((uintptr_t)d);
+    const int k = from + lane;
+    if (k < upto) dp[k] = s.ring[slot * SPMV_RING + (k & (SPMV_RING - 1))];
+}
+__device__ __forceinline__ void ghost_publish(const GhostOut& go, long long epoch, GhostStage& s, const GhostRoute& rt, int lane, double v) {
     const unsigned mk = rt.mk;
-    const int mybase = rt.base;
     const unsigned lower = (1u << lane) - 1u;
     const bool odd = (epoch & 1) != 0;
+    if (!s.started) {                               // first tile of this warp: the runs start at its bases
+        s.started = true;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (lane == r && r < go.n) {
+                s.dst = go.buf[r] + (odd ? go.stride[r] : 0u) + (uint32_t)rt.base;
+                s.phase = (int)(((uintptr_t)s.dst >> 3) & 31u);
+            }
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         if (r < go.n) {
-            const bool send = (mk >> r) & 1u;
+            const bool send = ((mk >> r) & 1u) && !((go.dbg & 1) && r != go.rank);
             const unsigned b = __ballot_sync(0xffffffffu, send);
-            const int br = __shfl_sync(0xffffffffu, mybase, r);
-            if (send) go.buf[r][(odd ? go.stride[r] : 0u) + (uint32_t)br + __popc(b & lower)] = v;
+            const int cur = __shfl_sync(0xffffffffu, s.cnt, r);
+            const int c = __popc(b);
+            if (r == go.rank) {                     // my own ghost vector: plain local stores
+                const unsigned long long d = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)s.dst, r);
+                if (send) reinterpret_cast<double*>((uintptr_t)d)[cur + __popc(b & lower)] = v;
+                if (lane == r) s.cnt = cur + c;
+            } else {
+                const int slot = r < go.rank ? r : r - 1;
+                if (send) s.ring[slot * SPMV_RING + ((cur + __popc(b & lower)) & (SPMV_RING - 1))] = v;
+                if (lane == r) s.cnt = cur + c;
+                int sent = __shfl_sync(0xffffffffu, s.sent, r);
+                const int ph = __shfl_sync(0xffffffffu, s.phase, r);
+                const int have = cur + c;
+                // next store ends where (phase + position) reaches a multiple of 32: a 256-byte boundary over there
+                int upto = ((ph + sent) / 32 + 1) * 32 - ph;
+                if (have >= upto) {
+                    __syncwarp();
+                    do {
+                        ghost_send(s, slot, r, sent, upto, lane);
+                        sent = upto;
+                        upto += 32;
+                    } while (have >= upto);
+                    if (lane == r) s.sent = sent;
+                }
+            }
         }
     }
 }
-__device__ __forceinline__ void ghost_release(const GhostOut& go, long long epoch) {
-    __syncthreads();                              // the CTA's peer stores happen before ...
-    if (threadIdx.x == 0) {
-        __threadfence_system();                   // ... this (cumulative) fence makes them visible system-wide
-        const unsigned old = atomicAdd(go.done, 1u);
-        if (old == gridDim.x - 1) {               // every CTA has passed its fence
-            *go.done = 0u;
-            __threadfence_system();
-            for (int r = 0; r < go.n; ++r) st_release_sys(go.flag[r] + go.rank, (unsigned long long)epoch);
+__device__ __forceinline__ void ghost_stage_flush(const GhostOut& go, GhostStage& s, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r < go.n && r != go.rank) {
+            const int slot = r < go.rank ? r : r - 1;
+            int sent = __shfl_sync(0xffffffffu, s.sent, r);
+            const int have = __shfl_sync(0xffffffffu, s.cnt, r);
+            while (sent < have) {
+                const int upto = min(have, sent + 32);
+                ghost_send(s, slot, r, sent, upto, lane);
+                sent = upto;
+            }
         }
     }
 }
@@ -164,6 +234,7 @@ struct PrimalEpi {
     GhostIn gin;        // y ghost (consumed)
     GhostOut gout;      // x-bar ghosts (produced)
     using Route = GhostRoute;
+    using Stage = GhostStage;
     struct Pre { double x, c, l, u, x0; };
     __device__ __forceinline__ const double* in(int i) const {
         return i == 0 ? x : i == 1 ? c : i == 2 ? l : i == 3 ? u : x0;
@@ -196,11 +267,16 @@ struct PrimalEpi {
     }
     // y of the previous iteration carries epoch_base + it; this launch produces epoch_base + it + 1
     __device__ __forceinline__ const double* acquire(int lane) const { return ghost_acquire(gin, P->epoch_base + it, lane); }
-    __device__ __forceinline__ Route route(int tile, int lane, bool owner, int row) const { return ghost_route(gout, tile, lane, owner, row); }
-    __device__ __forceinline__ void publish(const Route& rt, int lane, double v) const {
-        ghost_publish(gout, P->epoch_base + it + 1, rt, lane, v);
+    __device__ __forceinline__ const uint32_t* route_table() const { return gout.route; }
+    __device__ __forceinline__ Route route(const uint32_t* rec, int lane, bool owner, int row_in_tile) const {
+        return ghost_route(gout, rec, lane, owner, row_in_tile);
     }
-    __device__ __forceinline__ void release() const { ghost_release(gout, P->epoch_base + it + 1); }
+    __device__ __forceinline__ void stage_init(Stage& s, unsigned char* rings, int warp, int lane) const { ghost_stage_init(s, gout, rings, warp, lane); }
+    __device__ __forceinline__ void publish(Stage& s, const Route& rt, int lane, double v) const {
+        ghost_publish(gout, P->epoch_base + it + 1, s, rt, lane, v);
+    }
+    __device__ __forceinline__ void stage_flush(Stage& s, int lane) const { ghost_stage_flush(gout, s, lane); }
+    __host__ __device__ int rings() const { return gout.n > 1 ? gout.n - 1 : 0; }
 };
 
 // dual half.  ax = (A xbar)_i.  SCAT: the kernel then adds val[k] * y_new_i into scat[idx[k]] over the entries of row i,
@@ -223,6 +299,7 @@ struct DualEpi {
     GhostIn gin;        // x-bar ghost (consumed)
     GhostOut gout;      // y ghosts (produced)
     using Route = GhostRoute;
+    using Stage = GhostStage;
     struct Pre { double y, lc, uc, y0; };
     __device__ __forceinline__ const double* in(int i) const { return i == 0 ? y : i == 1 ? lc : i == 2 ? uc : y0; }
     __device__ __forceinline__ Pre preload(const double* s, int rt, int g) const {
@@ -257,11 +334,16 @@ struct DualEpi {
     }
     // the x-bar of this same iteration carries epoch_base + it + 1, and so does the y this launch produces
     __device__ __forceinline__ const double* acquire(int lane) const { return ghost_acquire(gin, P->epoch_base + it + 1, lane); }
-    __device__ __forceinline__ Route route(int tile, int lane, bool owner, int row) const { return ghost_route(gout, tile, lane, owner, row); }
-    __device__ __forceinline__ void publish(const Route& rt, int lane, double v) const {
-        ghost_publish(gout, P->epoch_base + it + 1, rt, lane, v);
+    __device__ __forceinline__ const uint32_t* route_table() const { return gout.route; }
+    __device__ __forceinline__ Route route(const uint32_t* rec, int lane, bool owner, int row_in_tile) const {
+        return ghost_route(gout, rec, lane, owner, row_in_tile);
     }
-    __device__ __forceinline__ void release() const { ghost_release(gout, P->epoch_base + it + 1); }
+    __device__ __forceinline__ void stage_init(Stage& s, unsigned char* rings, int warp, int lane) const { ghost_stage_init(s, gout, rings, warp, lane); }
+    __device__ __forceinline__ void publish(Stage& s, const Route& rt, int lane, double v) const {
+        ghost_publish(gout, P->epoch_base + it + 1, s, rt, lane, v);
+    }
+    __device__ __forceinline__ void stage_flush(Stage& s, int lane) const { ghost_stage_flush(gout, s, lane); }
+    __host__ __device__ int rings() const { return gout.n > 1 ? gout.n - 1 : 0; }
 };
 
 // Gather-free primal update of the scatter formulation: g = A'y was accumulated by the previous dual kernel.
@@ -635,10 +717,15 @@ __global__ void k_remap_idx(uint32_t nnz, const int* __restrict__ idx, const uin
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) out[i] = (int)pos[idx[i]];
 }
-// base[tile][r] = position, in rank r's ghost vector, of the first entry of my tile (pos = scan of r's marks)
-__global__ void k_tile_base(int ntiles, int rw, int first, const uint32_t* __restrict__ pos, int r, int* __restrict__ base) {
+// routing record of my tile t, word r = position, in rank r's ghost vector, of the tile's first entry (pos = scan of r's marks)
+__global__ void k_tile_base(int ntiles, int rw, int first, const uint32_t* __restrict__ pos, int r, uint32_t* __restrict__ route) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < ntiles) base[(size_t)t * 8 + r] = (int)pos[first + t * rw];
+    if (t < ntiles) route[(size_t)t * SPMV_ROUTE_WORDS + r] = pos[first + t * rw];
+}
+// bytes 32.. of the record: one mask per row of the tile
+__global__ void k_route_masks(int count, int rw, const unsigned char* __restrict__ mask, uint32_t* __restrict__ route) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < count) reinterpret_cast<unsigned char*>(route)[(size_t)(j / rw) * (SPMV_ROUTE_WORDS * 4) + 32 + (j % rw)] = mask[j];
 }
 __global__ void k_ghost_list(uint32_t count, const unsigned char* __restrict__ used, const uint32_t* __restrict__ pos, int* __restrict__ list) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -660,10 +747,11 @@ __global__ void k_compact(int count, const int* __restrict__ list, const double*
     if (k < count) out[k] = full[list[k]];
 }
 
-__global__ void k_ghost_signal_only(GhostOut go, const PdlpParams* __restrict__ P, int it) {
+// a rank without columns (rows) launches no K1 (K2): this stands in for the kernel's prologue
+__global__ void k_ghost_signal_only(GhostIn gi, const PdlpParams* __restrict__ P, int plus) {
     if (threadIdx.x == 0) {
         __threadfence_system();
-        for (int r = 0; r < go.n; ++r) st_release_sys(go.flag[r] + go.rank, (unsigned long long)(P->epoch_base + it + 1));
+        for (int r = 0; r < gi.n; ++r) st_relaxed_sys(gi.peer_flag[r] + gi.rank, (unsigned long long)(P->epoch_base + plus));
     }
 }
 
@@ -745,7 +833,7 @@ struct Pdlp {
     bool ghost = false;
     DevBuf<int> csr_idx_g, csc_idx_g;    // the matrix copies' ids in the compact numbering of my ghost vectors
     DevBuf<unsigned char> xmask, ymask;  // which ranks gather entry j of my x-bar / y block
-    DevBuf<int> xbase, ybase;            // [tiles][8] base positions in the consumers' ghost vectors
+    DevBuf<uint32_t> xroute, yroute;     // [tiles][SPMV_ROUTE_WORDS] routing records of what K1 / K2 produce
     DevBuf<int> ylist;                   // global (padded) ids of my y ghost entries, ascending
     DevBuf<unsigned char> ghost_mem;     // flag rows, error word, CTA counters, x-bar ghost x2, y ghost x2 (mapped by the peers)
     int gx = 0, gy = 0;                  // entries of my ghost vectors
@@ -786,7 +874,7 @@ struct Pdlp {
     // Builds the ghost exchange: which entries every rank gathers, their compact numbering, the producers' masks and
     // tile bases, and the peer mappings (same process: peer access; other processes: CUDA IPC).  Falls back to NCCL
     // all-gathers of the full vectors when the GPUs cannot reach each other's memory (or ELP_PDLP_P2P=0).
-    static constexpr size_t GH_FLAGS_BYTES = 512;      // x flags [0,64) y flags [64,128) err 128 done-x 136 done-y 140
+    static constexpr size_t GH_FLAGS_BYTES = 512;      // x flags [0,64) y flags [64,128) err 128
     void setup_ghost_exchange() {
         ghost = false;
         if (N <= 1 || N > 8 || env_int("ELP_PDLP_P2P", 1) == 0) return;
@@ -805,12 +893,13 @@ struct Pdlp {
         {
             ArenaScope k(keep);
             csr_idx_g.alloc(nnz + SPMV_PAD); csc_idx_g.alloc(nnzc + SPMV_PAD);
-            xbase.alloc((size_t)std::max(plan_c.ntiles, 1) * 8); ybase.alloc((size_t)std::max(plan_r.ntiles, 1) * 8);
+            xroute.alloc((size_t)std::max(plan_c.ntiles, 1) * SPMV_ROUTE_WORDS + 4);
+            yroute.alloc((size_t)std::max(plan_r.ntiles, 1) * SPMV_ROUTE_WORDS + 4);
             xmask.alloc((size_t)std::max(nl, 1)); ymask.alloc((size_t)std::max(m, 1));
             ylist.alloc(sy);                                       // at most every padded row
         }
         csr_idx_g.zero(st); csc_idx_g.zero(st);
-        xbase.zero(st); ybase.zero(st);
+        xroute.zero(st); yroute.zero(st);
         DevBuf<uint32_t> pos(std::max(sx, sy) + 1);
         ScanWorkspace sw;
         std::vector<uint32_t> gxs(N), gys(N);
@@ -819,7 +908,7 @@ struct Pdlp {
             exclusive_scan_u32(pos.p, sx + 1, sw, st);
             ELP_CUDA(cudaMemcpyAsync(&gxs[r], pos.p + sx, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             if (r == rank && nnz > 0) ELP_LAUNCH(k_remap_idx, ceil_div(nnz, 256), 256, 0, st, (uint32_t)nnz, csr_idx.p, pos.p, csr_idx_g.p);
-            if (nl > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_c.ntiles, 256), 256, 0, st, plan_c.ntiles, plan_c.rw(), n0, pos.p, r, xbase.p);
+            if (nl > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_c.ntiles, 256), 256, 0, st, plan_c.ntiles, plan_c.rw(), n0, pos.p, r, xroute.p);
             ELP_CUDA(cudaStreamSynchronize(st));
         }
         for (int r = 0; r < N; ++r) {
@@ -830,7 +919,7 @@ struct Pdlp {
                 if (nnzc > 0) ELP_LAUNCH(k_remap_idx, ceil_div(nnzc, 256), 256, 0, st, (uint32_t)nnzc, csc_idx.p, pos.p, csc_idx_g.p);
                 ELP_LAUNCH(k_ghost_list, ceil_div((int64_t)sy, 256), 256, 0, st, (uint32_t)sy, used_y.p + (size_t)r * sy, pos.p, ylist.p);
             }
-            if (m > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_r.ntiles, 256), 256, 0, st, plan_r.ntiles, plan_r.rw(), rank * mb, pos.p, r, ybase.p);
+            if (m > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_r.ntiles, 256), 256, 0, st, plan_r.ntiles, plan_r.rw(), rank * mb, pos.p, r, yroute.p);
             ELP_CUDA(cudaStreamSynchronize(st));
         }
         gx = (int)gxs[rank]; gy = (int)gys[rank];
@@ -839,6 +928,9 @@ struct Pdlp {
         sent.zero(st);
         if (nl > 0) ELP_LAUNCH(k_ghost_mask, grid1(nl), 256, 0, st, nl, n0, sx, N, used_x.p, xmask.p, sent.p);
         if (m > 0) ELP_LAUNCH(k_ghost_mask, grid1(m), 256, 0, st, m, rank * mb, sy, N, used_y.p, ymask.p, sent.p + 1);
+        ELP_REQUIRE(plan_c.rw() <= 32 && plan_r.rw() <= 32, "pdlp: routing records hold 32 rows per tile");
+        if (nl > 0) ELP_LAUNCH(k_route_masks, grid1(nl), 256, 0, st, nl, plan_c.rw(), xmask.p, xroute.p);
+        if (m > 0) ELP_LAUNCH(k_route_masks, grid1(m), 256, 0, st, m, plan_r.rw(), ymask.p, yroute.p);
         unsigned long long h[2] = {0, 0};
         ELP_CUDA(cudaMemcpyAsync(h, sent.p, sizeof h, cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
@@ -895,22 +987,23 @@ struct Pdlp {
             if (opt.verbose > 0 && rank == 0) fprintf(stderr, "[pdlp] no peer access between the GPUs: NCCL all-gather exchange\n");
             return;
         }
+        const int gdbg = env_int("ELP_GHOST_DEBUG", 0);
         xout = GhostOut{}; yout = GhostOut{};
-        xout.n = yout.n = N; xout.rank = yout.rank = rank;
-        xout.mask = xmask.p; yout.mask = ymask.p;
-        xout.base = xbase.p; yout.base = ybase.p;
-        xout.done = reinterpret_cast<unsigned int*>(ghost_mem.p + 136);
-        yout.done = reinterpret_cast<unsigned int*>(ghost_mem.p + 140);
+        xin = GhostIn{}; yin = GhostIn{};
+        xout.n = yout.n = xin.n = yin.n = N;
+        xout.rank = yout.rank = xin.rank = yin.rank = rank;
+        xout.dbg = yout.dbg = xin.dbg = yin.dbg = gdbg;
+        xout.route = xroute.p; yout.route = yroute.p;
         for (int r = 0; r < N; ++r) {
             double* g0 = reinterpret_cast<double*>(base[r] + GH_FLAGS_BYTES);
             xout.buf[r] = g0;                               xout.stride[r] = padded(gxs[r]);
             yout.buf[r] = g0 + 2 * (size_t)padded(gxs[r]);  yout.stride[r] = padded(gys[r]);
-            xout.flag[r] = reinterpret_cast<unsigned long long*>(base[r]);
-            yout.flag[r] = reinterpret_cast<unsigned long long*>(base[r] + 64);
+            xin.peer_flag[r] = reinterpret_cast<unsigned long long*>(base[r]);
+            yin.peer_flag[r] = reinterpret_cast<unsigned long long*>(base[r] + 64);
         }
         unsigned int* err = reinterpret_cast<unsigned int*>(ghost_mem.p + 128);
-        xin = GhostIn{xout.buf[rank], xout.stride[rank], xout.flag[rank], err, N};
-        yin = GhostIn{yout.buf[rank], yout.stride[rank], yout.flag[rank], err, N};
+        xin.vec = xout.buf[rank]; xin.stride = xout.stride[rank]; xin.flags = xin.peer_flag[rank]; xin.err = err;
+        yin.vec = yout.buf[rank]; yin.stride = yout.stride[rank]; yin.flags = yin.peer_flag[rank]; yin.err = err;
         ghost = true;
         if (opt.verbose > 0 || env_int("ELP_PDLP_DEBUG", 0))
             fprintf(stderr, "[pdlp] rank %d ghost exchange: gathers %d of %d x-bar entries and %d of %d y entries; sends %.1f %% / %.1f %% of a dense all-gather (%s)\n",
@@ -1348,8 +1441,8 @@ struct Pdlp {
 
     // ---- iteration pieces ------------------------------------------------------------------------
     // multi-GPU, a rank without columns / rows still owes its consumers the epoch
-    void signal_only(const GhostOut& go, int it) {
-        ELP_LAUNCH(k_ghost_signal_only, 1, 32, 0, st, go, params.p, it);
+    void signal_only(const GhostIn& gi, int plus) {
+        ELP_LAUNCH(k_ghost_signal_only, 1, 32, 0, st, gi, params.p, plus);
     }
     template <bool CHECK>
     void primal_step(int it) {
@@ -1361,7 +1454,7 @@ struct Pdlp {
         if (!CHECK && ghost) {              // gathers y from my ghost vector, publishes x-bar into the consumers' ghost vectors
             PrimalEpi<false, true> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, yin, xout};
             if (nl > 0) launch_spmv(plan_c, nl, csc_ptr.p, csc_idx_g.p, csc_val.p, yin.vec, epi, st);
-            else signal_only(xout, it);
+            else signal_only(yin, it);              // what K1's prologue would have said: my y of the previous epoch is out
             return;
         }
         PrimalEpi<CHECK> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, GhostIn{}, GhostOut{}};
@@ -1378,7 +1471,7 @@ struct Pdlp {
         if (!CHECK && ghost) {
             DualEpi<false, false, true> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, xin, yout};
             if (m > 0) launch_spmv(plan_r, m, csr_ptr.p, csr_idx_g.p, csr_val.p, xin.vec, epi, st);
-            else signal_only(yout, it);
+            else signal_only(xin, it + 1);          // what K2's prologue would have said: my x-bar of this epoch is out
             return;
         }
         DualEpi<CHECK> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, GhostIn{}, GhostOut{}};

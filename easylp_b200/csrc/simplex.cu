@@ -116,7 +116,7 @@ simplex_batch_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, con
                      const int8_t* __restrict__ senseg, int maximize, int max_pivots, int shared_model,
                      int32_t* __restrict__ status_out,
                      double* __restrict__ obj_out, double* __restrict__ x_out, double* __restrict__ y_out,
-                     int32_t* __restrict__ pivots_out) {
+                     int32_t* __restrict__ pivots_out, int32_t* __restrict__ basis_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SimplexSmemLayout lay(m, n);
     const int N = lay.N;
@@ -359,6 +359,8 @@ simplex_batch_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, con
         obj_out[lp] = maximize ? -obj : obj;
         if (pivots_out) pivots_out[lp] = pivots;
     }
+    if (basis_out)      // final basis, one column id per row (structural j < n, slack of row i = n + i): sensitivity ranging
+        for (int i = tid; i < m; i += THREADS) basis_out[lp * (int64_t)m + i] = basis[i];
     if (y_out) {
         double* yo = y_out + lp * (int64_t)m;
         for (int i = tid; i < m; i += THREADS) {
@@ -440,7 +442,7 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
                     const double* __restrict__ cg, const double* __restrict__ lbg, const double* __restrict__ ubg,
                     const int8_t* __restrict__ senseg, int maximize, int max_pivots, int shared_model, int use_tma,
                     int32_t* __restrict__ status_out, double* __restrict__ obj_out, double* __restrict__ x_out,
-                    double* __restrict__ y_out, int32_t* __restrict__ pivots_out) {
+                    double* __restrict__ y_out, int32_t* __restrict__ pivots_out, int32_t* __restrict__ basis_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NS = 32 * CPL + 2;
     const WarpSimplexLayout lay(MR, CPL);
@@ -730,6 +732,7 @@ simplex_warp_kernel(int64_t B, int m, int n, const double* __restrict__ Ag, cons
             obj_out[lp] = maximize ? -obj : obj;
             if (pivots_out) pivots_out[lp] = pivots;
         }
+        if (basis_out && lane < m) basis_out[lp * (int64_t)m + lane] = basis[lane];   // sensitivity ranging
         if (y_out) {
             // y_i = sum_k cost[basis[k]] * Tslack[k][i]: slack column n+i belongs to one lane
 #pragma unroll
@@ -779,7 +782,7 @@ template <int MR, int CPL>
 static void simplex_warp_launch_inst(int64_t B, int m, int n, const double* A, const double* b, const double* c,
                                      const double* lb, const double* ub, const int8_t* sense, int maximize, int max_pivots,
                                      int32_t* status, double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st,
-                                     int shared_model) {
+                                     int shared_model, int32_t* basis) {
     auto kern = simplex_warp_kernel<MR, CPL>;
     const WarpSimplexLayout lay(MR, CPL);
     const size_t smem = (size_t)SW_WARPS * lay.total;
@@ -792,13 +795,13 @@ static void simplex_warp_launch_inst(int64_t B, int m, int n, const double* A, c
     const int64_t want = (B + SW_WARPS - 1) / SW_WARPS;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * occ));
     ELP_LAUNCH(kern, grid, SW_WARPS * 32, smem, st, B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, shared_model, use_tma,
-               status, obj, x, y, pivots);
+               status, obj, x, y, pivots, basis);
 }
 
 static bool simplex_warp_launch(int64_t B, int m, int n, const double* A, const double* b, const double* c,
                                 const double* lb, const double* ub, const int8_t* sense, int maximize, int max_pivots,
                                 int32_t* status, double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st,
-                                int shared_model) {
+                                int shared_model, int32_t* basis) {
     if (!env_flag("ELP_SIMPLEX_WARP", 1)) return false;
     const int N = m + n;
     if (m > 32 || N > 96) return false;
@@ -808,7 +811,7 @@ static bool simplex_warp_launch(int64_t B, int m, int n, const double* A, const 
 #define ELP_SW(MR_, CPL_)                                                                                              \
     if (mr == MR_ && cpl == CPL_) {                                                                                    \
         simplex_warp_launch_inst<MR_, CPL_>(B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, status, obj, x, y, \
-                                            pivots, st, shared_model);                                                 \
+                                            pivots, st, shared_model, basis);                                          \
         return true;                                                                                                   \
     }
     ELP_SW(4, 1) ELP_SW(8, 1) ELP_SW(12, 1) ELP_SW(16, 1) ELP_SW(20, 1) ELP_SW(24, 1) ELP_SW(28, 1) ELP_SW(32, 1)
@@ -821,11 +824,12 @@ static bool simplex_warp_launch(int64_t B, int m, int n, const double* A, const 
 // all pointers are device pointers
 void simplex_batch_device(int64_t B, int m, int n, const double* A, const double* b, const double* c, const double* lb,
                           const double* ub, const int8_t* sense, int maximize, int max_pivots, int32_t* status,
-                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st, int shared_model) {
+                          double* obj, double* x, double* y, int32_t* pivots, cudaStream_t st, int shared_model,
+                          int32_t* basis) {
     if (B <= 0) return;
     ELP_REQUIRE(n > 0 && m >= 0, "simplex: bad shape %d x %d", m, n);
     ELP_REQUIRE(B < 0x7fffffffll, "simplex: batch too large");
-    if (simplex_warp_launch(B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, status, obj, x, y, pivots, st, shared_model)) return;
+    if (simplex_warp_launch(B, m, n, A, b, c, lb, ub, sense, maximize, max_pivots, status, obj, x, y, pivots, st, shared_model, basis)) return;
     const size_t smem = simplex_smem_bytes(m, n);
     ELP_REQUIRE(smem <= 227 * 1024, "simplex: tableau of %d x %d needs %zu bytes of shared memory (max 227 KB)", m, n,
                 smem);
@@ -835,7 +839,7 @@ void simplex_batch_device(int64_t B, int m, int n, const double* A, const double
         ELP_CUDA(cudaFuncSetAttribute(simplex_batch_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                       (int)smem));                                                                \
         ELP_LAUNCH((simplex_batch_kernel<T>), (unsigned)B, T, smem, st, B, m, n, A, b, c, lb, ub, sense, maximize, \
-                   max_pivots, shared_model, status, obj, x, y, pivots);                                          \
+                   max_pivots, shared_model, status, obj, x, y, pivots, basis);                                   \
     } while (0)
     if (threads == 32) ELP_SIMPLEX_LAUNCH(32);
     else if (threads == 64) ELP_SIMPLEX_LAUNCH(64);

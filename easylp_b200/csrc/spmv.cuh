@@ -35,17 +35,21 @@ constexpr int SPMV_PAD = 8;        // extra entries behind val / idx
 constexpr int SPMV_PTR_PAD = 4;    // extra ints behind ptr
 constexpr int SPMV_VPAD = 2;       // extra doubles behind every epilogue operand vector
 
+constexpr int SPMV_ROUTE_WORDS = 16;   // multi-GPU: one 64-byte routing record per tile (8 base positions + 32 mask bytes)
+
 struct SpmvStageLayout {          // byte offsets inside one stage of one warp
     int cap;                      // entries per stage (multiple of 4)
-    int off_idx, off_ptr, off_ops, bytes;
+    int off_idx, off_ptr, off_ops, off_route, bytes;
 };
-__host__ __device__ inline SpmvStageLayout spmv_stage_layout(int cap, int rw, int nin) {
+__host__ __device__ inline SpmvStageLayout spmv_stage_layout(int cap, int rw, int nin, bool route = false) {
     SpmvStageLayout s;
     s.cap = cap;
     s.off_idx = cap * 8;
     s.off_ptr = s.off_idx + cap * 4;
     s.off_ops = s.off_ptr + (rw + 4) * 4;
-    s.bytes = s.off_ops + nin * ((rw + 1) & ~1) * 8;
+    s.off_route = s.off_ops + nin * ((rw + 1) & ~1) * 8;
+    s.off_route = (s.off_route + 15) & ~15;
+    s.bytes = s.off_route + (route ? SPMV_ROUTE_WORDS * 4 : 0);
     s.bytes = (s.bytes + 15) & ~15;
     return s;
 }
@@ -53,7 +57,7 @@ __host__ __device__ inline SpmvStageLayout spmv_stage_layout(int cap, int rw, in
 constexpr int SPMV_WARPS = 4;      // warps per CTA (a CTA is only a container: warps never talk)
 
 template <int L, int RPL, int NSTW, class Epi>
-__global__ void __launch_bounds__(SPMV_WARPS * 32, 6 / RPL)
+__global__ void __launch_bounds__(SPMV_WARPS * 32, Epi::DIST ? 4 : 6 / RPL)   // (multi-GPU: the outgoing rings cap the residency at 4-5 CTAs anyway)
 spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, const int* __restrict__ idx,
                  const double* __restrict__ val, const double* __restrict__ vec, Epi epi, int l2flags) {
     // NSTW stages per warp: one being consumed, the others in flight (2; 3 is offered to the scatter epilogues, which
@@ -64,7 +68,7 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     constexpr int U = (L <= 2) ? 8 : 4;      // gathers in flight per lane
     constexpr int OPS = (RW + 1) & ~1;       // doubles per staged operand
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const SpmvStageLayout lay = spmv_stage_layout(cap, RW, NIN);
+    const SpmvStageLayout lay = spmv_stage_layout(cap, RW, NIN, Epi::DIST);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* ring = smem_raw + (size_t)warp * NSTW * lay.bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SPMV_WARPS * NSTW * lay.bytes) + warp * NSTW;
@@ -77,18 +81,28 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     const uint64_t pol_stream = l2_policy_evict_first();
     const L2Hints hints{pol_stream, l2_policy_evict_last(), l2flags};
     const int gw = blockIdx.x * SPMV_WARPS + warp, nw = gridDim.x * SPMV_WARPS;
+    // Tile walk.  Single GPU: warp-strided round robin.  Multi-GPU: every warp owns a CONTIGUOUS range of tiles, so that
+    // what it produces for one destination rank is one contiguous run of that rank's ghost vector and can leave in
+    // full 256-byte stores (see GhostStage in pdlp.cu) instead of one short store per tile.
+    const bool blocked = Epi::DIST && !(l2flags & 16);      // (bit 16: strided walk in a multi-GPU kernel — timing experiments only)
+    const int t_first = blocked ? (int)((int64_t)gw * ntiles / nw) : gw;
+    const int t_last = blocked ? (int)((int64_t)(gw + 1) * ntiles / nw) : ntiles;
+    const int t_step = blocked ? 1 : nw;
+    [[maybe_unused]] typename Epi::Stage stage_out;
+    if constexpr (Epi::DIST)
+        epi.stage_init(stage_out, smem_raw + (((size_t)SPMV_WARPS * NSTW * (lay.bytes + 8) + 15) & ~(size_t)15), warp, lane);
 
     // ---- producer cursor: the next piece to copy (uniform across the warp) --------------------------------
-    int p_tile = gw, p_piece = 0, p_s = 0, p_e = 0, n_s = 0, n_e = 0;
+    int p_tile = t_first, p_piece = 0, p_s = 0, p_e = 0, n_s = 0, n_e = 0;
     auto bounds = [&](int t, int& a, int& b) {
-        if (t < ntiles) {
+        if (t < t_last) {
             const int r0 = t * RW;
             a = __ldg(ptr + r0);
             b = __ldg(ptr + min(r0 + RW, nrows));
         } else { a = 0; b = 0; }
     };
     auto issue = [&](int stage) {
-        if (p_tile >= ntiles) return;
+        if (p_tile >= t_last) return;
         const int a0 = p_s & ~3, a1 = (p_e + 3) & ~3;
         const int pstart = a0 + p_piece * cap;
         const int pcnt = max(0, min(cap, a1 - pstart));
@@ -107,10 +121,15 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
         else if (p_piece == 0) {
             if (lane == 2) { src = ptr + r0; dst = sb + lay.off_ptr; bytes = ptr_bytes; }
             else if (lane < 3 + NIN) { src = epi.in(lane - 3) + r0; dst = sb + lay.off_ops + (lane - 3) * OPS * 8; bytes = op_bytes; }
+            else if (lane == 3 + NIN) {
+                if constexpr (Epi::DIST) {                // multi-GPU: the tile's routing record travels with its operands
+                    src = epi.route_table() + (size_t)p_tile * SPMV_ROUTE_WORDS; dst = sb + lay.off_route; bytes = SPMV_ROUTE_WORDS * 4;
+                }
+            }
         }
         if (lane == 0) {
             uint32_t tx = (uint32_t)pcnt * 12u;
-            if (p_piece == 0) tx += ptr_bytes + (uint32_t)NIN * op_bytes;
+            if (p_piece == 0) tx += ptr_bytes + (uint32_t)NIN * op_bytes + (Epi::DIST ? SPMV_ROUTE_WORDS * 4u : 0u);
             mbar_expect_tx(&full[stage], tx);
         }
         __syncwarp();
@@ -120,15 +139,15 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             else tma_load_1d(dst, src, bytes, &full[stage]);
         }
         if (last) {
-            p_tile += nw; p_piece = 0;
+            p_tile += t_step; p_piece = 0;
             p_s = n_s; p_e = n_e;
-            bounds(p_tile + nw, n_s, n_e);        // needed one tile later: its latency is hidden
+            bounds(p_tile + t_step, n_s, n_e);    // needed one tile later: its latency is hidden
         } else {
             ++p_piece;
         }
     };
     bounds(p_tile, p_s, p_e);
-    bounds(p_tile + nw, n_s, n_e);
+    bounds(p_tile + t_step, n_s, n_e);
 #pragma unroll
     for (int s = 0; s < NSTW; ++s) issue(s);
     // multi-GPU: the gathered vector is filled by the peers' stores.  The matrix stream is already on its way; wait
@@ -143,18 +162,13 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     const double* hv = nullptr;
     const int* hi = nullptr;
     int hstage = 0;
-    for (int tile = gw; tile < ntiles; tile += nw) {
+    for (int tile = t_first; tile < t_last; tile += t_step) {
         const int row0 = tile * RW + g;
         int st[RPL], en[RPL], a0 = 0, a1 = 0;
         typename Epi::Pre pre[RPL];
         double acc[RPL];
-        // multi-GPU: who reads this tile's outputs and where they go — fetched now so that the latency of these two
-        // loads hides behind the gathers instead of sitting on the warp's critical path after the row sum
+        // multi-GPU: who reads this tile's outputs and where they go (picked out of the staged routing record)
         [[maybe_unused]] typename Epi::Route route[RPL];
-        if constexpr (Epi::DIST) {
-#pragma unroll
-            for (int j = 0; j < RPL; ++j) route[j] = epi.route(tile, lane, sub == 0 && row0 + j * G < nrows, row0 + j * G);
-        }
 #pragma unroll
         for (int j = 0; j < RPL; ++j) { st[j] = 0; en[j] = 0; acc[j] = 0.0; pre[j] = typename Epi::Pre{}; }
         for (int piece = 0;; ++piece) {
@@ -173,6 +187,9 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
                         en[j] = sp[g + j * G + 1];
                         if (sub == 0) pre[j] = epi.preload(reinterpret_cast<const double*>(sb + lay.off_ops), OPS, g + j * G);
                     }
+                    if constexpr (Epi::DIST)
+                        route[j] = epi.route(reinterpret_cast<const uint32_t*>(sb + lay.off_route), lane,
+                                             sub == 0 && row0 + j * G < nrows, g + j * G);
                 }
             }
             const int pstart = a0 + piece * cap;
@@ -236,7 +253,7 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             const bool owner = sub == 0 && row0 + j * G < nrows;
             if (owner) mult = epi.apply(row0 + j * G, a, pre[j], hints);
             // multi-GPU: the value just produced goes into the ghost vector of every rank that gathers it (warp-collective)
-            if constexpr (Epi::DIST) epi.publish(route[j], lane, mult);
+            if constexpr (Epi::DIST) epi.publish(stage_out, route[j], lane, mult);
             if (Epi::SCATTER) {
                 // out[idx[k]] += val[k] * mult over this row's entries (fire-and-forget fp64 reductions: SASS RED.ADD.F64);
                 // rows whose multiplier is zero (inactive constraints) send nothing.
@@ -253,8 +270,7 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             issue(hstage);
         }
     }
-    // multi-GPU: the last CTA to finish tells every consumer that this rank's block of the epoch is complete
-    if constexpr (Epi::DIST) epi.release();
+    if constexpr (Epi::DIST) epi.stage_flush(stage_out, lane);        // what is left in the outgoing rings
 }
 
 // ---- long rows: one warp per row -----------------------------------------------------------------------
@@ -307,8 +323,11 @@ inline int pick_lanes(int64_t nnz, int64_t nrows) {
     return L;
 }
 
-inline size_t spmv_smem_bytes(const SpmvPlan& p, int nin) {
-    return (size_t)SPMV_WARPS * p.nst * (spmv_stage_layout(p.cap, p.rw(), nin).bytes + 8);
+constexpr int SPMV_RING = 64;      // multi-GPU: doubles per outgoing ring (one ring per warp and remote destination)
+inline size_t spmv_smem_bytes(const SpmvPlan& p, int nin, bool route = false, int rings = 0) {
+    size_t b = (size_t)SPMV_WARPS * p.nst * (spmv_stage_layout(p.cap, p.rw(), nin, route).bytes + 8);
+    if (rings > 0) b = ((b + 15) & ~(size_t)15) + (size_t)SPMV_WARPS * rings * SPMV_RING * sizeof(double);
+    return b;
 }
 
 // nin_max: the largest operand count among the epilogues that will run with this plan
@@ -347,7 +366,9 @@ template <int L, int RPL, int NSTW, class Epi>
 void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val,
                       const double* vec, const Epi& epi, cudaStream_t st) {
     auto kern = spmv_warp_kernel<L, RPL, NSTW, Epi>;
-    const size_t smem = spmv_smem_bytes(p, Epi::NIN);
+    int rings = 0;
+    if constexpr (Epi::DIST) rings = epi.rings();
+    const size_t smem = spmv_smem_bytes(p, Epi::NIN, Epi::DIST, rings);
     ELP_REQUIRE(smem <= 227 * 1024, "spmv: stage ring of %zu bytes does not fit in shared memory", smem);
     // per device and ring size: raise the dynamic shared-memory limit once and ask how many CTAs really fit
     static size_t cfg_smem[16] = {};
@@ -366,7 +387,8 @@ void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* i
                     Epi::NIN, p.cap, smem, p.ctas_per_sm, occ, p.ntiles);
     }
     // persistent grid: exactly one wave
-    const int per_sm = std::min(p.ctas_per_sm, cfg_occ[dev]);
+    int per_sm = std::min(p.ctas_per_sm, cfg_occ[dev]);
+    if (rings > 0) per_sm = std::max(1, std::min<int>(per_sm, (int)(196 * 1024 / (smem + 1024))));   // the L1 rule of plan_spmv
     const int grid = std::max(1, std::min(ceil_div(p.ntiles, SPMV_WARPS), kNumSMs * per_sm));
     // L2 residency hints (tma.cuh: L2Hints).  Default 3: the operand streams and the outputs nobody gathers from are
     // evict-first like the matrix stream, so that the vector the NEXT kernel gathers from survives in L2.  Measured in

@@ -1147,12 +1147,31 @@ class easylp:
     def status(self):
         return self._stat
 
+    # ---- $sensitivity_objective / $sensitivity_rhs  R/class.R:613-646 ----------------------------------------
+    def _sensitivity(self):
+        if self._stat != "optimal":
+            raise EasyLpError("Problem is not optimal.")
+        if self.any_integer():
+            raise EasyLpError("Sensitivity unavailable for problems with integer/binary variables")
+        lb, ub = self._bounds()
+        rp, ci, v = self._csr()
+        m = sum(b.nrow for b in self._blocks)
+        return _lib.sensitivity(m, self._n_var, rp, ci, v, self._dir_codes(_SENSE), self.constraint.rhs, self.objective_fun,
+                                lb, ub, maximize=self._dir == "max")
+
     @property
     def sensitivity_objective(self):
-        raise EasyLpError("sensitivity ranging needs a simplex basis from lp_solve; not provided by the GPU path "
-                          "(SURVEY.md §8f N3). Duals are available as `lp.duals`.")
+        """array [variable, (Lower, Current, Upper)] like R/class.R:619-628: the range of every objective coefficient
+        over which the optimal basis stays optimal (elp_sensitivity; infinite ends are +/-inf as after large_to_infinity)"""
+        _, _, _, of, ot, _, _, _ = self._sensitivity()
+        return np.column_stack([of, self.objective_fun, ot])
 
-    sensitivity_rhs = sensitivity_objective
+    @property
+    def sensitivity_rhs(self):
+        """array [constraint, (Lower, Current, Upper)] like R/class.R:636-645: the range of every right-hand side over
+        which the optimal basis stays feasible"""
+        _, _, _, _, _, rf, rt, _ = self._sensitivity()
+        return np.column_stack([rf, self.constraint.rhs, rt])
 
     def variable_names(self):
         """name_variable (R/utils.R:147-153), for every column"""

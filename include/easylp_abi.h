@@ -214,6 +214,23 @@ int elp_solve_mip(int32_t m, int32_t n,
                   const elp_options* opt /* may be NULL */,
                   int32_t* status, double* objval, double* x /* n */, elp_stats* stats /* may be NULL */);
 
+/* ---- (2c) sensitivity ranging: replaces lpSolveAPI::get.sensitivity.obj / get.sensitivity.rhs behind
+ *      `$sensitivity_objective` and `$sensitivity_rhs` (R/class.R:613-646).  Solves the LP on the simplex path (the model
+ *      must fit it: ranging needs a basis) and returns, per variable, the interval [obj_from, obj_till] of its cost over
+ *      which the optimal basis stays optimal and, per constraint, the interval [rhs_from, rhs_till] of its right-hand
+ *      side over which the basis stays feasible (the dual value `duals[i]` is valid there).  Infinite ends are IEEE
+ *      infinities.  Textbook basis-invariance ranges; lp_solve's conventions at degenerate vertices are not pinned
+ *      (csrc/sensitivity.cu). */
+int elp_sensitivity(int32_t m, int32_t n,
+                    const int32_t* row_ptr, const int32_t* col_idx, const double* vals,
+                    const int8_t* sense, const double* rhs,
+                    const double* c, int32_t maximize,
+                    const double* lb, const double* ub,
+                    const elp_options* opt /* may be NULL */,
+                    int32_t* status, double* objval, double* x /* n */,
+                    double* obj_from /* n */, double* obj_till /* n */,
+                    double* rhs_from /* m */, double* rhs_till /* m */, double* duals /* m */);
+
 /* ---- (3) a batch of small dense LPs (BASELINE config 3; additive entry point) ---
  * A is [B][m][n] row-major, b [B][m], c [B][n], lb/ub [B][n] (NULL => 0 / +Inf), sense [B][m]
  * (NULL => all "<=").  One LP per CTA; outputs status[B], obj[B], x[B][n]. */

@@ -123,6 +123,39 @@ easylp_solve_impl <- function(self, private, ...) {
     invisible(self)
 }
 
+# Replacement for the bodies of the active bindings sensitivity_objective / sensitivity_rhs (R/class.R:613-646): the
+# get.sensitivity.obj / get.sensitivity.rhs calls become one .Call; the arrays keep their shape and dimnames.
+easylp_sensitivity_impl <- function(self, private) {
+    if (private$stat != "optimal")
+        stop("Problem is not optimal.", call. = FALSE)
+    if (self$any_integer())
+        stop("Sensitivity unavailable for problems with integer/binary variables")
+    lower <- unlist(lapply(self$variables, function(x) rep(x$bound[1L], length(x$ind))))
+    upper <- unlist(lapply(self$variables, function(x) rep(x$bound[2L], length(x$ind))))
+    csr <- if (!is.null(private$terms)) easylp_model_csr(easylp_model(self, private)) else easylp_dense_to_csr(self$constraint$mat)
+    .Call("easylp_sensitivity", as.integer(csr$row_ptr), as.integer(csr$col_idx), as.double(csr$vals),
+          as.character(self$constraint$dir), as.double(self$constraint$rhs), as.double(self$objective_fun),
+          private$dir == "max", as.double(lower), as.double(upper), list())
+}
+easylp_sensitivity_objective_impl <- function(self, private) {
+    sens <- easylp_sensitivity_impl(self, private)
+    objective <- array(dim = c(length(self$objective_fun), 3L),
+                       dimnames = list(Variable = names2(private$sol), Bound = c("Lower", "Current", "Upper")))
+    objective[, "Lower"] <- sens$objfrom
+    objective[, "Upper"] <- sens$objtill
+    objective[, "Current"] <- self$objective_fun
+    objective
+}
+easylp_sensitivity_rhs_impl <- function(self, private) {
+    sens <- easylp_sensitivity_impl(self, private)
+    rhs <- array(dim = c(length(self$constraint$rhs), 3L),
+                 dimnames = list(Constraint = self$constraint$rownames, Bound = c("Lower", "Current", "Upper")))
+    rhs[, "Lower"] <- sens$rhsfrom
+    rhs[, "Upper"] <- sens$rhstill
+    rhs[, "Current"] <- self$constraint$rhs
+    rhs
+}
+
 # Replacement for private$feasible (R/class.R:533-540): mat %*% sol + compare_tol on the device.
 easylp_feasible_impl <- function(self, private, tol = 2e-8) {
     csr <- if (!is.null(private$terms)) easylp_model_csr(easylp_model(self, private)) else easylp_dense_to_csr(self$constraint$mat)

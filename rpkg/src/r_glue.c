@@ -200,6 +200,36 @@ SEXP easylp_solve_mip(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP dir, SEXP rhs,
     return out;
 }
 
+/* .Call("easylp_sensitivity", row_ptr, col_idx, vals, dir, rhs, objective_fun, maximize, lower, upper, control)
+ * Replaces get.sensitivity.obj(prob) / get.sensitivity.rhs(prob) behind `$sensitivity_objective` / `$sensitivity_rhs`
+ * (R/class.R:613-646).  Returns list(status, objfrom, objtill, rhsfrom, rhstill, duals); infinite ends are +/-Inf. */
+SEXP easylp_sensitivity(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP dir, SEXP rhs, SEXP cost, SEXP maximize,
+                        SEXP lower, SEXP upper, SEXP control) {
+    const int32_t m = (int32_t)XLENGTH(row_ptr) - 1, n = (int32_t)XLENGTH(cost);
+    if (XLENGTH(lower) != n || XLENGTH(upper) != n) Rf_error("bounds must have one entry per variable");
+    if (XLENGTH(dir) != m || XLENGTH(rhs) != m) Rf_error("dir/rhs must have one entry per constraint");
+    elp_options opt;
+    fill_options(&opt, control);
+    int8_t* sense = sense_codes(dir, 0);
+    int32_t* cols = zero_based(col_idx);
+    double* x = (double*)R_alloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    const char* names[] = {"status", "objfrom", "objtill", "rhsfrom", "rhstill", "duals"};
+    SEXP out = PROTECT(named_list(6, names));
+    SEXP of = PROTECT(Rf_allocVector(REALSXP, n)), ot = PROTECT(Rf_allocVector(REALSXP, n));
+    SEXP rf = PROTECT(Rf_allocVector(REALSXP, m)), rt = PROTECT(Rf_allocVector(REALSXP, m)), du = PROTECT(Rf_allocVector(REALSXP, m));
+    int32_t status = 0;
+    double objval = 0.0;
+    const int rc = elp_sensitivity(m, n, (const int32_t*)INTEGER(row_ptr), cols, REAL(vals), sense, REAL(rhs), REAL(cost),
+                                   Rf_asLogical(maximize) ? 1 : 0, REAL(lower), REAL(upper), &opt, &status, &objval, x,
+                                   REAL(of), REAL(ot), m > 0 ? REAL(rf) : NULL, m > 0 ? REAL(rt) : NULL, m > 0 ? REAL(du) : NULL);
+    if (rc) { UNPROTECT(6); elp_fail("easylp_sensitivity"); }
+    SET_VECTOR_ELT(out, 0, Rf_ScalarInteger(status));
+    SET_VECTOR_ELT(out, 1, of); SET_VECTOR_ELT(out, 2, ot); SET_VECTOR_ELT(out, 3, rf); SET_VECTOR_ELT(out, 4, rt);
+    SET_VECTOR_ELT(out, 5, du);
+    UNPROTECT(6);
+    return out;
+}
+
 /* .Call("easylp_check_feasible", row_ptr, col_idx, vals, sol, dir, rhs, tol) -> logical(m)
  * Replaces `lhs <- mat %*% sol` + compare_tol (R/class.R:533-540, R/utils.R:167-171). */
 SEXP easylp_check_feasible(SEXP row_ptr, SEXP col_idx, SEXP vals, SEXP sol, SEXP dir, SEXP rhs, SEXP tol) {
@@ -508,6 +538,7 @@ static const R_CallMethodDef call_methods[] = {
     {"easylp_model_valid", (DL_FUNC)&easylp_model_valid, 1},
     {"easylp_solve_lp", (DL_FUNC)&easylp_solve_lp, 10},
     {"easylp_solve_mip", (DL_FUNC)&easylp_solve_mip, 11},
+    {"easylp_sensitivity", (DL_FUNC)&easylp_sensitivity, 10},
     {"easylp_check_feasible", (DL_FUNC)&easylp_check_feasible, 7},
     {"easylp_solve_batch", (DL_FUNC)&easylp_solve_batch, 8},
     {"easylp_device_count", (DL_FUNC)&easylp_device_count, 0},

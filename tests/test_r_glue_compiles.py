@@ -26,7 +26,7 @@ def test_registered_routines_match_their_definitions():
     src = open(GLUE).read()
     table = dict((n, int(k)) for n, k in re.findall(r'\{"(easylp_\w+)",\s*\(DL_FUNC\)&\w+,\s*(\d+)\}', src))
     assert set(table) == {"easylp_assemble_csr", "easylp_assemble_lowered", "easylp_model_assemble", "easylp_model_csr",
-                          "easylp_model_solve", "easylp_model_valid", "easylp_solve_lp", "easylp_solve_mip",
+                          "easylp_model_solve", "easylp_model_valid", "easylp_solve_lp", "easylp_solve_mip", "easylp_sensitivity", "easylp_sensitivity",
                           "easylp_check_feasible", "easylp_solve_batch", "easylp_device_count"}
     for name, nargs in table.items():
         sig = re.search(r"SEXP %s\(([^)]*)\)" % name, src).group(1)
