@@ -19,6 +19,9 @@
 
 namespace elp {
 
+// bad[0]: a term lies outside the matrix; bad[1]: the stream is NOT already in (row, col) order.  `$con()` emits its
+// rows one after the other and most bodies walk their columns in ascending order, so the common stream is sorted as it
+// arrives: the host then skips the radix sort altogether (the fold only needs equal keys to be adjacent, in emission order).
 __global__ void asm_make_keys(const int32_t* __restrict__ row, const int32_t* __restrict__ col, uint32_t T,
                               uint32_t m, uint32_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ perm,
                               int* __restrict__ bad) {
@@ -27,8 +30,14 @@ __global__ void asm_make_keys(const int32_t* __restrict__ row, const int32_t* __
     const uint32_t r = (uint32_t)row[i], c = (uint32_t)col[i];
     const bool oob = (r >= m || c >= n);
     if (oob) atomicExch(bad, 1);
-    keys[i] = oob ? 0ull : (uint64_t)r * n + c;   // out-of-range terms are reported, never dereferenced
+    const uint64_t k = oob ? 0ull : (uint64_t)r * n + c;   // out-of-range terms are reported, never dereferenced
+    keys[i] = k;
     perm[i] = i;
+    if (i + 1 < T) {
+        const uint32_t r1 = (uint32_t)row[i + 1], c1 = (uint32_t)col[i + 1];
+        const uint64_t k1 = (r1 >= m || c1 >= n) ? 0ull : (uint64_t)r1 * n + c1;
+        if (k1 < k && bad[1] == 0) atomicExch(bad + 1, 1);
+    }
 }
 
 // One thread per sorted slot; the head of every equal-key run folds the run left-to-right.
@@ -162,7 +171,7 @@ struct AsmWorkspace {
         if (dev != device) { release(); device = dev; }
         auto grow = [](auto& b, size_t n) { if (b.n < n) b.alloc(n + n / 8); };
         grow(keys, T); grow(perm, T); grow(keep, T); grow(pos, T); grow(sums, T); grow(rows_c, T);
-        grow(nnz_d, 1); grow(bad, 1);
+        grow(nnz_d, 1); grow(bad, 2);
     }
     void ensure_io(size_t T, size_t m) {
         ensure(T);
@@ -239,15 +248,20 @@ int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_co
     DevBuf<double>& sums = w.sums;
     DevBuf<int32_t>& rows_c = w.rows_c;
     DevBuf<int>& bad = w.bad;
-    ELP_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    ELP_CUDA(cudaMemsetAsync(bad.p, 0, 2 * sizeof(int), st));
     RadixSortWorkspace& ws = w.sort;
     const int grid = ceil_div(T, 256);
     mark("alloc");
     ELP_LAUNCH(asm_make_keys, grid, 256, 0, st, d_row, d_col, Tu, (uint32_t)m, (uint32_t)n, keys.p, perm.p, bad.p);
     const int nbits = bit_length_u64((uint64_t)m * (uint64_t)n - 1);
     mark("keys");
-    radix_sort_pairs(keys.p, perm.p, T, nbits, ws, st);
-    mark("sort");
+    int unsorted = 1;
+    if (!getenv("ELP_ASM_ALWAYS_SORT")) {            // 4 bytes back and one synchronisation buy the whole sort when the stream is ordered
+        ELP_CUDA(cudaMemcpyAsync(&unsorted, bad.p + 1, sizeof unsorted, cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+    }
+    if (unsorted) radix_sort_pairs(keys.p, perm.p, T, nbits, ws, st);
+    mark(unsorted ? "sort" : "sort skipped");
     if (d_grp)
         ELP_LAUNCH(asm_segment_fold_grouped, grid, 256, 0, st, keys.p, perm.p, d_val, d_grp, d_groups, d_dtab, Tu, (uint32_t)n,
                    sums.p, keep.p);

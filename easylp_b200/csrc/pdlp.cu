@@ -53,7 +53,6 @@ struct StoreEpi {
     double* scat = nullptr;
     double* out;
     using Route = NoRoute;
-    using Stage = NoRoute;
     struct Pre {};
     __device__ __forceinline__ const double* in(int) const { return nullptr; }
     __device__ __forceinline__ Pre preload(const double*, int, int) const { return Pre{}; }
@@ -77,16 +76,15 @@ inline StoreEpi store_epi(double* out) { StoreEpi e; e.out = out; return e; }
 // in-producer variant — fence + last-CTA counter in every CTA — cost 21 us per iteration), and one warp per CTA then
 // polls the local flag row until all N slots have reached E while the first matrix tiles are already on their way.
 struct GhostOut {
-    double* buf[8];                    // rank r's ghost vector, buffer 0; buffer 1 lies stride[r] doubles further
-    uint32_t stride[8];
+    double* buf[8];                    // rank r's ghost vector
     const uint32_t* route;             // [tiles of my block][SPMV_ROUTE_WORDS]: words 0-7 position of the tile's first entry
                                        // in rank r's ghost vector, bytes 32-63 per row of the tile: bit r = rank r gathers it
     int n, rank;
-    int dbg;                           // measurement switches (ELP_GHOST_DEBUG): 1 no remote stores, 16 no routing
+    int dense, first;                  // dense != 0: no compaction — rank r's ghost vector is the whole vector and my block
+                                       // starts at `first` in it (chosen when the ranks read most of everything anyway)
 };
 struct GhostIn {
-    const double* vec;                 // my ghost vector, buffer 0
-    uint32_t stride;
+    const double* vec;                 // my ghost vector
     const unsigned long long* flags;   // my flag row for it (N slots)
     unsigned long long* peer_flag[8];  // rank r's flag row for the same vector; this rank writes slot `rank`
     unsigned int* err;                 // bit 0: a producer never showed up (the host turns it into an error)
@@ -117,99 +115,42 @@ __device__ __forceinline__ const double* ghost_acquire(const GhostIn& gi, long l
         __threadfence_system();                    // acquire: the gathers below are ordered behind the flags
     }
     __syncthreads();
-    return gi.vec + ((want & 1) ? gi.stride : 0u);
+    return gi.vec;
 }
-// producer side.  A warp owns a contiguous range of tiles (spmv.cuh), so what it produces for rank r is ONE contiguous
-// run of r's ghost vector.  Values for remote ranks are collected in a 64-entry shared-memory ring per destination and
-// leave in stores of up to 32 consecutive doubles that END on a 256-byte boundary of the destination (after the first,
-// partial one every store is a full, aligned 256-byte line pair): NVLink moves full packets instead of one short,
-// misaligned packet per tile and destination — measured at N = 8, where the per-tile stores were packet-rate bound.
-// Lane r keeps the bookkeeping of destination r: entries appended, entries sent, the run's start in r's vector.
+// producer side, per row of a warp tile (all 32 lanes call both; `owner` lanes carry a value).  The destination table is
+// a kernel parameter and the loops over the destinations are unrolled (constant-bank operands); reading the table from
+// device memory in rolled loops was measured 5 % slower at N = 2 (190 vs 180 us per iteration).
 struct GhostRoute { unsigned mk; int base; };
-struct GhostStage {
-    double* ring;          // this warp's rings: [remote destination slot][SPMV_RING]
-    double* dst;           // lane r: start of my run in rank r's ghost vector (buffer of this epoch)
-    int cnt, sent;         // lane r: entries appended to / sent from the run
-    int phase;             // lane r: (absolute position of the run's start) mod 32, for the alignment of the stores
-    bool started;
-};
 __device__ __forceinline__ GhostRoute ghost_route(const GhostOut& go, const uint32_t* rec, int lane, bool owner, int row_in_tile) {
     GhostRoute g;
-    g.mk = owner ? (unsigned)reinterpret_cast<const unsigned char*>(rec)[32 + row_in_tile] : 0u;
-    g.base = (int)rec[lane & 7];
-    if (go.dbg & 16) g.mk = 0u;
+    if (go.dense) { g.mk = owner ? 1u : 0u; g.base = 0; }        // no record is staged: everything goes everywhere
+    else {
+        g.mk = owner ? (unsigned)reinterpret_cast<const unsigned char*>(rec)[32 + row_in_tile] : 0u;
+        g.base = (int)rec[lane & 7];
+    }
     return g;
 }
-__device__ __forceinline__ void ghost_stage_init(GhostStage& s, const GhostOut& go, unsigned char* rings, int warp, int lane) {
-    s.ring = reinterpret_cast<double*>(rings) + (size_t)warp * (go.n - 1) * SPMV_RING;
-    s.dst = nullptr; s.cnt = 0; s.sent = 0; s.phase = 0; s.started = false;
-}
-// sends [sent, upto) of destination r's run; warp-uniform arguments
-__device__ __forceinline__ void ghost_send(const GhostStage& s, int slot, int r, int from, int upto, int lane) {
-    const unsigned long long d = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)s.dst, r);
-    double* dp = reinterpret_cast<double*>((uintptr_t)d);
-    const int k = from + lane;
-    if (k < upto) dp[k] = s.ring[slot * SPMV_RING + (k & (SPMV_RING - 1))];
-}
-__device__ __forceinline__ void ghost_publish(const GhostOut& go, long long epoch, GhostStage& s, const GhostRoute& rt, int lane, double v) {
+__device__ __forceinline__ void ghost_publish(const GhostOut& go, const GhostRoute& rt, int lane, int row, double v) {
+    if (go.dense) {
+        // everybody reads (almost) everything: the ghost vectors are plain copies of the whole vector, the value of row
+        // `row` of my block goes to position first + row of every copy — aligned, full 256-byte warp stores
+        if (rt.mk) {
+            const size_t at = (size_t)(go.first + row);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < go.n) go.buf[r][at] = v;
+        }
+        return;
+    }
     const unsigned mk = rt.mk;
     const unsigned lower = (1u << lane) - 1u;
-    const bool odd = (epoch & 1) != 0;
-    if (!s.started) {                               // first tile of this warp: the runs start at its bases
-        s.started = true;
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (lane == r && r < go.n) {
-                s.dst = go.buf[r] + (odd ? go.stride[r] : 0u) + (uint32_t)rt.base;
-                s.phase = (int)(((uintptr_t)s.dst >> 3) & 31u);
-            }
-    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         if (r < go.n) {
-            const bool send = ((mk >> r) & 1u) && !((go.dbg & 1) && r != go.rank);
+            const bool send = (mk >> r) & 1u;
             const unsigned b = __ballot_sync(0xffffffffu, send);
-            const int cur = __shfl_sync(0xffffffffu, s.cnt, r);
-            const int c = __popc(b);
-            if (r == go.rank) {                     // my own ghost vector: plain local stores
-                const unsigned long long d = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)s.dst, r);
-                if (send) reinterpret_cast<double*>((uintptr_t)d)[cur + __popc(b & lower)] = v;
-                if (lane == r) s.cnt = cur + c;
-            } else {
-                const int slot = r < go.rank ? r : r - 1;
-                if (send) s.ring[slot * SPMV_RING + ((cur + __popc(b & lower)) & (SPMV_RING - 1))] = v;
-                if (lane == r) s.cnt = cur + c;
-                int sent = __shfl_sync(0xffffffffu, s.sent, r);
-                const int ph = __shfl_sync(0xffffffffu, s.phase, r);
-                const int have = cur + c;
-                // next store ends where (phase + position) reaches a multiple of 32: a 256-byte boundary over there
-                int upto = ((ph + sent) / 32 + 1) * 32 - ph;
-                if (have >= upto) {
-                    __syncwarp();
-                    do {
-                        ghost_send(s, slot, r, sent, upto, lane);
-                        sent = upto;
-                        upto += 32;
-                    } while (have >= upto);
-                    if (lane == r) s.sent = sent;
-                }
-            }
-        }
-    }
-}
-__device__ __forceinline__ void ghost_stage_flush(const GhostOut& go, GhostStage& s, int lane) {
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        if (r < go.n && r != go.rank) {
-            const int slot = r < go.rank ? r : r - 1;
-            int sent = __shfl_sync(0xffffffffu, s.sent, r);
-            const int have = __shfl_sync(0xffffffffu, s.cnt, r);
-            while (sent < have) {
-                const int upto = min(have, sent + 32);
-                ghost_send(s, slot, r, sent, upto, lane);
-                sent = upto;
-            }
+            const int br = __shfl_sync(0xffffffffu, rt.base, r);
+            if (send) go.buf[r][(uint32_t)br + __popc(b & lower)] = v;
         }
     }
 }
@@ -234,7 +175,6 @@ struct PrimalEpi {
     GhostIn gin;        // y ghost (consumed)
     GhostOut gout;      // x-bar ghosts (produced)
     using Route = GhostRoute;
-    using Stage = GhostStage;
     struct Pre { double x, c, l, u, x0; };
     __device__ __forceinline__ const double* in(int i) const {
         return i == 0 ? x : i == 1 ? c : i == 2 ? l : i == 3 ? u : x0;
@@ -271,12 +211,9 @@ struct PrimalEpi {
     __device__ __forceinline__ Route route(const uint32_t* rec, int lane, bool owner, int row_in_tile) const {
         return ghost_route(gout, rec, lane, owner, row_in_tile);
     }
-    __device__ __forceinline__ void stage_init(Stage& s, unsigned char* rings, int warp, int lane) const { ghost_stage_init(s, gout, rings, warp, lane); }
-    __device__ __forceinline__ void publish(Stage& s, const Route& rt, int lane, double v) const {
-        ghost_publish(gout, P->epoch_base + it + 1, s, rt, lane, v);
+    __device__ __forceinline__ void publish(const Route& rt, int lane, int row, double v) const {
+        ghost_publish(gout, rt, lane, row, v);
     }
-    __device__ __forceinline__ void stage_flush(Stage& s, int lane) const { ghost_stage_flush(gout, s, lane); }
-    __host__ __device__ int rings() const { return gout.n > 1 ? gout.n - 1 : 0; }
 };
 
 // dual half.  ax = (A xbar)_i.  SCAT: the kernel then adds val[k] * y_new_i into scat[idx[k]] over the entries of row i,
@@ -299,7 +236,6 @@ struct DualEpi {
     GhostIn gin;        // x-bar ghost (consumed)
     GhostOut gout;      // y ghosts (produced)
     using Route = GhostRoute;
-    using Stage = GhostStage;
     struct Pre { double y, lc, uc, y0; };
     __device__ __forceinline__ const double* in(int i) const { return i == 0 ? y : i == 1 ? lc : i == 2 ? uc : y0; }
     __device__ __forceinline__ Pre preload(const double* s, int rt, int g) const {
@@ -338,12 +274,9 @@ struct DualEpi {
     __device__ __forceinline__ Route route(const uint32_t* rec, int lane, bool owner, int row_in_tile) const {
         return ghost_route(gout, rec, lane, owner, row_in_tile);
     }
-    __device__ __forceinline__ void stage_init(Stage& s, unsigned char* rings, int warp, int lane) const { ghost_stage_init(s, gout, rings, warp, lane); }
-    __device__ __forceinline__ void publish(Stage& s, const Route& rt, int lane, double v) const {
-        ghost_publish(gout, P->epoch_base + it + 1, s, rt, lane, v);
+    __device__ __forceinline__ void publish(const Route& rt, int lane, int row, double v) const {
+        ghost_publish(gout, rt, lane, row, v);
     }
-    __device__ __forceinline__ void stage_flush(Stage& s, int lane) const { ghost_stage_flush(gout, s, lane); }
-    __host__ __device__ int rings() const { return gout.n > 1 ? gout.n - 1 : 0; }
 };
 
 // Gather-free primal update of the scatter formulation: g = A'y was accumulated by the previous dual kernel.
@@ -888,6 +821,38 @@ struct Pdlp {
         if (nnzc > 0) ELP_LAUNCH(k_mark_used, ceil_div(nnzc, 256), 256, 0, st, (uint32_t)nnzc, csc_idx.p, used_y.p + (size_t)rank * sy);
         comm_allgather_bytes(used_x.p, sx, st);
         comm_allgather_bytes(used_y.p, sy, st);
+        // ---- 1b. compact or dense?  Compaction pays when the ranks read a small part of each other's blocks (a
+        // structured LP: config 5 keeps 23 % at N = 8 and runs 1.9x faster than with dense stores).  When they read
+        // most of everything (a random matrix: config 4 keeps 92 % at N = 2, 71 % at N = 4, 55 % at N = 8) the ballots,
+        // the positions and the misaligned short stores of the compact scheme cost more than the bytes they save —
+        // measured: N = 2 181 vs 159 us, N = 4 130 vs 110 us per iteration — so the ghost vectors are then plain
+        // copies of the whole vector (identity numbering, everything to everybody, aligned full-warp stores).
+        bool dense = false;
+        {
+            DevBuf<unsigned char> tmask((size_t)std::max(std::max(nl, m), 1));
+            DevBuf<unsigned long long> cnt(2);
+            cnt.zero(st);
+            if (nl > 0) ELP_LAUNCH(k_ghost_mask, grid1(nl), 256, 0, st, nl, n0, sx, N, used_x.p, tmask.p, cnt.p);
+            if (m > 0) ELP_LAUNCH(k_ghost_mask, grid1(m), 256, 0, st, m, rank * mb, sy, N, used_y.p, tmask.p, cnt.p + 1);
+            unsigned long long hc[2] = {0, 0};
+            ELP_CUDA(cudaMemcpyAsync(hc, cnt.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaStreamSynchronize(st));
+            double tot[2] = {(double)hc[0] + (double)hc[1], ((double)nl + (double)m) * N};
+            ELP_CUDA(cudaMemcpyAsync(scal.p, tot, sizeof tot, cudaMemcpyHostToDevice, st));
+            comm_allreduce_sum(scal.p, 2, st);
+            ELP_CUDA(cudaMemcpyAsync(tot, scal.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaStreamSynchronize(st));
+            const double kept = tot[1] > 0 ? tot[0] / tot[1] : 1.0;
+            const int force = env_int("ELP_PDLP_GHOST_DENSE", -1);
+            dense = force >= 0 ? force != 0 : kept >= 0.65;      // measured on config 4: 55 % kept (N = 8) compact 118 vs dense 131 us, 71 % (N = 4) equal
+            if (opt.verbose > 0 || env_int("ELP_PDLP_DEBUG", 0))
+                fprintf(stderr, "[pdlp] rank %d: the ranks read %.1f %% of each other's blocks -> %s ghost vectors\n", rank, 100.0 * kept,
+                        dense ? "dense" : "compact");
+            if (dense) {                   // "everybody reads everything": the generic code below then yields identity numbering
+                ELP_CUDA(cudaMemsetAsync(used_x.p, 1, (size_t)N * sx, st));
+                ELP_CUDA(cudaMemsetAsync(used_y.p, 1, (size_t)N * sy, st));
+            }
+        }
         // ---- 2. compact numbering per consumer; my ids, my lists, the tile bases of what I produce -----------------
         ELP_REQUIRE(plan_c.rpl == 1 && plan_r.rpl == 1, "pdlp: two rows per lane is a single-GPU option");
         {
@@ -938,7 +903,7 @@ struct Pdlp {
         exch_frac_y = m > 0 ? (double)h[1] / ((double)m * N) : 1.0;
         // ---- 4. my ghost memory, mapped by everybody -------------------------------------------------------------------
         auto padded = [](uint32_t g) { return (uint32_t)((g + SPMV_VPAD + 31) & ~31u); };
-        auto bytes_of = [&](int r) { return GH_FLAGS_BYTES + (size_t)8 * 2 * ((size_t)padded(gxs[r]) + padded(gys[r])); };
+        auto bytes_of = [&](int r) { return GH_FLAGS_BYTES + (size_t)8 * ((size_t)padded(gxs[r]) + padded(gys[r])); };
         {
             ArenaScope own(nullptr);                                // mapped by the peers: its own allocation
             ghost_mem.alloc(bytes_of(rank));
@@ -992,18 +957,26 @@ struct Pdlp {
         xin = GhostIn{}; yin = GhostIn{};
         xout.n = yout.n = xin.n = yin.n = N;
         xout.rank = yout.rank = xin.rank = yin.rank = rank;
-        xout.dbg = yout.dbg = xin.dbg = yin.dbg = gdbg;
-        xout.route = xroute.p; yout.route = yroute.p;
+        xin.dbg = yin.dbg = gdbg;
+        xout.route = dense ? nullptr : xroute.p; yout.route = dense ? nullptr : yroute.p;     // dense: no routing records at all
+        xout.dense = yout.dense = dense ? 1 : 0;
+        xout.first = n0; yout.first = rank * mb;
         for (int r = 0; r < N; ++r) {
             double* g0 = reinterpret_cast<double*>(base[r] + GH_FLAGS_BYTES);
-            xout.buf[r] = g0;                               xout.stride[r] = padded(gxs[r]);
-            yout.buf[r] = g0 + 2 * (size_t)padded(gxs[r]);  yout.stride[r] = padded(gys[r]);
+            // ONE buffer per vector (stride 0).  The hand-off in the consumer's prologue already orders a producer's stores
+            // behind the last reader: rank A stores x-bar(i+1) into B only after it has seen B's flag y(i), which B raises
+            // at the start of its K1(i+1), i.e. after its K2(i) — the last reader of x-bar(i) — has completed; likewise for
+            // y.  A second, alternating buffer (first version) doubled the L2 footprint of the gathered vectors and made
+            // the stale copy a dead write-back every iteration.
+            xout.buf[r] = g0;
+            yout.buf[r] = g0 + (size_t)padded(gxs[r]);
             xin.peer_flag[r] = reinterpret_cast<unsigned long long*>(base[r]);
             yin.peer_flag[r] = reinterpret_cast<unsigned long long*>(base[r] + 64);
         }
         unsigned int* err = reinterpret_cast<unsigned int*>(ghost_mem.p + 128);
-        xin.vec = xout.buf[rank]; xin.stride = xout.stride[rank]; xin.flags = xin.peer_flag[rank]; xin.err = err;
-        yin.vec = yout.buf[rank]; yin.stride = yout.stride[rank]; yin.flags = yin.peer_flag[rank]; yin.err = err;
+        xin.vec = xout.buf[rank]; xin.flags = xin.peer_flag[rank]; xin.err = err;
+        yin.vec = yout.buf[rank]; yin.flags = yin.peer_flag[rank]; yin.err = err;
+
         ghost = true;
         if (opt.verbose > 0 || env_int("ELP_PDLP_DEBUG", 0))
             fprintf(stderr, "[pdlp] rank %d ghost exchange: gathers %d of %d x-bar entries and %d of %d y entries; sends %.1f %% / %.1f %% of a dense all-gather (%s)\n",
@@ -1015,7 +988,7 @@ struct Pdlp {
     void refresh_y() {
         gather_y(y_full.p);
         if (ghost && gy > 0)
-            ELP_LAUNCH(k_compact, grid1(gy), 256, 0, st, gy, ylist.p, y_full.p, const_cast<double*>(yin.vec) + ((epoch_base & 1) ? yin.stride : 0u));
+            ELP_LAUNCH(k_compact, grid1(gy), 256, 0, st, gy, ylist.p, y_full.p, const_cast<double*>(yin.vec));
     }
     void check_device_error() {          // a consumer gave up waiting for a peer: report, do not hang or trap
         if (!ghost) return;

@@ -57,7 +57,7 @@ __host__ __device__ inline SpmvStageLayout spmv_stage_layout(int cap, int rw, in
 constexpr int SPMV_WARPS = 4;      // warps per CTA (a CTA is only a container: warps never talk)
 
 template <int L, int RPL, int NSTW, class Epi>
-__global__ void __launch_bounds__(SPMV_WARPS * 32, Epi::DIST ? 4 : 6 / RPL)   // (multi-GPU: the outgoing rings cap the residency at 4-5 CTAs anyway)
+__global__ void __launch_bounds__(SPMV_WARPS * 32, 6 / RPL)
 spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, const int* __restrict__ idx,
                  const double* __restrict__ val, const double* __restrict__ vec, Epi epi, int l2flags) {
     // NSTW stages per warp: one being consumed, the others in flight (2; 3 is offered to the scatter epilogues, which
@@ -81,16 +81,11 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     const uint64_t pol_stream = l2_policy_evict_first();
     const L2Hints hints{pol_stream, l2_policy_evict_last(), l2flags};
     const int gw = blockIdx.x * SPMV_WARPS + warp, nw = gridDim.x * SPMV_WARPS;
-    // Tile walk.  Single GPU: warp-strided round robin.  Multi-GPU: every warp owns a CONTIGUOUS range of tiles, so that
-    // what it produces for one destination rank is one contiguous run of that rank's ghost vector and can leave in
-    // full 256-byte stores (see GhostStage in pdlp.cu) instead of one short store per tile.
-    const bool blocked = Epi::DIST && !(l2flags & 16);      // (bit 16: strided walk in a multi-GPU kernel — timing experiments only)
-    const int t_first = blocked ? (int)((int64_t)gw * ntiles / nw) : gw;
-    const int t_last = blocked ? (int)((int64_t)(gw + 1) * ntiles / nw) : ntiles;
-    const int t_step = blocked ? 1 : nw;
-    [[maybe_unused]] typename Epi::Stage stage_out;
-    if constexpr (Epi::DIST)
-        epi.stage_init(stage_out, smem_raw + (((size_t)SPMV_WARPS * NSTW * (lay.bytes + 8) + 15) & ~(size_t)15), warp, lane);
+    // Tile walk: warp-strided round robin, also in the multi-GPU kernels.  (Tried there: a contiguous range of tiles per warp
+    // with the outgoing values collected in shared-memory rings and sent as aligned 256-byte stores.  The rings and the
+    // extra registers cost two resident CTAs per SM, and losing them cost 38 us per iteration at N = 2 — far more than
+    // the fuller NVLink packets could return; profiles/r2_multi_gpu_exchange.md.)
+    const int t_first = gw, t_last = ntiles, t_step = nw;
 
     // ---- producer cursor: the next piece to copy (uniform across the warp) --------------------------------
     int p_tile = t_first, p_piece = 0, p_s = 0, p_e = 0, n_s = 0, n_e = 0;
@@ -123,13 +118,16 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             else if (lane < 3 + NIN) { src = epi.in(lane - 3) + r0; dst = sb + lay.off_ops + (lane - 3) * OPS * 8; bytes = op_bytes; }
             else if (lane == 3 + NIN) {
                 if constexpr (Epi::DIST) {                // multi-GPU: the tile's routing record travels with its operands
-                    src = epi.route_table() + (size_t)p_tile * SPMV_ROUTE_WORDS; dst = sb + lay.off_route; bytes = SPMV_ROUTE_WORDS * 4;
+                    if (epi.route_table() != nullptr) {
+                        src = epi.route_table() + (size_t)p_tile * SPMV_ROUTE_WORDS; dst = sb + lay.off_route; bytes = SPMV_ROUTE_WORDS * 4;
+                    }
                 }
             }
         }
         if (lane == 0) {
             uint32_t tx = (uint32_t)pcnt * 12u;
-            if (p_piece == 0) tx += ptr_bytes + (uint32_t)NIN * op_bytes + (Epi::DIST ? SPMV_ROUTE_WORDS * 4u : 0u);
+            if (p_piece == 0) tx += ptr_bytes + (uint32_t)NIN * op_bytes;
+            if constexpr (Epi::DIST) { if (p_piece == 0 && epi.route_table() != nullptr) tx += SPMV_ROUTE_WORDS * 4u; }
             mbar_expect_tx(&full[stage], tx);
         }
         __syncwarp();
@@ -253,7 +251,7 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             const bool owner = sub == 0 && row0 + j * G < nrows;
             if (owner) mult = epi.apply(row0 + j * G, a, pre[j], hints);
             // multi-GPU: the value just produced goes into the ghost vector of every rank that gathers it (warp-collective)
-            if constexpr (Epi::DIST) epi.publish(stage_out, route[j], lane, mult);
+            if constexpr (Epi::DIST) epi.publish(route[j], lane, row0 + j * G, mult);
             if (Epi::SCATTER) {
                 // out[idx[k]] += val[k] * mult over this row's entries (fire-and-forget fp64 reductions: SASS RED.ADD.F64);
                 // rows whose multiplier is zero (inactive constraints) send nothing.
@@ -270,7 +268,6 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             issue(hstage);
         }
     }
-    if constexpr (Epi::DIST) epi.stage_flush(stage_out, lane);        // what is left in the outgoing rings
 }
 
 // ---- long rows: one warp per row -----------------------------------------------------------------------
@@ -323,11 +320,8 @@ inline int pick_lanes(int64_t nnz, int64_t nrows) {
     return L;
 }
 
-constexpr int SPMV_RING = 64;      // multi-GPU: doubles per outgoing ring (one ring per warp and remote destination)
-inline size_t spmv_smem_bytes(const SpmvPlan& p, int nin, bool route = false, int rings = 0) {
-    size_t b = (size_t)SPMV_WARPS * p.nst * (spmv_stage_layout(p.cap, p.rw(), nin, route).bytes + 8);
-    if (rings > 0) b = ((b + 15) & ~(size_t)15) + (size_t)SPMV_WARPS * rings * SPMV_RING * sizeof(double);
-    return b;
+inline size_t spmv_smem_bytes(const SpmvPlan& p, int nin, bool route = false) {
+    return (size_t)SPMV_WARPS * p.nst * (spmv_stage_layout(p.cap, p.rw(), nin, route).bytes + 8);
 }
 
 // nin_max: the largest operand count among the epilogues that will run with this plan
@@ -366,9 +360,7 @@ template <int L, int RPL, int NSTW, class Epi>
 void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* idx, const double* val,
                       const double* vec, const Epi& epi, cudaStream_t st) {
     auto kern = spmv_warp_kernel<L, RPL, NSTW, Epi>;
-    int rings = 0;
-    if constexpr (Epi::DIST) rings = epi.rings();
-    const size_t smem = spmv_smem_bytes(p, Epi::NIN, Epi::DIST, rings);
+    const size_t smem = spmv_smem_bytes(p, Epi::NIN, Epi::DIST);
     ELP_REQUIRE(smem <= 227 * 1024, "spmv: stage ring of %zu bytes does not fit in shared memory", smem);
     // per device and ring size: raise the dynamic shared-memory limit once and ask how many CTAs really fit
     static size_t cfg_smem[16] = {};
@@ -387,8 +379,7 @@ void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* i
                     Epi::NIN, p.cap, smem, p.ctas_per_sm, occ, p.ntiles);
     }
     // persistent grid: exactly one wave
-    int per_sm = std::min(p.ctas_per_sm, cfg_occ[dev]);
-    if (rings > 0) per_sm = std::max(1, std::min<int>(per_sm, (int)(196 * 1024 / (smem + 1024))));   // the L1 rule of plan_spmv
+    const int per_sm = std::min(p.ctas_per_sm, cfg_occ[dev]);
     const int grid = std::max(1, std::min(ceil_div(p.ntiles, SPMV_WARPS), kNumSMs * per_sm));
     // L2 residency hints (tma.cuh: L2Hints).  Default 3: the operand streams and the outputs nobody gathers from are
     // evict-first like the matrix stream, so that the vector the NEXT kernel gathers from survives in L2.  Measured in

@@ -52,6 +52,25 @@ def test_assemble_long_duplicate_run_order():
     assert ci.tolist() == [2] and v[0] == s
 
 
+@pytest.mark.parametrize("T,m,n,seed", [(5000, 40, 60, 3), (200_000, 3000, 5000, 8)])
+def test_assemble_already_ordered_stream_skips_the_sort(T, m, n, seed, monkeypatch):
+    """`$con()` emits row after row and most bodies walk their columns upwards: the stream arrives in (row, col) order, with
+    duplicates adjacent in emission order.  The device detects that and skips the radix sort; same bits either way."""
+    rng = np.random.default_rng(seed)
+    row = rng.integers(0, m, size=T).astype(np.int32)
+    col = rng.integers(0, n, size=T).astype(np.int32)
+    val = rng.normal(size=T) * 10.0 ** rng.integers(-8, 8, size=T)
+    order = np.lexsort((col, row))                       # stable: equal (row, col) keep their emission order
+    row, col, val = row[order], col[order], val[order]
+    rp0, ci0, v0 = _assemble_ref(row, col, val, m, n)
+    rp, ci, v, st_fast = L.assemble_csr(row, col, val, m, n)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and v.tobytes() == v0.tobytes()
+    monkeypatch.setenv("ELP_ASM_ALWAYS_SORT", "1")
+    rp2, ci2, v2, st_sort = L.assemble_csr(row, col, val, m, n)
+    assert np.array_equal(rp2, rp0) and np.array_equal(ci2, ci0) and v2.tobytes() == v0.tobytes()
+    assert st_fast.kernel_launches < st_sort.kernel_launches
+
+
 def test_assemble_rejects_out_of_range():
     with pytest.raises(L.ElpError):
         L.assemble_csr([0, 5], [0, 0], [1.0, 1.0], 2, 2)
