@@ -670,7 +670,12 @@ def run_reference(args):
         base = r
     base = dict(base)
     base["value"] = v
-    line.update({"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line.update({"impl": "reference",
+                 "reference_is": "CPU PORT of this repo's own algorithm (oracle/, C + OpenMP, all host threads) — NOT lp_solve: "
+                                 "R and lpSolveAPI are not in the image, and the reference's dense DSL cannot even build "
+                                 "configs 2-5 (SURVEY 0.3).  A real CPU solver (HiGHS dual simplex, stand-in) is timed in the "
+                                 "main arm's cpu_baseline.alt.",
+                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                  "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                  "cpu_baseline": base, "gpu_launches": 0,
                  "e2e": {"value": v, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})

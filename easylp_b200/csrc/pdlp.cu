@@ -82,14 +82,16 @@ struct GhostOut {
     int n, rank;
     int dense, first;                  // dense != 0: no compaction — rank r's ghost vector is the whole vector and my block
                                        // starts at `first` in it (chosen when the ranks read most of everything anyway)
+    int self_only;                     // measurement switch (ELP_GHOST_LOCAL_ONLY): nothing leaves the GPU (timing only)
 };
 struct GhostIn {
     const double* vec;                 // my ghost vector
     const unsigned long long* flags;   // my flag row for it (N slots)
     unsigned long long* peer_flag[8];  // rank r's flag row for the same vector; this rank writes slot `rank`
     unsigned int* err;                 // bit 0: a producer never showed up (the host turns it into an error)
-    int n, rank;
-    int dbg;                           // 2 no wait, 4 no signal
+    unsigned long long* trace;         // ELP_GHOST_DEBUG bit 64: [4096][4] globaltimer stamps (entry, signalled, flags seen) per kernel
+    int n, rank, kind;                 // kind: 0 the kernel consumes y (K1), 1 it consumes x-bar (K2)
+    int dbg;                           // 2 no wait, 4 no signal, 64 trace
 };
 // flag store AFTER an explicit system fence: relaxed is enough (a st.release would repeat the fence per destination)
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
@@ -101,11 +103,20 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 // consumer prologue: signal my part of epoch `want`, wait for everybody's; returns the buffer that holds the epoch
-__device__ __forceinline__ const double* ghost_acquire(const GhostIn& gi, long long want, int lane) {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void ghost_acquire(const GhostIn& gi, long long want, int lane) {
+    const bool tracer = (gi.dbg & 64) && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long* tr = tracer ? gi.trace + (size_t)((2 * want + gi.kind) & 4095) * 4 : nullptr;
+    if (tracer) { tr[0] = globaltimer_ns(); tr[3] = (unsigned long long)want; }
     if (blockIdx.x == 0 && threadIdx.x == 0 && !(gi.dbg & 4)) {
         __threadfence_system();
         for (int r = 0; r < gi.n; ++r) st_relaxed_sys(gi.peer_flag[r] + gi.rank, (unsigned long long)want);
     }
+    if (tracer) tr[1] = globaltimer_ns();
     if (!(gi.dbg & 2) && (threadIdx.x >> 5) == 0 && lane < gi.n) {
         unsigned long long spins = 0;
         while ((long long)ld_volatile_u64(gi.flags + lane) < want) {
@@ -115,7 +126,7 @@ __device__ __forceinline__ const double* ghost_acquire(const GhostIn& gi, long l
         __threadfence_system();                    // acquire: the gathers below are ordered behind the flags
     }
     __syncthreads();
-    return gi.vec;
+    if (tracer) tr[2] = globaltimer_ns();
 }
 // producer side, per row of a warp tile (all 32 lanes call both; `owner` lanes carry a value).  The destination table is
 // a kernel parameter and the loops over the destinations are unrolled (constant-bank operands); reading the table from
@@ -138,7 +149,7 @@ __device__ __forceinline__ void ghost_publish(const GhostOut& go, const GhostRou
             const size_t at = (size_t)(go.first + row);
 #pragma unroll
             for (int r = 0; r < 8; ++r)
-                if (r < go.n) go.buf[r][at] = v;
+                if (r < go.n && (!go.self_only || r == go.rank)) go.buf[r][at] = v;
         }
         return;
     }
@@ -147,7 +158,7 @@ __device__ __forceinline__ void ghost_publish(const GhostOut& go, const GhostRou
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         if (r < go.n) {
-            const bool send = (mk >> r) & 1u;
+            const bool send = ((mk >> r) & 1u) && (!go.self_only || r == go.rank);
             const unsigned b = __ballot_sync(0xffffffffu, send);
             const int br = __shfl_sync(0xffffffffu, rt.base, r);
             if (send) go.buf[r][(uint32_t)br + __popc(b & lower)] = v;
@@ -206,7 +217,7 @@ struct PrimalEpi {
         return GHOST ? xb : 0.0;
     }
     // y of the previous iteration carries epoch_base + it; this launch produces epoch_base + it + 1
-    __device__ __forceinline__ const double* acquire(int lane) const { return ghost_acquire(gin, P->epoch_base + it, lane); }
+    __device__ __forceinline__ void acquire(int lane) const { ghost_acquire(gin, P->epoch_base + it, lane); }
     __device__ __forceinline__ const uint32_t* route_table() const { return gout.route; }
     __device__ __forceinline__ Route route(const uint32_t* rec, int lane, bool owner, int row_in_tile) const {
         return ghost_route(gout, rec, lane, owner, row_in_tile);
@@ -269,7 +280,7 @@ struct DualEpi {
         return 0.0;
     }
     // the x-bar of this same iteration carries epoch_base + it + 1, and so does the y this launch produces
-    __device__ __forceinline__ const double* acquire(int lane) const { return ghost_acquire(gin, P->epoch_base + it + 1, lane); }
+    __device__ __forceinline__ void acquire(int lane) const { ghost_acquire(gin, P->epoch_base + it + 1, lane); }
     __device__ __forceinline__ const uint32_t* route_table() const { return gout.route; }
     __device__ __forceinline__ Route route(const uint32_t* rec, int lane, bool owner, int row_in_tile) const {
         return ghost_route(gout, rec, lane, owner, row_in_tile);
@@ -768,6 +779,7 @@ struct Pdlp {
     DevBuf<unsigned char> xmask, ymask;  // which ranks gather entry j of my x-bar / y block
     DevBuf<uint32_t> xroute, yroute;     // [tiles][SPMV_ROUTE_WORDS] routing records of what K1 / K2 produce
     DevBuf<int> ylist;                   // global (padded) ids of my y ghost entries, ascending
+    DevBuf<unsigned long long> ghost_trace;   // ELP_GHOST_DEBUG bit 64
     DevBuf<unsigned char> ghost_mem;     // flag rows, error word, CTA counters, x-bar ghost x2, y ghost x2 (mapped by the peers)
     int gx = 0, gy = 0;                  // entries of my ghost vectors
     GhostIn xin{}, yin{};
@@ -797,9 +809,34 @@ struct Pdlp {
     int graph_len = 0;
     int64_t h2d = 0, d2h = 0;
 
+    // ELP_GHOST_DEBUG bit 64: per-kernel timeline of the last ~2000 iterations (rank 0 prints a summary)
+    void dump_trace() {
+        if (!ghost_trace.p || rank != 0) return;
+        std::vector<unsigned long long> h(4096 * 4);
+        if (cudaMemcpy(h.data(), ghost_trace.p, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+        // consecutive slots: (epoch E, K1) at 2E, (E+?, K2) ... slot index = 2 * want + kind; K1 wants E-1, K2 wants E
+        double wait[2] = {0, 0}, sig[2] = {0, 0}, span[2] = {0, 0};
+        long cnt[2] = {0, 0}, scnt[2] = {0, 0};
+        for (int s = 0; s < 4096; ++s) {
+            const unsigned long long* a = &h[(size_t)s * 4];
+            if (!a[0] || !a[2]) continue;
+            const int kind = s & 1;
+            wait[kind] += (double)(a[2] - a[1]); sig[kind] += (double)(a[1] - a[0]); ++cnt[kind];
+            // next kernel in program order: K1(want=E-1, slot 2E-2) -> K2(want=E, slot 2E+1) -> K1(want=E, slot 2E)
+            const int nxt = kind == 0 ? ((s + 3) & 4095) : ((s - 1) & 4095);
+            const unsigned long long* b = &h[(size_t)nxt * 4];
+            if (b[0] > a[2] && b[0] - a[2] < 2000000ull) { span[kind] += (double)(b[0] - a[2]); ++scnt[kind]; }
+        }
+        for (int k = 0; k < 2; ++k)
+            if (cnt[k])
+                fprintf(stderr, "[pdlp trace] rank 0 %s: signal %.2f us, wait for the peers %.2f us, flags-seen -> next kernel's entry %.2f us (%ld samples)\n",
+                        k == 0 ? "K1 (A'y + primal)" : "K2 (A xbar + dual)", sig[k] / cnt[k] * 1e-3, wait[k] / cnt[k] * 1e-3,
+                        scnt[k] ? span[k] / scnt[k] * 1e-3 : 0.0, cnt[k]);
+    }
     ~Pdlp() {
         if (graph) cudaGraphExecDestroy(graph);
         if (st) cudaStreamSynchronize(st);
+        dump_trace();
         for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
         if (st) cudaStreamDestroy(st);
     }
@@ -961,6 +998,7 @@ struct Pdlp {
         xout.route = dense ? nullptr : xroute.p; yout.route = dense ? nullptr : yroute.p;     // dense: no routing records at all
         xout.dense = yout.dense = dense ? 1 : 0;
         xout.first = n0; yout.first = rank * mb;
+        xout.self_only = env_int("ELP_GHOST_LOCAL_ONLY", 0) & 1; yout.self_only = (env_int("ELP_GHOST_LOCAL_ONLY", 0) >> 1) & 1;
         for (int r = 0; r < N; ++r) {
             double* g0 = reinterpret_cast<double*>(base[r] + GH_FLAGS_BYTES);
             // ONE buffer per vector (stride 0).  The hand-off in the consumer's prologue already orders a producer's stores
@@ -974,8 +1012,14 @@ struct Pdlp {
             yin.peer_flag[r] = reinterpret_cast<unsigned long long*>(base[r] + 64);
         }
         unsigned int* err = reinterpret_cast<unsigned int*>(ghost_mem.p + 128);
-        xin.vec = xout.buf[rank]; xin.flags = xin.peer_flag[rank]; xin.err = err;
-        yin.vec = yout.buf[rank]; yin.flags = yin.peer_flag[rank]; yin.err = err;
+        xin.vec = xout.buf[rank]; xin.flags = xin.peer_flag[rank]; xin.err = err; xin.kind = 1;
+        yin.vec = yout.buf[rank]; yin.flags = yin.peer_flag[rank]; yin.err = err; yin.kind = 0;
+        if (gdbg & 64) {
+            ArenaScope own(nullptr);
+            ghost_trace.alloc(4096 * 4);
+            ghost_trace.zero(st);
+            xin.trace = yin.trace = ghost_trace.p;
+        }
 
         ghost = true;
         if (opt.verbose > 0 || env_int("ELP_PDLP_DEBUG", 0))
@@ -1426,7 +1470,7 @@ struct Pdlp {
         }
         if (!CHECK && ghost) {              // gathers y from my ghost vector, publishes x-bar into the consumers' ghost vectors
             PrimalEpi<false, true> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, yin, xout};
-            if (nl > 0) launch_spmv(plan_c, nl, csc_ptr.p, csc_idx_g.p, csc_val.p, yin.vec, epi, st);
+            if (nl > 0) launch_spmv(plan_c, nl, csc_ptr.p, xout.dense ? csc_idx.p : csc_idx_g.p, csc_val.p, yin.vec, epi, st);   // dense ghosts: identity numbering
             else signal_only(yin, it);              // what K1's prologue would have said: my y of the previous epoch is out
             return;
         }
@@ -1443,7 +1487,7 @@ struct Pdlp {
         }
         if (!CHECK && ghost) {
             DualEpi<false, false, true> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, xin, yout};
-            if (m > 0) launch_spmv(plan_r, m, csr_ptr.p, csr_idx_g.p, csr_val.p, xin.vec, epi, st);
+            if (m > 0) launch_spmv(plan_r, m, csr_ptr.p, yout.dense ? csr_idx.p : csr_idx_g.p, csr_val.p, xin.vec, epi, st);
             else signal_only(xin, it + 1);          // what K2's prologue would have said: my x-bar of this epoch is out
             return;
         }

@@ -150,7 +150,7 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     for (int s = 0; s < NSTW; ++s) issue(s);
     // multi-GPU: the gathered vector is filled by the peers' stores.  The matrix stream is already on its way; wait
     // here — once per warp — until every producer has published the epoch this launch consumes.
-    if constexpr (Epi::DIST) vec = epi.acquire(lane);
+    if constexpr (Epi::DIST) epi.acquire(lane);         // (`vec` stays the kernel parameter: uniform address arithmetic in the gathers)
 
     // ---- consumer ------------------------------------------------------------------------------------------
     const int g = lane / L;                // first row of the tile this lane group owns

@@ -16,6 +16,10 @@ p = gen.sparse_planted(int(2_000_000 * a.scale), seed=0)
 for v in a.variants.split(","):
     os.environ.pop("ELP_PDLP_P2P", None)
     os.environ.pop("ELP_SPMV_L2HINTS", None)
+    os.environ.pop("ELP_GHOST_LOCAL_ONLY", None)
+    if v.startswith("local"):                   # e.g. local1: K1 keeps x-bar at home, local2: K2 keeps y at home, local3: both
+        os.environ["ELP_GHOST_LOCAL_ONLY"] = v[5:]
+        v = "64"
     os.environ["ELP_GHOST_DEBUG"] = "0"
     if v.startswith("hint"):                    # e.g. hint19: ELP_SPMV_L2HINTS=19 (bit 16 = strided tile walk, timing only)
         os.environ["ELP_SPMV_L2HINTS"] = v[4:]
