@@ -178,6 +178,17 @@ class Dist:
         self.td.broadcast_object_list(box, src=0)
         return box[0]
 
+    # CPU-side hand-off through the rendezvous store: a rank that waits in an NCCL barrier keeps a spinning kernel on its
+    # GPU, which must be idle while rank 0 drives ALL GPUs from one process (e2e_single_call)
+    def cpu_signal(self, key):
+        if self.td:
+            self.td.distributed_c10d._get_default_store().set(key, "1")
+
+    def cpu_wait(self, key):
+        if self.td:
+            import datetime
+            self.td.distributed_c10d._get_default_store().wait([key], datetime.timedelta(minutes=30))
+
     def close(self):
         if self.td:
             self.td.barrier()
@@ -232,6 +243,9 @@ def e2e_single_call(args, dist, L, p, steps):
                "breakdown": {"setup_s": round(r.stats.setup_ms * 1e-3, 4), "run_device_s": round(r.stats.solve_ms * 1e-3, 4)},
                "path": f"elp_solve_lp(host CSR, devices={N}): one process, one blocking call, {N} worker threads",
                "_stats": r.stats, "_obj": r.objval}
+        dist.cpu_signal(f"e2e_done_{p['m']}_{p['n']}")
+    else:
+        dist.cpu_wait(f"e2e_done_{p['m']}_{p['n']}")        # on the host: this rank's GPU stays idle for rank 0's workers
     dist.barrier()
     return out
 

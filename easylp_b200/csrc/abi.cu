@@ -64,6 +64,16 @@ void solve_mip(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t* col_
                const uint8_t* is_int, const elp_options& o, int32_t* status, double* objval, double* x, elp_stats* stats);
 
 void pool_release();            // shuts the multi-GPU worker pool down (defined next to it, below)
+// a pair of timing events that cannot leak when something between create and destroy throws
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() { ELP_CUDA(cudaEventCreate(&a)); if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); throw Error("cudaEventCreate failed"); } }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+    float ms() const { float t = 0; cudaEventElapsedTime(&t, a, b); return t; }
+};
+
 static void require_device() {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -416,8 +426,8 @@ int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* te
         ELP_CUDA(cudaMemcpyAsync(io.col, term_col, T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         ELP_CUDA(cudaMemcpyAsync(io.val, term_val, T * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    cudaEvent_t e0, e1;
-    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    EventPair ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     ELP_CUDA(cudaEventRecord(e0, st));
     const int64_t nnz = assemble_csr_device(n_terms, io.row, io.col, io.val, m, n, io.out_ptr, io.out_col, io.out_val, st);
     ELP_CUDA(cudaEventRecord(e1, st));
@@ -429,7 +439,6 @@ int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* te
     ELP_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *nnz_out = nnz;
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -443,7 +452,8 @@ int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* te
 }
 
 // checks a family against the table sizes and returns the number of terms it emits
-static int64_t check_family(const elp_term_family& f, int64_t n_itab, int64_t n_dtab, int32_t n_groups, int32_t m) {
+static int64_t check_family(const elp_term_family& f, int64_t n_itab, int64_t n_dtab, int32_t n_groups, int32_t m,
+                            const int32_t* itab = nullptr, int64_t* row_lo = nullptr, int64_t* row_hi = nullptr) {
     ELP_REQUIRE(f.n_loops >= 0 && f.n_loops <= ELP_MAX_LOOPS, "lowered: family with %d loops (max %d)", f.n_loops, ELP_MAX_LOOPS);
     ELP_REQUIRE(f.group >= 0 && f.group < std::max(n_groups, 1), "lowered: family names group %d of %d", f.group, n_groups);
     ELP_REQUIRE(f.out_stride >= 1 && f.out_offset >= 0, "lowered: bad stream placement");
@@ -465,6 +475,21 @@ static int64_t check_family(const elp_term_family& f, int64_t n_itab, int64_t n_
         ELP_REQUIRE(f.coef_tab >= 0 && coef_max < n_dtab, "lowered: coefficient table outside dtab");
         ELP_REQUIRE(f.row0 >= 0 && row_max < m, "lowered: family rows outside the matrix");
     }
+    // rows this family touches: row0 plus, per loop, a stride term or an entry of its row table
+    if (row_lo && row_hi && count > 0) {
+        int64_t lo = f.row0, hi = f.row0;
+        for (int l = 0; l < f.n_loops; ++l) {
+            if (f.extent[l] <= 0) continue;
+            if (f.row_tab[l] >= 0 && itab) {
+                int32_t a = itab[f.row_tab[l]], b = a;
+                for (int32_t q = 1; q < f.extent[l]; ++q) { a = std::min(a, itab[f.row_tab[l] + q]); b = std::max(b, itab[f.row_tab[l] + q]); }
+                lo += a; hi += b;
+            } else if (f.row_tab[l] < 0) {
+                hi += (int64_t)f.row_stride[l] * (f.extent[l] - 1);
+            }
+        }
+        *row_lo = lo; *row_hi = hi;
+    }
     return count;
 }
 
@@ -479,10 +504,19 @@ static int64_t stage_lowered(int64_t n_terms, const int32_t* term_row, const int
     ELP_REQUIRE(n_terms >= 0 && n_families >= 0 && n_itab >= 0 && n_dtab >= 0 && n_groups >= 0, "lowered: negative size");
     int64_t total = 0;
     std::vector<int> order;
+    const size_t n_g = (groups && n_groups != 0x7fffffff) ? (size_t)std::max(n_groups, 1) : 1;
+    std::vector<int64_t> g_lo(n_g, INT64_MAX), g_hi(n_g, -1);
     for (int i = 0; i < n_families; ++i) {
-        const int64_t cnt = check_family(families[i], n_itab, n_dtab, n_groups, m);
+        int64_t lo = 0, hi = -1;
+        const int64_t cnt = check_family(families[i], n_itab, n_dtab, n_groups, m, itab, &lo, &hi);
         total += cnt;
-        if (cnt > 0) order.push_back(i);
+        if (cnt > 0) {
+            order.push_back(i);
+            if ((size_t)families[i].group < n_g && n_g > 1) {
+                g_lo[families[i].group] = std::min(g_lo[families[i].group], lo);
+                g_hi[families[i].group] = std::max(g_hi[families[i].group], hi);
+            }
+        }
     }
     // The families must tile the stream exactly: a group of k families with stride k interleaves the k body terms of
     // each cell over one region; regions follow one another without holes or overlap (every slot is written once).
@@ -504,8 +538,16 @@ static int64_t stage_lowered(int64_t n_terms, const int32_t* term_row, const int
     ELP_REQUIRE(groups != nullptr || n_groups == 0 || n_groups == 0x7fffffff, "lowered: groups missing");
     for (int g = 0; groups && g < n_groups; ++g) {
         ELP_REQUIRE(groups[g].n_mul >= 0 && groups[g].n_mul <= ELP_MAX_GROUP_MUL, "lowered: group with %d multipliers", groups[g].n_mul);
-        for (int k = 0; k < groups[g].n_mul; ++k)
+        for (int k = 0; k < groups[g].n_mul; ++k) {
             ELP_REQUIRE(groups[g].mul_tab[k] >= 0 && groups[g].mul_tab[k] < std::max<int64_t>(n_dtab, 1), "lowered: multiplier outside dtab");
+            if (groups[g].mul_per_row[k] && (size_t)g < n_g && g_hi[g] >= 0) {
+                // asm_finish_group reads dtab[mul_tab + (row - row0)]: the table must cover every row the group's families touch
+                ELP_REQUIRE(groups[g].row0 <= g_lo[g], "lowered: group %d has a per-row multiplier but starts at row %d, after its first term row %lld",
+                            g, groups[g].row0, (long long)g_lo[g]);
+                ELP_REQUIRE(groups[g].mul_tab[k] + (g_hi[g] - groups[g].row0) < n_dtab,
+                            "lowered: per-row multiplier table of group %d ends before row %lld", g, (long long)g_hi[g]);
+            }
+        }
     }
     const size_t T = (size_t)(n_terms + total);
     ELP_REQUIRE(T < 0xffffffffull, "lowered: too many terms");
@@ -536,8 +578,8 @@ int elp_assemble_lowered(int64_t n_terms, const int32_t* term_row, const int32_t
     const int64_t l0 = g_launches.load();
     ELP_REQUIRE(m >= 0 && n >= 0 && row_ptr && nnz_out, "lowered: bad arguments");
     cudaStream_t st = 0;
-    cudaEvent_t e0, e1;
-    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    EventPair ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     AsmIo io; AsmLowered lo;
     ELP_CUDA(cudaEventRecord(e0, st));
     const int64_t T = stage_lowered(n_terms, term_row, term_col, term_val, n_families, families, n_itab, itab, n_dtab, dtab,
@@ -554,7 +596,6 @@ int elp_assemble_lowered(int64_t n_terms, const int32_t* term_row, const int32_t
     ELP_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *nnz_out = nnz;
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -606,8 +647,8 @@ static void solve_small(int32_t m, int32_t n, const int32_t* row_ptr, const int3
     if (m > 0) { ptr.upload(row_ptr, (size_t)m + 1, st); idx.upload(col_idx, nnz, st); val.upload(vals, nnz, st);
                  b.upload(rhs, m, st); sd.upload(sense, m, st); }
     cd.upload(c, n, st); lbd.upload(lb, n, st); ubd.upload(ub, n, st);
-    cudaEvent_t e0, e1;
-    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    EventPair ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     ELP_CUDA(cudaEventRecord(e0, st));
     densify_device(m, n, ptr.p, idx.p, val.p, A.p, st);
     simplex_batch_device(1, m, n, A.p, b.p, cd.p, lbd.p, ubd.p, sd.p, maximize, o.max_iter, stat.p, obj.p, xd.p, yd.p,
@@ -619,7 +660,6 @@ static void solve_small(int32_t m, int32_t n, const int32_t* row_ptr, const int3
     ELP_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *status = s;
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -745,8 +785,8 @@ int elp_model_assemble(int64_t n_terms, const int32_t* term_row, const int32_t* 
     const int64_t l0 = g_launches.load();
     ELP_REQUIRE(m >= 0 && n >= 0 && out, "elp_model_assemble: bad arguments");
     cudaStream_t st = 0;
-    cudaEvent_t e0, e1;
-    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    EventPair ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     AsmIo io; AsmLowered lo;
     ELP_CUDA(cudaEventRecord(e0, st));
     const int64_t T = stage_lowered(n_terms, term_row, term_col, term_val, n_families, families, n_itab, itab, n_dtab, dtab,
@@ -770,7 +810,6 @@ int elp_model_assemble(int64_t n_terms, const int32_t* term_row, const int32_t* 
     }
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *out = reinterpret_cast<elp_model*>(h);
     if (nnz_out) *nnz_out = nnz;
     if (stats) {
@@ -876,8 +915,8 @@ int elp_batch_run(elp_batch* hh, const elp_options* opt, elp_stats* stats) {
     WallTimer wall;
     const int64_t l0 = g_launches.load();
     cudaStream_t st = 0;
-    cudaEvent_t e0, e1;
-    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    EventPair ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     ELP_CUDA(cudaEventRecord(e0, st));
     simplex_batch_device(h->B, h->m, h->n, h->A.p, h->b.p, h->c.p, h->has_lb ? h->lb.p : nullptr,
                          h->has_ub ? h->ub.p : nullptr, h->has_sense ? h->sense.p : nullptr, h->maximize, o.max_iter,
@@ -886,7 +925,6 @@ int elp_batch_run(elp_batch* hh, const elp_options* opt, elp_stats* stats) {
     ELP_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->method_used = ELP_METHOD_SIMPLEX;
@@ -938,8 +976,8 @@ int elp_solve_batch(int64_t B, int32_t m, int32_t n, const double* A, const doub
     chunk = std::min(chunk, B);
     const int64_t nchunks = (B + chunk - 1) / chunk;
     w.ensure((size_t)chunk, (size_t)B, m, n, lb != nullptr, ub != nullptr, sense != nullptr);
-    cudaEvent_t e0, e1;
-    ELP_CUDA(cudaEventCreate(&e0)); ELP_CUDA(cudaEventCreate(&e1));
+    EventPair ev;
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     ELP_CUDA(cudaEventRecord(e0, w.st[0]));
     for (int64_t i = 0; i < nchunks; ++i) {
         const int s = (int)(i % BatchStreamWorkspace::NS);
@@ -968,7 +1006,6 @@ int elp_solve_batch(int64_t B, int32_t m, int32_t n, const double* A, const doub
     ELP_CUDA(cudaStreamSynchronize(w.st[0]));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->method_used = ELP_METHOD_SIMPLEX;

@@ -86,7 +86,9 @@ struct GhostOut {
 };
 struct GhostIn {
     const double* vec;                 // my ghost vector
+    unsigned int len;                  // its length in doubles
     const unsigned long long* flags;   // my flag row for it (N slots)
+    unsigned long long* go;            // local word: block 0 releases the epoch here for the other CTAs of the kernel
     unsigned long long* peer_flag[8];  // rank r's flag row for the same vector; this rank writes slot `rank`
     unsigned int* err;                 // bit 0: a producer never showed up (the host turns it into an error)
     unsigned long long* trace;         // ELP_GHOST_DEBUG bit 64: [4096][4] globaltimer stamps (entry, signalled, flags seen) per kernel
@@ -108,25 +110,60 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Consumer prologue.  Block 0: thread 0 publishes this rank's part of epoch `want` to every rank, the first N lanes poll
+// the local flag row until every rank's slot reached `want`, ONE system fence orders the gathers behind the flags, and
+// a local "go" word is released at GPU scope.  Every other CTA only spins on that go word with GPU-scope acquire loads:
+// no system-scope fence per CTA (888 of them at once when the flags flip were the constant cost that kept K2 from
+// scaling), no system-scope traffic at all outside block 0.
 __device__ __forceinline__ void ghost_acquire(const GhostIn& gi, long long want, int lane) {
     const bool tracer = (gi.dbg & 64) && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned long long* tr = tracer ? gi.trace + (size_t)((2 * want + gi.kind) & 4095) * 4 : nullptr;
     if (tracer) { tr[0] = globaltimer_ns(); tr[3] = (unsigned long long)want; }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !(gi.dbg & 4)) {
-        __threadfence_system();
-        for (int r = 0; r < gi.n; ++r) st_relaxed_sys(gi.peer_flag[r] + gi.rank, (unsigned long long)want);
-    }
-    if (tracer) tr[1] = globaltimer_ns();
-    if (!(gi.dbg & 2) && (threadIdx.x >> 5) == 0 && lane < gi.n) {
-        unsigned long long spins = 0;
-        while ((long long)ld_volatile_u64(gi.flags + lane) < want) {
-            if (++spins > (1ull << 25)) { atomicOr(gi.err, 1u); break; }      // ~10 s: a peer died; fail, do not hang
-            if (spins > 16) __nanosleep(20);
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0 && !(gi.dbg & 4)) {
+            __threadfence_system();
+            for (int r = 0; r < gi.n; ++r) st_relaxed_sys(gi.peer_flag[r] + gi.rank, (unsigned long long)want);
         }
-        __threadfence_system();                    // acquire: the gathers below are ordered behind the flags
+        if (tracer) tr[1] = globaltimer_ns();
+        if (!(gi.dbg & 2) && (threadIdx.x >> 5) == 0) {
+            if (lane < gi.n) {
+                unsigned long long spins = 0;
+                while ((long long)ld_volatile_u64(gi.flags + lane) < want) {
+                    if (++spins > (1ull << 25)) { atomicOr(gi.err, 1u); break; }      // ~10 s: a peer died; fail, do not hang
+                    if (spins > 16) __nanosleep(20);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_system();                // acquire at system scope, once
+                st_release_gpu(gi.go, (unsigned long long)want);
+            }
+        }
+    } else if (!(gi.dbg & 2) && threadIdx.x == 0) {
+        unsigned long long spins = 0;
+        while ((long long)ld_acquire_gpu(gi.go) < want) {
+            if (++spins > (1ull << 25)) { atomicOr(gi.err, 1u); break; }
+            if (spins > 8) __nanosleep(20);
+        }
     }
     __syncthreads();
     if (tracer) tr[2] = globaltimer_ns();
+    // Experiment kept behind dbg bit 128: pull the whole ghost vector into L2 with sequential prefetches (what the peers
+    // stored arrived over NVLink; if it sat in HBM only, the first gather of every sector would be a random HBM access).
+    // Measured at N = 2: 181.8 us per iteration with it, 177.7 without — the gathers are not where K2 loses its time.
+    if (gi.dbg & 128) {
+        const size_t lines = ((size_t)gi.len * 8 + 127) / 128;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (size_t)gridDim.x * blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gi.vec) + i * 128));
+    }
 }
 // producer side, per row of a warp tile (all 32 lanes call both; `owner` lanes carry a value).  The destination table is
 // a kernel parameter and the loops over the destinations are unrolled (constant-bank operands); reading the table from
@@ -794,7 +831,9 @@ struct Pdlp {
     int k = 0, total = 0, restarts = 0;
     double fpe0 = -1.0, fpe_prev = -1.0;
     double beta_artificial = 0.36;   // artificial restart once the epoch is this fraction of all iterations so far
-    double w_kp = 0.5, w_ki = 0.0, w_kd = 0.0, w_ismooth = 0.3, w_err_sum = 0.0, w_err_prev = 0.0;   // primal-weight controller
+    // primal-weight controller.  kp = 0.5 is PDLP's geometric-mean smoothing (round 1); 0.85 measured at full size
+    // (profiles/r2_primal_weight.jsonl): config 2 19 408 -> 10 510 iterations, config 5 2 764 -> 1 675, config 4 unchanged
+    double w_kp = 0.85, w_ki = 0.0, w_kd = 0.0, w_ismooth = 0.3, w_err_sum = 0.0, w_err_prev = 0.0;
     int gap_rule = 0;                // 0: PDLP's gap test at eps/4; 1: gap + residual-induced objective error bound <= gap_factor * eps
     double gap_factor = 1.0, obj_err = 0.0;
     bool need_fpe0 = true;
@@ -844,7 +883,7 @@ struct Pdlp {
     // Builds the ghost exchange: which entries every rank gathers, their compact numbering, the producers' masks and
     // tile bases, and the peer mappings (same process: peer access; other processes: CUDA IPC).  Falls back to NCCL
     // all-gathers of the full vectors when the GPUs cannot reach each other's memory (or ELP_PDLP_P2P=0).
-    static constexpr size_t GH_FLAGS_BYTES = 512;      // x flags [0,64) y flags [64,128) err 128
+    static constexpr size_t GH_FLAGS_BYTES = 512;      // x flags [0,64) y flags [64,128) err 128, go words 256 (x) and 384 (y)
     void setup_ghost_exchange() {
         ghost = false;
         if (N <= 1 || N > 8 || env_int("ELP_PDLP_P2P", 1) == 0) return;
@@ -1012,8 +1051,10 @@ struct Pdlp {
             yin.peer_flag[r] = reinterpret_cast<unsigned long long*>(base[r] + 64);
         }
         unsigned int* err = reinterpret_cast<unsigned int*>(ghost_mem.p + 128);
-        xin.vec = xout.buf[rank]; xin.flags = xin.peer_flag[rank]; xin.err = err; xin.kind = 1;
-        yin.vec = yout.buf[rank]; yin.flags = yin.peer_flag[rank]; yin.err = err; yin.kind = 0;
+        xin.vec = xout.buf[rank]; xin.flags = xin.peer_flag[rank]; xin.err = err; xin.kind = 1; xin.len = (unsigned)gx;
+        xin.go = reinterpret_cast<unsigned long long*>(ghost_mem.p + 256);
+        yin.vec = yout.buf[rank]; yin.flags = yin.peer_flag[rank]; yin.err = err; yin.kind = 0; yin.len = (unsigned)gy;
+        yin.go = reinterpret_cast<unsigned long long*>(ghost_mem.p + 384);
         if (gdbg & 64) {
             ArenaScope own(nullptr);
             ghost_trace.alloc(4096 * 4);
@@ -1611,7 +1652,8 @@ struct Pdlp {
             const double ddx = std::sqrt(hc[2]), ddy = std::sqrt(hr[3]);
             if (ddx > 1e-10 && ddy > 1e-10) {
                 // PID-style controller on log w (cuPDLPx): e = log(w dx / dy) is the imbalance of the two movements;
-                // kp = 0.5, ki = kd = 0 is PDLP's geometric-mean smoothing
+                // kp = 0.5, ki = kd = 0 is PDLP's geometric-mean smoothing; an integral term (ki > 0) diverged on
+                // configs 2 and 5 in the CPU lab, so only the proportional gain is used
                 const double e = std::log(w * ddx / ddy);
                 w_err_sum = w_ismooth * w_err_sum + e;
                 w = std::exp(std::log(w) - (w_kp * e + w_ki * w_err_sum + w_kd * (e - w_err_prev)));

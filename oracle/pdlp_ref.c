@@ -279,7 +279,8 @@ int elpo_pdlp(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, cons
         fpe_prev = fpe;
         if (restart) {
             const double ddx = sqrt(ddx2), ddy = sqrt(ddy2);
-            if (ddx > 1e-10 && ddy > 1e-10) w = exp(0.5 * log(ddy / ddx) + 0.5 * log(w));
+            /* primal weight: log w moves 85 % of the way to the balance log(ddy / ddx) (pdlp.cu: w_kp = 0.85) */
+            if (ddx > 1e-10 && ddy > 1e-10) w = exp(log(w) - 0.85 * log(w * ddx / ddy));
             for (j = 0; j < n; ++j) { x[j] = xp[j]; x0[j] = xp[j]; }
             for (i = 0; i < m; ++i) { y[i] = yp[i]; y0[i] = yp[i]; }
             k = 0; ++restarts; need_fpe0 = 1; fpe_prev = -1;

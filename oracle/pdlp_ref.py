@@ -121,7 +121,7 @@ def kkt(A, AT, c, lc, uc, l, u, x, y, ax=None, aty=None, at_lo=None, at_hi=None)
 
 def solve(m, n, row_ptr, col_idx, vals, sense, rhs, c, lb, ub, maximize=False,
           eps=1e-6, max_iter=200_000, check_every=64, verbose=False, ruiz_iters=10,
-          kp=0.5, ki=0.0, kd=0.0, i_smooth=0.3, history=None):
+          kp=0.85, ki=0.0, kd=0.0, i_smooth=0.3, history=None):
     A0 = sp.csr_matrix((vals, col_idx, row_ptr), shape=(m, n))
     c0 = -np.asarray(c, dtype=float) if maximize else np.asarray(c, dtype=float)
     lc0, uc0 = row_bounds(np.asarray(sense), np.asarray(rhs, dtype=float))

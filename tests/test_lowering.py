@@ -253,6 +253,31 @@ def test_device_expansion_and_assembly_equal_eager(name):
 
 
 @pytest.mark.gpu
+def test_malformed_fold_group_is_refused_before_it_reaches_the_device():
+    """a per-row multiplier table must cover every row its group's families touch (asm_finish_group reads
+    dtab[mul_tab + row - row0]): a group that starts after its first term row, or a table that ends early, is an error
+    code — not an out-of-bounds device read"""
+    l = _build("repeated", True)
+    rows, cols, vals, packed, m, _ = _lowered_parts(l)
+    n = l._n_var
+    fam, n_fam, itab, dtab, grp, n_grp, n_low = packed
+    per_row = [(g, k) for g in range(n_grp) for k in range(grp[g].n_mul) if grp[g].mul_per_row[k]]
+    assert per_row, "the model scales a folded sum by k[s]: a per-row multiplier must exist"
+    g, k = per_row[0]
+    L.assemble_lowered(rows, cols, vals, packed, m, n)                 # well-formed: accepted
+    keep = grp[g].row0
+    grp[g].row0 = keep + 1                                             # the group now starts after its first row
+    with pytest.raises(L.ElpError, match="per-row multiplier"):
+        L.assemble_lowered(rows, cols, vals, packed, m, n)
+    grp[g].row0 = keep
+    tab = grp[g].mul_tab[k]
+    grp[g].mul_tab[k] = dtab.size - 1                                  # the table ends before the group's last row
+    with pytest.raises(L.ElpError, match="per-row multiplier"):
+        L.assemble_lowered(rows, cols, vals, packed, m, n)
+    grp[g].mul_tab[k] = tab
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("K,gw,gh,extra", [(4, 10, 8, 40), (50, 100, 200, 20_600)])
 def test_mcnf_through_the_dsl_is_the_generator_matrix(K, gw, gh, extra):
     """config 5 written with for / sum_for over ragged arc sets: 2 traces instead of ~11 M body evaluations; the device
