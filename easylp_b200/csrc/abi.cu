@@ -245,7 +245,7 @@ struct DevicePool {
     }
     void shutdown() {
         if (workers.empty()) return;
-        try { run([](int) { cudaDeviceSynchronize(); comm_destroy(); }); } catch (...) {}
+        try { run([](int) { cudaDeviceSynchronize(); comm_destroy(); g_arena_cache.clear(); }); } catch (...) {}
         {
             std::lock_guard<std::mutex> lk(mu);
             stop = true;
@@ -407,6 +407,7 @@ int elp_release_workspace(void) {
     asm_workspace_release();
     batch_stream_workspace().release();
     pool_release();
+    g_arena_cache.clear();              // parked arenas of this thread (the pool's workers empty theirs when they shut down)
     ELP_CATCH
 }
 

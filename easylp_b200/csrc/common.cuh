@@ -57,6 +57,39 @@ extern thread_local std::string g_last_error;
 // size (scripts/malloc_probe.cu: 1.2 GB in one piece 2 + 6 ms), and a PDLP handle used to make ~60 of them.  While an
 // ArenaScope is active on the calling thread, DevBuf::alloc takes its memory from the arena (256-byte aligned, never
 // returned piecewise; the arena is freed as a whole by its owner) and falls back to cudaMalloc when the arena is full.
+// Released arenas are parked in a small per-thread cache instead of going back to the driver: cudaFree of a ~1 GB block
+// was measured at 0.8 / 83 / 661 ms on three consecutive solves of config 5 (scripts/gpu_close_probe.py), more than the
+// solve itself.  elp_release_workspace() (and the end of the thread) empties the cache.
+struct ArenaCache {
+    struct Block { char* p; size_t cap; int dev; };
+    std::vector<Block> blocks;
+    ~ArenaCache() { clear(); }
+    void clear() {
+        for (Block& b : blocks) cudaFree(b.p);
+        blocks.clear();
+        cudaGetLastError();
+    }
+    char* take(size_t bytes, size_t* cap_out) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); ++i)
+            if (blocks[i].dev == dev && blocks[i].cap >= bytes && blocks[i].cap <= 4 * bytes + (64u << 20) &&
+                (best < 0 || blocks[i].cap < blocks[best].cap)) best = i;
+        if (best < 0) return nullptr;
+        char* p = blocks[best].p;
+        *cap_out = blocks[best].cap;
+        blocks.erase(blocks.begin() + best);
+        return p;
+    }
+    void park(char* p, size_t cap) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || blocks.size() >= 4) { cudaFree(p); return; }
+        blocks.push_back(Block{p, cap, dev});
+    }
+};
+inline thread_local ArenaCache g_arena_cache;
+
 struct Arena {
     char* base = nullptr;
     size_t cap = 0, used = 0;
@@ -66,7 +99,9 @@ struct Arena {
     ~Arena() { release(); }
     void reserve(size_t bytes) {
         release();
-        if (bytes && cudaMalloc(&base, bytes) == cudaSuccess) cap = bytes;
+        if (!bytes) return;
+        if (char* p = g_arena_cache.take(bytes, &cap)) { base = p; return; }
+        if (cudaMalloc(&base, bytes) == cudaSuccess) cap = bytes;
         else { base = nullptr; cap = 0; cudaGetLastError(); }      // no arena: every buffer gets its own allocation
     }
     void* take(size_t bytes) {
@@ -76,7 +111,7 @@ struct Arena {
         return base + at;
     }
     void release() {
-        if (base) cudaFree(base);
+        if (base) g_arena_cache.park(base, cap);
         base = nullptr; cap = used = 0;
     }
 };

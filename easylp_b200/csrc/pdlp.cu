@@ -873,11 +873,18 @@ struct Pdlp {
                         scnt[k] ? span[k] / scnt[k] * 1e-3 : 0.0, cnt[k]);
     }
     ~Pdlp() {
+        const bool dbg = getenv("ELP_PDLP_DEBUG") != nullptr;
+        WallTimer t;
         if (graph) cudaGraphExecDestroy(graph);
+        const double t_graph = t.ms();
         if (st) cudaStreamSynchronize(st);
         dump_trace();
         for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
         if (st) cudaStreamDestroy(st);
+        const double t_stream = t.ms();
+        scratch.release();
+        arena.release();                 // (the DevBufs inside are arena pieces: their destructors free nothing)
+        if (dbg) fprintf(stderr, "[pdlp destroy] graph %.3f ms, stream %.3f ms, arenas %.3f ms\n", t_graph, t_stream - t_graph, t.ms() - t_stream);
     }
 
     // Builds the ghost exchange: which entries every rank gathers, their compact numbering, the producers' masks and

@@ -175,7 +175,7 @@ int elpo_pdlp_lab(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, 
         }
         smax = s;
     }
-    const double eta = smax > 0 ? 0.998 / smax : 1.0;
+    const double eta = (smax > 0 ? 0.998 / smax : 1.0) * envd("LAB_ETA", 1.0);
     double nb = 0, nc = nrm2(c, n);
     for (int i = 0; i < m; ++i) { double a = fmax(isfinite(lc[i]) ? fabs(lc[i]) : 0, isfinite(uc[i]) ? fabs(uc[i]) : 0); nb += a * a; }
     nb = sqrt(nb);
