@@ -1,4 +1,4 @@
-// simplex.cu — batched dense simplex: one LP per CTA, tableau resident in shared memory.
+// simplex.cu — batched dense simplex: one LP per warp (one per CTA for the larger shapes), tableau resident in shared memory.
 //
 // Replaces `status <- solve(prob)` (/root/reference/R/class.R:276) for LPs whose dense tableau fits in
 // one SM's shared memory, and is the engine of the additive batch entry point (BASELINE config 3:

@@ -1270,7 +1270,7 @@ def _warn_decreasing_transformation(f, lower, upper):    # R/utils.R:199-217
 
 def solve_batch(A, b, c, lower=0.0, upper=np.inf, dir="<=", sense="min", **control):
     """Additive batch entry point (BASELINE config 3): many independent small dense LPs
-    `min/max c_k'x  s.t.  A_k x dir b_k, lower <= x <= upper`, one LP per CTA.  Returns (status strings,
+    `min/max c_k'x  s.t.  A_k x dir b_k, lower <= x <= upper`, one LP per warp (per CTA for the larger shapes).  Returns (status strings,
     objective values, solutions)."""
     A = np.asarray(A, dtype=float)
     B, m, n = A.shape

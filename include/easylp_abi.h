@@ -233,7 +233,8 @@ int elp_sensitivity(int32_t m, int32_t n,
 
 /* ---- (3) a batch of small dense LPs (BASELINE config 3; additive entry point) ---
  * A is [B][m][n] row-major, b [B][m], c [B][n], lb/ub [B][n] (NULL => 0 / +Inf), sense [B][m]
- * (NULL => all "<=").  One LP per CTA; outputs status[B], obj[B], x[B][n]. */
+ * (NULL => all "<=").  One LP per WARP with the tableau in shared memory (shapes with m > 32 or m + n > 96: one LP
+ * per CTA); outputs status[B], obj[B], x[B][n]. */
 int elp_solve_batch(int64_t B, int32_t m, int32_t n,
                     const double* A, const double* b, const double* c,
                     const double* lb, const double* ub, const int8_t* sense, int32_t maximize,
@@ -289,7 +290,9 @@ int elp_model_pdlp_create(const elp_model* model, const int8_t* sense, const dou
                           int32_t maximize, const double* lb, const double* ub, const elp_options* opt,
                           elp_pdlp** out, elp_stats* stats);
 
-/* ---- multi-GPU plumbing (one process per GPU; NCCL resolved with dlopen at first use) -------- */
+/* ---- multi-GPU plumbing for callers that run one process (or one host thread) per GPU.  The communicator belongs to the
+ * CALLING THREAD; NCCL is resolved with dlopen at first use.  A caller that just wants one solve spread over the box sets
+ * elp_options.devices instead and needs none of this. -------- */
 #define ELP_UNIQUE_ID_BYTES 128
 int elp_comm_unique_id(void* id /* ELP_UNIQUE_ID_BYTES */);
 int elp_comm_init(int32_t nranks, int32_t rank, const void* id);
