@@ -83,6 +83,8 @@ struct GhostOut {
     int dense, first;                  // dense != 0: no compaction — rank r's ghost vector is the whole vector and my block
                                        // starts at `first` in it (chosen when the ranks read most of everything anyway)
     int self_only;                     // measurement switch (ELP_GHOST_LOCAL_ONLY): nothing leaves the GPU (timing only)
+    unsigned int* seg_cnt;             // push mode: tiles completed per segment of seg_tiles tiles (cumulative over launches);
+    int seg_tiles;                     // buf[r] of a remote rank then is a LOCAL outbox and k_ghost_push moves it (nullptr: off)
 };
 struct GhostIn {
     const double* vec;                 // my ghost vector
@@ -203,6 +205,80 @@ __device__ __forceinline__ void ghost_publish(const GhostOut& go, const GhostRou
     }
 }
 
+// push mode: this warp's tile is in the local outboxes — count it for the pusher (release: the lanes' stores, ordered by the
+// warp barrier, are visible to whoever acquires the counter)
+__device__ __forceinline__ void ghost_tile_done(const GhostOut& go, int tile, int lane) {
+    if (go.seg_cnt == nullptr) return;
+    __syncwarp();
+    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(go.seg_cnt + tile / go.seg_tiles) : "memory");
+}
+
+// ---- push mode: the NVLink traffic leaves through the TMA engine of a companion kernel ------------------------------
+// Remote stores issued by the SpMV warps share the SM's load/store path with the gathers: when the link is saturated
+// they stall the whole pipeline, so at N = 8 transfer and compute add up (kernel bodies of 45 / 50 us for 23 / 19 us of
+// work).  In push mode the epilogues write what other ranks read into LOCAL outboxes (same compact layout, same
+// positions) and count finished tiles per segment; this kernel — a few one-warp CTAs running NEXT TO the SpMV kernel on a
+// second stream — waits for a segment to be complete and moves it to every destination with bulk copies (global ->
+// shared -> peer global, 8 KB pieces, two in flight per CTA), i.e. asynchronously and in full-size packets.
+// MEASURED (config 4 forced compact, N = 2): 320 us per iteration against 176 us with the epilogues' own peer stores.  The
+// SpMV grid is one full wave of resident CTAs, so the pusher's CTAs get an SM slot only when SpMV CTAs retire: the two
+// kernels serialise instead of overlapping.  Kept behind ELP_GHOST_PUSH=1 (default off) as the record of that attempt.
+struct PushPlan {
+    const uint32_t* route;             // the producer's routing records (+ one closing record): word r = base in rank r's vector
+    unsigned int* seg_cnt;
+    const double* src[8];              // local outbox of rank r, shifted so that it is indexed like r's ghost vector
+    double* dst[8];                    // rank r's ghost vector
+    const PdlpParams* P;
+    int ntiles, seg_tiles, nseg, n, rank;
+};
+constexpr int PUSH_CHUNK = 1024;       // doubles per bulk copy
+__global__ void __launch_bounds__(32)
+k_ghost_push(PushPlan pl, int it) {
+    __shared__ __align__(128) double stage[2][PUSH_CHUNK];
+    __shared__ uint64_t bar[2];
+    const int lane = threadIdx.x;
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncwarp();
+    const unsigned long long epoch = (unsigned long long)(pl.P->epoch_base + it + 1);     // launches of the producer so far
+    uint32_t nchunk = 0;                // bulk copies issued by this CTA (stage = nchunk & 1, mbarrier parity = (nchunk >> 1) & 1)
+    for (int seg = blockIdx.x; seg < pl.nseg; seg += gridDim.x) {
+        const int t0 = seg * pl.seg_tiles, t1 = min(t0 + pl.seg_tiles, pl.ntiles);
+        const unsigned long long need = (unsigned long long)(t1 - t0) * epoch;
+        if (lane == 0) {
+            unsigned int v;
+            unsigned long long spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pl.seg_cnt + seg) : "memory");
+                if ((uint32_t)(v - (uint32_t)need) < 0x80000000u) break;         // v >= need (the counters only grow; wrap-safe)
+                if (++spins > 16) __nanosleep(40);
+            } while (spins < (1ull << 24));
+        }
+        __syncwarp();
+        for (int r = 0; r < pl.n; ++r) {
+            if (r == pl.rank) continue;
+            uint32_t a = pl.route[(size_t)t0 * SPMV_ROUTE_WORDS + r], b = pl.route[(size_t)t1 * SPMV_ROUTE_WORDS + r];
+            const double* src = pl.src[r];
+            double* dst = pl.dst[r];
+            if (lane == 0) {
+                if (a < b && (a & 1u)) { dst[a] = src[a]; ++a; }            // odd ends: one plain 8-byte store each
+                if (a < b && (b & 1u)) { dst[b - 1] = src[b - 1]; --b; }
+                for (uint32_t p = a; p < b; p += PUSH_CHUNK) {
+                    const uint32_t cnt = min((uint32_t)PUSH_CHUNK, b - p), s = nchunk & 1u;
+                    if (nchunk >= 2) tma_store_wait_read<1>();              // the copy that last used this stage has read it
+                    mbar_expect_tx(&bar[s], cnt * 8u);
+                    tma_load_1d(stage[s], src + p, cnt * 8u, &bar[s]);
+                    mbar_wait(&bar[s], (nchunk >> 1) & 1u);
+                    fence_proxy_async();
+                    tma_store_1d(dst + p, stage[s], cnt * 8u);
+                    tma_store_commit();
+                    ++nchunk;
+                }
+            }
+        }
+    }
+    if (lane == 0) { tma_store_wait_all(); __threadfence_system(); }
+}
+
 // primal half of T(z) + reflection + Halpern combine.  g = (A'y)_j
 // GHOST (multi-GPU plain iterations): gathers y from this rank's ghost vector and publishes x-bar into the peers'.
 template <bool CHECK, bool GHOST = false>
@@ -262,6 +338,7 @@ struct PrimalEpi {
     __device__ __forceinline__ void publish(const Route& rt, int lane, int row, double v) const {
         ghost_publish(gout, rt, lane, row, v);
     }
+    __device__ __forceinline__ void tile_done(int tile, int lane) const { ghost_tile_done(gout, tile, lane); }
 };
 
 // dual half.  ax = (A xbar)_i.  SCAT: the kernel then adds val[k] * y_new_i into scat[idx[k]] over the entries of row i,
@@ -325,6 +402,7 @@ struct DualEpi {
     __device__ __forceinline__ void publish(const Route& rt, int lane, int row, double v) const {
         ghost_publish(gout, rt, lane, row, v);
     }
+    __device__ __forceinline__ void tile_done(int tile, int lane) const { ghost_tile_done(gout, tile, lane); }
 };
 
 // Gather-free primal update of the scatter formulation: g = A'y was accumulated by the previous dual kernel.
@@ -699,9 +777,10 @@ __global__ void k_remap_idx(uint32_t nnz, const int* __restrict__ idx, const uin
     if (i < nnz) out[i] = (int)pos[idx[i]];
 }
 // routing record of my tile t, word r = position, in rank r's ghost vector, of the tile's first entry (pos = scan of r's marks)
-__global__ void k_tile_base(int ntiles, int rw, int first, const uint32_t* __restrict__ pos, int r, uint32_t* __restrict__ route) {
+// (record `ntiles` closes the table: the position just behind my block, `count` rows after `first`)
+__global__ void k_tile_base(int ntiles, int rw, int first, int count, const uint32_t* __restrict__ pos, int r, uint32_t* __restrict__ route) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < ntiles) route[(size_t)t * SPMV_ROUTE_WORDS + r] = pos[first + t * rw];
+    if (t <= ntiles) route[(size_t)t * SPMV_ROUTE_WORDS + r] = pos[first + min(t * rw, count)];
 }
 // bytes 32.. of the record: one mask per row of the tile
 __global__ void k_route_masks(int count, int rw, const unsigned char* __restrict__ mask, uint32_t* __restrict__ route) {
@@ -822,6 +901,13 @@ struct Pdlp {
     GhostIn xin{}, yin{};
     GhostOut xout{}, yout{};
     long long epoch_base = 0;            // never reset: the flag rows only grow
+    // push mode (compact ghosts): local outboxes + companion kernel on a second stream, see k_ghost_push
+    bool push = false;
+    DevBuf<double> xoutbox, youtbox;
+    DevBuf<unsigned int> seg_cnt;        // [segments of K1 | segments of K2]
+    PushPlan xpush{}, ypush{};
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double exch_frac_x = 1.0, exch_frac_y = 1.0;   // fraction of the dense (N-1)-copy exchange that is actually sent
     std::vector<void*> ipc_opened;
     DevBuf<double> partials, scal;                              // scal: 2*NACC
@@ -880,6 +966,9 @@ struct Pdlp {
         if (st) cudaStreamSynchronize(st);
         dump_trace();
         for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+        if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (st) cudaStreamDestroy(st);
         const double t_stream = t.ms();
         scratch.release();
@@ -941,8 +1030,8 @@ struct Pdlp {
         {
             ArenaScope k(keep);
             csr_idx_g.alloc(nnz + SPMV_PAD); csc_idx_g.alloc(nnzc + SPMV_PAD);
-            xroute.alloc((size_t)std::max(plan_c.ntiles, 1) * SPMV_ROUTE_WORDS + 4);
-            yroute.alloc((size_t)std::max(plan_r.ntiles, 1) * SPMV_ROUTE_WORDS + 4);
+            xroute.alloc((size_t)(std::max(plan_c.ntiles, 1) + 1) * SPMV_ROUTE_WORDS + 4);      // + the closing record
+            yroute.alloc((size_t)(std::max(plan_r.ntiles, 1) + 1) * SPMV_ROUTE_WORDS + 4);
             xmask.alloc((size_t)std::max(nl, 1)); ymask.alloc((size_t)std::max(m, 1));
             ylist.alloc(sy);                                       // at most every padded row
         }
@@ -956,7 +1045,7 @@ struct Pdlp {
             exclusive_scan_u32(pos.p, sx + 1, sw, st);
             ELP_CUDA(cudaMemcpyAsync(&gxs[r], pos.p + sx, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             if (r == rank && nnz > 0) ELP_LAUNCH(k_remap_idx, ceil_div(nnz, 256), 256, 0, st, (uint32_t)nnz, csr_idx.p, pos.p, csr_idx_g.p);
-            if (nl > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_c.ntiles, 256), 256, 0, st, plan_c.ntiles, plan_c.rw(), n0, pos.p, r, xroute.p);
+            if (nl > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_c.ntiles + 1, 256), 256, 0, st, plan_c.ntiles, plan_c.rw(), n0, nl, pos.p, r, xroute.p);
             ELP_CUDA(cudaStreamSynchronize(st));
         }
         for (int r = 0; r < N; ++r) {
@@ -967,7 +1056,7 @@ struct Pdlp {
                 if (nnzc > 0) ELP_LAUNCH(k_remap_idx, ceil_div(nnzc, 256), 256, 0, st, (uint32_t)nnzc, csc_idx.p, pos.p, csc_idx_g.p);
                 ELP_LAUNCH(k_ghost_list, ceil_div((int64_t)sy, 256), 256, 0, st, (uint32_t)sy, used_y.p + (size_t)r * sy, pos.p, ylist.p);
             }
-            if (m > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_r.ntiles, 256), 256, 0, st, plan_r.ntiles, plan_r.rw(), rank * mb, pos.p, r, yroute.p);
+            if (m > 0) ELP_LAUNCH(k_tile_base, ceil_div(plan_r.ntiles + 1, 256), 256, 0, st, plan_r.ntiles, plan_r.rw(), rank * mb, m, pos.p, r, yroute.p);
             ELP_CUDA(cudaStreamSynchronize(st));
         }
         gx = (int)gxs[rank]; gy = (int)gys[rank];
@@ -1067,6 +1156,61 @@ struct Pdlp {
             ghost_trace.alloc(4096 * 4);
             ghost_trace.zero(st);
             xin.trace = yin.trace = ghost_trace.p;
+        }
+
+        // ---- 5. push mode: remote destinations become local outboxes, a companion kernel moves them (k_ghost_push) -----
+        push = !dense && env_int("ELP_GHOST_PUSH", 0) != 0;      // measured slower (see the note at k_ghost_push): opt-in
+        if (push) {
+            const int SEG = 128;                         // tiles per segment: ~15 KB per destination on config 4 at N = 8
+            std::vector<uint32_t> rec0(2 * SPMV_ROUTE_WORDS), rec1(2 * SPMV_ROUTE_WORDS);   // first / closing records of x and y
+            ELP_CUDA(cudaMemcpyAsync(rec0.data(), xroute.p, SPMV_ROUTE_WORDS * 4, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaMemcpyAsync(rec1.data(), xroute.p + (size_t)plan_c.ntiles * SPMV_ROUTE_WORDS, SPMV_ROUTE_WORDS * 4, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaMemcpyAsync(rec0.data() + SPMV_ROUTE_WORDS, yroute.p, SPMV_ROUTE_WORDS * 4, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaMemcpyAsync(rec1.data() + SPMV_ROUTE_WORDS, yroute.p + (size_t)plan_r.ntiles * SPMV_ROUTE_WORDS, SPMV_ROUTE_WORDS * 4, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaStreamSynchronize(st));
+            auto layout = [&](const uint32_t* a, const uint32_t* b, size_t* off) {      // outbox offsets with the parity of the bases
+                size_t at = 0;
+                for (int r = 0; r < N; ++r) {
+                    if (r == rank) { off[r] = 0; continue; }
+                    at = (at + 31) & ~(size_t)31;
+                    if ((at ^ a[r]) & 1u) ++at;            // same 16-byte phase as the destination: bulk copies need it
+                    off[r] = at;
+                    at += (size_t)(b[r] - a[r]);
+                }
+                return at + 32;
+            };
+            size_t offx[8] = {}, offy[8] = {};
+            const size_t nx = nl > 0 ? layout(rec0.data(), rec1.data(), offx) : 32;
+            const size_t ny = m > 0 ? layout(rec0.data() + SPMV_ROUTE_WORDS, rec1.data() + SPMV_ROUTE_WORDS, offy) : 32;
+            const int nsx = ceil_div(std::max(plan_c.ntiles, 1), SEG), nsy = ceil_div(std::max(plan_r.ntiles, 1), SEG);
+            {
+                ArenaScope k(keep);
+                xoutbox.alloc(nx); youtbox.alloc(ny); seg_cnt.alloc((size_t)nsx + nsy);
+            }
+            xoutbox.zero(st); youtbox.zero(st); seg_cnt.zero(st);
+            xpush = PushPlan{}; ypush = PushPlan{};
+            xpush.route = xroute.p; ypush.route = yroute.p;
+            xpush.seg_cnt = seg_cnt.p; ypush.seg_cnt = seg_cnt.p + nsx;
+            xpush.P = ypush.P = params.p;
+            xpush.ntiles = plan_c.ntiles; ypush.ntiles = plan_r.ntiles;
+            xpush.seg_tiles = ypush.seg_tiles = SEG;
+            xpush.nseg = nl > 0 ? nsx : 0; ypush.nseg = m > 0 ? nsy : 0;
+            xpush.n = ypush.n = N; xpush.rank = ypush.rank = rank;
+            for (int r = 0; r < N; ++r) {
+                xpush.dst[r] = xout.buf[r]; ypush.dst[r] = yout.buf[r];
+                if (r == rank) continue;
+                // the epilogues index an outbox like the destination's ghost vector: shift it by the block's first position
+                xpush.src[r] = xoutbox.p + offx[r] - rec0[r];
+                ypush.src[r] = youtbox.p + offy[r] - rec0[SPMV_ROUTE_WORDS + r];
+                xout.buf[r] = const_cast<double*>(xpush.src[r]);
+                yout.buf[r] = const_cast<double*>(ypush.src[r]);
+            }
+            xout.seg_cnt = xpush.seg_cnt; yout.seg_cnt = ypush.seg_cnt;
+            xout.seg_tiles = yout.seg_tiles = SEG;
+            ELP_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+            ELP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            ELP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+            ELP_CUDA(cudaStreamSynchronize(st));
         }
 
         ghost = true;
@@ -1509,6 +1653,19 @@ struct Pdlp {
     void signal_only(const GhostIn& gi, int plus) {
         ELP_LAUNCH(k_ghost_signal_only, 1, 32, 0, st, gi, params.p, plus);
     }
+    // push mode: the companion kernel starts on the second stream next to the SpMV kernel and both join before the next one
+    void push_fork(const PushPlan& pl, int it) {
+        if (!push || pl.nseg <= 0) return;
+        ELP_CUDA(cudaEventRecord(ev_fork, st));
+        ELP_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
+        const int grid = std::min(pl.nseg, env_int("ELP_GHOST_PUSH_CTAS", 128));
+        ELP_LAUNCH(k_ghost_push, grid, 32, 0, st2, pl, it);
+    }
+    void push_join() {
+        if (!push) return;
+        ELP_CUDA(cudaEventRecord(ev_join, st2));
+        ELP_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    }
     template <bool CHECK>
     void primal_step(int it) {
         if (!CHECK && scatter) {            // g = A'y is already in gcol (left there by the dual kernel's scatter)
@@ -1518,8 +1675,11 @@ struct Pdlp {
         }
         if (!CHECK && ghost) {              // gathers y from my ghost vector, publishes x-bar into the consumers' ghost vectors
             PrimalEpi<false, true> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, yin, xout};
-            if (nl > 0) launch_spmv(plan_c, nl, csc_ptr.p, xout.dense ? csc_idx.p : csc_idx_g.p, csc_val.p, yin.vec, epi, st);   // dense ghosts: identity numbering
-            else signal_only(yin, it);              // what K1's prologue would have said: my y of the previous epoch is out
+            if (nl > 0) {
+                push_fork(xpush, it);
+                launch_spmv(plan_c, nl, csc_ptr.p, xout.dense ? csc_idx.p : csc_idx_g.p, csc_val.p, yin.vec, epi, st);   // dense ghosts: identity numbering
+                push_join();
+            } else signal_only(yin, it);            // what K1's prologue would have said: my y of the previous epoch is out
             return;
         }
         PrimalEpi<CHECK> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, GhostIn{}, GhostOut{}};
@@ -1535,15 +1695,18 @@ struct Pdlp {
         }
         if (!CHECK && ghost) {
             DualEpi<false, false, true> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, xin, yout};
-            if (m > 0) launch_spmv(plan_r, m, csr_ptr.p, yout.dense ? csr_idx.p : csr_idx_g.p, csr_val.p, xin.vec, epi, st);
-            else signal_only(xin, it + 1);          // what K2's prologue would have said: my x-bar of this epoch is out
+            if (m > 0) {
+                push_fork(ypush, it);
+                launch_spmv(plan_r, m, csr_ptr.p, yout.dense ? csr_idx.p : csr_idx_g.p, csr_val.p, xin.vec, epi, st);
+                push_join();
+            } else signal_only(xin, it + 1);        // what K2's prologue would have said: my x-bar of this epoch is out
             return;
         }
         DualEpi<CHECK> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, GhostIn{}, GhostOut{}};
         launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
         if (!CHECK) gather_y(y_full.p);                      // a check iteration does not change y here
     }
-    int kernels_per_iter() const { return ghost ? 2 : (m > 0 ? 1 : 0) + (nl > 0 ? 1 : 0); }
+    int kernels_per_iter() const { return ghost ? (push ? 4 : 2) : (m > 0 ? 1 : 0) + (nl > 0 ? 1 : 0); }
 
     void plain_iterations(int count) {
         if (count <= 0) return;

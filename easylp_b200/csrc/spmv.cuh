@@ -267,6 +267,7 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             __syncwarp();
             issue(hstage);
         }
+        if constexpr (Epi::DIST) epi.tile_done(tile, lane);      // multi-GPU push mode: the tile is in the local outboxes
     }
 }
 
