@@ -83,8 +83,11 @@ struct GhostOut {
     int dense, first;                  // dense != 0: no compaction — rank r's ghost vector is the whole vector and my block
                                        // starts at `first` in it (chosen when the ranks read most of everything anyway)
     int self_only;                     // measurement switch (ELP_GHOST_LOCAL_ONLY): nothing leaves the GPU (timing only)
-    unsigned int* seg_cnt;             // push mode: tiles completed per segment of seg_tiles tiles (cumulative over launches);
-    int seg_tiles;                     // buf[r] of a remote rank then is a LOCAL outbox and k_ghost_push moves it (nullptr: off)
+    // push mode (see ghost_push_role): buf[r] of a remote rank is a LOCAL outbox indexed like r's ghost vector, the last
+    // `push_ctas` CTAs of the kernel move segments of seg_tiles tiles to remote[r] as soon as their values have landed
+    double* remote[8];                 // rank r's ghost vector
+    unsigned int* err;                 // bit 1: a segment never completed
+    int seg_tiles, nseg, ntiles, push_ctas;      // push_ctas == 0: push mode off
 };
 struct GhostIn {
     const double* vec;                 // my ghost vector
@@ -205,78 +208,64 @@ __device__ __forceinline__ void ghost_publish(const GhostOut& go, const GhostRou
     }
 }
 
-// push mode: this warp's tile is in the local outboxes — count it for the pusher (release: the lanes' stores, ordered by the
-// warp barrier, are visible to whoever acquires the counter)
-__device__ __forceinline__ void ghost_tile_done(const GhostOut& go, int tile, int lane) {
-    if (go.seg_cnt == nullptr) return;
-    __syncwarp();
-    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(go.seg_cnt + tile / go.seg_tiles) : "memory");
+// ---- push mode: the NVLink traffic leaves through dedicated CTAs of the same kernel ----------------------------------
+// Remote stores issued by the SpMV warps share the SM's load/store path with the gathers, and a warp's compacted run for
+// one destination is ~18 doubles at an arbitrary 8-byte phase: 160 K short, misaligned NVLink writes per rank and
+// iteration at N = 8.  The kernels are held back by them: bodies of 45 / 50 us for 23 / 19 us of work.  In push mode the
+// epilogues write what other ranks read into LOCAL outboxes (same compact layout, same positions); the LAST `push_ctas`
+// CTAs of the grid do no SpMV — each of their warps owns (segment, destination) items and forwards them in aligned
+// groups of 32 consecutive doubles (256-byte warp stores, 8 groups in flight per warp).
+// Readiness travels IN the data: an outbox holds a NaN sentinel wherever this launch has not stored yet; the pusher reads
+// a group through L2 (ld.relaxed.gpu), forwards it once no lane sees the sentinel and puts the sentinel back.  Every
+// value is one 8-byte store, so a non-sentinel read IS the value: the producers need no fence, no counter, nothing.
+// History (config 4 forced compact, N = 2, 173 us per iteration with the epilogues' own peer stores):
+//   * companion KERNEL on a second stream + per-segment counters + bulk copies                         320 us
+//   * pusher CTAs inside the grid, polling the counters with ld.acquire.gpu (= LDG.STRONG.GPU + CCTL.IVALL: an L1
+//     invalidation per poll on every SM takes the gathered vector away from the SpMV CTAs next door)     308 us
+//   * relaxed polls, no fence at the pushers' end                                                       252 us (148 CTAs), 239 (74)
+//   * what remained was the producers' red.release.gpu per tile (MEMBAR.ALL.GPU under a saturated memory system)
+//     -> the sentinel protocol below.
+constexpr unsigned long long GHOST_SENTINEL = 0xFFF85EED0BADC0DEull;       // a quiet NaN no iterate ever holds
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const void* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
-
-// ---- push mode: the NVLink traffic leaves through the TMA engine of a companion kernel ------------------------------
-// Remote stores issued by the SpMV warps share the SM's load/store path with the gathers: when the link is saturated
-// they stall the whole pipeline, so at N = 8 transfer and compute add up (kernel bodies of 45 / 50 us for 23 / 19 us of
-// work).  In push mode the epilogues write what other ranks read into LOCAL outboxes (same compact layout, same
-// positions) and count finished tiles per segment; this kernel — a few one-warp CTAs running NEXT TO the SpMV kernel on a
-// second stream — waits for a segment to be complete and moves it to every destination with bulk copies (global ->
-// shared -> peer global, 8 KB pieces, two in flight per CTA), i.e. asynchronously and in full-size packets.
-// MEASURED (config 4 forced compact, N = 2): 320 us per iteration against 176 us with the epilogues' own peer stores.  The
-// SpMV grid is one full wave of resident CTAs, so the pusher's CTAs get an SM slot only when SpMV CTAs retire: the two
-// kernels serialise instead of overlapping.  Kept behind ELP_GHOST_PUSH=1 (default off) as the record of that attempt.
-struct PushPlan {
-    const uint32_t* route;             // the producer's routing records (+ one closing record): word r = base in rank r's vector
-    unsigned int* seg_cnt;
-    const double* src[8];              // local outbox of rank r, shifted so that it is indexed like r's ghost vector
-    double* dst[8];                    // rank r's ghost vector
-    const PdlpParams* P;
-    int ntiles, seg_tiles, nseg, n, rank;
-};
-constexpr int PUSH_CHUNK = 1024;       // doubles per bulk copy
-__global__ void __launch_bounds__(32)
-k_ghost_push(PushPlan pl, int it) {
-    __shared__ __align__(128) double stage[2][PUSH_CHUNK];
-    __shared__ uint64_t bar[2];
-    const int lane = threadIdx.x;
-    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
-    __syncwarp();
-    const unsigned long long epoch = (unsigned long long)(pl.P->epoch_base + it + 1);     // launches of the producer so far
-    uint32_t nchunk = 0;                // bulk copies issued by this CTA (stage = nchunk & 1, mbarrier parity = (nchunk >> 1) & 1)
-    for (int seg = blockIdx.x; seg < pl.nseg; seg += gridDim.x) {
-        const int t0 = seg * pl.seg_tiles, t1 = min(t0 + pl.seg_tiles, pl.ntiles);
-        const unsigned long long need = (unsigned long long)(t1 - t0) * epoch;
-        if (lane == 0) {
-            unsigned int v;
+__device__ __forceinline__ void ghost_push_role(const GhostOut& go, int pw, int npw, int lane) {
+    constexpr int U = 8;
+    const int nd = go.n - 1;
+    const int nitems = go.nseg * nd;
+    for (int item = pw; item < nitems; item += npw) {
+        const int seg = item / nd, di = item - seg * nd;
+        const int r = di < go.rank ? di : di + 1;
+        const int t0 = seg * go.seg_tiles, t1 = min(t0 + go.seg_tiles, go.ntiles);
+        const uint32_t a = go.route[(size_t)t0 * SPMV_ROUTE_WORDS + r], b = go.route[(size_t)t1 * SPMV_ROUTE_WORDS + r];
+        unsigned long long* src = reinterpret_cast<unsigned long long*>(go.buf[r]);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(go.remote[r]);
+        for (uint32_t p0 = a & ~31u; p0 < b; p0 += 32u * U) {          // groups aligned in the destination's index space
             unsigned long long spins = 0;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pl.seg_cnt + seg) : "memory");
-                if ((uint32_t)(v - (uint32_t)need) < 0x80000000u) break;         // v >= need (the counters only grow; wrap-safe)
-                if (++spins > 16) __nanosleep(40);
-            } while (spins < (1ull << 24));
-        }
-        __syncwarp();
-        for (int r = 0; r < pl.n; ++r) {
-            if (r == pl.rank) continue;
-            uint32_t a = pl.route[(size_t)t0 * SPMV_ROUTE_WORDS + r], b = pl.route[(size_t)t1 * SPMV_ROUTE_WORDS + r];
-            const double* src = pl.src[r];
-            double* dst = pl.dst[r];
-            if (lane == 0) {
-                if (a < b && (a & 1u)) { dst[a] = src[a]; ++a; }            // odd ends: one plain 8-byte store each
-                if (a < b && (b & 1u)) { dst[b - 1] = src[b - 1]; --b; }
-                for (uint32_t p = a; p < b; p += PUSH_CHUNK) {
-                    const uint32_t cnt = min((uint32_t)PUSH_CHUNK, b - p), s = nchunk & 1u;
-                    if (nchunk >= 2) tma_store_wait_read<1>();              // the copy that last used this stage has read it
-                    mbar_expect_tx(&bar[s], cnt * 8u);
-                    tma_load_1d(stage[s], src + p, cnt * 8u, &bar[s]);
-                    mbar_wait(&bar[s], (nchunk >> 1) & 1u);
-                    fence_proxy_async();
-                    tma_store_1d(dst + p, stage[s], cnt * 8u);
-                    tma_store_commit();
-                    ++nchunk;
+            for (;;) {
+                unsigned long long v[U];
+                bool ok = true;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t p = p0 + (uint32_t)u * 32u + (uint32_t)lane;
+                    v[u] = (p >= a && p < b) ? ld_relaxed_gpu_u64(src + p) : 0ull;
+                    ok &= v[u] != GHOST_SENTINEL;
                 }
+                if (__all_sync(0xffffffffu, ok)) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t p = p0 + (uint32_t)u * 32u + (uint32_t)lane;
+                        if (p >= a && p < b) { dst[p] = v[u]; src[p] = GHOST_SENTINEL; }
+                    }
+                    break;
+                }
+                if (++spins > (1ull << 22)) { if (lane == 0) atomicOr(go.err, 2u); return; }     // seconds: fail, do not hang
+                __nanosleep(spins < 64 ? 100 : 400);
             }
         }
     }
-    if (lane == 0) { tma_store_wait_all(); __threadfence_system(); }
 }
 
 // primal half of T(z) + reflection + Halpern combine.  g = (A'y)_j
@@ -338,7 +327,8 @@ struct PrimalEpi {
     __device__ __forceinline__ void publish(const Route& rt, int lane, int row, double v) const {
         ghost_publish(gout, rt, lane, row, v);
     }
-    __device__ __forceinline__ void tile_done(int tile, int lane) const { ghost_tile_done(gout, tile, lane); }
+    __host__ __device__ __forceinline__ int push_ctas() const { return gout.push_ctas; }
+    __device__ __forceinline__ void push(int pw, int npw, int lane) const { ghost_push_role(gout, pw, npw, lane); }
 };
 
 // dual half.  ax = (A xbar)_i.  SCAT: the kernel then adds val[k] * y_new_i into scat[idx[k]] over the entries of row i,
@@ -402,7 +392,8 @@ struct DualEpi {
     __device__ __forceinline__ void publish(const Route& rt, int lane, int row, double v) const {
         ghost_publish(gout, rt, lane, row, v);
     }
-    __device__ __forceinline__ void tile_done(int tile, int lane) const { ghost_tile_done(gout, tile, lane); }
+    __host__ __device__ __forceinline__ int push_ctas() const { return gout.push_ctas; }
+    __device__ __forceinline__ void push(int pw, int npw, int lane) const { ghost_push_role(gout, pw, npw, lane); }
 };
 
 // Gather-free primal update of the scatter formulation: g = A'y was accumulated by the previous dual kernel.
@@ -776,6 +767,10 @@ __global__ void k_remap_idx(uint32_t nnz, const int* __restrict__ idx, const uin
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) out[i] = (int)pos[idx[i]];
 }
+__global__ void k_fill_u64(size_t n, unsigned long long* __restrict__ out, unsigned long long v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
 // routing record of my tile t, word r = position, in rank r's ghost vector, of the tile's first entry (pos = scan of r's marks)
 // (record `ntiles` closes the table: the position just behind my block, `count` rows after `first`)
 __global__ void k_tile_base(int ntiles, int rw, int first, int count, const uint32_t* __restrict__ pos, int r, uint32_t* __restrict__ route) {
@@ -901,13 +896,9 @@ struct Pdlp {
     GhostIn xin{}, yin{};
     GhostOut xout{}, yout{};
     long long epoch_base = 0;            // never reset: the flag rows only grow
-    // push mode (compact ghosts): local outboxes + companion kernel on a second stream, see k_ghost_push
+    // push mode (compact ghosts): local outboxes + pusher CTAs inside the SpMV grids, see ghost_push_role
     bool push = false;
     DevBuf<double> xoutbox, youtbox;
-    DevBuf<unsigned int> seg_cnt;        // [segments of K1 | segments of K2]
-    PushPlan xpush{}, ypush{};
-    cudaStream_t st2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double exch_frac_x = 1.0, exch_frac_y = 1.0;   // fraction of the dense (N-1)-copy exchange that is actually sent
     std::vector<void*> ipc_opened;
     DevBuf<double> partials, scal;                              // scal: 2*NACC
@@ -966,9 +957,6 @@ struct Pdlp {
         if (st) cudaStreamSynchronize(st);
         dump_trace();
         for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
-        if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); }
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_join) cudaEventDestroy(ev_join);
         if (st) cudaStreamDestroy(st);
         const double t_stream = t.ms();
         scratch.release();
@@ -1000,6 +988,7 @@ struct Pdlp {
         // measured: N = 2 181 vs 159 us, N = 4 130 vs 110 us per iteration — so the ghost vectors are then plain
         // copies of the whole vector (identity numbering, everything to everybody, aligned full-warp stores).
         bool dense = false;
+        double kept_all = 1.0;
         {
             DevBuf<unsigned char> tmask((size_t)std::max(std::max(nl, m), 1));
             DevBuf<unsigned long long> cnt(2);
@@ -1015,6 +1004,7 @@ struct Pdlp {
             ELP_CUDA(cudaMemcpyAsync(tot, scal.p, sizeof tot, cudaMemcpyDeviceToHost, st));
             ELP_CUDA(cudaStreamSynchronize(st));
             const double kept = tot[1] > 0 ? tot[0] / tot[1] : 1.0;
+            kept_all = kept;
             const int force = env_int("ELP_PDLP_GHOST_DENSE", -1);
             dense = force >= 0 ? force != 0 : kept >= 0.65;      // measured on config 4: 55 % kept (N = 8) compact 118 vs dense 131 us, 71 % (N = 4) equal
             if (opt.verbose > 0 || env_int("ELP_PDLP_DEBUG", 0))
@@ -1158,22 +1148,24 @@ struct Pdlp {
             xin.trace = yin.trace = ghost_trace.p;
         }
 
-        // ---- 5. push mode: remote destinations become local outboxes, a companion kernel moves them (k_ghost_push) -----
-        push = !dense && env_int("ELP_GHOST_PUSH", 0) != 0;      // measured slower (see the note at k_ghost_push): opt-in
+        // ---- 5. push mode: remote destinations become local outboxes, pusher CTAs move them (ghost_push_role) ----------
+        // Pays when a rank sends several copies' worth of its block: config 4 at N = 8 (55 % kept, 3.9 copies) 106 -> 90 us
+        // per iteration; config 5 at N = 8 (23 %, 1.6 copies) 67 -> 75 us and everything at N = 2 (stores are free there,
+        // the pushers' SM slots are not) lose.  `kept` is the all-reduced fraction, so every rank decides alike.
+        push = !dense && env_int("ELP_GHOST_PUSH", kept_all * (N - 1) >= 3.0 ? 1 : 0) != 0;
         if (push) {
-            const int SEG = 128;                         // tiles per segment: ~15 KB per destination on config 4 at N = 8
+            const int SEG = std::max(1, env_int("ELP_GHOST_PUSH_SEG", 32));          // tiles per segment
             std::vector<uint32_t> rec0(2 * SPMV_ROUTE_WORDS), rec1(2 * SPMV_ROUTE_WORDS);   // first / closing records of x and y
             ELP_CUDA(cudaMemcpyAsync(rec0.data(), xroute.p, SPMV_ROUTE_WORDS * 4, cudaMemcpyDeviceToHost, st));
             ELP_CUDA(cudaMemcpyAsync(rec1.data(), xroute.p + (size_t)plan_c.ntiles * SPMV_ROUTE_WORDS, SPMV_ROUTE_WORDS * 4, cudaMemcpyDeviceToHost, st));
             ELP_CUDA(cudaMemcpyAsync(rec0.data() + SPMV_ROUTE_WORDS, yroute.p, SPMV_ROUTE_WORDS * 4, cudaMemcpyDeviceToHost, st));
             ELP_CUDA(cudaMemcpyAsync(rec1.data() + SPMV_ROUTE_WORDS, yroute.p + (size_t)plan_r.ntiles * SPMV_ROUTE_WORDS, SPMV_ROUTE_WORDS * 4, cudaMemcpyDeviceToHost, st));
             ELP_CUDA(cudaStreamSynchronize(st));
-            auto layout = [&](const uint32_t* a, const uint32_t* b, size_t* off) {      // outbox offsets with the parity of the bases
+            auto layout = [&](const uint32_t* a, const uint32_t* b, size_t* off) {      // outbox offsets with the 256-byte phase of the bases
                 size_t at = 0;
                 for (int r = 0; r < N; ++r) {
                     if (r == rank) { off[r] = 0; continue; }
-                    at = (at + 31) & ~(size_t)31;
-                    if ((at ^ a[r]) & 1u) ++at;            // same 16-byte phase as the destination: bulk copies need it
+                    at = ((at + 31) & ~(size_t)31) + (a[r] & 31u);     // a group of 32 is aligned on both sides of the copy
                     off[r] = at;
                     at += (size_t)(b[r] - a[r]);
                 }
@@ -1185,31 +1177,24 @@ struct Pdlp {
             const int nsx = ceil_div(std::max(plan_c.ntiles, 1), SEG), nsy = ceil_div(std::max(plan_r.ntiles, 1), SEG);
             {
                 ArenaScope k(keep);
-                xoutbox.alloc(nx); youtbox.alloc(ny); seg_cnt.alloc((size_t)nsx + nsy);
+                xoutbox.alloc(nx); youtbox.alloc(ny);
             }
-            xoutbox.zero(st); youtbox.zero(st); seg_cnt.zero(st);
-            xpush = PushPlan{}; ypush = PushPlan{};
-            xpush.route = xroute.p; ypush.route = yroute.p;
-            xpush.seg_cnt = seg_cnt.p; ypush.seg_cnt = seg_cnt.p + nsx;
-            xpush.P = ypush.P = params.p;
-            xpush.ntiles = plan_c.ntiles; ypush.ntiles = plan_r.ntiles;
-            xpush.seg_tiles = ypush.seg_tiles = SEG;
-            xpush.nseg = nl > 0 ? nsx : 0; ypush.nseg = m > 0 ? nsy : 0;
-            xpush.n = ypush.n = N; xpush.rank = ypush.rank = rank;
+            // all bytes 0xFF is not the sentinel: fill with the pattern
+            ELP_LAUNCH(k_fill_u64, ceil_div((int64_t)nx, 256), 256, 0, st, (size_t)nx, reinterpret_cast<unsigned long long*>(xoutbox.p), GHOST_SENTINEL);
+            ELP_LAUNCH(k_fill_u64, ceil_div((int64_t)ny, 256), 256, 0, st, (size_t)ny, reinterpret_cast<unsigned long long*>(youtbox.p), GHOST_SENTINEL);
+            const int pctas = std::max(1, env_int("ELP_GHOST_PUSH_CTAS", kNumSMs));
             for (int r = 0; r < N; ++r) {
-                xpush.dst[r] = xout.buf[r]; ypush.dst[r] = yout.buf[r];
+                xout.remote[r] = xout.buf[r]; yout.remote[r] = yout.buf[r];
                 if (r == rank) continue;
                 // the epilogues index an outbox like the destination's ghost vector: shift it by the block's first position
-                xpush.src[r] = xoutbox.p + offx[r] - rec0[r];
-                ypush.src[r] = youtbox.p + offy[r] - rec0[SPMV_ROUTE_WORDS + r];
-                xout.buf[r] = const_cast<double*>(xpush.src[r]);
-                yout.buf[r] = const_cast<double*>(ypush.src[r]);
+                xout.buf[r] = xoutbox.p + offx[r] - rec0[r];
+                yout.buf[r] = youtbox.p + offy[r] - rec0[SPMV_ROUTE_WORDS + r];
             }
-            xout.seg_cnt = xpush.seg_cnt; yout.seg_cnt = ypush.seg_cnt;
             xout.seg_tiles = yout.seg_tiles = SEG;
-            ELP_CUDA(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-            ELP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-            ELP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+            xout.nseg = nsx; yout.nseg = nsy;
+            xout.ntiles = plan_c.ntiles; yout.ntiles = plan_r.ntiles;
+            xout.push_ctas = nl > 0 ? pctas : 0; yout.push_ctas = m > 0 ? pctas : 0;
+            xout.err = yout.err = xin.err;
             ELP_CUDA(cudaStreamSynchronize(st));
         }
 
@@ -1653,19 +1638,6 @@ struct Pdlp {
     void signal_only(const GhostIn& gi, int plus) {
         ELP_LAUNCH(k_ghost_signal_only, 1, 32, 0, st, gi, params.p, plus);
     }
-    // push mode: the companion kernel starts on the second stream next to the SpMV kernel and both join before the next one
-    void push_fork(const PushPlan& pl, int it) {
-        if (!push || pl.nseg <= 0) return;
-        ELP_CUDA(cudaEventRecord(ev_fork, st));
-        ELP_CUDA(cudaStreamWaitEvent(st2, ev_fork, 0));
-        const int grid = std::min(pl.nseg, env_int("ELP_GHOST_PUSH_CTAS", 128));
-        ELP_LAUNCH(k_ghost_push, grid, 32, 0, st2, pl, it);
-    }
-    void push_join() {
-        if (!push) return;
-        ELP_CUDA(cudaEventRecord(ev_join, st2));
-        ELP_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-    }
     template <bool CHECK>
     void primal_step(int it) {
         if (!CHECK && scatter) {            // g = A'y is already in gcol (left there by the dual kernel's scatter)
@@ -1675,11 +1647,8 @@ struct Pdlp {
         }
         if (!CHECK && ghost) {              // gathers y from my ghost vector, publishes x-bar into the consumers' ghost vectors
             PrimalEpi<false, true> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, yin, xout};
-            if (nl > 0) {
-                push_fork(xpush, it);
-                launch_spmv(plan_c, nl, csc_ptr.p, xout.dense ? csc_idx.p : csc_idx_g.p, csc_val.p, yin.vec, epi, st);   // dense ghosts: identity numbering
-                push_join();
-            } else signal_only(yin, it);            // what K1's prologue would have said: my y of the previous epoch is out
+            if (nl > 0) launch_spmv(plan_c, nl, csc_ptr.p, xout.dense ? csc_idx.p : csc_idx_g.p, csc_val.p, yin.vec, epi, st);   // dense ghosts: identity numbering
+            else signal_only(yin, it);            // what K1's prologue would have said: my y of the previous epoch is out
             return;
         }
         PrimalEpi<CHECK> epi{nullptr, c.p, l.p, u.p, x0.p, x.p, xbar(), xp.p, params.p, it, GhostIn{}, GhostOut{}};
@@ -1695,18 +1664,15 @@ struct Pdlp {
         }
         if (!CHECK && ghost) {
             DualEpi<false, false, true> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, xin, yout};
-            if (m > 0) {
-                push_fork(ypush, it);
-                launch_spmv(plan_r, m, csr_ptr.p, yout.dense ? csr_idx.p : csr_idx_g.p, csr_val.p, xin.vec, epi, st);
-                push_join();
-            } else signal_only(xin, it + 1);        // what K2's prologue would have said: my x-bar of this epoch is out
+            if (m > 0) launch_spmv(plan_r, m, csr_ptr.p, yout.dense ? csr_idx.p : csr_idx_g.p, csr_val.p, xin.vec, epi, st);
+            else signal_only(xin, it + 1);        // what K2's prologue would have said: my x-bar of this epoch is out
             return;
         }
         DualEpi<CHECK> epi{nullptr, lc.p, uc.p, y0.p, y(), yp.p, axbar.p, params.p, it, GhostIn{}, GhostOut{}};
         launch_spmv(plan_r, m, csr_ptr.p, csr_idx.p, csr_val.p, xbar_full.p, epi, st);
         if (!CHECK) gather_y(y_full.p);                      // a check iteration does not change y here
     }
-    int kernels_per_iter() const { return ghost ? (push ? 4 : 2) : (m > 0 ? 1 : 0) + (nl > 0 ? 1 : 0); }
+    int kernels_per_iter() const { return ghost ? 2 : (m > 0 ? 1 : 0) + (nl > 0 ? 1 : 0); }
 
     void plain_iterations(int count) {
         if (count <= 0) return;

@@ -80,7 +80,21 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
     __syncwarp();
     const uint64_t pol_stream = l2_policy_evict_first();
     const L2Hints hints{pol_stream, l2_policy_evict_last(), l2flags};
-    const int gw = blockIdx.x * SPMV_WARPS + warp, nw = gridDim.x * SPMV_WARPS;
+    // multi-GPU push mode: the last CTAs of the grid run no SpMV — they forward the local outboxes to the peers in aligned
+    // full-warp stores as the values land (pdlp.cu: ghost_push_role)
+    int nctas = gridDim.x;
+    if constexpr (Epi::DIST) {
+        const int pc = epi.push_ctas();
+        if (pc > 0) {
+            nctas -= pc;
+            if ((int)blockIdx.x >= nctas) {
+                epi.acquire(lane);          // the peers' last readers of what the copies overwrite have finished
+                epi.push(((int)blockIdx.x - nctas) * SPMV_WARPS + warp, pc * SPMV_WARPS, lane);
+                return;
+            }
+        }
+    }
+    const int gw = blockIdx.x * SPMV_WARPS + warp, nw = nctas * SPMV_WARPS;
     // Tile walk: warp-strided round robin, also in the multi-GPU kernels.  (Tried there: a contiguous range of tiles per warp
     // with the outgoing values collected in shared-memory rings and sent as aligned 256-byte stores.  The rings and the
     // extra registers cost two resident CTAs per SM, and losing them cost 38 us per iteration at N = 2 — far more than
@@ -267,7 +281,6 @@ spmv_warp_kernel(int nrows, int ntiles, int cap, const int* __restrict__ ptr, co
             __syncwarp();
             issue(hstage);
         }
-        if constexpr (Epi::DIST) epi.tile_done(tile, lane);      // multi-GPU push mode: the tile is in the local outboxes
     }
 }
 
@@ -381,7 +394,14 @@ void launch_spmv_inst(const SpmvPlan& p, int nrows, const int* ptr, const int* i
     }
     // persistent grid: exactly one wave
     const int per_sm = std::min(p.ctas_per_sm, cfg_occ[dev]);
-    const int grid = std::max(1, std::min(ceil_div(p.ntiles, SPMV_WARPS), kNumSMs * per_sm));
+    int grid = std::max(1, std::min(ceil_div(p.ntiles, SPMV_WARPS), kNumSMs * per_sm));
+    if constexpr (Epi::DIST) {      // push mode: the pusher CTAs are part of the one resident wave
+        const int pc = epi.push_ctas();
+        if (pc > 0) {
+            ELP_REQUIRE(pc < kNumSMs * per_sm, "spmv: %d pusher CTAs leave no room for the SpMV (%d CTAs fit)", pc, kNumSMs * per_sm);
+            grid = std::max(1, std::min(ceil_div(p.ntiles, SPMV_WARPS), kNumSMs * per_sm - pc)) + pc;
+        }
+    }
     // L2 residency hints (tma.cuh: L2Hints).  Default 3: the operand streams and the outputs nobody gathers from are
     // evict-first like the matrix stream, so that the vector the NEXT kernel gathers from survives in L2.  Measured in
     // alternation K1,K2,K1,... on C4: 0.2766 ms per iteration vs 0.2823 without (gpurun_out/r3c_hints.log).

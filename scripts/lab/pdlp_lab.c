@@ -188,6 +188,8 @@ int elpo_pdlp_lab(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, 
     const int OBJTEST = (int)envd("LAB_OBJTEST", 0);
     const double ISMOOTH = envd("LAB_ISMOOTH", 1.0);
     const int WAVG = (int)envd("LAB_WAVG", 0);
+    const double PMAX = envd("LAB_PMAX", 1e18);
+    const int TRACE = getenv("LAB_TRACE") != NULL;
     double e_int = 0.0, e_prev = 0.0;
     const int ce = check_every > 1 ? check_every : 64;
     const int limit = max_iter > 0 ? max_iter : 2000000;
@@ -246,7 +248,7 @@ int elpo_pdlp_lab(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, 
         pobj = po; dobj = dobj_r + dobj_c;
         rp = sqrt(pres2) / (1 + norm_b); rd = sqrt(dres2) / (1 + norm_c);
         rg = fabs(pobj - dobj) / (1 + fabs(pobj) + fabs(dobj));
-        if (getenv("LAB_TRACE")) fprintf(stderr, "%d %.4e %.4e %.4e %.4e %.4e %.10e\n", total, rp, rd, rg, corr_p / (1 + fabs(pobj) + fabs(dobj)), corr_d / (1 + fabs(pobj) + fabs(dobj)), pobj);
+        if (TRACE) fprintf(stderr, "%d %.4e %.4e %.4e %.4e %.4e %.10e\n", total, rp, rd, rg, corr_p / (1 + fabs(pobj) + fabs(dobj)), corr_d / (1 + fabs(pobj) + fabs(dobj)), pobj);
         if (OBJTEST) { const double e = (fabs(pobj - dobj) + fabs(corr_p) + fabs(corr_d)) / (1 + fabs(pobj) + fabs(dobj)); if (rp <= eps && rd <= eps && e <= GAPF * eps) { status = 0; break; } }
         else if (rp <= eps && rd <= eps && rg <= GAPF * eps) { status = 0; break; }   /* gap at eps/4: see pdlp.cu */
         if (need_fpe0) { fpe0 = fpe; need_fpe0 = 0; }
@@ -254,7 +256,7 @@ int elpo_pdlp_lab(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, 
         if (k > 0) {
             if (fpe <= B_SUFF * fpe0) restart = 1;
             else if (fpe <= B_NEC * fpe0 && fpe_prev >= 0 && fpe > fpe_prev) restart = 1;
-            else if ((double)k >= B_ART * (double)total) restart = 1;
+            else if ((double)k >= B_ART * (double)total || (double)k >= PMAX) restart = 1;
         }
         fpe_prev = fpe;
         if (restart) {

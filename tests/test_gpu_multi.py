@@ -100,3 +100,25 @@ def test_more_devices_than_rows_and_time_limit():
     big = gen.sparse_planted(200_000, seed=2)
     t = _solve(big, 2, time_limit_s=0.05)
     assert t.status == L.STATUS_TIMEOUT and t.stats.iterations > 0
+
+
+@needs2
+@pytest.mark.parametrize("make", [lambda: gen.sparse_planted(60_000, seed=3),
+                                  lambda: gen.mcnf(K=4, gw=40, gh=50, extra_arcs=1500, seed=1)], ids=["planted", "mcnf"])
+def test_push_mode_moves_the_same_values(make, monkeypatch):
+    # compact ghost vectors, once filled by the epilogues' own peer stores and once through local outboxes and the pusher
+    # CTAs of the same grid (pdlp.cu: ghost_push_role; picked by itself only when a rank sends several copies of its
+    # block, e.g. config 4 at N = 8).  Only the transport differs: iterations, objective and x must be identical.
+    p = make()
+    n = min(_ndev(), 8)
+    monkeypatch.setenv("ELP_PDLP_GHOST_DENSE", "0")
+    monkeypatch.setenv("ELP_GHOST_PUSH", "0")
+    a = _solve(p, n)
+    monkeypatch.setenv("ELP_GHOST_PUSH", "1")
+    b = _solve(p, n)
+    monkeypatch.setenv("ELP_GHOST_PUSH_CTAS", "9")          # few pushers: every warp walks many items
+    c = _solve(p, n)
+    assert a.status == L.STATUS_OPTIMAL
+    for r in (b, c):
+        assert r.status == a.status and r.stats.iterations == a.stats.iterations
+        assert r.objval == a.objval and np.array_equal(r.x, a.x) and np.array_equal(r.y, a.y)
