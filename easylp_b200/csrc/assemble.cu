@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <cstdlib>
 #include "primitives.cuh"
+#include "bucket_sort.cuh"
 #include "../../include/easylp_abi.h"
 
 namespace elp {
@@ -38,6 +39,15 @@ __global__ void asm_make_keys(const int32_t* __restrict__ row, const int32_t* __
         const uint64_t k1 = (r1 >= m || c1 >= n) ? 0ull : (uint64_t)r1 * n + c1;
         if (k1 < k && bad[1] == 0) atomicExch(bad + 1, 1);
     }
+}
+
+// 4096 adjacent pairs spread over the stream: one inversion proves the stream unordered before anything is written for it
+__global__ void asm_sample_order(const int32_t* __restrict__ row, const int32_t* __restrict__ col, uint32_t T, int* __restrict__ flag) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (T < 2) return;
+    const uint32_t i = (uint32_t)(((uint64_t)t * (T - 1)) >> 12);
+    const uint32_t r0 = (uint32_t)row[i], r1 = (uint32_t)row[i + 1];
+    if (r1 < r0 || (r1 == r0 && (uint32_t)col[i + 1] < (uint32_t)col[i])) *flag = 1;
 }
 
 // One thread per sorted slot; the head of every equal-key run folds the run left-to-right.
@@ -142,6 +152,11 @@ __global__ void asm_row_ptr(const int32_t* __restrict__ rows_c, const uint32_t* 
     for (int32_t r = prev + 1; r <= cur; ++r) row_ptr[r] = (int32_t)i;
 }
 
+static bool env_flag(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e ? atoi(e) : dflt) != 0;
+}
+
 __global__ void asm_empty_row_ptr(int32_t* row_ptr, uint32_t m) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= m) row_ptr[i] = 0;
@@ -156,6 +171,7 @@ struct AsmWorkspace {
     DevBuf<int32_t> rows_c;
     DevBuf<int> bad;
     RadixSortWorkspace sort;
+    BucketWorkspace bucket;
     // staging of the host entry point (elp_assemble_csr)
     DevBuf<int32_t> in_row, in_col, out_ptr, out_col;
     DevBuf<double> in_val, out_val;
@@ -252,13 +268,45 @@ int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_co
     RadixSortWorkspace& ws = w.sort;
     const int grid = ceil_div(T, 256);
     mark("alloc");
+    const bool always_sort = getenv("ELP_ASM_ALWAYS_SORT") != nullptr;
+    // Unordered plain streams: one split into row buckets + a shared-memory sort-and-fold per bucket (bucket_sort.cuh)
+    // instead of six global radix passes.  Grouped (lowered) folds and streams with a bucket that does not fit keep the sort.
+    const bool may_bucket = !always_sort && !d_grp && T >= 2048 && env_flag("ELP_ASM_BUCKETED", 1);
+    auto try_buckets = [&](int64_t* nnz_out) {
+        uint32_t nnz_b = 0;
+        int bad_b = 0;
+        const bool ok = assemble_bucketed(Tu, d_row, d_col, d_val, (uint32_t)m, (uint32_t)n, d_row_ptr, d_col_idx, d_vals, &nnz_b,
+                                          bad.p, &bad_b, w.bucket, st);
+        ELP_REQUIRE(!bad_b, "assemble: a term has row/col outside [0,%d) x [0,%d)", m, n);
+        mark(ok ? "bucketed" : "bucket path refused");
+        *nnz_out = (int64_t)nnz_b;
+        return ok;
+    };
+    bool tried = false;
+    if (may_bucket) {                                // a sample of adjacent pairs: an inversion there spares the key pass
+        int inv = 0;
+        ELP_LAUNCH(asm_sample_order, 16, 256, 0, st, d_row, d_col, Tu, bad.p + 1);
+        ELP_CUDA(cudaMemcpyAsync(&inv, bad.p + 1, sizeof inv, cudaMemcpyDeviceToHost, st));
+        ELP_CUDA(cudaStreamSynchronize(st));
+        if (inv) {
+            int64_t nnz_b = 0;
+            if (try_buckets(&nnz_b)) return nnz_b;
+            tried = true;
+        }
+    }
     ELP_LAUNCH(asm_make_keys, grid, 256, 0, st, d_row, d_col, Tu, (uint32_t)m, (uint32_t)n, keys.p, perm.p, bad.p);
     const int nbits = bit_length_u64((uint64_t)m * (uint64_t)n - 1);
     mark("keys");
-    int unsorted = 1;
-    if (!getenv("ELP_ASM_ALWAYS_SORT")) {            // 4 bytes back and one synchronisation buy the whole sort when the stream is ordered
-        ELP_CUDA(cudaMemcpyAsync(&unsorted, bad.p + 1, sizeof unsorted, cudaMemcpyDeviceToHost, st));
+    int flags[2] = {0, 1};                           // [0] a term outside the matrix, [1] the stream is not in (row, col) order
+    if (!always_sort) {                              // 8 bytes back and one synchronisation buy the whole sort when the stream is ordered
+        ELP_CUDA(cudaMemcpyAsync(flags, bad.p, sizeof flags, cudaMemcpyDeviceToHost, st));
         ELP_CUDA(cudaStreamSynchronize(st));
+        ELP_REQUIRE(!flags[0], "assemble: a term has row/col outside [0,%d) x [0,%d)", m, n);
+    }
+    const int unsorted = flags[1];
+    if (unsorted && may_bucket && !tried) {          // the sample saw no inversion, the full pass did
+        int64_t nnz_b = 0;
+        if (try_buckets(&nnz_b)) return nnz_b;
     }
     if (unsorted) radix_sort_pairs(keys.p, perm.p, T, nbits, ws, st);
     mark(unsorted ? "sort" : "sort skipped");

@@ -71,6 +71,61 @@ def test_assemble_already_ordered_stream_skips_the_sort(T, m, n, seed, monkeypat
     assert st_fast.kernel_launches < st_sort.kernel_launches
 
 
+def _stream(kind, rng):
+    if kind == "random":            # ~150 terms per row, columns spread, duplicates and cancellations
+        T, m, n = 300_000, 2000, 100_000
+        row = rng.integers(0, m, T); col = rng.integers(0, n, T)
+    elif kind == "duplicates":      # few distinct columns: long equal-key runs whose sums depend on the order
+        T, m, n = 120_000, 700, 40
+        row = rng.integers(0, m, T); col = rng.integers(0, n, T)
+    elif kind == "empty_rows":      # most rows have no term at all
+        T, m, n = 50_000, 100_000, 3000
+        row = rng.integers(0, m, T) // 7 * 7; col = rng.integers(0, n, T)
+    elif kind == "one_column":
+        T, m, n = 30_000, 5000, 1
+        row = rng.integers(0, m, T); col = np.zeros(T, np.int64)
+    elif kind == "long_rows_fit":   # one row per bucket, ~1300 terms each, ranked quadratically
+        T, m, n = 2600, 2, 900
+        row = np.arange(T) % 2; col = rng.integers(0, n, T)
+    elif kind == "wide":            # 31 column bits leave one bit for the row inside a bucket
+        T, m, n = 50_000, 1000, 2_000_000_000
+        row = rng.integers(0, m, T); col = rng.integers(0, n, T)
+    elif kind == "skewed":          # one row holds more terms than a bucket: the call falls back to the radix sort
+        T, m, n = 60_000, 3000, 5000
+        row = rng.integers(0, m, T); row[: T // 3] = 17; col = rng.integers(0, n, T)
+    val = rng.normal(size=T) * 10.0 ** rng.integers(-8, 8, size=T)
+    row = row.astype(np.int32); col = col.astype(np.int32)
+    row[1], col[1], val[1] = row[0], col[0], -val[0]          # an exact cancellation
+    return row, col, val, m, n
+
+
+@pytest.mark.parametrize("kind", ["random", "duplicates", "empty_rows", "one_column", "long_rows_fit", "wide", "skewed"])
+def test_assemble_bucketed_equals_sorted(kind, monkeypatch):
+    """Unordered streams are split into row buckets that one CTA sorts and folds in shared memory (bucket_sort.cuh); the
+    stable radix sort stays for streams with a bucket that does not fit.  Same bits as the sort and as the left fold of
+    /root/reference/R/methods.R:248-250 restated on the host."""
+    row, col, val, m, n = _stream(kind, np.random.default_rng(11))
+    rp, ci, v, st_b = L.assemble_csr(row, col, val, m, n)
+    monkeypatch.setenv("ELP_ASM_BUCKETED", "0")
+    rp2, ci2, v2, st_s = L.assemble_csr(row, col, val, m, n)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2) and v.tobytes() == v2.tobytes()
+    rp0, ci0, v0 = _assemble_ref(row, col, val, m, n)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and v.tobytes() == v0.tobytes()
+    if kind == "skewed":
+        assert st_b.kernel_launches > st_s.kernel_launches          # tried the buckets, then sorted
+    else:
+        assert st_b.kernel_launches < st_s.kernel_launches
+
+
+def test_assemble_bucketed_is_deterministic():
+    # the order inside a bucket depends on the atomics of the split; the ranking by (col, stream index) removes it
+    row, col, val, m, n = _stream("duplicates", np.random.default_rng(5))
+    a = L.assemble_csr(row, col, val, m, n)
+    for _ in range(3):
+        b = L.assemble_csr(row, col, val, m, n)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].tobytes() == b[2].tobytes()
+
+
 def test_assemble_rejects_out_of_range():
     with pytest.raises(L.ElpError):
         L.assemble_csr([0, 5], [0, 0], [1.0, 1.0], 2, 2)
