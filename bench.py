@@ -529,7 +529,9 @@ def bench_batch(args, dist, L, d):
                 "d2h_bytes_per_step": int(st2.d2h_bytes * N), "path": "elp_solve_batch(host arrays)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "simplex_warp_kernel<MR,CPL> (one LP per warp, tableau in shared memory)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "peak_source": peak_src, "traffic": None, "bytes_per_launch": bytes_lp * Bl,
+                     "frac": ach / peak, "peak_source": peak_src,
+                     "traffic": ncu_traffic("batch") if (dist.world == 1 and B == 200_000 and m == 20 and n == 30) else None,
+                     "bytes_per_launch": bytes_lp * Bl,
                      "ms_per_launch": ms,
                      "note": "HBM fraction is the mandated figure; shared-memory bandwidth and instruction issue of the pivot chain bound this kernel (ncu: LSU wavefronts 76 %, issue 56 %)"},
         "clocks": clocks,
@@ -580,7 +582,8 @@ def bench_assembly(args, L, p):
                                     if st.kernel_launches < 20 else "radix sort passes + ordered fold + scan + scatter")
                                    + f" ({int(st.kernel_launches)} launches)",
                          "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                         "traffic": ncu_traffic("assembly") if (st.kernel_launches < 20 and args.scale == 1.0) else None,
                          "bytes_per_launch": alg, "ms_per_launch": ms,
                          "note": "algorithmic bytes 16 T + 12 nnz + 4 (m+1) over the whole assembly, unordered stream; "
                                  "round 1 sorted with 6 LSD passes (~8x the algorithmic bytes, 3.4 ms); the bucket path "
