@@ -54,6 +54,37 @@ easylp_assemble_lowered <- function(term_row, term_col, term_val, families, grou
           families, groups, as.integer(nrow), as.integer(ncol))
 }
 
+# R producer of `private$terms` — the term list the device-resident model is assembled from.  With the reference's
+# dense DSL unchanged, `$con()` calls this right after `self$constraint <- join_constraints(...)` (R/class.R:206,217)
+# with the rows it has just appended: their non-zero entries are added to the list in row-major order (the emission
+# order of a dense row: one term per (row, col), so the fold on the device has nothing to add up), and the device
+# model is dropped so that the next `$solve()` re-assembles it.  `$uncon()` / `$var()` call easylp_terms_reset() and
+# the list is rebuilt from `self$constraint$mat` on demand.  The sparse term-list DSL (easylp_b200/model.py is its
+# executable specification) appends its atoms' terms here instead and never materialises `constraint$mat`.
+easylp_terms_append <- function(private, new_rows, first_row) {
+    if (is.null(private$terms))
+        private$terms <- list(row = integer(), col = integer(), val = double(), families = list(), groups = list())
+    if (nrow(new_rows) > 0L) {
+        tm <- t(new_rows)
+        nz <- which(tm != 0, arr.ind = TRUE)               # column-major walk of the transpose = row-major walk of the rows
+        private$terms$row <- c(private$terms$row, as.integer(first_row - 1L + nz[, 2L]))
+        private$terms$col <- c(private$terms$col, as.integer(nz[, 1L]))
+        private$terms$val <- c(private$terms$val, tm[nz])
+    }
+    private$model <- NULL
+    invisible(private$terms)
+}
+easylp_terms_reset <- function(private) {
+    private$terms <- NULL
+    private$model <- NULL
+    invisible(NULL)
+}
+easylp_terms_ensure <- function(self, private) {
+    if (is.null(private$terms))
+        easylp_terms_append(private, self$constraint$mat, 1L)
+    private$terms
+}
+
 # Device-resident model: the same assembly, but the canonical CSR stays in HBM behind an external pointer (with a
 # finalizer).  `$con()`/`$uncon()`/`$var()` set `private$model <- NULL`; `$solve()` builds it on demand and solves
 # on it, so the matrix crosses PCIe at most once (as descriptors or terms) between `$con()` and the solution.
@@ -62,7 +93,7 @@ easylp_model <- function(self, private) {
     # rebuild only when there is no live device model: never built, invalidated by $con()/$var(), or a pointer that did
     # not survive a clone / readRDS (external pointers come back NULL).  Interrupts and real errors propagate.
     if (is.null(private$model) || !.Call("easylp_model_valid", private$model)) {
-        t <- private$terms                 # list(row, col, val, families, groups) kept by the sparse term-list DSL
+        t <- easylp_terms_ensure(self, private)     # list(row, col, val, families, groups): appended by $con(), see above
         private$model <- .Call("easylp_model_assemble", as.integer(t$row), as.integer(t$col), as.double(t$val),
                                t$families, t$groups, length(self$constraint$rhs), private$n_var)
     }
