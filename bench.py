@@ -575,8 +575,8 @@ def bench_assembly(args, L, p):
                                "achieved_gbs": alg_of(T, nnz, m) / (float(np.mean(s_ms)) * 1e-3) / 1e9,
                                "frac": alg_of(T, nnz, m) / (float(np.mean(s_ms)) * 1e-3) / 1e9 / peak,
                                "gpu_launches": int(st2.kernel_launches),
-                               "note": "same terms in `$con()` emission order (rows ascending, columns ascending): the device "
-                                       "detects the order in the key pass and skips the radix sort"},
+                               "note": "same terms in `$con()` emission order (rows ascending, columns ascending): two passes "
+                                       "straight over the stream (order + counts, fold + emit), no keys, no sort"},
             "roofline": {"bound": "hbm",
                          "kernel": ("row-bucket split + shared-memory sort-and-fold per bucket + emit (bucket_sort.cuh)"
                                     if st.kernel_launches < 20 else "radix sort passes + ordered fold + scan + scatter")

@@ -50,6 +50,59 @@ __global__ void asm_sample_order(const int32_t* __restrict__ row, const int32_t*
     if (r1 < r0 || (r1 == r0 && (uint32_t)col[i + 1] < (uint32_t)col[i])) *flag = 1;
 }
 
+// ---- ordered streams: (row, col) never decreases, so no keys and no permutation are needed ------------------------------
+// `$con()` emits its rows one after the other and most bodies walk their columns upwards.  Two passes straight over the
+// stream: (1) bounds, order and, per tile of 256 terms, how many folded entries survive; (2) after a scan of the tile
+// counts the same fold again, survivors written to their final place.  32 + 12 bytes per term instead of the 80 of the
+// key / fold / scan / compact pipeline (0.74 ms for the 21 M terms of config 4).
+__device__ __forceinline__ bool asm_head_fold(const int32_t* __restrict__ row, const int32_t* __restrict__ col,
+                                              const double* __restrict__ val, uint32_t T, uint32_t i, int32_t r, int32_t c, double& s) {
+    if (i > 0 && row[i - 1] == r && col[i - 1] == c) return false;
+    s = val[i];
+    for (uint32_t j = i + 1; j < T && row[j] == r && col[j] == c; ++j) s = __dadd_rn(s, val[j]);     // left to right
+    return true;
+}
+__global__ void __launch_bounds__(256)
+asm_ordered_count(const int32_t* __restrict__ row, const int32_t* __restrict__ col, const double* __restrict__ val, uint32_t T,
+                  uint32_t m, uint32_t n, uint32_t* __restrict__ tile_cnt, int* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    bool keep = false;
+    if (i < T) {
+        const int32_t r = row[i], c = col[i];
+        if ((uint32_t)r >= m || (uint32_t)c >= n) bad[0] = 1;
+        if (i + 1 < T) {
+            const uint32_t r1 = (uint32_t)row[i + 1], c1 = (uint32_t)col[i + 1];
+            if (r1 < (uint32_t)r || (r1 == (uint32_t)r && c1 < (uint32_t)c)) bad[1] = 1;
+        }
+        double s;
+        if (asm_head_fold(row, col, val, T, i, r, c, s)) keep = s != 0.0;
+    }
+    const int cnt = __syncthreads_count(keep);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = (uint32_t)cnt;
+}
+__global__ void __launch_bounds__(256)
+asm_ordered_emit(const int32_t* __restrict__ row, const int32_t* __restrict__ col, const double* __restrict__ val, uint32_t T,
+                 const uint32_t* __restrict__ tile_off, int32_t* __restrict__ col_idx, double* __restrict__ vals,
+                 int32_t* __restrict__ rows_c, uint32_t* __restrict__ nnz_out) {
+    __shared__ uint32_t wsum[8];
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool keep = false;
+    int32_t r = 0, c = 0;
+    double s = 0.0;
+    if (i < T) {
+        r = row[i]; c = col[i];
+        if (asm_head_fold(row, col, val, T, i, r, c, s)) keep = s != 0.0;
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = __popc(b);
+    __syncthreads();
+    uint32_t p = tile_off[blockIdx.x] + __popc(b & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) p += wsum[w];
+    if (keep) { col_idx[p] = c; vals[p] = s; rows_c[p] = r; }
+    if (i == T - 1) *nnz_out = p + (keep ? 1u : 0u);
+}
+
 // One thread per sorted slot; the head of every equal-key run folds the run left-to-right.
 __global__ void asm_segment_fold(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
                                  const double* __restrict__ val, uint32_t T, double* __restrict__ sums,
@@ -283,12 +336,32 @@ int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_co
         return ok;
     };
     bool tried = false;
-    if (may_bucket) {                                // a sample of adjacent pairs: an inversion there spares the key pass
+    if (!always_sort && !d_grp) {
         int inv = 0;
-        ELP_LAUNCH(asm_sample_order, 16, 256, 0, st, d_row, d_col, Tu, bad.p + 1);
-        ELP_CUDA(cudaMemcpyAsync(&inv, bad.p + 1, sizeof inv, cudaMemcpyDeviceToHost, st));
-        ELP_CUDA(cudaStreamSynchronize(st));
-        if (inv) {
+        if (T >= 2048) {                             // a sample of adjacent pairs: an inversion there spares a full pass
+            ELP_LAUNCH(asm_sample_order, 16, 256, 0, st, d_row, d_col, Tu, bad.p + 1);
+            ELP_CUDA(cudaMemcpyAsync(&inv, bad.p + 1, sizeof inv, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaStreamSynchronize(st));
+        }
+        if (!inv) {                                  // probably ordered: bounds, order and the tile counts in one pass
+            int flags[2] = {0, 0};
+            ELP_LAUNCH(asm_ordered_count, grid, 256, 0, st, d_row, d_col, d_val, Tu, (uint32_t)m, (uint32_t)n, pos.p, bad.p);
+            ELP_CUDA(cudaMemcpyAsync(flags, bad.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaStreamSynchronize(st));
+            ELP_REQUIRE(!flags[0], "assemble: a term has row/col outside [0,%d) x [0,%d)", m, n);
+            inv = flags[1];
+            if (!inv) {
+                exclusive_scan_u32(pos.p, (size_t)grid, ws.scan, st);
+                ELP_LAUNCH(asm_ordered_emit, grid, 256, 0, st, d_row, d_col, d_val, Tu, pos.p, d_col_idx, d_vals, rows_c.p, nnz_d.p);
+                ELP_LAUNCH(asm_row_ptr, ceil_div(T + 1, 256), 256, 0, st, rows_c.p, nnz_d.p, (uint32_t)m, d_row_ptr, Tu);
+                uint32_t nnz_o = 0;
+                ELP_CUDA(cudaMemcpyAsync(&nnz_o, nnz_d.p, sizeof nnz_o, cudaMemcpyDeviceToHost, st));
+                ELP_CUDA(cudaStreamSynchronize(st));
+                mark("ordered");
+                return (int64_t)nnz_o;
+            }
+        }
+        if (inv && may_bucket) {
             int64_t nnz_b = 0;
             if (try_buckets(&nnz_b)) return nnz_b;
             tried = true;

@@ -17,3 +17,11 @@ ok = np.array_equal(rp, p["row_ptr"]) and np.array_equal(ci, p["col_idx"]) and v
 alg = 16 * T + 12 * nnz + 4 * (m + 1)
 print(json.dumps(dict(T=int(T), m=m, n=n, nnz=nnz, bit_exact=bool(ok), device_ms=st.solve_ms, total_ms=st.total_ms,
                       launches=int(st.kernel_launches), alg_bytes=alg, gbs=alg / st.solve_ms / 1e6)))
+# the same terms in `$con()` emission order (rows ascending, columns ascending): the two-pass ordered path
+order = np.lexsort((c, r))
+sr, sc, sv = r[order], c[order], v[order]
+for _ in range(reps):
+    rp, ci, vv, st = L.assemble_csr(sr, sc, sv, m, n)
+ok = np.array_equal(rp, p["row_ptr"]) and np.array_equal(ci, p["col_idx"]) and vv.tobytes() == p["vals"].tobytes()
+print(json.dumps(dict(stream="ordered", bit_exact=bool(ok), device_ms=st.solve_ms, launches=int(st.kernel_launches),
+                      gbs=alg / st.solve_ms / 1e6)))
