@@ -111,8 +111,10 @@ int elpo_pdlp_lab(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, 
     norm_b = sqrt(norm_b); norm_c = sqrt(norm_c);
     /* Ruiz (10) + Pock-Chambolle (alpha = 1) */
     double *rs = (double *)malloc(sizeof(double) * (m + 1)), *cs = (double *)malloc(sizeof(double) * n);
-    for (int it = 0; it <= 10; ++it) {
-        const int pc = it == 10;
+    const int NRUIZ = (int)envd("LAB_RUIZ", 10), USEPC = (int)envd("LAB_PC", 1);
+    for (int it = 0; it <= NRUIZ; ++it) {
+        const int pc = it == NRUIZ;
+        if (pc && !USEPC) break;
         int i, j;
 #pragma omp parallel for schedule(static)
         for (i = 0; i < m; ++i) {
