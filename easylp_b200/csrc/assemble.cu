@@ -52,55 +52,190 @@ __global__ void asm_sample_order(const int32_t* __restrict__ row, const int32_t*
 
 // ---- ordered streams: (row, col) never decreases, so no keys and no permutation are needed ------------------------------
 // `$con()` emits its rows one after the other and most bodies walk their columns upwards.  Two passes straight over the
-// stream: (1) bounds, order and, per tile of 256 terms, how many folded entries survive; (2) after a scan of the tile
-// counts the same fold again, survivors written to their final place.  32 + 12 bytes per term instead of the 80 of the
-// key / fold / scan / compact pipeline (0.74 ms for the 21 M terms of config 4).
-__device__ __forceinline__ bool asm_head_fold(const int32_t* __restrict__ row, const int32_t* __restrict__ col,
-                                              const double* __restrict__ val, uint32_t T, uint32_t i, int32_t r, int32_t c, double& s) {
-    if (i > 0 && row[i - 1] == r && col[i - 1] == c) return false;
-    s = val[i];
-    for (uint32_t j = i + 1; j < T && row[j] == r && col[j] == c; ++j) s = __dadd_rn(s, val[j]);     // left to right
-    return true;
-}
-__global__ void __launch_bounds__(256)
-asm_ordered_count(const int32_t* __restrict__ row, const int32_t* __restrict__ col, const double* __restrict__ val, uint32_t T,
-                  uint32_t m, uint32_t n, uint32_t* __restrict__ tile_cnt, int* __restrict__ bad) {
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    bool keep = false;
-    if (i < T) {
-        const int32_t r = row[i], c = col[i];
-        if ((uint32_t)r >= m || (uint32_t)c >= n) bad[0] = 1;
-        if (i + 1 < T) {
-            const uint32_t r1 = (uint32_t)row[i + 1], c1 = (uint32_t)col[i + 1];
-            if (r1 < (uint32_t)r || (r1 == (uint32_t)r && c1 < (uint32_t)c)) bad[1] = 1;
+// stream: (1) bounds, order and, per tile of 1 024 terms, how many folded entries survive and the row of the last one;
+// (2) after a scan of the tile counts the same fold again, survivors written to their final place together with the
+// row pointers (an entry whose predecessor among the survivors sits in another row starts the rows in between).
+// 32 + 12 bytes per term instead of the 80 of the key / fold / scan / compact pipeline (0.74 ms for the 21 M terms of
+// config 4).  A thread owns four consecutive terms (vector loads; one term per thread ran both passes at 2.1 TB/s).
+constexpr int AO_V = 4, AO_THREADS = 256, AO_TILE = AO_V * AO_THREADS;
+struct AoTerms {
+    int32_t r[AO_V], c[AO_V];
+    double v[AO_V];
+    int32_t pr, pc, nr, nc;          // neighbours of the four: the term before the first, the term behind the last
+    uint32_t cnt;                    // terms of the four that exist (the stream may end inside)
+};
+// loads the thread's terms and their neighbours; out-of-stream slots repeat sentinels that never compare equal
+__device__ __forceinline__ void ao_load(const int32_t* __restrict__ row, const int32_t* __restrict__ col, const double* __restrict__ val,
+                                        uint32_t T, uint64_t i0, int lane, bool vec, AoTerms& t) {
+    t.cnt = i0 >= T ? 0u : (uint32_t)min((uint64_t)AO_V, (uint64_t)T - i0);
+    if (t.cnt == AO_V && vec) {               // vec: the three arrays start on 16-byte boundaries
+        const int4 rr = *reinterpret_cast<const int4*>(row + i0), cc = *reinterpret_cast<const int4*>(col + i0);
+        const double2 v0 = *reinterpret_cast<const double2*>(val + i0), v1 = *reinterpret_cast<const double2*>(val + i0 + 2);
+        t.r[0] = rr.x; t.r[1] = rr.y; t.r[2] = rr.z; t.r[3] = rr.w;
+        t.c[0] = cc.x; t.c[1] = cc.y; t.c[2] = cc.z; t.c[3] = cc.w;
+        t.v[0] = v0.x; t.v[1] = v0.y; t.v[2] = v1.x; t.v[3] = v1.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < AO_V; ++k) {
+            const bool in = (uint32_t)k < t.cnt;
+            t.r[k] = in ? row[i0 + k] : -2; t.c[k] = in ? col[i0 + k] : -2; t.v[k] = in ? val[i0 + k] : 0.0;
         }
-        double s;
-        if (asm_head_fold(row, col, val, T, i, r, c, s)) keep = s != 0.0;
     }
-    const int cnt = __syncthreads_count(keep);
-    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = (uint32_t)cnt;
+    // neighbours: the lane below / above holds them, the warp's ends read them from memory
+    int32_t pr = __shfl_up_sync(0xffffffffu, t.r[AO_V - 1], 1), pc = __shfl_up_sync(0xffffffffu, t.c[AO_V - 1], 1);
+    int32_t nr = __shfl_down_sync(0xffffffffu, t.r[0], 1), nc = __shfl_down_sync(0xffffffffu, t.c[0], 1);
+    if (lane == 0) {
+        const bool has = i0 > 0 && i0 <= T;
+        pr = has ? row[i0 - 1] : -1; pc = has ? col[i0 - 1] : -1;
+    }
+    if (lane == 31) {
+        const bool has = i0 + AO_V < T;
+        nr = has ? row[i0 + AO_V] : -3; nc = has ? col[i0 + AO_V] : -3;
+    }
+    if (t.cnt < AO_V) { nr = -3; nc = -3; }       // the stream ends inside my four (the slots behind carry -2)
+    t.pr = pr; t.pc = pc; t.nr = nr; t.nc = nc;
 }
-__global__ void __launch_bounds__(256)
-asm_ordered_emit(const int32_t* __restrict__ row, const int32_t* __restrict__ col, const double* __restrict__ val, uint32_t T,
-                 const uint32_t* __restrict__ tile_off, int32_t* __restrict__ col_idx, double* __restrict__ vals,
-                 int32_t* __restrict__ rows_c, uint32_t* __restrict__ nnz_out) {
-    __shared__ uint32_t wsum[8];
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool keep = false;
-    int32_t r = 0, c = 0;
-    double s = 0.0;
-    if (i < T) {
-        r = row[i]; c = col[i];
-        if (asm_head_fold(row, col, val, T, i, r, c, s)) keep = s != 0.0;
+// folds the runs that START inside the thread's four: keep[k] / s[k] for their heads
+__device__ __forceinline__ void ao_fold(const int32_t* __restrict__ row, const int32_t* __restrict__ col, const double* __restrict__ val,
+                                        uint32_t T, uint64_t i0, const AoTerms& t, bool* keep, double* s) {
+#pragma unroll
+    for (int k = 0; k < AO_V; ++k) {
+        keep[k] = false; s[k] = 0.0;
+        if ((uint32_t)k >= t.cnt) continue;
+        const int32_t r = t.r[k], c = t.c[k];
+        const bool head = k == 0 ? !(t.pr == r && t.pc == c) : !(t.r[k - 1] == r && t.c[k - 1] == c);
+        if (!head) continue;
+        double acc = t.v[k];
+        bool open = true;                         // the run is still going
+#pragma unroll
+        for (int j = k + 1; j < AO_V; ++j) {
+            open = open && (uint32_t)j < t.cnt && t.r[j] == r && t.c[j] == c;
+            if (open) acc = __dadd_rn(acc, t.v[j]);
+        }
+        if (open && t.nr == r && t.nc == c)       // it runs on behind my four: straight from the stream, left to right
+            for (uint64_t j = i0 + AO_V; j < T && row[j] == r && col[j] == c; ++j) acc = __dadd_rn(acc, val[j]);
+        s[k] = acc;
+        keep[k] = acc != 0.0;
     }
-    const uint32_t b = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) wsum[warp] = __popc(b);
+}
+__global__ void __launch_bounds__(AO_THREADS)
+asm_ordered_count(const int32_t* __restrict__ row, const int32_t* __restrict__ col, const double* __restrict__ val, uint32_t T,
+                  uint32_t m, uint32_t n, uint32_t* __restrict__ tile_cnt, int32_t* __restrict__ tile_last, int* __restrict__ bad,
+                  bool vec) {
+    __shared__ int skip;                 // an inversion is already known (the sample launched just before, or another
+    __shared__ uint32_t wcnt[AO_THREADS / 32];
+    __shared__ int wlast[AO_THREADS / 32];
+    if (threadIdx.x == 0) skip = bad[1]; // block of this pass): nothing this block computes will be used
     __syncthreads();
-    uint32_t p = tile_off[blockIdx.x] + __popc(b & ((1u << lane) - 1u));
-    for (int w = 0; w < warp; ++w) p += wsum[w];
-    if (keep) { col_idx[p] = c; vals[p] = s; rows_c[p] = r; }
-    if (i == T - 1) *nnz_out = p + (keep ? 1u : 0u);
+    if (skip) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * AO_THREADS + threadIdx.x) * AO_V;
+    AoTerms t;
+    ao_load(row, col, val, T, i0, lane, vec, t);
+    bool oob = false, inv = false;
+#pragma unroll
+    for (int k = 0; k < AO_V; ++k) {
+        if ((uint32_t)k >= t.cnt) continue;
+        oob |= (uint32_t)t.r[k] >= m || (uint32_t)t.c[k] >= n;
+        const bool has_next = k + 1 < AO_V ? (uint32_t)(k + 1) < t.cnt : t.nr != -3;
+        const uint32_t r1 = (uint32_t)(k + 1 < AO_V ? t.r[k + 1] : t.nr), c1 = (uint32_t)(k + 1 < AO_V ? t.c[k + 1] : t.nc);
+        inv |= has_next && (r1 < (uint32_t)t.r[k] || (r1 == (uint32_t)t.r[k] && c1 < (uint32_t)t.c[k]));
+    }
+    if (oob) bad[0] = 1;
+    if (inv) bad[1] = 1;
+    bool keep[AO_V];
+    double s[AO_V];
+    ao_fold(row, col, val, T, i0, t, keep, s);
+    uint32_t mine = 0;
+    int last = -1;
+#pragma unroll
+    for (int k = 0; k < AO_V; ++k)
+        if (keep[k]) { ++mine; last = t.r[k]; }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    last = __reduce_max_sync(0xffffffffu, last);          // rows never decrease: the largest is the last
+    if (lane == 0) { wcnt[warp] = mine; wlast[warp] = last; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t c = 0;
+        int l = -1;
+        for (int w = 0; w < AO_THREADS / 32; ++w) { c += wcnt[w]; l = max(l, wlast[w]); }
+        tile_cnt[blockIdx.x] = c;
+        tile_last[blockIdx.x] = l;
+    }
+}
+__global__ void __launch_bounds__(AO_THREADS)
+asm_ordered_emit(const int32_t* __restrict__ row, const int32_t* __restrict__ col, const double* __restrict__ val, uint32_t T,
+                 const uint32_t* __restrict__ tile_off, const int32_t* __restrict__ tile_last, int32_t* __restrict__ col_idx,
+                 double* __restrict__ vals, int32_t* __restrict__ row_ptr, uint32_t* __restrict__ nnz_out,
+                 int32_t* __restrict__ last_row_out, const int* __restrict__ bad, bool vec) {
+    __shared__ uint32_t wsum[AO_THREADS / 32];
+    __shared__ int wlast[AO_THREADS / 32];
+    __shared__ int base_last, near, skip;
+    if (threadIdx.x == 0) { skip = bad[1]; base_last = -1; near = 0x7fffffff; }
+    __syncthreads();
+    if (skip) return;                    // the stream is not ordered: the host takes another path
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * AO_THREADS + threadIdx.x) * AO_V;
+    AoTerms t;
+    ao_load(row, col, val, T, i0, lane, vec, t);
+    bool keep[AO_V];
+    double s[AO_V];
+    ao_fold(row, col, val, T, i0, t, keep, s);
+    uint32_t mine = 0;
+    int last = -1;
+#pragma unroll
+    for (int k = 0; k < AO_V; ++k)
+        if (keep[k]) { ++mine; last = t.r[k]; }
+    // inside the warp: exclusive sum of the counts, exclusive max of the last surviving rows
+    uint32_t inc = mine;
+    int lmax = last;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, inc, o);
+        const int b = __shfl_up_sync(0xffffffffu, lmax, o);
+        if (lane >= o) { inc += a; lmax = max(lmax, b); }
+    }
+    int pr = __shfl_up_sync(0xffffffffu, lmax, 1);
+    if (lane == 0) pr = -1;
+    if (lane == 31) { wsum[warp] = inc; wlast[warp] = lmax; }
+    // the last surviving row before this tile: normally the previous tile's; the block looks back 256 tiles per round
+    for (int64_t top = (int64_t)blockIdx.x - 1; top >= 0; top -= AO_THREADS) {
+        const int64_t tt = top - threadIdx.x;
+        if (tt >= 0 && tile_last[tt] >= 0) atomicMin(&near, (int)threadIdx.x);
+        __syncthreads();
+        const int k = near;
+        __syncthreads();                         // everybody has read `near` before the next round may lower it
+        if (k != 0x7fffffff) {
+            if (threadIdx.x == 0) base_last = tile_last[top - k];
+            break;                               // uniform: every thread read the same `near`
+        }
+    }
+    __syncthreads();
+    uint32_t p = tile_off[blockIdx.x] + inc - mine;
+    int before = base_last;
+    for (int w = 0; w < warp; ++w) {
+        p += wsum[w];
+        before = max(before, wlast[w]);
+    }
+    pr = max(pr, before);
+#pragma unroll
+    for (int k = 0; k < AO_V; ++k) {
+        if (!keep[k]) continue;
+        col_idx[p] = t.c[k]; vals[p] = s[k];
+        for (int32_t rr = pr + 1; rr <= t.r[k]; ++rr) row_ptr[rr] = (int32_t)p;
+        pr = t.r[k];
+        ++p;
+    }
+    if (i0 < T && i0 + AO_V >= T) {              // the thread that holds the last term
+        *nnz_out = p;
+        *last_row_out = pr;                      // asm_row_ptr_tail closes the rows behind it
+    }
+}
+__global__ void asm_row_ptr_tail(const int32_t* __restrict__ last_row, const uint32_t* __restrict__ nnz, uint32_t m, int32_t* __restrict__ row_ptr,
+                                 const int* __restrict__ bad) {
+    if (bad[1]) return;
+    const int64_t rr = (int64_t)*last_row + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rr <= (int64_t)m) row_ptr[rr] = (int32_t)*nnz;
 }
 
 // One thread per sorted slot; the head of every equal-key run folds the run left-to-right.
@@ -338,28 +473,33 @@ int64_t assemble_csr_device(int64_t T, const int32_t* d_row, const int32_t* d_co
     bool tried = false;
     if (!always_sort && !d_grp) {
         int inv = 0;
-        if (T >= 2048) {                             // a sample of adjacent pairs: an inversion there spares a full pass
-            ELP_LAUNCH(asm_sample_order, 16, 256, 0, st, d_row, d_col, Tu, bad.p + 1);
-            ELP_CUDA(cudaMemcpyAsync(&inv, bad.p + 1, sizeof inv, cudaMemcpyDeviceToHost, st));
-            ELP_CUDA(cudaStreamSynchronize(st));
-        }
-        if (!inv) {                                  // probably ordered: bounds, order and the tile counts in one pass
+        // a sample of adjacent pairs first: an inversion there makes the full pass return at once (no synchronisation
+        // in between: the pass reads the flag on the device)
+        if (T >= 2048) ELP_LAUNCH(asm_sample_order, 16, 256, 0, st, d_row, d_col, Tu, bad.p + 1);
+        {   // bounds, order and the tile counts; scan; fold + emit — launched back to back, the later ones return at once when
+            // an inversion is flagged.  One synchronisation, at the end.
+            const int tiles = ceil_div(T, AO_TILE);
+            int32_t* tile_last = reinterpret_cast<int32_t*>(keep.p);          // one word per tile (the workspace holds T)
+            const bool vec = (((uintptr_t)d_row | (uintptr_t)d_col | (uintptr_t)d_val) & 15u) == 0;
+            ELP_LAUNCH(asm_ordered_count, tiles, AO_THREADS, 0, st, d_row, d_col, d_val, Tu, (uint32_t)m, (uint32_t)n, pos.p, tile_last,
+                       bad.p, vec);
+            exclusive_scan_u32(pos.p, (size_t)tiles, ws.scan, st);
+            ELP_LAUNCH(asm_ordered_emit, tiles, AO_THREADS, 0, st, d_row, d_col, d_val, Tu, pos.p, tile_last, d_col_idx, d_vals, d_row_ptr,
+                       nnz_d.p, rows_c.p, bad.p, vec);
+            // rows behind the last surviving entry (all rows when nothing survived)
+            ELP_LAUNCH(asm_row_ptr_tail, ceil_div((int64_t)m + 1, 256), 256, 0, st, rows_c.p, nnz_d.p, (uint32_t)m, d_row_ptr, bad.p);
             int flags[2] = {0, 0};
-            ELP_LAUNCH(asm_ordered_count, grid, 256, 0, st, d_row, d_col, d_val, Tu, (uint32_t)m, (uint32_t)n, pos.p, bad.p);
+            uint32_t nnz_o = 0;
             ELP_CUDA(cudaMemcpyAsync(flags, bad.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+            ELP_CUDA(cudaMemcpyAsync(&nnz_o, nnz_d.p, sizeof nnz_o, cudaMemcpyDeviceToHost, st));
             ELP_CUDA(cudaStreamSynchronize(st));
-            ELP_REQUIRE(!flags[0], "assemble: a term has row/col outside [0,%d) x [0,%d)", m, n);
             inv = flags[1];
             if (!inv) {
-                exclusive_scan_u32(pos.p, (size_t)grid, ws.scan, st);
-                ELP_LAUNCH(asm_ordered_emit, grid, 256, 0, st, d_row, d_col, d_val, Tu, pos.p, d_col_idx, d_vals, rows_c.p, nnz_d.p);
-                ELP_LAUNCH(asm_row_ptr, ceil_div(T + 1, 256), 256, 0, st, rows_c.p, nnz_d.p, (uint32_t)m, d_row_ptr, Tu);
-                uint32_t nnz_o = 0;
-                ELP_CUDA(cudaMemcpyAsync(&nnz_o, nnz_d.p, sizeof nnz_o, cudaMemcpyDeviceToHost, st));
-                ELP_CUDA(cudaStreamSynchronize(st));
+                ELP_REQUIRE(!flags[0], "assemble: a term has row/col outside [0,%d) x [0,%d)", m, n);
                 mark("ordered");
                 return (int64_t)nnz_o;
             }
+            mark("not ordered");
         }
         if (inv && may_bucket) {
             int64_t nnz_b = 0;

@@ -126,6 +126,31 @@ def test_assemble_bucketed_is_deterministic():
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].tobytes() == b[2].tobytes()
 
 
+def test_assemble_ordered_stream_row_pointers_across_empty_tiles():
+    """Ordered path (assemble.cu: asm_ordered_count / _emit): row pointers are written by the surviving entries themselves,
+    each starting the rows since its predecessor.  Stretches of the stream in which nothing survives (cancelling pairs over
+    many tiles of 256 terms), empty rows in front, between and behind, and a stream in which nothing survives at all."""
+    rng = np.random.default_rng(3)
+    m, n = 5000, 700
+    # rows 10..19 carry entries, 20..2999 nothing, 3000 carries 40 000 terms that cancel pairwise, 3001..4000 entries again
+    row = np.concatenate([np.repeat(np.arange(10, 20), 30), np.full(40_000, 3000), np.repeat(np.arange(3001, 4001), 5)])
+    col = np.concatenate([np.tile(np.arange(30) * 3, 10), np.repeat(np.arange(100), 400), np.tile(np.arange(5) * 7, 1000)])
+    val = rng.normal(size=row.size)
+    blk = slice(300, 40_300)
+    v = val[blk].reshape(100, 400)
+    v[:, 1::2] = -v[:, 0::2]                        # every (row 3000, col) run: x, -x, y, -y, ... folds to exactly 0
+    val[blk] = v.ravel()
+    row = row.astype(np.int32); col = col.astype(np.int32)
+    assert np.all(np.diff(row.astype(np.int64) * n + col) >= 0)
+    rp, ci, vv, st = L.assemble_csr(row, col, val, m, n)
+    rp0, ci0, v0 = _assemble_ref(row, col, val, m, n)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and vv.tobytes() == v0.tobytes()
+    assert rp[3000] == rp[3001] == 300                  # the cancelled row is empty
+    # nothing survives at all
+    rp, ci, vv, _ = L.assemble_csr(row[blk], col[blk], val[blk], m, n)
+    assert ci.size == 0 and not rp.any()
+
+
 def test_assemble_rejects_out_of_range():
     with pytest.raises(L.ElpError):
         L.assemble_csr([0, 5], [0, 0], [1.0, 1.0], 2, 2)
