@@ -575,6 +575,7 @@ def bench_assembly(args, L, p):
                                "achieved_gbs": alg_of(T, nnz, m) / (float(np.mean(s_ms)) * 1e-3) / 1e9,
                                "frac": alg_of(T, nnz, m) / (float(np.mean(s_ms)) * 1e-3) / 1e9 / peak,
                                "gpu_launches": int(st2.kernel_launches),
+                               "traffic": ncu_traffic("assembly_ordered") if args.scale == 1.0 else None,
                                "note": "same terms in `$con()` emission order (rows ascending, columns ascending): two passes "
                                        "straight over the stream (order + counts, fold + emit), no keys, no sort"},
             "roofline": {"bound": "hbm",
