@@ -60,26 +60,121 @@ def _as_vec(k):
 
 
 def _rsum(v):
-    """R sum() of doubles: sequential long double accumulation (src/main/summary.c rsum)."""
-    v = np.asarray(v, dtype=float).ravel()
-    return float(np.cumsum(v.astype(LD))[-1]) if v.size else 0.0
+    """R sum() of doubles: one long-double accumulator walked front to back (src/main/summary.c rsum).
+    Written as the plain loop it is (round 2: no code shared with easylp_b200/model.py, which uses a vector cumsum)."""
+    acc = LD(0.0)
+    for t in np.asarray(v, dtype=float).ravel().tolist():
+        acc = acc + LD(t)
+    return float(acc)
 
 
 def _recycle(a, b):
-    a = np.asarray(a, dtype=float).ravel()
-    b = np.asarray(b, dtype=float).ravel()
-    if a.size == b.size:
-        return a, b
-    if a.size == 1:
-        return np.repeat(a, b.size), b
-    if b.size == 1:
-        return a, np.repeat(b, a.size)
-    raise RError("longer object length is not a multiple of shorter object length")
+    """R's recycling of two operands, for the two cases the DSL meets: equal lengths, or one scalar."""
+    la = [float(t) for t in np.asarray(a, dtype=float).ravel().tolist()]
+    lb = [float(t) for t in np.asarray(b, dtype=float).ravel().tolist()]
+    if len(la) != len(lb):
+        if len(la) == 1:
+            la = la * len(lb)
+        elif len(lb) == 1:
+            lb = lb * len(la)
+        else:
+            raise RError("longer object length is not a multiple of shorter object length")
+    return np.array(la, dtype=float), np.array(lb, dtype=float)
 
 
 # ------------------------------------------------------------------------------------------------
+# Subscripts.  Restated from /root/reference/R/utils.R:108-145 (is_index_valid, find_incorrect_index) and R's own `[`,
+# element by element: an index is a list of 1-based numbers or of names; everything is resolved to 0-based positions with
+# explicit loops and column-major arithmetic.  (Round 1 shared this block with easylp_b200/model.py; it is now written
+# independently so that the differential tests compare two implementations.)
+def _index_items(ind):
+    """The elements of one subscript as a Python list, and their kind: 'missing', 'num', 'chr' or 'bad'."""
+    if ind is None or (isinstance(ind, slice) and ind.start is None and ind.stop is None and ind.step is None):
+        return None, "missing"
+    if isinstance(ind, (str, np.str_)):
+        return [str(ind)], "chr"
+    if isinstance(ind, (bool, np.bool_)):
+        return None, "bad"
+    if isinstance(ind, (int, float, np.integer, np.floating)):
+        return [ind], "num"
+    if isinstance(ind, slice):
+        return None, "bad"
+    try:
+        items = np.asarray(ind).ravel().tolist() if isinstance(ind, np.ndarray) else list(ind)
+    except TypeError:
+        return None, "bad"
+    flat = []
+    for it in items:                                  # one level of nesting is what callers pass (lists, ranges, arrays)
+        if isinstance(it, (list, tuple, np.ndarray)):
+            flat.extend(np.asarray(it).ravel().tolist())
+        else:
+            flat.append(it)
+    if len(flat) == 0:
+        return [], "num"                              # numeric(0) is a valid (empty) numeric subscript: all() of nothing
+    if all(isinstance(it, (str, np.str_)) for it in flat):
+        return [str(it) for it in flat], "chr"
+    if any(isinstance(it, (bool, np.bool_)) for it in flat):
+        return None, "bad"
+    if all(isinstance(it, (int, float, np.integer, np.floating)) for it in flat):
+        return flat, "num"
+    return None, "bad"
+
+
+def _resolve(ind, length, names):
+    """is_index_valid + the positions R's `[` would pick; None when the subscript is invalid."""
+    items, kind = _index_items(ind)
+    if kind == "missing":
+        return list(range(length))
+    if kind == "num":
+        out = []
+        for v in items:
+            if not (v >= 1 and v < length + 1):       # all(ind >= 1) && all(ind < len + 1)
+                return None
+            out.append(int(v) - 1)                    # R truncates a fractional subscript towards zero
+        return out
+    if kind == "chr":
+        if names is None:
+            return None
+        out = []
+        for name in items:
+            hit = -1
+            for pos, cand in enumerate(names):        # match(): the first name that is equal
+                if cand == name:
+                    hit = pos
+                    break
+            if hit < 0:
+                return None
+            out.append(hit)
+        return out
+    return None
+
+
+def _positions(shape, dimnames, titles, key):
+    """0-based positions per subscript (numpy int arrays), or the reference's error."""
+    ndim = len(shape)
+    if len(key) == 1:
+        total = 1
+        for d in shape:
+            total *= int(d)
+        names = dimnames[0] if (dimnames is not None and ndim == 1) else None
+        got = _resolve(key[0], total, names)
+        if got is None:
+            raise RError("Invalid subscript")
+        return [np.array(got, dtype=np.int64)]
+    if len(key) != ndim:
+        raise RError("Invalid subscript: incorrect number of dimensions")
+    out = []
+    for d in range(ndim):
+        got = _resolve(key[d], int(shape[d]), dimnames[d] if dimnames is not None else None)
+        if got is None:
+            title = titles[d] if (titles and titles[d]) else d + 1
+            raise RError(f"Invalid subscript on dimension '{title}'")
+        out.append(np.array(got, dtype=np.int64))
+    return out
+
+
 class Param:
-    """parameter(): named array (R/utils.R:356-375)."""
+    """parameter(): named array (R/utils.R:356-375), stored as the column-major vector R keeps plus its dim."""
 
     def __init__(self, a, dimnames):
         self.a = np.asarray(a, dtype=float)
@@ -94,80 +189,71 @@ class Param:
     def __getitem__(self, key):
         if not isinstance(key, tuple):
             key = (key,)
-        pos = _positions(self.a.shape, self.dimnames, None, key)
-        if pos is None:
+        shape = self.a.shape
+        flat = self.a.flatten(order="F").tolist()         # R's storage order
+        try:
+            pos = _positions(shape, self.dimnames, None, key)
+        except RError:
             raise RError("subscript out of bounds")
-        if len(key) == 1 and self.a.ndim > 1:
-            out = self.a.flatten(order="F")[pos[0]]
+        if len(key) == 1:
+            picked = [flat[p] for p in pos[0].tolist()]
+            dims = [len(picked)]
         else:
-            out = self.a[np.ix_(*pos)]
-        out = np.asarray(out)
-        return float(out.ravel()[0]) if out.size == 1 else out.squeeze()
+            # R's `[` with one index vector per dimension: the result is the outer grid, first subscript fastest
+            dims = [len(p) for p in pos]
+            strides, acc = [], 1
+            for d in shape:
+                strides.append(acc)
+                acc *= int(d)
+            picked = []
+            count = 1
+            for d in dims:
+                count *= d
+            for lin in range(count):
+                rest, offset = lin, 0
+                for d in range(len(dims)):
+                    k = rest % dims[d]
+                    rest //= dims[d]
+                    offset += int(pos[d][k]) * strides[d]
+                picked.append(flat[offset])
+        if len(picked) == 1:
+            return float(picked[0])
+        kept = [d for d in dims if d != 1]                # drop = TRUE
+        arr = np.array(picked, dtype=float)
+        return arr.reshape(kept, order="F") if len(kept) > 1 else arr
 
 
 def parameter(x, *sets, byrow=False, **named):
-    sets = list(sets) + list(named.values())
-    if not sets:
+    sets = [list(s) for s in sets] + [list(s) for s in named.values()]
+    if len(sets) == 0:
         raise RError("Parameter does not have any sets.")
-    dims = tuple(len(s) for s in sets)
-    x = np.asarray(x, dtype=float).ravel()
-    if x.size == 1:
-        x = np.repeat(x, int(np.prod(dims)))
-    elif x.size != int(np.prod(dims)):
+    dims = [len(s) for s in sets]
+    total = 1
+    for d in dims:
+        total *= d
+    vals = [float(t) for t in np.asarray(x, dtype=float).ravel().tolist()]
+    if len(vals) == 1:
+        vals = vals * total
+    elif len(vals) != total:
         raise RError("Dimensions of the parameter don't match dimensions of the sets.")
     dn = [[_chr(v) for v in s] for s in sets]
     if byrow:
         if len(sets) != 2:
             raise RError("Use 'byrow = TRUE' only with 2-dimensional arrays.")
-        return Param(x.reshape(dims, order="C"), dn)
-    return Param(x.reshape(dims, order="F"), dn)
-
-
-def _positions(shape, dimnames, titles, key):
-    """find_incorrect_index + R `[` (R/utils.R:108-145): 0-based positions per subscript, or raises."""
-    def one(ind, length, names):
-        if ind is None or (isinstance(ind, slice) and ind == slice(None)):
-            return np.arange(length)
-        if isinstance(ind, (str, np.str_)):
-            ind = [ind]
-        if isinstance(ind, range):
-            ind = list(ind)
-        arr = np.asarray(ind)
-        if arr.dtype == bool:
-            return None
-        if arr.dtype.kind in "iuf":
-            arr = arr.ravel()
-            if not (np.all(arr >= 1) and np.all(arr < length + 1)):
-                return None
-            return arr.astype(np.int64) - 1
-        if arr.dtype.kind in "US":
-            if names is None:
-                return None
-            out = []
-            for s in arr.ravel().tolist():
-                if s not in names:
-                    return None
-                out.append(names.index(s))
-            return np.asarray(out, dtype=np.int64)
-        return None
-
-    if len(key) == 1:
-        n = int(np.prod(shape))
-        names = dimnames[0] if (dimnames is not None and len(shape) == 1) else None
-        p = one(key[0], n, names)
-        if p is None:
-            raise RError("Invalid subscript")
-        return [p]
-    if len(key) != len(shape):
-        raise RError("Invalid subscript: incorrect number of dimensions")
-    out = []
-    for d, k in enumerate(key):
-        p = one(k, shape[d], dimnames[d] if dimnames is not None else None)
-        if p is None:
-            t = titles[d] if titles and titles[d] else d + 1
-            raise RError(f"Invalid subscript on dimension '{t}'")
-        out.append(p)
-    return out
+        # matrix(x, nrow, byrow = TRUE): x fills row after row
+        out = np.empty((dims[0], dims[1]), dtype=float)
+        for k, v in enumerate(vals):
+            out[k // dims[1], k % dims[1]] = v
+        return Param(out, dn)
+    # array(x, dim): x fills in storage order, first subscript fastest
+    out = np.empty(dims, dtype=float)
+    for lin, v in enumerate(vals):
+        rest, idx = lin, []
+        for d in dims:
+            idx.append(rest % d)
+            rest //= d
+        out[tuple(idx)] = v
+    return Param(out, dn)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -445,36 +531,49 @@ def diag(x):
 
 
 def apply(X, MARGIN, FUN):
+    """base::apply over a linear variable: FUN on every slice that fixes the MARGIN dimensions, results laid out as
+    array(dim = dim(X)[MARGIN]) — the first margin runs fastest.  (Independent of easylp_b200/model.py since round 2:
+    the cells are walked with an explicit mixed-radix counter.)"""
     _ensure_not_con(X, "apply")
     if not _is_var(X):
         raise RError("apply(): only linear variables are supported by this restatement")
-    if isinstance(MARGIN, str) or (isinstance(MARGIN, (list, tuple)) and MARGIN and isinstance(MARGIN[0], str)):
+    margins = MARGIN if isinstance(MARGIN, (list, tuple, np.ndarray, range)) else [MARGIN]
+    margins = list(margins)
+    if any(isinstance(v, (str, np.str_)) for v in margins):
         raise RError("Not all elements of 'MARGIN' are names of dimensions.")
-    MARGIN = [int(v) for v in np.atleast_1d(np.asarray(MARGIN))]
-    nd = X.ind.ndim
-    if any(v < 1 or v > nd for v in MARGIN):
-        raise RError("'MARGIN' does not match dim(X).")
-    mdims = [X.ind.shape[v - 1] for v in MARGIN]
-    cells = list(itertools.product(*[range(1, d + 1) for d in reversed(mdims)]))
-    coef = np.zeros((len(cells), X.coef.shape[1]))
-    add = np.zeros(len(cells))
-    for k, cell in enumerate(cells):
-        cell = list(reversed(cell))                      # first margin fastest
-        ind = [np.arange(1, d + 1) for d in X.ind.shape]
-        for v, c in zip(MARGIN, cell):
-            ind[v - 1] = c
-        y = X[tuple(ind)]
-        z = FUN(y)
+    margins = [int(v) for v in margins]
+    shape = list(X.ind.shape)
+    for v in margins:
+        if v < 1 or v > len(shape):
+            raise RError("'MARGIN' does not match dim(X).")
+    mdims = [shape[v - 1] for v in margins]
+    ncell = 1
+    for d in mdims:
+        ncell *= d
+    coef_rows, adds = [], []
+    counter = [1] * len(margins)                       # 1-based position along every margin, first one fastest
+    for _ in range(ncell):
+        key = [np.arange(1, d + 1) for d in shape]     # a missing subscript = the whole extent
+        for v, cpos in zip(margins, counter):
+            key[v - 1] = cpos
+        z = FUN(X[tuple(key)])
         if z.coef.shape[0] != 1:
             raise RError("number of items to replace is not a multiple of replacement length")
-        coef[k, :] = z.coef[0]
-        add[k] = z.add[0]
+        coef_rows.append(np.array(z.coef[0], dtype=float))
+        adds.append(float(z.add[0]))
+        for d in range(len(counter)):                  # advance the counter
+            counter[d] += 1
+            if counter[d] <= mdims[d]:
+                break
+            counter[d] = 1
     out = X.copy()
-    out.ind = np.arange(1, len(cells) + 1).reshape(mdims, order="F")
-    out.dimnames = [X.dimnames[v - 1] for v in MARGIN] if X.dimnames is not None else None
-    out.dimtitles = [X.dimtitles[v - 1] for v in MARGIN] if X.dimtitles is not None else None
+    out.ind = np.arange(1, ncell + 1).reshape(mdims, order="F")
+    out.dimnames = [X.dimnames[v - 1] for v in margins] if X.dimnames is not None else None
+    out.dimtitles = [X.dimtitles[v - 1] for v in margins] if X.dimtitles is not None else None
     out.has_dim = True
-    out.coef, out.add, out.raw = coef, add, False
+    out.coef = np.vstack(coef_rows) if coef_rows else np.zeros((0, X.coef.shape[1]))
+    out.add = np.array(adds, dtype=float)
+    out.raw = False
     return out
 
 
