@@ -772,8 +772,17 @@ int elp_sensitivity(int32_t m, int32_t n, const int32_t* row_ptr, const int32_t*
 struct Model {
     int32_t m = 0, n = 0;
     int64_t nnz = 0;
-    DevBuf<int32_t> ptr, idx;
+    DevBuf<unsigned char> slab;          // ONE allocation (cudaMalloc costs 2-13 ms per call on these boxes, with outliers):
+    DevBuf<int32_t> ptr, idx;            // ptr, idx and val are views into it
     DevBuf<double> val;
+    void alloc(size_t m1, size_t nz) {
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_val = up(nz * sizeof(double)), b_idx = up(nz * sizeof(int32_t)), b_ptr = up(m1 * sizeof(int32_t));
+        slab.alloc(b_val + b_idx + b_ptr);
+        val.p = reinterpret_cast<double*>(slab.p); val.n = nz; val.owned = false;
+        idx.p = reinterpret_cast<int32_t*>(slab.p + b_val); idx.n = nz; idx.owned = false;
+        ptr.p = reinterpret_cast<int32_t*>(slab.p + b_val + b_idx); ptr.n = m1; ptr.owned = false;
+    }
 };
 
 int elp_model_assemble(int64_t n_terms, const int32_t* term_row, const int32_t* term_col, const double* term_val,
@@ -797,7 +806,7 @@ int elp_model_assemble(int64_t n_terms, const int32_t* term_row, const int32_t* 
     auto* h = new Model();
     try {
         h->m = m; h->n = n; h->nnz = nnz;
-        h->ptr.alloc((size_t)m + 1); h->idx.alloc((size_t)std::max<int64_t>(nnz, 1)); h->val.alloc((size_t)std::max<int64_t>(nnz, 1));
+        h->alloc((size_t)m + 1, (size_t)std::max<int64_t>(nnz, 1));
         ELP_CUDA(cudaMemcpyAsync(h->ptr.p, io.out_ptr, ((size_t)m + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
         if (nnz) {
             ELP_CUDA(cudaMemcpyAsync(h->idx.p, io.out_col, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
