@@ -112,7 +112,10 @@ int elp_release_workspace(void);                     /* frees the calling thread
  * expression tree is folded in).  Output: canonical CSR = entries of the dense matrix that are != 0,
  * row-major, ascending column; duplicates of one (row, col) are summed strictly left-to-right in
  * emission order so the result is bit-identical to the reference's dense arithmetic.
- * row_ptr has m+1 entries; col_idx/vals must have room for n_terms entries; *nnz_out receives the count. */
+ * row_ptr has m+1 entries; col_idx/vals must have room for n_terms entries; *nnz_out receives the count.
+ * On the device: a stream that already is in (row, col) order — what `$con()` emits — takes two passes and no sort; any
+ * other order is split into row buckets that one CTA each sorts and folds in shared memory; streams with a row too long
+ * for a bucket fall back to a stable radix sort.  The three paths give the same bytes. */
 int elp_assemble_csr(int64_t n_terms, const int32_t* term_row, const int32_t* term_col,
                      const double* term_val, int32_t m, int32_t n,
                      int32_t* row_ptr, int32_t* col_idx, double* vals, int64_t* nnz_out,
