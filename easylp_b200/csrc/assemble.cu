@@ -171,9 +171,10 @@ asm_ordered_emit(const int32_t* __restrict__ row, const int32_t* __restrict__ co
     __shared__ uint32_t wsum[AO_THREADS / 32];
     __shared__ int wlast[AO_THREADS / 32];
     __shared__ int base_last, near, skip;
-    if (threadIdx.x == 0) { skip = bad[1]; base_last = -1; near = 0x7fffffff; }
+    if (threadIdx.x == 0) { skip = bad[0] | bad[1]; base_last = -1; near = 0x7fffffff; }
     __syncthreads();
-    if (skip) return;                    // the stream is not ordered: the host takes another path
+    if (skip) return;                    // not ordered: the host takes another path; a term outside the matrix: the host
+                                         // reports it (its row must never index row_ptr)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t i0 = ((uint64_t)blockIdx.x * AO_THREADS + threadIdx.x) * AO_V;
     AoTerms t;
@@ -233,9 +234,9 @@ asm_ordered_emit(const int32_t* __restrict__ row, const int32_t* __restrict__ co
 }
 __global__ void asm_row_ptr_tail(const int32_t* __restrict__ last_row, const uint32_t* __restrict__ nnz, uint32_t m, int32_t* __restrict__ row_ptr,
                                  const int* __restrict__ bad) {
-    if (bad[1]) return;
+    if (bad[0] | bad[1]) return;         // the emit pass did not run
     const int64_t rr = (int64_t)*last_row + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (rr <= (int64_t)m) row_ptr[rr] = (int32_t)*nnz;
+    if (rr >= 0 && rr <= (int64_t)m) row_ptr[rr] = (int32_t)*nnz;
 }
 
 // One thread per sorted slot; the head of every equal-key run folds the run left-to-right.

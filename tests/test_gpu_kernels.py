@@ -156,6 +156,33 @@ def test_assemble_rejects_out_of_range():
         L.assemble_csr([0, 5], [0, 0], [1.0, 1.0], 2, 2)
 
 
+@pytest.mark.parametrize("order", ["ordered", "unordered"])
+@pytest.mark.parametrize("what", ["row_high", "row_negative", "col_high"])
+def test_assemble_rejects_out_of_range_in_long_streams(order, what):
+    # every path (two-pass ordered, buckets, radix sort) reports the term and never uses it as an index; the library
+    # stays usable afterwards
+    rng = np.random.default_rng(2)
+    T, m, n = 6000, 50, 40
+    row = np.sort(rng.integers(0, m, T)).astype(np.int32)
+    col = rng.integers(0, n, T).astype(np.int32)
+    o = np.lexsort((col, row))
+    row, col = row[o], col[o]
+    val = rng.normal(size=T)
+    if what == "row_high":
+        row[-1] = 2_000_000_000
+    elif what == "row_negative":
+        row[0] = -7
+    else:
+        col[T // 2] = n
+    if order == "unordered":
+        p = rng.permutation(T)
+        row, col, val = row[p], col[p], val[p]
+    with pytest.raises(L.ElpError):
+        L.assemble_csr(row, col, val, m, n)
+    rp, ci, v, _ = L.assemble_csr([0, 1], [1, 0], [1.0, 2.0], 2, 2)
+    assert rp.tolist() == [0, 1, 2] and ci.tolist() == [1, 0] and v.tolist() == [1.0, 2.0]
+
+
 def test_spmv_and_feasible():
     p = gen.sparse_planted(3000, seed=1)
     x = np.random.default_rng(0).normal(size=p["n"])
